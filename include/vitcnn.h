@@ -1,0 +1,123 @@
+/* libvitcnn.so -- C ABI of the B200-native ViT-CNN hot path.
+ *
+ * Drop-in boundary: the reference toolkit is pure Python on stock
+ * PyTorch ops; its hot path is entered through
+ *   datasets.py:550-593      MultiModalX.__getitem__  (per-pixel patch slice, HWC->CHW)
+ *   utils.py:357-415         sliding_window / count_sliding_window
+ *   model_utils.py:1067-1132 test()  (batch assembly, forward, logits scatter)
+ *   model_utils.py:921,1118  net(data, data2)  (model forward)
+ * Each entry point below names the reference interface it replaces.  The Python binding a
+ * maintainer adds is a ctypes stub; torch only supplies device buffers and
+ * the stream.
+ *
+ * Conventions: every pointer is a DEVICE pointer unless stated; the caller owns all buffers
+ * (inputs, outputs, workspaces); nothing is allocated, freed or retained by the library; all
+ * work is enqueued on `stream` (a cudaStream_t passed as void*); functions never throw and
+ * return 0 (VC_OK) or a negative code, vc_last_error() giving a thread-local description.
+ */
+#ifndef VITCNN_H_
+#define VITCNN_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VC_ABI_VERSION 1
+
+/* Parameters of one model instance in kernel-ready form (built by vc-side packing, see
+ * vitcnn_b200/model.py::pack_for_inference).  Conv weights: bf16 [nsplit][taps][S_in][N/nsplit][8]
+ * (tap = ky*3+kx, S_in = padded Cin / 8); scale/bias: fp32 [N] = BatchNorm folded with the
+ * conv bias.  tparams: blob described by vc_tparams_layout(). */
+typedef struct vc_model {
+  int32_t C1, C2, P, K;        /* HSI bands, LiDAR bands, patch size, classes            */
+  int32_t S1, S2;              /* input slices: ceil(C/16)*2                              */
+  int32_t nsplit_h[3];         /* CTA split of the output channels, HSI stem convs        */
+  int32_t nsplit_l[3];         /* ... LiDAR stem convs                                    */
+  const void* w_h[3];          /* HSI stem: C1->128->64->32                               */
+  const float* scale_h[3];
+  const float* bias_h[3];
+  const void* w_l[3];          /* LiDAR stem: C2->8->16->32 (8 padded to 16)              */
+  const float* scale_l[3];
+  const float* bias_l[3];
+  const void* tparams;         /* fusion 1x1 + cls/pos + 2 blocks + norm + head           */
+} vc_model;
+
+int vc_abi_version(void);
+const char* vc_last_error(void);
+
+/* ---- instrumentation (bench.py): kernels launched by this library so far in the process, and
+ * per-kernel-class device time between vc_profile_begin/vc_profile_end on the calling thread
+ * (CUDA events around each launch).  Classes: 0 window index, 1 pack (patch gather to SPS),
+ * 2/3/4 HSI stem conv 1/2/3, 5 LiDAR stem convs, 6 token stage, 7 halo zeroing. */
+#define VC_KERNEL_CLASSES 8
+int64_t vc_launch_count(void);
+int vc_profile_begin(void);
+int vc_profile_end(double* ms_per_class, int64_t* launches_per_class, int32_t n_classes);
+
+/* ---- geometry of the SPS activation layout (rows per chunk of n patches) ------------------- */
+int64_t vc_sps_rows(int32_t n_patches, int32_t P);
+/* bytes of workspace vc_forward_* needs for a chunk of n patches */
+int64_t vc_workspace_bytes(int32_t n_patches, int32_t P, int32_t C1, int32_t C2);
+/* byte offsets of the token-stage parameter blob: fills out[0..n) and returns n (or the
+ * needed n if out is NULL).  Order: total, wfus, fus_scale, fus_bias, cls, lnf_g, lnf_b,
+ * whead, bhead, pos, then per layer (2x): wqkv, wproj, wfc1, wfc2, ln1_g, ln1_b, bqkv,
+ * bproj, ln2_g, ln2_b, bfc1, bfc2. */
+int32_t vc_tparams_layout(int32_t P, int32_t K, int64_t* out, int32_t n);
+
+/* ---- exact patch extraction ----------------------------------------------------------------
+ * Replaces MultiModalX.__getitem__ + default_collate (datasets.py:550-593, main.py:434-447)
+ * when center_mode=1 (xy = patch centres) and test()'s batch assembly (model_utils.py:1103-
+ * 1112, windows from utils.sliding_window) when center_mode=0 (xy = top-left corners).
+ * img1/img2: f32 [H][W][C] rasters; xy: int32 [n][2]; hsi: f32 [n][C1][P][P]; lidar: f32
+ * [n][C2][P][P]; labels (nullable with gt): int64 [n] = gt[centre]; gt element size 1/4/8 B.
+ * Bit-exact copies. */
+int vc_gather_patches_f32(const float* img1, const float* img2, const void* gt, int32_t gt_elem_bytes, int32_t H,
+                          int32_t W, int32_t C1, int32_t C2, const int32_t* xy, int32_t n, int32_t P,
+                          int32_t center_mode, float* hsi, float* lidar, int64_t* labels, void* stream);
+
+/* Window enumeration of utils.sliding_window (utils.py:374-397) for windows [first, first+count)
+ * given the per-axis start lists xs[nx], ys[ny] (int32, device): xy int32 [count][2] (nullable),
+ * off1/off2 = element offsets of the window corner in img1/img2 (nullable), out_idx = pixel
+ * index (x+P/2)*W + (y+P/2) that test() scatters to (model_utils.py:1127-1129). */
+int vc_scene_index(const int32_t* xs, const int32_t* ys, int32_t nx, int32_t ny, int32_t first, int32_t count,
+                   int32_t W, int32_t C1, int32_t C2, int32_t P, int64_t* off1, int64_t* off2, int64_t* out_idx,
+                   int32_t* xy, void* stream);
+
+/* ---- building blocks (exposed for tests and profiling) --------------------------------------- */
+/* fp32 patches (any strides, in elements) or raster windows (patch_off != NULL: per-patch
+ * element offset, sb ignored) -> bf16 SPS buffer [S][rows][8]. */
+int vc_pack_sps(const float* src, int64_t sb, int64_t sc, int64_t si, int64_t sj, const int64_t* patch_off,
+                int32_t n_patches, int32_t C, int32_t P, void* sps, int32_t S, void* stream);
+/* 3x3 pad-1 (taps=9) or 1x1 (taps=1) conv + per-channel affine (+ReLU) over SPS buffers.
+ * impl 0 = tcgen05 tensor-core kernel, impl 1 = SIMT twin for cross-checks. */
+int vc_conv_sps(const void* in_sps, int32_t S_in, const void* w_packed, const float* scale, const float* bias,
+                void* out_sps, int32_t out_slice_off, int32_t n_out, int32_t nsplit, int32_t n_patches, int32_t P,
+                int32_t taps, int32_t relu, int32_t impl, int32_t debug_flags, void* stream);
+/* token stage on the fused 64-channel SPS feature buffer -> logits f32 [n][K] (row b, or row
+ * out_index[b] when given); argmax_map (nullable, uint8) receives argmax at out_index[b]. */
+int vc_tokens_forward(const void* f_sps, const void* tparams, int32_t n_patches, int32_t P, int32_t K, float* logits,
+                      const int64_t* out_index, uint8_t* argmax_map, void* stream);
+
+/* ---- model forward: replaces net(data, data2) at model_utils.py:921/1118/1144 (eval) ---------
+ * hsi/lidar: f32 [n][C][P][P] with arbitrary element strides (sb, sc, si, sj) -- contiguous
+ * NCHW from the DataLoader or the NHWC-memory view test() builds.  logits: f32 [n][K]. */
+int vc_forward_patches(const vc_model* m, const float* hsi, const int64_t hsi_strides[4], const float* lidar,
+                       const int64_t lidar_strides[4], int32_t n, void* workspace, int64_t workspace_bytes,
+                       float* logits, void* stream);
+
+/* ---- full-scene inference: replaces the loop of test() (model_utils.py:1086-1129) ------------
+ * Windows are enumerated on the device from xs/ys (see vc_scene_index), processed in chunks of
+ * `chunk` windows [first_window, first_window+n_windows); logits land in logits_map f32
+ * [H][W][K] at the window centre (untouched pixels are left as they are: zero-fill first),
+ * argmax_map (nullable) uint8 [H][W].  Row-band sharding = disjoint window ranges per GPU. */
+int vc_scene_infer(const vc_model* m, const float* img1, const float* img2, int32_t H, int32_t W, const int32_t* xs,
+                   const int32_t* ys, int32_t nx, int32_t ny, int64_t first_window, int64_t n_windows, int32_t chunk,
+                   void* workspace, int64_t workspace_bytes, float* logits_map, uint8_t* argmax_map, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITCNN_H_ */

@@ -1,0 +1,82 @@
+"""-m gpu: exact patch extraction through the C-ABI vs the numpy oracle and the committed
+reference-generated fixtures.  Bit-exact (fp32 copies, int64 labels)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import data_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _gather(img1, img2, gt, xy, P, center):
+    from vitcnn_b200 import ops
+    d = _dev()
+    h, l, lab = ops.gather_patches(torch.from_numpy(img1).to(d), torch.from_numpy(img2).to(d),
+                                   torch.from_numpy(np.ascontiguousarray(xy, dtype=np.int32)).to(d), P,
+                                   center_mode=center, gt=None if gt is None else torch.from_numpy(gt).to(d))
+    torch.cuda.synchronize()
+    return h.cpu().numpy(), l.cpu().numpy(), None if lab is None else lab.cpu().numpy()
+
+
+def test_golden_multimodalx_samples(data_golden):
+    g = data_golden
+    for ci, (H, W, C1, C2, P, n) in enumerate(g["ds_cases"]):
+        idx = g[f"ds{ci}_indices"][:n]
+        h, l, lab = _gather(g[f"ds{ci}_img1"], g[f"ds{ci}_img2"], g[f"ds{ci}_gt"], idx, int(P), True)
+        assert h.tobytes() == g[f"ds{ci}_hsi"].tobytes()
+        assert l.tobytes() == g[f"ds{ci}_lidar"].tobytes()
+        assert np.array_equal(lab, g[f"ds{ci}_label"])
+
+
+@pytest.mark.parametrize("P", [1, 5, 7, 8, 9, 11, 15])
+@pytest.mark.parametrize("C1,C2", [(144, 1), (64, 2), (180, 1), (7, 3)])
+def test_random_shapes_vs_oracle(P, C1, C2):
+    rng = np.random.default_rng(P * 1000 + C1)
+    H, W = P + 9, P + 14
+    img1 = rng.random((H, W, C1), dtype=np.float32)
+    img2 = rng.random((H, W, C2), dtype=np.float32)
+    gt = rng.integers(0, 9, size=(H, W)).astype(np.int64)
+    corners = R.sliding_window_corners((H, W), 1, (P, P))
+    h, l, _ = _gather(img1, img2, None, corners, P, False)
+    wh, wl = R.gather_corners(img1, img2, corners, P)
+    assert h.tobytes() == wh.tobytes() and l.tobytes() == wl.tobytes()
+    centers = corners + P // 2
+    h, l, lab = _gather(img1, img2, gt, centers, P, True)
+    assert h.tobytes() == wh.tobytes() and l.tobytes() == wl.tobytes()
+    assert np.array_equal(lab, gt[centers[:, 0], centers[:, 1]])
+
+
+def test_houston_size_checksum():
+    """Full-size property: every window of a Houston-shaped row band, checked through sums
+    the oracle can produce without materialising the patches (a patch sum is a box filter)."""
+    from vitcnn_b200 import ops
+    rng = np.random.default_rng(3)
+    H, W, C1, C2, P = 40, 1905, 144, 1, 11
+    img1 = rng.integers(0, 256, size=(H, W, C1)).astype(np.float32)   # integers: fp32 sums are exact
+    img2 = rng.integers(0, 256, size=(H, W, C2)).astype(np.float32)
+    corners = R.sliding_window_corners((H, W), 1, (P, P))
+    d = _dev()
+    t1, t2 = torch.from_numpy(img1).to(d), torch.from_numpy(img2).to(d)
+    xy = torch.from_numpy(corners.astype(np.int32)).to(d)
+    tot = np.zeros(len(corners))
+    for s in range(0, len(corners), 8192):
+        h, l, _ = ops.gather_patches(t1, t2, xy[s:s + 8192], P, center_mode=False)
+        tot[s:s + 8192] = (h.double().sum((1, 2, 3)) + l.double().sum((1, 2, 3))).cpu().numpy()
+    plane = img1.astype(np.float64).sum(2) + img2.astype(np.float64).sum(2)
+    ii = np.pad(plane.cumsum(0).cumsum(1), ((1, 0), (1, 0)))
+    x, y = corners[:, 0], corners[:, 1]
+    want = ii[x + P, y + P] - ii[x, y + P] - ii[x + P, y] + ii[x, y]
+    assert np.array_equal(tot, want)
+
+
+def test_empty_batch():
+    from vitcnn_b200 import ops
+    d = _dev()
+    h, l, _ = ops.gather_patches(torch.rand(12, 12, 4, device=d), torch.rand(12, 12, 1, device=d),
+                                 torch.zeros(0, 2, dtype=torch.int32, device=d), 5)
+    assert h.shape == (0, 4, 5, 5) and l.shape == (0, 1, 5, 5)

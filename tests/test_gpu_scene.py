@@ -1,0 +1,58 @@
+"""-m gpu: full-scene sliding-window inference (the loop of test(), model_utils.py:1067-1132)
+vs the oracle's restatement of that loop driving the fp32 oracle model."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import data_ref as R
+from tests.test_gpu_model import DEV, REL_TOL, make_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_probs(ref, img1, img2, P, K, stride, bs=64):
+    def net(h, l):
+        with torch.no_grad():
+            return ref(torch.from_numpy(h), torch.from_numpy(l)).numpy()
+    return R.scene_test(net, img1, img2, P, bs, K, stride)
+
+
+@pytest.mark.parametrize("cfg", [(24, 31, 16, 1, 5, 4, 1), (30, 26, 64, 2, 7, 12, 2), (27, 40, 144, 1, 11, 16, 1),
+                                 (29, 33, 20, 1, 9, 5, 3)])
+def test_scene_vs_oracle_loop(cfg):
+    import vitcnn_b200
+    H, W, C1, C2, P, K, stride = cfg
+    ref, ours = make_pair(C1, C2, P, K)
+    img1, img2, _ = R.synthetic_scene(H, W, C1, C2, K, seed=1)
+    want = _oracle_probs(ref, img1, img2, P, K, stride)
+    hp = dict(patch_size=P, center_pixel=True, batch_size=64, device=torch.device(DEV), n_classes=K,
+              applyPCA=False, test_stride=stride, scene_chunk=100)   # several chunks, short last one
+    got = vitcnn_b200.test(0, ours, img1, img2, hp)
+    assert got.dtype == np.float64 and got.shape == want.shape
+    assert np.array_equal(got == 0, want == 0)          # untouched pixels stay exactly zero
+    assert np.abs(got - want).max() <= REL_TOL * np.abs(want).max()
+
+
+def test_scene_equals_batched_forward_and_row_bands():
+    """The scene path must give bit-identical logits to forward() on the same windows, and a
+    row-band split (any number of ranks) must reproduce the single-pass map bit for bit."""
+    from vitcnn_b200.utils import row_band_ranges, window_starts
+    H, W, C1, C2, P, K = 33, 45, 144, 1, 11, 16
+    ref, ours = make_pair(C1, C2, P, K)
+    img1, img2, _ = R.synthetic_scene(H, W, C1, C2, K, seed=4)
+    t1, t2 = torch.from_numpy(img1).to(DEV), torch.from_numpy(img2).to(DEV)
+    full, amax = ours.predict_scene(t1, t2, chunk=257)
+    corners = R.sliding_window_corners((H, W), 1, (P, P))
+    h, l = R.gather_corners(img1, img2, corners, P)
+    with torch.no_grad():
+        lg = ours(torch.from_numpy(h).to(DEV), torch.from_numpy(l).to(DEV))
+    cx, cy = corners[:, 0] + P // 2, corners[:, 1] + P // 2
+    assert torch.equal(full[cx, cy], lg)
+    assert torch.equal(amax[cx, cy].long(), lg.argmax(1))
+    nx, ny = len(window_starts(H, P, 1)), len(window_starts(W, P, 1))
+    for world in (2, 3, 8):
+        acc = torch.zeros_like(full)
+        am = torch.zeros_like(amax)
+        for first, count in row_band_ranges(nx, ny, world):
+            ours.predict_scene(t1, t2, chunk=300, window_range=(first, count), logits_map=acc, argmax_map=am)
+        assert torch.equal(acc, full) and torch.equal(am, amax)

@@ -1,0 +1,275 @@
+// 3x3 'same' (or 1x1) convolution over the SPS activation layout as shifted GEMMs on the
+// 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by the TMA unit
+// with 1-D bulk copies).  Replaces the reference idiom Conv2d(k=3,pad=1) -> BatchNorm2d ->
+// ReLU (S2ENet conv_bn_relu; model/Multimodality_Mamba/Mutimodality_Mamba7.py:1035-1048,
+// 1152-1153) for inference (BN folded into a per-channel affine).
+//
+// GEMM view: M = stacked patch rows (128 per tile, tiles ignore patch boundaries),
+// N = output channels handled by this CTA (16..128), K = taps x input channels.
+// A tile for tap (dy,dx) = rows [R0+shift, R0+shift+128) of the input, a contiguous slab
+// per 8-channel slice, so one resident stage [2 slices][128+2*halo rows][16 B] serves all
+// nine taps by moving the descriptor start address.  Weights stay resident in shared memory
+// for the life of the (persistent) CTA.
+#include "vc_common.cuh"
+#include "vc_kernels.h"
+
+namespace vc {
+
+struct ConvArgs {
+  const __nv_bfloat16* in;   // [S_in][RT][8]
+  const __nv_bfloat16* w;    // [nsplit][ntaps][S_in][ncta][8]
+  const float* scale;        // [nsplit*ncta]
+  const float* bias;         // [nsplit*ncta]
+  __nv_bfloat16* out;        // [S_out_total][RT][8]
+  long long RT;
+  int S_in, ncta, ntaps, P, n_patches, ntiles, out_slice_off, relu, nstages, debug_flags;
+};
+
+constexpr int kConvThreads = 192;  // warp0 producer, warp1 MMA issuer, warps 2..5 epilogue
+
+__global__ void __launch_bounds__(kConvThreads, 1) conv_sps_tc_kernel(ConvArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HALO = sps_halo(a.P), ROWS = 128 + 2 * HALO, PP = sps_pp(a.P), PW = a.P + 1;
+  const uint32_t slice_bytes = (uint32_t)ROWS * 16u, stage_bytes = 2u * slice_bytes;
+  const uint32_t wbytes = (uint32_t)a.ntaps * a.S_in * a.ncta * 16u;
+  const int KS = a.S_in / 2;  // K=16 steps per tap
+  const int half = blockIdx.y;
+
+  uint8_t* w_s = smem;
+  uint8_t* stage_s = smem + ((wbytes + 127u) & ~127u);
+  uint8_t* tail = stage_s + (size_t)a.nstages * stage_bytes;
+  float* sc_s = reinterpret_cast<float*>(tail);
+  float* bi_s = sc_s + a.ncta;
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bi_s + a.ncta) + 7) & ~uintptr_t(7));
+  uint64_t* full = bars;
+  uint64_t* empty = bars + a.nstages;
+  uint64_t* wfull = bars + 2 * a.nstages;
+  uint64_t* tfull = wfull + 1;   // [2]
+  uint64_t* tempty = wfull + 3;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 5);
+
+  const uint32_t tmem_cols = (2 * a.ncta <= 32) ? 32u : (2 * a.ncta <= 64) ? 64u : (2 * a.ncta <= 128) ? 128u : 256u;
+
+  for (int i = threadIdx.x; i < a.ncta; i += blockDim.x) {
+    sc_s[i] = a.scale[half * a.ncta + i];
+    bi_s[i] = a.bias[half * a.ncta + i];
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.nstages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(wfull, 1);
+    mbar_init(&tfull[0], 1);
+    mbar_init(&tfull[1], 1);
+    mbar_init(&tempty[0], 128);
+    mbar_init(&tempty[1], 128);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer: weights once, then one stage (2 channel slices) per K=16 step =====
+    if (lane == 0) {
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) + (size_t)half * wbytes;
+      mbar_arrive_expect_tx(wfull, wbytes);
+      for (uint32_t off = 0; off < wbytes; off += 32768u) {
+        uint32_t n = wbytes - off < 32768u ? wbytes - off : 32768u;
+        bulk_g2s(w_s + off, wsrc + off, n, wfull);
+      }
+      int st = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const long long row0 = (long long)tile * 128;  // = R0 - HALO
+        for (int ks = 0; ks < KS; ++ks) {
+          mbar_wait(&empty[st], ph ^ 1u);
+          mbar_arrive_expect_tx(&full[st], stage_bytes);
+          uint8_t* dst = stage_s + (size_t)st * stage_bytes;
+          const __nv_bfloat16* s0 = a.in + ((long long)(2 * ks) * a.RT + row0) * 8;
+          const __nv_bfloat16* s1 = a.in + ((long long)(2 * ks + 1) * a.RT + row0) * 8;
+          bulk_g2s(dst, s0, slice_bytes, &full[st]);
+          bulk_g2s(dst + slice_bytes, s1, slice_bytes, &full[st]);
+          if (++st == a.nstages) { st = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread drives the tensor core =====
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, a.ncta);
+      const bool swap = (a.debug_flags & 1) != 0;   // debug: exchange LBO/SBO roles
+      const uint32_t a_lbo = swap ? 128u : slice_bytes, a_sbo = swap ? slice_bytes : 128u;
+      const uint32_t b_lbo = swap ? 128u : (uint32_t)a.ncta * 16u, b_sbo = swap ? (uint32_t)a.ncta * 16u : 128u;
+      const uint32_t w_addr = smem_u32(w_s);
+      mbar_wait(wfull, 0);
+      int st = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t accph = 0;
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], accph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.ncta);
+        for (int ks = 0; ks < KS; ++ks) {
+          mbar_wait(&full[st], ph);
+          tc_fence_after();
+          const uint32_t s_addr = smem_u32(stage_s + (size_t)st * stage_bytes);
+          for (int tap = 0; tap < a.ntaps; ++tap) {
+            const int shift = (a.ntaps == 9) ? ((tap / 3 - 1) * PW + (tap % 3 - 1)) : 0;
+            const uint64_t ad = umma_desc(s_addr + (uint32_t)(HALO + shift) * 16u, a_lbo, a_sbo);
+            const uint64_t bd = umma_desc(w_addr + (uint32_t)((tap * a.S_in + 2 * ks) * a.ncta) * 16u, b_lbo, b_sbo);
+            umma_bf16(d_tmem, ad, bd, idesc, (ks | tap) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[st]);
+          if (++st == a.nstages) { st = 0; ph ^= 1u; }
+        }
+        umma_commit(&tfull[acc]);
+        if (++acc == 2) { acc = 0; accph ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> affine (+ReLU) -> bf16 -> SPS rows =====
+    const int quarter = warp & 3;  // TMEM lanes this warp may touch
+    const int row_in_tile = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t accph = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      const long long r = (long long)tile * 128 + row_in_tile;  // row index without the lead halo
+      const long long R = r + HALO;
+      const long long b = r / PP;
+      const int q = (int)(r - b * PP);
+      const int i = q / PW, j = q - i * PW;
+      const bool valid = (b < a.n_patches) && (i < a.P) && (j < a.P);
+      mbar_wait(&tfull[acc], accph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * a.ncta);
+      for (int c0 = 0; c0 < a.ncta; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        tc_wait_ld();
+        uint32_t pk[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float y0 = __uint_as_float(v[2 * k]) * sc_s[c0 + 2 * k] + bi_s[c0 + 2 * k];
+          float y1 = __uint_as_float(v[2 * k + 1]) * sc_s[c0 + 2 * k + 1] + bi_s[c0 + 2 * k + 1];
+          if (a.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+          if (!valid) { y0 = 0.f; y1 = 0.f; }
+          pk[k] = pack_bf16(y0, y1);
+        }
+        const int slice = a.out_slice_off + (half * a.ncta + c0) / 8;
+        uint4* o0 = reinterpret_cast<uint4*>(a.out + ((long long)slice * a.RT + R) * 8);
+        uint4* o1 = reinterpret_cast<uint4*>(a.out + ((long long)(slice + 1) * a.RT + R) * 8);
+        *o0 = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *o1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; accph ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ---- plain SIMT twin (tests / bring-up cross-check only; same arguments, same layouts) ------
+__global__ void conv_sps_simt_kernel(ConvArgs a, int nsplit) {
+  const int HALO = sps_halo(a.P), PP = sps_pp(a.P), PW = a.P + 1;
+  const int ntot = a.ncta * nsplit;
+  const long long total = (long long)a.ntiles * 128 * ntot;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int oc = (int)(idx % ntot);
+    const long long r = idx / ntot;
+    const long long R = r + HALO;
+    const long long b = r / PP;
+    const int q = (int)(r - b * PP);
+    const int i = q / PW, j = q - i * PW;
+    const bool valid = (b < a.n_patches) && (i < a.P) && (j < a.P);
+    const int half = oc / a.ncta, n = oc % a.ncta;
+    float acc = 0.f;
+    if (valid) {
+      for (int tap = 0; tap < a.ntaps; ++tap) {
+        const int shift = (a.ntaps == 9) ? ((tap / 3 - 1) * PW + (tap % 3 - 1)) : 0;
+        for (int s = 0; s < a.S_in; ++s) {
+          const __nv_bfloat16* x = a.in + ((long long)s * a.RT + R + shift) * 8;
+          const __nv_bfloat16* w = a.w + ((((long long)half * a.ntaps + tap) * a.S_in + s) * a.ncta + n) * 8;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc += __bfloat162float(x[k]) * __bfloat162float(w[k]);
+        }
+      }
+      acc = acc * a.scale[oc] + a.bias[oc];
+      if (a.relu) acc = fmaxf(acc, 0.f);
+    }
+    a.out[((long long)(a.out_slice_off + oc / 8) * a.RT + R) * 8 + (oc & 7)] = __float2bfloat16_rn(acc);
+  }
+}
+
+static size_t conv_smem_bytes(int S_in, int ncta, int ntaps, int P, int nstages) {
+  const int ROWS = 128 + 2 * sps_halo(P);
+  size_t wbytes = ((size_t)ntaps * S_in * ncta * 16 + 127) & ~size_t(127);
+  return wbytes + (size_t)nstages * 2 * ROWS * 16 + (size_t)ncta * 8 + 8 + (2 * nstages + 5) * 8 + 16;
+}
+
+int conv_sps_launch(const void* in, int S_in, const void* w, const float* scale, const float* bias, void* out,
+                    int out_slice_off, int n_out, int nsplit, int n_patches, int P, int ntaps, int relu, int impl,
+                    int debug_flags, cudaStream_t stream) {
+  if (S_in <= 0 || (S_in & 1) || nsplit <= 0 || n_out % nsplit) return VC_ERR_ARG;
+  const int ncta = n_out / nsplit;
+  if (ncta % 16 || ncta < 16 || ncta > 128 || (ntaps != 9 && ntaps != 1) || P < 1 || n_patches <= 0) return VC_ERR_ARG;
+  ConvArgs a;
+  a.in = (const __nv_bfloat16*)in;
+  a.w = (const __nv_bfloat16*)w;
+  a.scale = scale;
+  a.bias = bias;
+  a.out = (__nv_bfloat16*)out;
+  a.RT = sps_rows(n_patches, P);
+  a.S_in = S_in;
+  a.ncta = ncta;
+  a.ntaps = ntaps;
+  a.P = P;
+  a.n_patches = n_patches;
+  a.ntiles = sps_tiles(n_patches, P);
+  a.out_slice_off = out_slice_off;
+  a.relu = relu;
+  a.debug_flags = debug_flags;
+  a.nstages = 0;
+  if (impl == 1) {
+    long long total = (long long)a.ntiles * 128 * n_out;
+    int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    conv_sps_simt_kernel<<<blocks, 256, 0, stream>>>(a, nsplit);
+    return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
+  }
+  static int max_smem = 0, num_sms = 0;
+  if (!max_smem) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int nst = 8;
+  while (nst > 2 && conv_smem_bytes(S_in, ncta, ntaps, P, nst) > (size_t)max_smem) --nst;
+  const size_t smem = conv_smem_bytes(S_in, ncta, ntaps, P, nst);
+  if (smem > (size_t)max_smem) return VC_ERR_UNSUPPORTED;
+  a.nstages = nst;
+  if (cudaFuncSetAttribute(conv_sps_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return VC_ERR_CUDA;
+  int gx = num_sms / nsplit;
+  if (gx < 1) gx = 1;
+  if (gx > a.ntiles) gx = a.ntiles;
+  dim3 grid(gx, nsplit);
+  conv_sps_tc_kernel<<<grid, kConvThreads, smem, stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
+}
+
+}  // namespace vc

@@ -1,0 +1,399 @@
+// Token stage of the ViT-CNN hybrid as ONE kernel per chunk of patches: 1x1 fusion conv
+// (+folded BN, ReLU) -> cls token + pos-embed -> 2 x [LN -> MHSA -> +res -> LN -> MLP(GELU)
+// -> +res] -> LN -> head on the cls token.  Spec: SURVEY.md App. A (R0), following
+// model/compare_method/vit/timm/models/vision_transformer.py:57-105 (Attention), :123-166
+// (Block), :598-629 (cls/pos), :680-701 (norm/head) and timm/layers/mlp.py:13-47.
+//
+// One CTA owns one patch at a time; warp w owns token rows 16w..16w+15 and keeps their
+// residual stream in registers in the mma.sync accumulator layout for the whole stage, so
+// LayerNorm is a GEMM prologue (quad shuffles), bias/GELU/residual are GEMM epilogues and
+// QK^T -> online softmax (exp2, warp-shuffle row reductions) -> PV never leaves registers;
+// only K and V^T of the current layer go through shared memory (whole token set resident).
+#include <math.h>
+#include "vc_common.cuh"
+#include "vc_kernels.h"
+#include "vc_tparams.h"
+
+namespace vc {
+
+struct TArgs {
+  const __nv_bfloat16* f;  // [8][RT][8] : slices 0-3 HSI stem, 4-7 LiDAR stem
+  const uint8_t* blob;
+  float* logits;               // [n][K] or scattered through out_index
+  const long long* out_index;  // nullable: logits row of patch b
+  unsigned char* argmax_map;   // nullable: argmax written at out_index[b]
+  long long RT;
+  int n_patches, P, K, T;
+};
+
+__device__ __forceinline__ uint32_t lds32(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return v;
+}
+__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }
+
+// LayerNorm (eps 1e-6) of the two token rows this thread shares with its quad; result as the
+// two K=16 A fragments of the following GEMM.
+__device__ __forceinline__ void ln_to_afrag(const float (&x)[4][4], const float* gam, const float* bet, int q,
+                                            uint32_t (&A)[2][4]) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { s0 += x[j][0] + x[j][1]; s1 += x[j][2] + x[j][3]; }
+  const float m0 = quad_sum(s0) * (1.f / kD), m1 = quad_sum(s1) * (1.f / kD);
+  float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float d;
+    d = x[j][0] - m0; v0 += d * d;
+    d = x[j][1] - m0; v0 += d * d;
+    d = x[j][2] - m1; v1 += d * d;
+    d = x[j][3] - m1; v1 += d * d;
+  }
+  const float rs0 = rsqrtf(quad_sum(v0) * (1.f / kD) + 1e-6f), rs1 = rsqrtf(quad_sum(v1) * (1.f / kD) + 1e-6f);
+  float y[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 gg = *reinterpret_cast<const float2*>(gam + 8 * j + 2 * q);
+    const float2 bb = *reinterpret_cast<const float2*>(bet + 8 * j + 2 * q);
+    y[j][0] = (x[j][0] - m0) * rs0 * gg.x + bb.x;
+    y[j][1] = (x[j][1] - m0) * rs0 * gg.y + bb.y;
+    y[j][2] = (x[j][2] - m1) * rs1 * gg.x + bb.x;
+    y[j][3] = (x[j][3] - m1) * rs1 * gg.y + bb.y;
+  }
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk) {
+    A[kk][0] = pack_bf16(y[2 * kk][0], y[2 * kk][1]);
+    A[kk][1] = pack_bf16(y[2 * kk][2], y[2 * kk][3]);
+    A[kk][2] = pack_bf16(y[2 * kk + 1][0], y[2 * kk + 1][1]);
+    A[kk][3] = pack_bf16(y[2 * kk + 1][2], y[2 * kk + 1][3]);
+  }
+}
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) transformer_fwd_kernel(TArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  constexpr int TP = 16 * NW;    // padded token count
+  constexpr int LDV = TP + 8;    // pitch of V^T rows
+  constexpr int NKB = (2 * NW + 7) / 8;  // key blocks of 64
+  const TLayout L = tlayout(a.P, a.K);
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem + L.total);  // [TP][40]
+  __nv_bfloat16* Vt = Ks + TP * kLdD;                                    // [32][LDV]
+  float* cls_s = reinterpret_cast<float*>(Vt + kD * LDV);                // [32]
+  float* logit_s = cls_s + kD;                                           // [K]
+
+  {  // parameters -> shared memory (once per persistent CTA)
+    const uint4* src = reinterpret_cast<const uint4*>(a.blob);
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    for (int i = threadIdx.x; i < L.total / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  const int r0 = 16 * warp + g, r1 = r0 + 8;
+  const int T = a.T, P = a.P, PW = P + 1, PP = sps_pp(P), HALO = sps_halo(P);
+  const __nv_bfloat16* wfus = reinterpret_cast<const __nv_bfloat16*>(smem + L.wfus);
+  const float* fus_scale = reinterpret_cast<const float*>(smem + L.fus_scale);
+  const float* fus_bias = reinterpret_cast<const float*>(smem + L.fus_bias);
+  const float* cls = reinterpret_cast<const float*>(smem + L.cls);
+  const float* pos = reinterpret_cast<const float*>(smem + L.pos);
+  const float qscale = 0.35355339059327376220f * 1.44269504088896340736f;  // hd^-0.5 * log2(e)
+
+  for (int b = blockIdx.x; b < a.n_patches; b += gridDim.x) {
+    // ---------------- tokens: fusion 1x1 conv over the concatenated stems ----------------
+    float x[4][4];
+    {
+      long long R0 = -1, R1 = -1;
+      if (r0 >= 1 && r0 < T) { const int p = r0 - 1; R0 = HALO + (long long)b * PP + (p / P) * PW + (p % P); }
+      if (r1 >= 1 && r1 < T) { const int p = r1 - 1; R1 = HALO + (long long)b * PP + (p / P) * PW + (p % P); }
+      float acc[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < kFusK / 16; ++kk) {
+        uint32_t A[4];
+        const __nv_bfloat16* s0 = a.f + (long long)(2 * kk) * a.RT * 8 + 2 * q;
+        const __nv_bfloat16* s1 = a.f + (long long)(2 * kk + 1) * a.RT * 8 + 2 * q;
+        A[0] = R0 >= 0 ? __ldg(reinterpret_cast<const uint32_t*>(s0 + R0 * 8)) : 0u;
+        A[1] = R1 >= 0 ? __ldg(reinterpret_cast<const uint32_t*>(s0 + R1 * 8)) : 0u;
+        A[2] = R0 >= 0 ? __ldg(reinterpret_cast<const uint32_t*>(s1 + R0 * 8)) : 0u;
+        A[3] = R1 >= 0 ? __ldg(reinterpret_cast<const uint32_t*>(s1 + R1 * 8)) : 0u;
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) {
+          const __nv_bfloat16* w = wfus + (8 * jn + g) * kLdFus + 16 * kk + 2 * q;
+          mma16816(acc[jn], A, lds32(w), lds32(w + 8));
+        }
+      }
+#pragma unroll
+      for (int jn = 0; jn < 4; ++jn) {
+        const int col = 8 * jn + 2 * q;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = (e < 2) ? r0 : r1, c = col + (e & 1);
+          float v = 0.f;
+          if (r == 0) v = cls[c] + pos[c];
+          else if (r < T) v = fmaxf(acc[jn][e] * fus_scale[c] + fus_bias[c], 0.f) + pos[r * kD + c];
+          x[jn][e] = v;
+        }
+      }
+    }
+
+#pragma unroll 1
+    for (int l = 0; l < kLayers; ++l) {
+      const TLayerOff& O = L.layer[l];
+      const __nv_bfloat16* wqkv = reinterpret_cast<const __nv_bfloat16*>(smem + O.wqkv);
+      const __nv_bfloat16* wproj = reinterpret_cast<const __nv_bfloat16*>(smem + O.wproj);
+      const __nv_bfloat16* wfc1 = reinterpret_cast<const __nv_bfloat16*>(smem + O.wfc1);
+      const __nv_bfloat16* wfc2 = reinterpret_cast<const __nv_bfloat16*>(smem + O.wfc2);
+      const float* bqkv = reinterpret_cast<const float*>(smem + O.bqkv);
+      const float* bproj = reinterpret_cast<const float*>(smem + O.bproj);
+      const float* bfc1 = reinterpret_cast<const float*>(smem + O.bfc1);
+      const float* bfc2 = reinterpret_cast<const float*>(smem + O.bfc2);
+
+      // ---- LN1 -> qkv GEMM; Q stays in registers, K and V^T go to shared memory ----
+      uint32_t A1[2][4];
+      ln_to_afrag(x, reinterpret_cast<const float*>(smem + O.ln1_g), reinterpret_cast<const float*>(smem + O.ln1_b), q, A1);
+      uint32_t qa[kHeads][2];
+#pragma unroll
+      for (int jn = 0; jn < 12; ++jn) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const __nv_bfloat16* w = wqkv + (8 * jn + g) * kLdD + 16 * kk + 2 * q;
+          mma16816(c, A1[kk], lds32(w), lds32(w + 8));
+        }
+        const float2 bb = *reinterpret_cast<const float2*>(bqkv + 8 * jn + 2 * q);
+        c[0] += bb.x; c[1] += bb.y; c[2] += bb.x; c[3] += bb.y;
+        if (jn < 4) {
+          qa[jn][0] = pack_bf16(c[0] * qscale, c[1] * qscale);
+          qa[jn][1] = pack_bf16(c[2] * qscale, c[3] * qscale);
+        } else if (jn < 8) {
+          const int col = 8 * (jn - 4) + 2 * q;
+          *reinterpret_cast<uint32_t*>(Ks + r0 * kLdD + col) = pack_bf16(c[0], c[1]);
+          *reinterpret_cast<uint32_t*>(Ks + r1 * kLdD + col) = pack_bf16(c[2], c[3]);
+        } else {
+          const int d = 8 * (jn - 8) + 2 * q;
+          Vt[d * LDV + r0] = __float2bfloat16_rn(c[0]);
+          Vt[(d + 1) * LDV + r0] = __float2bfloat16_rn(c[1]);
+          Vt[d * LDV + r1] = __float2bfloat16_rn(c[2]);
+          Vt[(d + 1) * LDV + r1] = __float2bfloat16_rn(c[3]);
+        }
+      }
+      __syncthreads();
+
+      // ---- attention: per head QK^T -> online softmax -> PV, all in registers ----
+      uint32_t oa[2][4];  // attention output as the two K=16 A fragments of the proj GEMM
+#pragma unroll
+      for (int h = 0; h < kHeads; ++h) {
+        float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+        float oh[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb) {
+          constexpr int kFull = 8;
+          const int ntile = (2 * NW - 8 * kb) < kFull ? (2 * NW - 8 * kb) : kFull;
+          float s[8][4];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            if (t < ntile) {
+              s[t][0] = s[t][1] = s[t][2] = s[t][3] = 0.f;
+              const int key0 = (8 * kb + t) * 8;
+              mma1688(s[t], qa[h][0], qa[h][1], lds32(Ks + (key0 + g) * kLdD + 8 * h + 2 * q));
+              const int kc = key0 + 2 * q;
+              if (kc >= T) { s[t][0] = -INFINITY; s[t][2] = -INFINITY; }
+              if (kc + 1 >= T) { s[t][1] = -INFINITY; s[t][3] = -INFINITY; }
+            }
+          }
+          float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            if (t < ntile) {
+              bm0 = fmaxf(bm0, fmaxf(s[t][0], s[t][1]));
+              bm1 = fmaxf(bm1, fmaxf(s[t][2], s[t][3]));
+            }
+          const float mn0 = fmaxf(m0, quad_max(bm0)), mn1 = fmaxf(m1, quad_max(bm1));
+          const float al0 = exp2f(m0 - mn0), al1 = exp2f(m1 - mn1);
+          m0 = mn0; m1 = mn1;
+          l0 *= al0; l1 *= al1;
+          oh[0] *= al0; oh[1] *= al0; oh[2] *= al1; oh[3] *= al1;
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            if (t < ntile) {
+              s[t][0] = exp2f(s[t][0] - mn0); s[t][1] = exp2f(s[t][1] - mn0);
+              s[t][2] = exp2f(s[t][2] - mn1); s[t][3] = exp2f(s[t][3] - mn1);
+              l0 += s[t][0] + s[t][1];
+              l1 += s[t][2] + s[t][3];
+            }
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            if (2 * kk < ntile) {
+              uint32_t Pa[4];
+              Pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+              Pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+              Pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+              Pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+              const __nv_bfloat16* v = Vt + (8 * h + g) * LDV + (8 * kb + 2 * kk) * 8 + 2 * q;
+              mma16816(oh, Pa, lds32(v), lds32(v + 8));
+            }
+        }
+        const float il0 = 1.f / quad_sum(l0), il1 = 1.f / quad_sum(l1);
+        oa[h >> 1][(h & 1) * 2 + 0] = pack_bf16(oh[0] * il0, oh[1] * il0);
+        oa[h >> 1][(h & 1) * 2 + 1] = pack_bf16(oh[2] * il1, oh[3] * il1);
+      }
+
+      // ---- proj GEMM, bias + residual epilogue ----
+#pragma unroll
+      for (int jn = 0; jn < 4; ++jn) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const __nv_bfloat16* w = wproj + (8 * jn + g) * kLdD + 16 * kk + 2 * q;
+          mma16816(c, oa[kk], lds32(w), lds32(w + 8));
+        }
+        const float2 bb = *reinterpret_cast<const float2*>(bproj + 8 * jn + 2 * q);
+        x[jn][0] += c[0] + bb.x; x[jn][1] += c[1] + bb.y; x[jn][2] += c[2] + bb.x; x[jn][3] += c[3] + bb.y;
+      }
+
+      // ---- LN2 -> fc1 (+bias, GELU) -> fc2 (+bias, +residual), 16 hidden units at a time ----
+      uint32_t A2[2][4];
+      ln_to_afrag(x, reinterpret_cast<const float*>(smem + O.ln2_g), reinterpret_cast<const float*>(smem + O.ln2_b), q, A2);
+      float acc2[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc2[j][e] = 0.f;
+#pragma unroll
+      for (int hk = 0; hk < kHidden / 16; ++hk) {
+        float h0[4] = {0.f, 0.f, 0.f, 0.f}, h1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const __nv_bfloat16* w0 = wfc1 + (16 * hk + g) * kLdD + 16 * kk + 2 * q;
+          const __nv_bfloat16* w1 = w0 + 8 * kLdD;
+          mma16816(h0, A2[kk], lds32(w0), lds32(w0 + 8));
+          mma16816(h1, A2[kk], lds32(w1), lds32(w1 + 8));
+        }
+        const float2 b0 = *reinterpret_cast<const float2*>(bfc1 + 16 * hk + 2 * q);
+        const float2 b1 = *reinterpret_cast<const float2*>(bfc1 + 16 * hk + 8 + 2 * q);
+        uint32_t Ha[4];
+        Ha[0] = pack_bf16(gelu_erf(h0[0] + b0.x), gelu_erf(h0[1] + b0.y));
+        Ha[1] = pack_bf16(gelu_erf(h0[2] + b0.x), gelu_erf(h0[3] + b0.y));
+        Ha[2] = pack_bf16(gelu_erf(h1[0] + b1.x), gelu_erf(h1[1] + b1.y));
+        Ha[3] = pack_bf16(gelu_erf(h1[2] + b1.x), gelu_erf(h1[3] + b1.y));
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) {
+          const __nv_bfloat16* w = wfc2 + (8 * jn + g) * kLdHid + 16 * hk + 2 * q;
+          mma16816(acc2[jn], Ha, lds32(w), lds32(w + 8));
+        }
+      }
+#pragma unroll
+      for (int jn = 0; jn < 4; ++jn) {
+        const float2 bb = *reinterpret_cast<const float2*>(bfc2 + 8 * jn + 2 * q);
+        x[jn][0] += acc2[jn][0] + bb.x; x[jn][1] += acc2[jn][1] + bb.y;
+        x[jn][2] += acc2[jn][2] + bb.x; x[jn][3] += acc2[jn][3] + bb.y;
+      }
+      __syncthreads();  // every warp is done with this layer's K / V^T
+    }
+
+    // ---------------- final LayerNorm on the cls token, head ----------------
+    if (warp == 0) {
+      float s0 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s0 += x[j][0] + x[j][1];
+      const float m0 = quad_sum(s0) * (1.f / kD);
+      float v0 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float d = x[j][0] - m0; v0 += d * d;
+        d = x[j][1] - m0; v0 += d * d;
+      }
+      const float rs0 = rsqrtf(quad_sum(v0) * (1.f / kD) + 1e-6f);
+      if (g == 0) {
+        const float* gam = reinterpret_cast<const float*>(smem + L.lnf_g);
+        const float* bet = reinterpret_cast<const float*>(smem + L.lnf_b);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = 8 * j + 2 * q;
+          cls_s[c] = (x[j][0] - m0) * rs0 * gam[c] + bet[c];
+          cls_s[c + 1] = (x[j][1] - m0) * rs0 * gam[c + 1] + bet[c + 1];
+        }
+      }
+    }
+    __syncthreads();
+    const long long orow = a.out_index ? a.out_index[b] : (long long)b;
+    if ((int)threadIdx.x < a.K) {
+      const float* wh = reinterpret_cast<const float*>(smem + L.whead) + threadIdx.x * kD;
+      float acc = reinterpret_cast<const float*>(smem + L.bhead)[threadIdx.x];
+#pragma unroll
+      for (int d = 0; d < kD; ++d) acc += wh[d] * cls_s[d];
+      a.logits[orow * a.K + threadIdx.x] = acc;
+      logit_s[threadIdx.x] = acc;
+    }
+    if (a.argmax_map) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int best = 0;
+        float bv = logit_s[0];
+        for (int k = 1; k < a.K; ++k)
+          if (logit_s[k] > bv) { bv = logit_s[k]; best = k; }  // first maximum, like np.argmax
+        a.argmax_map[orow] = (unsigned char)best;
+      }
+    }
+  }
+}
+
+size_t tparams_bytes(int P, int K) { return (size_t)tlayout(P, K).total; }
+
+template <int NW>
+static int launch_nw(const TArgs& a, cudaStream_t stream) {
+  const TLayout L = tlayout(a.P, a.K);
+  const size_t smem = (size_t)L.total + (size_t)(16 * NW) * kLdD * 2 + (size_t)kD * (16 * NW + 8) * 2 + kD * 4 +
+                      (size_t)a.K * 4 + 16;
+  int dev = 0, max_smem = 0, num_sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (smem > (size_t)max_smem) return VC_ERR_UNSUPPORTED;
+  if (cudaFuncSetAttribute(transformer_fwd_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+      cudaSuccess)
+    return VC_ERR_CUDA;
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, transformer_fwd_kernel<NW>, NW * 32, smem);
+  if (occ < 1) occ = 1;
+  long long blocks = (long long)num_sms * occ;
+  if (blocks > a.n_patches) blocks = a.n_patches;
+  transformer_fwd_kernel<NW><<<(int)blocks, NW * 32, smem, stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
+}
+
+int transformer_fwd_launch(const void* f_sps, const void* tparams, int n_patches, int P, int K, float* logits,
+                           const long long* out_index, unsigned char* argmax_map, cudaStream_t stream) {
+  if (n_patches <= 0 || P < 1 || K < 1 || K > 64) return VC_ERR_ARG;
+  TArgs a;
+  a.f = (const __nv_bfloat16*)f_sps;
+  a.blob = (const uint8_t*)tparams;
+  a.logits = logits;
+  a.out_index = out_index;
+  a.argmax_map = argmax_map;
+  a.RT = sps_rows(n_patches, P);
+  a.n_patches = n_patches;
+  a.P = P;
+  a.K = K;
+  a.T = P * P + 1;
+  const int NW = (a.T + 15) / 16;
+  switch (NW) {
+#define VC_CASE(N) case N: return launch_nw<N>(a, stream);
+    VC_CASE(1) VC_CASE(2) VC_CASE(3) VC_CASE(4) VC_CASE(5) VC_CASE(6) VC_CASE(7) VC_CASE(8)
+    VC_CASE(9) VC_CASE(10) VC_CASE(11) VC_CASE(12) VC_CASE(13) VC_CASE(14) VC_CASE(15)
+#undef VC_CASE
+    default: return VC_ERR_UNSUPPORTED;  // P > 15
+  }
+}
+
+}  // namespace vc

@@ -1,0 +1,60 @@
+"""Host-side mirror of the reference's window utilities (utils.py:357-415, 567-582) with the
+same names and argument meaning, plus the vectorised forms the CUDA path consumes."""
+from __future__ import annotations
+
+import itertools
+
+import numpy as np
+
+
+def window_starts(extent: int, win: int, step: int) -> np.ndarray:
+    """Start offsets along one axis, exactly the values utils.sliding_window visits
+    (utils.py:374-397): ``range(0, extent-win+offset+1, step)`` with ``offset =
+    (extent-win) % step`` and overshooting starts clamped to ``extent-win``."""
+    if win > extent:
+        return np.zeros((0,), dtype=np.int32)
+    offset = (extent - win) % step
+    s = np.arange(0, extent - win + offset + 1, step, dtype=np.int64)
+    s[s + win > extent] = extent - win
+    return s.astype(np.int32)
+
+
+def sliding_window(image1, image2, step=10, window_size=(20, 20), with_data=True):
+    """Generator with the reference's signature and order (utils.py:357-401)."""
+    w, h = window_size
+    for x in window_starts(image1.shape[0], w, step):
+        for y in window_starts(image1.shape[1], h, step):
+            x, y = int(x), int(y)
+            if with_data:
+                yield image1[x:x + w, y:y + h], image2[x:x + w, y:y + h], x, y, w, h
+            else:
+                yield x, y, w, h
+
+
+def count_sliding_window(top, top2, step=10, window_size=(20, 20)):
+    """utils.py:404-415, in closed form."""
+    w, h = window_size
+    return int(len(window_starts(top.shape[0], w, step)) * len(window_starts(top.shape[1], h, step)))
+
+
+def grouper(n, iterable):
+    """utils.py:567-582."""
+    it = iter(iterable)
+    while True:
+        chunk = tuple(itertools.islice(it, n))
+        if not chunk:
+            return
+        yield chunk
+
+
+def row_band_ranges(n_rows: int, n_cols: int, world_size: int):
+    """Split the window rows into ``world_size`` contiguous bands; returns (first_window,
+    n_windows) per rank in the reference's row-major window order.  Rank r needs raster rows
+    [x_first, x_last + P) only: its band plus a halo of P//2 rows on each side."""
+    base, rem = divmod(n_rows, world_size)
+    out, r0 = [], 0
+    for r in range(world_size):
+        rows = base + (1 if r < rem else 0)
+        out.append((r0 * n_cols, rows * n_cols))
+        r0 += rows
+    return out
