@@ -1,0 +1,278 @@
+"""Headline benchmark: full-scene ViT-CNN inference on a synthetic Houston2013-shaped raster
+(349 x 1905, 144 + 1 bands, 16 classes, patch 11, stride 1), BASELINE.json configs[1].
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = N_gpus scenes, every scene split into N_gpus row bands (one per rank, halo rows
+included, no collective), i.e. one scene's worth of windows per GPU per step (weak scaling).
+Prints ONE JSON line (rank 0).  `value` = pixels/s with rasters resident in HBM; `e2e` = the
+same through the public host-buffer API (pinned H2D of the band + D2H of its logits/argmax
+every step); `roofline` = the dominant kernel (HSI stem conv 1, tcgen05) from a CUDA-event
+profiled pass of the same step; `cpu_baseline` = the fp32 oracle on the host cores on a
+bounded sample.  --impl reference times that CPU path alone (the reference has no GPU code
+of its own and ships no ViT-CNN source: the oracle port is its stand-in).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, C1, C2, K, P = 349, 1905, 144, 1, 16, 11
+WORKLOAD = "houston2013_full_scene_inference_p11_stride1"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        d = json.load(open(path))
+        return d["hbm_gbs"], d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_rate(seconds: float, threads: int):
+    """fp32 oracle model fed by the oracle's restatement of test()'s batch assembly, on the host
+    cores, for about `seconds` of work on windows taken from the centre rows of the scene."""
+    from oracle import data_ref as R
+    from oracle.model_ref import ViTCNNRef
+    torch.set_num_threads(threads)
+    rng = np.random.default_rng(0)
+    rows = P + 3                                   # a band of 4 window rows
+    img1 = rng.random((rows, W, C1), dtype=np.float32)
+    img2 = rng.random((rows, W, C2), dtype=np.float32)
+    torch.manual_seed(0)
+    ref = ViTCNNRef(C1, C2, patch_size=P, num_classes=K).eval()
+    corners = R.sliding_window_corners((rows, W), 1, (P, P))
+    probs = np.zeros((rows, W, K))
+    done, t0 = 0, time.perf_counter()
+    with torch.no_grad():
+        for s in range(0, len(corners), 64):       # batch 64 = the reference's default
+            chunk = corners[s:s + 64]
+            h, l = R.gather_corners(img1, img2, chunk, P)
+            out = ref(torch.from_numpy(h), torch.from_numpy(l)).numpy()
+            for (x, y), o in zip(chunk, out):
+                probs[x + P // 2, y + P // 2] += o
+            done += len(chunk)
+            if time.perf_counter() - t0 > seconds:
+                break
+    dt = time.perf_counter() - t0
+    n_windows = (H - P + 1) * (W - P + 1)
+    return done / dt * (H * W) / n_windows, done, dt   # pixels/s of a full scene at this window rate
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    for _ in range(max(args.warmup, 0)):
+        cpu_oracle_rate(1.0, threads)
+    vals, samples = [], 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, n, _ = cpu_oracle_rate(8.0, threads)
+        vals.append(v)
+        samples += n
+    dt = time.perf_counter() - t0
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": "full_scene_inference_pixels_per_s", "value": v, "unit": "pixels/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "fp32 oracle port on host cores (reference ships no ViT-CNN source)"},
+            "cpu_baseline": {"value": v, "unit": "pixels/s", "cores": threads, "kind": "port",
+                             "sample": f"{samples} windows of a {P + 3}-row band, batch 64, extrapolated to the scene"},
+            "e2e": {"value": v, "unit": "pixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chunk", type=int, default=int(os.environ.get("VITCNN_CHUNK", "2048")))
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--windows", type=int, default=0, help="profiling aid: only the first N windows of the band")
+    ap.add_argument("--no-cpu", action="store_true", help="profiling aid: skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the e2e leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    import vitcnn_b200
+    from vitcnn_b200 import _lib
+    from vitcnn_b200.utils import row_band_ranges, window_starts
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    rng = np.random.default_rng(0)
+    img1_h = torch.from_numpy(rng.random((H, W, C1), dtype=np.float32)).pin_memory()
+    img2_h = torch.from_numpy(rng.random((H, W, C2), dtype=np.float32)).pin_memory()
+    torch.manual_seed(0)
+    net = vitcnn_b200.ViTCNN(C1, C2, patch_size=P, num_classes=K).to(dev).eval()
+    img1, img2 = img1_h.to(dev), img2_h.to(dev)
+    nx, ny = len(window_starts(H, P, 1)), len(window_starts(W, P, 1))
+    first, count = row_band_ranges(nx, ny, world)[rank]
+    if args.windows:
+        count = min(count, args.windows)
+    scenes = world                                        # scenes per step (weak scaling)
+    logits_map = torch.zeros(H, W, K, dtype=torch.float32, device=dev)
+    argmax_map = torch.zeros(H, W, dtype=torch.uint8, device=dev)
+
+    def step():
+        for _ in range(scenes):
+            net.predict_scene(img1, img2, chunk=args.chunk, window_range=(first, count), logits_map=logits_map,
+                              argmax_map=argmax_map)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = _lib.lib().vc_launch_count()
+    ms = timed(step, args.steps)
+    launches = _lib.lib().vc_launch_count() - l0
+    clocks = sampler.stop()
+    pixels_per_step = scenes * H * W * (count * world / (nx * ny) if args.windows else 1.0)
+    value = pixels_per_step * args.steps / (ms / 1e3)
+
+    # ---- end to end through the host-buffer API --------------------------------------------
+    x_first, x_last = first // ny, (first + count - 1) // ny          # window rows of this band
+    band = slice(x_first, x_last + P)                                 # raster rows incl. halo
+    out_rows = slice(x_first + P // 2, x_last + P // 2 + 1)           # rows this band writes
+    lg_h = torch.empty(H, W, K, dtype=torch.float32).pin_memory()
+    am_h = torch.empty(H, W, dtype=torch.uint8).pin_memory()
+
+    def e2e_step():
+        for _ in range(scenes):
+            vitcnn_b200.predict_scene_host(net, img1_h, img2_h, rank=rank, world=world, chunk=args.chunk,
+                                           logits_out=lg_h, argmax_out=am_h)
+    if args.no_e2e or args.windows:
+        ms_e2e = float("nan")
+    else:
+        for _ in range(2):
+            e2e_step()
+        ms_e2e = timed(e2e_step, args.steps)
+    band_rows = band.stop - band.start
+    h2d = scenes * band_rows * W * (C1 + C2) * 4
+    d2h = scenes * (out_rows.stop - out_rows.start) * W * (K * 4 + 1)
+    e2e_val = pixels_per_step * args.steps / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel: CUDA-event profiled pass of the same step ----------
+    _lib.profile_begin()
+    step()
+    prof = _lib.profile_end()
+    total_ms = sum(v[0] for v in prof.values())
+    c1_ms, c1_n = prof["conv_h1"]
+    hbm, tf_burst, tf_sust, which = peaks()
+    flops_c1 = 2.0 * P * P * 128 * C1 * 9 * count * scenes            # algorithmic (App. D), this rank
+    achieved = flops_c1 / (c1_ms / 1e3) / 1e12 if c1_ms > 0 else 0.0
+    roofline = {"kernel": "conv_sps_tc_kernel (HSI stem conv1, tcgen05)", "bound": "tensor",
+                "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s", "frac": achieved / tf_sust,
+                "peak_source": which + " bf16 sustained", "traffic": None,
+                "launches": c1_n, "avg_launch_ms": c1_ms / max(c1_n, 1),
+                "share_of_step": c1_ms / total_ms if total_ms else None,
+                "breakdown_ms": {k: round(v[0], 3) for k, v in prof.items()}}
+
+    if rank == 0:
+        cpu_v, cpu_n, cpu_dt = (float("nan"), 0, 0.0) if args.no_cpu else cpu_oracle_rate(args.cpu_seconds,
+                                                                                         os.cpu_count() or 1)
+        line = {"metric": "full_scene_inference_pixels_per_s", "value": value, "unit": "pixels/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "scene": [H, W, C1, C2], "classes": K, "patch": P,
+                           "windows_per_scene": nx * ny, "scenes_per_step": scenes, "sharding": "row-band",
+                           "chunk_windows": args.chunk, "l2": "inputs larger than L2 (385 MB raster)"},
+                "windows_per_s": nx * ny * scenes * args.steps / (ms / 1e3),
+                "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": e2e_val, "unit": "pixels/s", "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps},
+                "roofline": roofline,
+                "cpu_baseline": {"value": cpu_v, "unit": "pixels/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                 "sample": f"{cpu_n} windows ({cpu_dt:.1f} s) of a {P + 3}-row band, batch 64, "
+                                           "extrapolated to the scene"}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -4,5 +4,6 @@ reference toolkit's own get_model('ViT-CNN') / forward(hsi, lidar) interface."""
 from . import _lib  # noqa: F401
 from .model import ViTCNN  # noqa: F401
 from .model_utils import get_model, test, val  # noqa: F401
+from .scene import predict_scene_host  # noqa: F401
 
-__all__ = ["ViTCNN", "get_model", "test", "val"]
+__all__ = ["ViTCNN", "get_model", "test", "val", "predict_scene_host"]

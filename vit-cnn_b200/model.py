@@ -271,12 +271,13 @@ class ViTCNN(nn.Module):
     # ---- full-scene inference ---------------------------------------------------------------------
     @torch.no_grad()
     def predict_scene(self, img1: torch.Tensor, img2: torch.Tensor, stride: int = 1, chunk: int = 2048,
-                      window_range=None, logits_map=None, argmax_map=None):
+                      window_range=None, logits_map=None, argmax_map=None, xs=None, ys=None):
         """Sliding-window inference over device-resident rasters img1 f32 [H,W,C1], img2 f32
         [H,W,C2] (the loop of test(), model_utils.py:1086-1129).  Returns (logits_map f32
         [H,W,K], argmax_map uint8 [H,W]); pixels no window is centred on stay 0.
         ``window_range=(first, count)`` restricts to a contiguous run of windows in the
-        reference's row-major order (row-band sharding)."""
+        reference's row-major order (row-band sharding); ``xs`` / ``ys`` override the window
+        start lists (a row band uploaded on its own keeps the scene's starts)."""
         from .utils import window_starts
         if self.training:
             raise RuntimeError("predict_scene is an eval-mode path: call model.eval() first")
@@ -289,8 +290,13 @@ class ViTCNN(nn.Module):
         if C1 != self.n_bands or img2.shape[2] != self.n_bands2 or tuple(img2.shape[:2]) != (H, W):
             raise ValueError("raster shapes do not match the model")
         dev = img1.device
-        xs = torch.from_numpy(window_starts(H, P, stride)).to(device=dev, dtype=torch.int32)
-        ys = torch.from_numpy(window_starts(W, P, stride)).to(device=dev, dtype=torch.int32)
+        import numpy as np
+        xs = window_starts(H, P, stride) if xs is None else np.ascontiguousarray(xs, dtype=np.int32)
+        ys = window_starts(W, P, stride) if ys is None else np.ascontiguousarray(ys, dtype=np.int32)
+        if len(xs) and (xs.min() < 0 or xs.max() + P > H) or len(ys) and (ys.min() < 0 or ys.max() + P > W):
+            raise ValueError("window starts fall outside the raster")
+        xs = torch.from_numpy(xs).to(device=dev, dtype=torch.int32)
+        ys = torch.from_numpy(ys).to(device=dev, dtype=torch.int32)
         nx, ny = xs.numel(), ys.numel()
         first, count = (0, nx * ny) if window_range is None else window_range
         if logits_map is None:

@@ -77,11 +77,12 @@ def test(run, net, img1, img2, hyperparams):
         raise ValueError("ViT-CNN predicts the centre pixel of each window (center_pixel=True)")
     if not isinstance(net, ViTCNN) or net.patch_size != patch_size or net.num_classes != n_classes:
         raise ValueError("hyperparams do not describe this network")
-    t1 = torch.as_tensor(np.ascontiguousarray(img1, dtype=np.float32)).to(device)
-    t2 = torch.as_tensor(np.ascontiguousarray(img2, dtype=np.float32)).to(device)
+    from .scene import predict_scene_host
+    t1 = torch.as_tensor(np.ascontiguousarray(img1, dtype=np.float32))
+    t2 = torch.as_tensor(np.ascontiguousarray(img2, dtype=np.float32))
     chunk = int(hyperparams.get("scene_chunk", 2048))
-    logits_map, _ = net.predict_scene(t1, t2, stride=hyperparams["test_stride"], chunk=chunk)
-    return logits_map.to("cpu").numpy().astype(np.float64)
+    logits_map, _ = predict_scene_host(net, t1, t2, stride=hyperparams["test_stride"], chunk=chunk, device=device)
+    return logits_map.numpy().astype(np.float64)
 
 
 def val(net, data_loader, device="cpu", supervision="full"):
