@@ -87,14 +87,19 @@ Workspace carve(void* base, int n, int P, int S1, int S2) {
 inline int slices_for(int C) { return (C + 15) / 16 * 2; }
 
 // stems + token stage on packed inputs already in w.a0 / w.l0
-int forward_sps(const vc_model* m, const Workspace& w, int n, float* logits, const long long* out_index,
-                uint8_t* argmax_map, cudaStream_t st) {
-  const int P = m->P;
-  // lead / trailing halo rows of the intermediates are read by the next conv: keep them zero
+// lead / trailing halo rows of the intermediates are read by the next conv and written by no
+// kernel: zero them once per workspace geometry (they stay zero across chunks of equal size)
+int zero_halos(const Workspace& w, int n, int P, cudaStream_t st) {
   VC_LAUNCH(KC_HALO, st, vc::zero_halo_launch(w.a1, 16, n, P, st));
   VC_LAUNCH(KC_HALO, st, vc::zero_halo_launch(w.a2, 8, n, P, st));
   VC_LAUNCH(KC_HALO, st, vc::zero_halo_launch(w.l1, 2, n, P, st));
   VC_LAUNCH(KC_HALO, st, vc::zero_halo_launch(w.l2, 2, n, P, st));
+  return VC_OK;
+}
+
+int forward_sps(const vc_model* m, const Workspace& w, int n, float* logits, const long long* out_index,
+                uint8_t* argmax_map, cudaStream_t st) {
+  const int P = m->P;
   VC_LAUNCH(KC_CONV_H1, st, vc::conv_sps_launch(w.a0, m->S1, m->w_h[0], m->scale_h[0], m->bias_h[0], w.a1, 0, 128, m->nsplit_h[0], n, P, 9,
                              1, 0, 0, st));
   VC_LAUNCH(KC_CONV_H2, st, vc::conv_sps_launch(w.a1, 16, m->w_h[1], m->scale_h[1], m->bias_h[1], w.a2, 0, 64, m->nsplit_h[1], n, P, 9, 1,
@@ -236,6 +241,7 @@ int vc_forward_patches(const vc_model* m, const float* hsi, const int64_t hs[4],
   const Workspace w = carve(workspace, n, m->P, m->S1, m->S2);
   VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(hsi, hs[0], hs[1], hs[2], hs[3], nullptr, n, m->C1, m->P, w.a0, m->S1, st));
   VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(lidar, ls[0], ls[1], ls[2], ls[3], nullptr, n, m->C2, m->P, w.l0, m->S2, st));
+  VC_TRY(zero_halos(w, n, m->P, st));
   return forward_sps(m, w, n, logits, nullptr, nullptr, st);
 }
 
@@ -253,6 +259,7 @@ int vc_scene_infer(const vc_model* m, const float* img1, const float* img2, int3
     const int n = (int)((n_windows - done) < chunk ? (n_windows - done) : chunk);
     // the SPS geometry depends on n: carve per chunk (only the last chunk differs)
     const Workspace w = carve(workspace, n, m->P, m->S1, m->S2);
+    if (done == 0 || n != chunk) VC_TRY(zero_halos(w, n, m->P, st));
     VC_LAUNCH(KC_INDEX, st, vc::scene_index_launch(xs, ys, nx, ny, (int)(first_window + done), n, W, m->C1, m->C2, m->P,
                                                    m->K, w.off1, w.off2, w.oidx, nullptr, st));
     VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(img1, 0, 1, s1, m->C1, w.off1, n, m->C1, m->P, w.a0, m->S1, st));

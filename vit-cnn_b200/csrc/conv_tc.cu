@@ -103,12 +103,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_sps_tc_kernel(ConvArgs a
     }
   } else if (warp == 1) {
     // ===== MMA issuer: one thread drives the tensor core =====
+    // Descriptors are built once; inside the loop a tap / K-step is one 32-bit add on the
+    // start-address field (units of 16 B = one SPS row), so issue costs a few instructions.
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, a.ncta);
-      const bool swap = (a.debug_flags & 1) != 0;   // debug: exchange LBO/SBO roles
-      const uint32_t a_lbo = swap ? 128u : slice_bytes, a_sbo = swap ? slice_bytes : 128u;
-      const uint32_t b_lbo = swap ? 128u : (uint32_t)a.ncta * 16u, b_sbo = swap ? (uint32_t)a.ncta * 16u : 128u;
-      const uint32_t w_addr = smem_u32(w_s);
+      const uint64_t a_hi = umma_desc(0, slice_bytes, 128) & 0xFFFFFFFF00000000ull;
+      const uint64_t b_hi = umma_desc(0, (uint32_t)a.ncta * 16u, 128) & 0xFFFFFFFF00000000ull;
+      const uint32_t a_lbo_lo = (uint32_t)(umma_desc(0, slice_bytes, 128) & 0xFFFF0000u);
+      const uint32_t b_lbo_lo = (uint32_t)(umma_desc(0, (uint32_t)a.ncta * 16u, 128) & 0xFFFF0000u);
+      const uint32_t w_lo = b_lbo_lo | ((smem_u32(w_s) & 0x3FFFFu) >> 4);
+      const uint32_t b_tap = (uint32_t)(a.S_in * a.ncta);   // rows (16 B units) between taps
+      const uint32_t b_ks = (uint32_t)(2 * a.ncta);         // ... between K=16 steps
       mbar_wait(wfull, 0);
       int st = 0;
       uint32_t ph = 0;
@@ -121,12 +126,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_sps_tc_kernel(ConvArgs a
         for (int ks = 0; ks < KS; ++ks) {
           mbar_wait(&full[st], ph);
           tc_fence_after();
-          const uint32_t s_addr = smem_u32(stage_s + (size_t)st * stage_bytes);
-          for (int tap = 0; tap < a.ntaps; ++tap) {
-            const int shift = (a.ntaps == 9) ? ((tap / 3 - 1) * PW + (tap % 3 - 1)) : 0;
-            const uint64_t ad = umma_desc(s_addr + (uint32_t)(HALO + shift) * 16u, a_lbo, a_sbo);
-            const uint64_t bd = umma_desc(w_addr + (uint32_t)((tap * a.S_in + 2 * ks) * a.ncta) * 16u, b_lbo, b_sbo);
-            umma_bf16(d_tmem, ad, bd, idesc, (ks | tap) != 0 ? 1u : 0u);
+          const uint32_t a_lo = a_lbo_lo | (((smem_u32(stage_s + (size_t)st * stage_bytes) & 0x3FFFFu) >> 4) + (uint32_t)HALO);
+          const uint32_t b_lo = w_lo + (uint32_t)ks * b_ks;
+          if (a.ntaps == 9) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const int shift = (tap / 3 - 1) * PW + (tap % 3 - 1);
+              umma_bf16(d_tmem, a_hi | (uint64_t)(a_lo + (uint32_t)shift), b_hi | (uint64_t)(b_lo + (uint32_t)tap * b_tap), idesc,
+                        (ks | tap) != 0 ? 1u : 0u);
+            }
+          } else {
+            umma_bf16(d_tmem, a_hi | (uint64_t)a_lo, b_hi | (uint64_t)b_lo, idesc, ks != 0 ? 1u : 0u);
           }
           umma_commit(&empty[st]);
           if (++st == a.nstages) { st = 0; ph ^= 1u; }

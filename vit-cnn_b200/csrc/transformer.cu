@@ -24,6 +24,7 @@ struct TArgs {
   unsigned char* argmax_map;   // nullable: argmax written at out_index[b]
   long long RT;
   int n_patches, P, K, T;
+  TLayout L;  // parameter-blob offsets (kernel-argument space: constant-bank reads)
 };
 
 __device__ __forceinline__ uint32_t lds32(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
@@ -37,7 +38,24 @@ __device__ __forceinline__ float quad_max(float v) {
   v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
   return v;
 }
-__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }
+__device__ __forceinline__ float ex2(float v) {  // 2^v, one MUFU (flush-to-zero on underflow)
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+// exact-erf GELU (nn.GELU default, mlp.py:21) with erf from Abramowitz-Stegun 7.1.26
+// (|error| <= 1.5e-7, far below bf16 resolution): one RCP + one EX2 + a few FMAs.
+__device__ __forceinline__ float gelu_erf(float v) {
+  const float z = fabsf(v) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = p * t * ex2(-1.44269504088896340736f * z * z);   // 1 - erf(z)
+  const float half_erfc = 0.5f * e;                                  // v>=0: Phi = 1 - e/2, v<0: Phi = e/2
+  return v * (v >= 0.f ? 1.f - half_erfc : half_erfc);
+}
 
 // LayerNorm (eps 1e-6) of the two token rows this thread shares with its quad; result as the
 // two K=16 A fragments of the following GEMM.
@@ -76,17 +94,55 @@ __device__ __forceinline__ void ln_to_afrag(const float (&x)[4][4], const float*
   }
 }
 
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ float g_sum(float v) {  // sum over the 8 row groups of a warp (lane bits 2..4)
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+
+// Hand-off buffer between the token warps and the cls-tail warp (double buffered).
 template <int NW>
-__global__ void __launch_bounds__(NW * 32) transformer_fwd_kernel(TArgs a) {
+struct TailBuf {
+  float o[NW][kD];       // per-warp partial sum_j p_j * v_j of the cls query, all heads
+  float l[NW][kHeads];   // per-warp partial sum_j p_j
+  float x0[kD];          // residual stream of the cls token before the last attention
+};
+
+// NW token warps (rows 16w..16w+15) + 1 tail warp.  The last block only needs the cls
+// token's output (the head reads x[:, 0], vision_transformer.py:692-701), so there the token
+// warps only produce K / V for every token and the cls query's attention partials; the tail
+// warp finishes the cls row (proj, MLP, final LN, head) while the token warps already work
+// on the next patch.
+template <int NW>
+__global__ void __launch_bounds__((NW + 1) * 32) transformer_fwd_kernel(TArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr int TP = 16 * NW;    // padded token count
   constexpr int LDV = TP + 8;    // pitch of V^T rows
   constexpr int NKB = (2 * NW + 7) / 8;  // key blocks of 64
-  const TLayout L = tlayout(a.P, a.K);
+  constexpr int NMAIN = NW * 32, NALL = (NW + 1) * 32;
+  enum { BAR_MAIN = 1, BAR_READY0 = 2, BAR_READY1 = 3, BAR_FREE0 = 4, BAR_FREE1 = 5 };
+  const TLayout& L = a.L;
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem + L.total);  // [TP][40]
   __nv_bfloat16* Vt = Ks + TP * kLdD;                                    // [32][LDV]
-  float* cls_s = reinterpret_cast<float*>(Vt + kD * LDV);                // [32]
-  float* logit_s = cls_s + kD;                                           // [K]
+  float* q0_s = reinterpret_cast<float*>(Vt + kD * LDV);                 // [32] cls query (scaled)
+  float* max_s = q0_s + kD;                                              // [NW][4]
+  TailBuf<NW>* tb = reinterpret_cast<TailBuf<NW>*>(max_s + NW * kHeads); // [2]
+  float* h_s = reinterpret_cast<float*>(tb + 2);                         // [128] tail: MLP hidden
+  float* logit_s = h_s + kHidden;                                        // [K]
 
   {  // parameters -> shared memory (once per persistent CTA)
     const uint4* src = reinterpret_cast<const uint4*>(a.blob);
@@ -96,8 +152,103 @@ __global__ void __launch_bounds__(NW * 32) transformer_fwd_kernel(TArgs a) {
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  const int T = a.T, P = a.P;
+  const int my_patches = (a.n_patches - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const TLayerOff& OL = L.layer[kLayers - 1];   // the cls-only block
+
+  if (warp == NW) {
+    // ======================= tail warp: finish the cls token, one channel per lane ==============
+    const __nv_bfloat16* wproj = reinterpret_cast<const __nv_bfloat16*>(smem + OL.wproj);
+    const __nv_bfloat16* wfc1 = reinterpret_cast<const __nv_bfloat16*>(smem + OL.wfc1);
+    const __nv_bfloat16* wfc2 = reinterpret_cast<const __nv_bfloat16*>(smem + OL.wfc2);
+    const float* f32 = reinterpret_cast<const float*>(smem);
+    for (int it = 0; it < my_patches; ++it) {
+      const int b = blockIdx.x + it * gridDim.x, par = it & 1;
+      bar_sync(BAR_READY0 + par, NALL);
+      const TailBuf<NW>& B = tb[par];
+      float o = 0.f, l = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) { o += B.o[w][lane]; l += B.l[w][lane >> 3]; }
+      const float att = o / l;
+      float x0 = B.x0[lane];
+      if (it + 2 < my_patches) bar_arrive(BAR_FREE0 + par, NALL);   // buffer may be refilled
+      // proj (+bias, +residual)
+      float y = f32[OL.bproj / 4 + lane];
+#pragma unroll
+      for (int k2 = 0; k2 < kD / 2; ++k2) {
+        const uint32_t wv = lds32(wproj + lane * kLdD + 2 * k2);
+        y = fmaf(bf_lo(wv), __shfl_sync(0xffffffffu, att, 2 * k2), y);
+        y = fmaf(bf_hi(wv), __shfl_sync(0xffffffffu, att, 2 * k2 + 1), y);
+      }
+      x0 += y;
+      // LN2
+      float mean = warp_sum(x0) * (1.f / kD);
+      float d = x0 - mean;
+      float rstd = rsqrtf(warp_sum(d * d) * (1.f / kD) + 1e-6f);
+      const float y2 = d * rstd * f32[OL.ln2_g / 4 + lane] + f32[OL.ln2_b / 4 + lane];
+      // fc1 + GELU: hidden unit j = lane + 32 i
+      float hacc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) hacc[i] = f32[OL.bfc1 / 4 + lane + 32 * i];
+#pragma unroll
+      for (int k2 = 0; k2 < kD / 2; ++k2) {
+        const float ya = __shfl_sync(0xffffffffu, y2, 2 * k2), yb = __shfl_sync(0xffffffffu, y2, 2 * k2 + 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t wv = lds32(wfc1 + (lane + 32 * i) * kLdD + 2 * k2);
+          hacc[i] = fmaf(bf_lo(wv), ya, fmaf(bf_hi(wv), yb, hacc[i]));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h_s[lane + 32 * i] = gelu_erf(hacc[i]);
+      __syncwarp();
+      // fc2 (+bias, +residual)
+      float z = f32[OL.bfc2 / 4 + lane];
+#pragma unroll 8
+      for (int k2 = 0; k2 < kHidden / 2; ++k2) {
+        const uint32_t wv = lds32(wfc2 + lane * kLdHid + 2 * k2);
+        const float2 hh = *reinterpret_cast<const float2*>(h_s + 2 * k2);
+        z = fmaf(bf_lo(wv), hh.x, fmaf(bf_hi(wv), hh.y, z));
+      }
+      __syncwarp();
+      x0 += z;
+      // final LayerNorm + head
+      mean = warp_sum(x0) * (1.f / kD);
+      d = x0 - mean;
+      rstd = rsqrtf(warp_sum(d * d) * (1.f / kD) + 1e-6f);
+      const float c = d * rstd * f32[L.lnf_g / 4 + lane] + f32[L.lnf_b / 4 + lane];
+      const long long orow = a.out_index ? a.out_index[b] : (long long)b;
+      for (int k0 = 0; k0 < a.K; k0 += 32) {
+        const int k = k0 + lane;
+        float acc = k < a.K ? f32[L.bhead / 4 + k] : 0.f;
+#pragma unroll
+        for (int dd = 0; dd < kD; ++dd) {
+          const float cd = __shfl_sync(0xffffffffu, c, dd);
+          if (k < a.K) acc = fmaf(f32[L.whead / 4 + k * kD + dd], cd, acc);
+        }
+        if (k < a.K) {
+          a.logits[orow * a.K + k] = acc;
+          logit_s[k] = acc;
+        }
+      }
+      if (a.argmax_map) {
+        __syncwarp();
+        if (lane == 0) {
+          int best = 0;
+          float bv = logit_s[0];
+          for (int k = 1; k < a.K; ++k)
+            if (logit_s[k] > bv) { bv = logit_s[k]; best = k; }  // first maximum, like np.argmax
+          a.argmax_map[orow] = (unsigned char)best;
+        }
+        __syncwarp();
+      }
+    }
+    return;
+  }
+
+  // ============================== token warps ====================================================
   const int r0 = 16 * warp + g, r1 = r0 + 8;
-  const int T = a.T, P = a.P, PW = P + 1, PP = sps_pp(P), HALO = sps_halo(P);
+  const int PW = P + 1, PP = sps_pp(P), HALO = sps_halo(P);
   const __nv_bfloat16* wfus = reinterpret_cast<const __nv_bfloat16*>(smem + L.wfus);
   const float* fus_scale = reinterpret_cast<const float*>(smem + L.fus_scale);
   const float* fus_bias = reinterpret_cast<const float*>(smem + L.fus_bias);
@@ -105,7 +256,8 @@ __global__ void __launch_bounds__(NW * 32) transformer_fwd_kernel(TArgs a) {
   const float* pos = reinterpret_cast<const float*>(smem + L.pos);
   const float qscale = 0.35355339059327376220f * 1.44269504088896340736f;  // hd^-0.5 * log2(e)
 
-  for (int b = blockIdx.x; b < a.n_patches; b += gridDim.x) {
+  for (int it = 0; it < my_patches; ++it) {
+    const int b = blockIdx.x + it * gridDim.x, par = it & 1;
     // ---------------- tokens: fusion 1x1 conv over the concatenated stems ----------------
     float x[4][4];
     {
@@ -146,8 +298,9 @@ __global__ void __launch_bounds__(NW * 32) transformer_fwd_kernel(TArgs a) {
       }
     }
 
+    // ---------------- full transformer blocks (all but the last) ----------------
 #pragma unroll 1
-    for (int l = 0; l < kLayers; ++l) {
+    for (int l = 0; l < kLayers - 1; ++l) {
       const TLayerOff& O = L.layer[l];
       const __nv_bfloat16* wqkv = reinterpret_cast<const __nv_bfloat16*>(smem + O.wqkv);
       const __nv_bfloat16* wproj = reinterpret_cast<const __nv_bfloat16*>(smem + O.wproj);
@@ -187,7 +340,7 @@ __global__ void __launch_bounds__(NW * 32) transformer_fwd_kernel(TArgs a) {
           Vt[(d + 1) * LDV + r1] = __float2bfloat16_rn(c[3]);
         }
       }
-      __syncthreads();
+      bar_sync(BAR_MAIN, NMAIN);
 
       // ---- attention: per head QK^T -> online softmax -> PV, all in registers ----
       uint32_t oa[2][4];  // attention output as the two K=16 A fragments of the proj GEMM
@@ -206,9 +359,11 @@ __global__ void __launch_bounds__(NW * 32) transformer_fwd_kernel(TArgs a) {
               s[t][0] = s[t][1] = s[t][2] = s[t][3] = 0.f;
               const int key0 = (8 * kb + t) * 8;
               mma1688(s[t], qa[h][0], qa[h][1], lds32(Ks + (key0 + g) * kLdD + 8 * h + 2 * q));
-              const int kc = key0 + 2 * q;
-              if (kc >= T) { s[t][0] = -INFINITY; s[t][2] = -INFINITY; }
-              if (kc + 1 >= T) { s[t][1] = -INFINITY; s[t][3] = -INFINITY; }
+              if (8 * kb + t >= 2 * NW - 2) {   // only the last 16 keys can be padding (T > 16(NW-1))
+                const int kc = key0 + 2 * q;
+                if (kc >= T) { s[t][0] = -INFINITY; s[t][2] = -INFINITY; }
+                if (kc + 1 >= T) { s[t][1] = -INFINITY; s[t][3] = -INFINITY; }
+              }
             }
           }
           float bm0 = -INFINITY, bm1 = -INFINITY;
@@ -219,15 +374,17 @@ __global__ void __launch_bounds__(NW * 32) transformer_fwd_kernel(TArgs a) {
               bm1 = fmaxf(bm1, fmaxf(s[t][2], s[t][3]));
             }
           const float mn0 = fmaxf(m0, quad_max(bm0)), mn1 = fmaxf(m1, quad_max(bm1));
-          const float al0 = exp2f(m0 - mn0), al1 = exp2f(m1 - mn1);
+          if (kb > 0) {
+            const float al0 = ex2(m0 - mn0), al1 = ex2(m1 - mn1);
+            l0 *= al0; l1 *= al1;
+            oh[0] *= al0; oh[1] *= al0; oh[2] *= al1; oh[3] *= al1;
+          }
           m0 = mn0; m1 = mn1;
-          l0 *= al0; l1 *= al1;
-          oh[0] *= al0; oh[1] *= al0; oh[2] *= al1; oh[3] *= al1;
 #pragma unroll
           for (int t = 0; t < 8; ++t)
             if (t < ntile) {
-              s[t][0] = exp2f(s[t][0] - mn0); s[t][1] = exp2f(s[t][1] - mn0);
-              s[t][2] = exp2f(s[t][2] - mn1); s[t][3] = exp2f(s[t][3] - mn1);
+              s[t][0] = ex2(s[t][0] - mn0); s[t][1] = ex2(s[t][1] - mn0);
+              s[t][2] = ex2(s[t][2] - mn1); s[t][3] = ex2(s[t][3] - mn1);
               l0 += s[t][0] + s[t][1];
               l1 += s[t][2] + s[t][3];
             }
@@ -298,52 +455,84 @@ __global__ void __launch_bounds__(NW * 32) transformer_fwd_kernel(TArgs a) {
         x[jn][0] += acc2[jn][0] + bb.x; x[jn][1] += acc2[jn][1] + bb.y;
         x[jn][2] += acc2[jn][2] + bb.x; x[jn][3] += acc2[jn][3] + bb.y;
       }
-      __syncthreads();  // every warp is done with this layer's K / V^T
+      bar_sync(BAR_MAIN, NMAIN);  // every warp is done with this layer's K / V^T
     }
 
-    // ---------------- final LayerNorm on the cls token, head ----------------
-    if (warp == 0) {
-      float s0 = 0.f;
+    // ---------------- last block: K, V for every token, attention of the cls query only -------
+    {
+      const __nv_bfloat16* wqkv = reinterpret_cast<const __nv_bfloat16*>(smem + OL.wqkv);
+      const float* bqkv = reinterpret_cast<const float*>(smem + OL.bqkv);
+      uint32_t A1[2][4];
+      ln_to_afrag(x, reinterpret_cast<const float*>(smem + OL.ln1_g), reinterpret_cast<const float*>(smem + OL.ln1_b), q, A1);
+      float kc[kHeads][4], vv[kHeads][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) s0 += x[j][0] + x[j][1];
-      const float m0 = quad_sum(s0) * (1.f / kD);
-      float v0 = 0.f;
+      for (int jn = 4; jn < 12; ++jn) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float d = x[j][0] - m0; v0 += d * d;
-        d = x[j][1] - m0; v0 += d * d;
-      }
-      const float rs0 = rsqrtf(quad_sum(v0) * (1.f / kD) + 1e-6f);
-      if (g == 0) {
-        const float* gam = reinterpret_cast<const float*>(smem + L.lnf_g);
-        const float* bet = reinterpret_cast<const float*>(smem + L.lnf_b);
+        for (int kk = 0; kk < 2; ++kk) {
+          const __nv_bfloat16* w = wqkv + (8 * jn + g) * kLdD + 16 * kk + 2 * q;
+          mma16816(c, A1[kk], lds32(w), lds32(w + 8));
+        }
+        const float2 bb = *reinterpret_cast<const float2*>(bqkv + 8 * jn + 2 * q);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = 8 * j + 2 * q;
-          cls_s[c] = (x[j][0] - m0) * rs0 * gam[c] + bet[c];
-          cls_s[c + 1] = (x[j][1] - m0) * rs0 * gam[c + 1] + bet[c + 1];
+        for (int e = 0; e < 4; ++e) {
+          const float v = c[e] + ((e & 1) ? bb.y : bb.x);
+          if (jn < 8) kc[jn - 4][e] = v; else vv[jn - 8][e] = v;
         }
       }
-    }
-    __syncthreads();
-    const long long orow = a.out_index ? a.out_index[b] : (long long)b;
-    if ((int)threadIdx.x < a.K) {
-      const float* wh = reinterpret_cast<const float*>(smem + L.whead) + threadIdx.x * kD;
-      float acc = reinterpret_cast<const float*>(smem + L.bhead)[threadIdx.x];
+      if (it >= 2) bar_sync(BAR_FREE0 + par, NALL);   // tail warp has consumed this buffer
+      TailBuf<NW>& B = tb[par];
+      if (warp == 0) {   // the cls token is row 0: its query and its residual stream
 #pragma unroll
-      for (int d = 0; d < kD; ++d) acc += wh[d] * cls_s[d];
-      a.logits[orow * a.K + threadIdx.x] = acc;
-      logit_s[threadIdx.x] = acc;
-    }
-    if (a.argmax_map) {
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        int best = 0;
-        float bv = logit_s[0];
-        for (int k = 1; k < a.K; ++k)
-          if (logit_s[k] > bv) { bv = logit_s[k]; best = k; }  // first maximum, like np.argmax
-        a.argmax_map[orow] = (unsigned char)best;
+        for (int jn = 0; jn < 4; ++jn) {
+          float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const __nv_bfloat16* w = wqkv + (8 * jn + g) * kLdD + 16 * kk + 2 * q;
+            mma16816(c, A1[kk], lds32(w), lds32(w + 8));
+          }
+          if (g == 0) {
+            const float2 bb = *reinterpret_cast<const float2*>(bqkv + 8 * jn + 2 * q);
+            q0_s[8 * jn + 2 * q] = (c[0] + bb.x) * qscale;
+            q0_s[8 * jn + 2 * q + 1] = (c[1] + bb.y) * qscale;
+            B.x0[8 * jn + 2 * q] = x[jn][0];
+            B.x0[8 * jn + 2 * q + 1] = x[jn][1];
+          }
+        }
       }
+      bar_sync(BAR_MAIN, NMAIN);
+      float s0[kHeads], s1[kHeads];
+#pragma unroll
+      for (int h = 0; h < kHeads; ++h) {
+        const float2 qq = *reinterpret_cast<const float2*>(q0_s + 8 * h + 2 * q);
+        s0[h] = quad_sum(qq.x * kc[h][0] + qq.y * kc[h][1]);
+        s1[h] = quad_sum(qq.x * kc[h][2] + qq.y * kc[h][3]);
+        if (r0 >= T) s0[h] = -INFINITY;
+        if (r1 >= T) s1[h] = -INFINITY;
+        float m = fmaxf(s0[h], s1[h]);
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+        if (lane == 0) max_s[warp * kHeads + h] = m;
+      }
+      bar_sync(BAR_MAIN, NMAIN);
+#pragma unroll
+      for (int h = 0; h < kHeads; ++h) {
+        float m = max_s[h];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) m = fmaxf(m, max_s[w * kHeads + h]);
+        const float p0 = ex2(s0[h] - m), p1 = ex2(s1[h] - m);
+        const float ls = g_sum(p0 + p1);
+        const float oa_ = g_sum(p0 * vv[h][0] + p1 * vv[h][2]);
+        const float ob_ = g_sum(p0 * vv[h][1] + p1 * vv[h][3]);
+        if (g == 0) {
+          B.o[warp][8 * h + 2 * q] = oa_;
+          B.o[warp][8 * h + 2 * q + 1] = ob_;
+          if (q == 0) B.l[warp][h] = ls;
+        }
+      }
+      bar_arrive(BAR_READY0 + par, NALL);
+      // q0_s / max_s are rewritten only after the next patch's BAR_MAIN syncs
     }
   }
 }
@@ -354,7 +543,7 @@ template <int NW>
 static int launch_nw(const TArgs& a, cudaStream_t stream) {
   const TLayout L = tlayout(a.P, a.K);
   const size_t smem = (size_t)L.total + (size_t)(16 * NW) * kLdD * 2 + (size_t)kD * (16 * NW + 8) * 2 + kD * 4 +
-                      (size_t)a.K * 4 + 16;
+                      (size_t)NW * kHeads * 4 + 2 * sizeof(TailBuf<NW>) + kHidden * 4 + (size_t)a.K * 4 + 16;
   int dev = 0, max_smem = 0, num_sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -364,11 +553,11 @@ static int launch_nw(const TArgs& a, cudaStream_t stream) {
       cudaSuccess)
     return VC_ERR_CUDA;
   int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, transformer_fwd_kernel<NW>, NW * 32, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, transformer_fwd_kernel<NW>, (NW + 1) * 32, smem);
   if (occ < 1) occ = 1;
   long long blocks = (long long)num_sms * occ;
   if (blocks > a.n_patches) blocks = a.n_patches;
-  transformer_fwd_kernel<NW><<<(int)blocks, NW * 32, smem, stream>>>(a);
+  transformer_fwd_kernel<NW><<<(int)blocks, (NW + 1) * 32, smem, stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
 }
 
@@ -386,6 +575,7 @@ int transformer_fwd_launch(const void* f_sps, const void* tparams, int n_patches
   a.P = P;
   a.K = K;
   a.T = P * P + 1;
+  a.L = tlayout(P, K);
   const int NW = (a.T + 15) / 16;
   switch (NW) {
 #define VC_CASE(N) case N: return launch_nw<N>(a, stream);
