@@ -22,7 +22,7 @@ struct ConvArgs {
   const float* bias;         // [nsplit*ncta]
   __nv_bfloat16* out;        // [S_out_total][RT][8]
   long long RT;
-  int S_in, ncta, ntaps, P, n_patches, ntiles, out_slice_off, relu, nstages, debug_flags;
+  int S_in, ncta, ntaps, P, n_patches, ntiles, out_slice_off, relu, nstages, kpb, debug_flags;
 };
 
 constexpr int kConvThreads = 192;  // warp0 producer, warp1 MMA issuer, warps 2..5 epilogue
@@ -31,7 +31,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_sps_tc_kernel(ConvArgs a
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int HALO = sps_halo(a.P), ROWS = 128 + 2 * HALO, PP = sps_pp(a.P), PW = a.P + 1;
-  const uint32_t slice_bytes = (uint32_t)ROWS * 16u, stage_bytes = 2u * slice_bytes;
+  const int KPB = a.kpb;  // K=16 steps per pipeline stage
+  const uint32_t slice_bytes = (uint32_t)ROWS * 16u, kstep_bytes = 2u * slice_bytes, stage_bytes = (uint32_t)KPB * kstep_bytes;
   const uint32_t wbytes = (uint32_t)a.ntaps * a.S_in * a.ncta * 16u;
   const int KS = a.S_in / 2;  // K=16 steps per tap
   const int half = blockIdx.y;
@@ -75,6 +76,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_sps_tc_kernel(ConvArgs a
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  long long dbg_c0 = 0, dbg_t0 = 0;
+  if ((a.debug_flags & 64) && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+    dbg_c0 = clock64();
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(dbg_t0));
+  }
 
   if (warp == 0) {
     // ===== producer: weights once, then one stage (2 channel slices) per K=16 step =====
@@ -87,63 +93,75 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_sps_tc_kernel(ConvArgs a
       }
       int st = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < ((a.debug_flags & 8) ? 0 : a.ntiles); tile += gridDim.x) {
         const long long row0 = (long long)tile * 128;  // = R0 - HALO
-        for (int ks = 0; ks < KS; ++ks) {
+        for (int ks0 = 0; ks0 < KS; ks0 += KPB) {
+          const int nk = KS - ks0 < KPB ? KS - ks0 : KPB;
           mbar_wait(&empty[st], ph ^ 1u);
-          mbar_arrive_expect_tx(&full[st], stage_bytes);
-          uint8_t* dst = stage_s + (size_t)st * stage_bytes;
-          const __nv_bfloat16* s0 = a.in + ((long long)(2 * ks) * a.RT + row0) * 8;
-          const __nv_bfloat16* s1 = a.in + ((long long)(2 * ks + 1) * a.RT + row0) * 8;
-          bulk_g2s(dst, s0, slice_bytes, &full[st]);
-          bulk_g2s(dst + slice_bytes, s1, slice_bytes, &full[st]);
+          if (a.debug_flags & 2) {   // timing probe: no operand traffic
+            mbar_arrive(&full[st]);
+          } else {
+            mbar_arrive_expect_tx(&full[st], (uint32_t)nk * kstep_bytes);
+            uint8_t* dst = stage_s + (size_t)st * stage_bytes;
+            for (int sl = 0; sl < 2 * nk; ++sl)
+              bulk_g2s(dst + (size_t)sl * slice_bytes, a.in + ((long long)(2 * ks0 + sl) * a.RT + row0) * 8, slice_bytes,
+                       &full[st]);
+          }
           if (++st == a.nstages) { st = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: one thread drives the tensor core =====
+    // ===== MMA issuer: warp-uniform control flow, one elected lane drives the tensor core =====
     // Descriptors are built once; inside the loop a tap / K-step is one 32-bit add on the
     // start-address field (units of 16 B = one SPS row), so issue costs a few instructions.
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, a.ncta);
-      const uint64_t a_hi = umma_desc(0, slice_bytes, 128) & 0xFFFFFFFF00000000ull;
-      const uint64_t b_hi = umma_desc(0, (uint32_t)a.ncta * 16u, 128) & 0xFFFFFFFF00000000ull;
-      const uint32_t a_lbo_lo = (uint32_t)(umma_desc(0, slice_bytes, 128) & 0xFFFF0000u);
-      const uint32_t b_lbo_lo = (uint32_t)(umma_desc(0, (uint32_t)a.ncta * 16u, 128) & 0xFFFF0000u);
-      const uint32_t w_lo = b_lbo_lo | ((smem_u32(w_s) & 0x3FFFFu) >> 4);
-      const uint32_t b_tap = (uint32_t)(a.S_in * a.ncta);   // rows (16 B units) between taps
-      const uint32_t b_ks = (uint32_t)(2 * a.ncta);         // ... between K=16 steps
-      mbar_wait(wfull, 0);
-      int st = 0;
-      uint32_t ph = 0;
-      int acc = 0;
-      uint32_t accph = 0;
-      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        mbar_wait(&tempty[acc], accph ^ 1u);
+    const uint32_t idesc = umma_idesc_bf16(128, a.ncta);
+    const uint64_t a_hi = umma_desc(0, slice_bytes, 128) & 0xFFFFFFFF00000000ull;
+    const uint64_t b_hi = umma_desc(0, (uint32_t)a.ncta * 16u, 128) & 0xFFFFFFFF00000000ull;
+    const uint32_t a_lbo_lo = (uint32_t)(umma_desc(0, slice_bytes, 128) & 0xFFFF0000u);
+    const uint32_t b_lbo_lo = (uint32_t)(umma_desc(0, (uint32_t)a.ncta * 16u, 128) & 0xFFFF0000u);
+    const uint32_t w_lo = b_lbo_lo | ((smem_u32(w_s) & 0x3FFFFu) >> 4);
+    const uint32_t a_lo0 = a_lbo_lo | (((smem_u32(stage_s) & 0x3FFFFu) >> 4) + (uint32_t)HALO);
+    const uint32_t a_stage = stage_bytes >> 4;              // 16 B units between stages
+    const uint32_t b_tap = (uint32_t)(a.S_in * a.ncta);     // ... between taps
+    const uint32_t b_ks = (uint32_t)(2 * a.ncta);           // ... between K=16 steps
+    const bool nine = a.ntaps == 9;
+    mbar_wait(wfull, 0);
+    int st = 0;
+    uint32_t ph = 0;
+    int acc = 0;
+    uint32_t accph = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      if (!(a.debug_flags & 32)) mbar_wait(&tempty[acc], accph ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.ncta);
+      for (int ks0 = 0; ks0 < KS; ks0 += KPB) {
+        const int nk = KS - ks0 < KPB ? KS - ks0 : KPB;
+        if (!(a.debug_flags & 8)) mbar_wait(&full[st], ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.ncta);
-        for (int ks = 0; ks < KS; ++ks) {
-          mbar_wait(&full[st], ph);
-          tc_fence_after();
-          const uint32_t a_lo = a_lbo_lo | (((smem_u32(stage_s + (size_t)st * stage_bytes) & 0x3FFFFu) >> 4) + (uint32_t)HALO);
-          const uint32_t b_lo = w_lo + (uint32_t)ks * b_ks;
-          if (a.ntaps == 9) {
+        if (elect_one()) {
+          for (int kl = 0; kl < nk; ++kl) {
+            const int ks = ks0 + kl;
+            const uint32_t a_lo = a_lo0 + (uint32_t)st * a_stage + (uint32_t)kl * (kstep_bytes >> 4);
+            const uint32_t b_lo = w_lo + (uint32_t)ks * b_ks;
+            if (nine) {
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const int shift = (tap / 3 - 1) * PW + (tap % 3 - 1);
-              umma_bf16(d_tmem, a_hi | (uint64_t)(a_lo + (uint32_t)shift), b_hi | (uint64_t)(b_lo + (uint32_t)tap * b_tap), idesc,
-                        (ks | tap) != 0 ? 1u : 0u);
+              for (int tap = 0; tap < 9; ++tap) {
+                const int shift = (tap / 3 - 1) * PW + (tap % 3 - 1);
+                umma_bf16(d_tmem, a_hi | (uint64_t)(a_lo + (uint32_t)shift), b_hi | (uint64_t)(b_lo + (uint32_t)tap * b_tap),
+                          idesc, (ks | tap) != 0 ? 1u : 0u);
+              }
+            } else {
+              umma_bf16(d_tmem, a_hi | (uint64_t)a_lo, b_hi | (uint64_t)b_lo, idesc, ks != 0 ? 1u : 0u);
             }
-          } else {
-            umma_bf16(d_tmem, a_hi | (uint64_t)a_lo, b_hi | (uint64_t)b_lo, idesc, ks != 0 ? 1u : 0u);
           }
           umma_commit(&empty[st]);
-          if (++st == a.nstages) { st = 0; ph ^= 1u; }
+          if (ks0 + nk == KS) umma_commit(&tfull[acc]);
         }
-        umma_commit(&tfull[acc]);
-        if (++acc == 2) { acc = 0; accph ^= 1u; }
+        __syncwarp();
+        if (++st == a.nstages) { st = 0; ph ^= 1u; }
       }
+      if (++acc == 2) { acc = 0; accph ^= 1u; }
     }
   } else {
     // ===== epilogue: TMEM -> registers -> affine (+ReLU) -> bf16 -> SPS rows =====
@@ -158,10 +176,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_sps_tc_kernel(ConvArgs a
       const int q = (int)(r - b * PP);
       const int i = q / PW, j = q - i * PW;
       const bool valid = (b < a.n_patches) && (i < a.P) && (j < a.P);
-      mbar_wait(&tfull[acc], accph);
+      if (a.debug_flags & 128) {       // probe: one polling lane per warp
+        if (lane == 0) mbar_wait(&tfull[acc], accph);
+        __syncwarp();
+      } else {
+        mbar_wait(&tfull[acc], accph);
+      }
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * a.ncta);
-      for (int c0 = 0; c0 < a.ncta; c0 += 16) {
+      for (int c0 = 0; c0 < ((a.debug_flags & 16) ? 0 : a.ncta); c0 += 16) {
         uint32_t v[16];
         tmem_ld16(taddr + (uint32_t)c0, v);
         tc_wait_ld();
@@ -177,8 +200,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_sps_tc_kernel(ConvArgs a
         const int slice = a.out_slice_off + (half * a.ncta + c0) / 8;
         uint4* o0 = reinterpret_cast<uint4*>(a.out + ((long long)slice * a.RT + R) * 8);
         uint4* o1 = reinterpret_cast<uint4*>(a.out + ((long long)(slice + 1) * a.RT + R) * 8);
-        *o0 = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *o1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        if (!(a.debug_flags & 4)) {
+          *o0 = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *o1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
@@ -190,6 +215,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_sps_tc_kernel(ConvArgs a
   __syncthreads();
   tc_fence_after();
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+  if ((a.debug_flags & 64) && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+    long long t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+    const long long c1 = clock64();
+    printf("conv dbg: %lld cycles in %lld ns -> %.0f MHz\n", c1 - dbg_c0, t1 - dbg_t0,
+           1e3 * (double)(c1 - dbg_c0) / (double)(t1 - dbg_t0));
+  }
 }
 
 // ---- plain SIMT twin (tests / bring-up cross-check only; same arguments, same layouts) ------
@@ -225,10 +257,10 @@ __global__ void conv_sps_simt_kernel(ConvArgs a, int nsplit) {
   }
 }
 
-static size_t conv_smem_bytes(int S_in, int ncta, int ntaps, int P, int nstages) {
+static size_t conv_smem_bytes(int S_in, int ncta, int ntaps, int P, int nstages, int kpb) {
   const int ROWS = 128 + 2 * sps_halo(P);
   size_t wbytes = ((size_t)ntaps * S_in * ncta * 16 + 127) & ~size_t(127);
-  return wbytes + (size_t)nstages * 2 * ROWS * 16 + (size_t)ncta * 8 + 8 + (2 * nstages + 5) * 8 + 16;
+  return wbytes + (size_t)nstages * kpb * 2 * ROWS * 16 + (size_t)ncta * 8 + 8 + (2 * nstages + 5) * 8 + 16;
 }
 
 int conv_sps_launch(const void* in, int S_in, const void* w, const float* scale, const float* bias, void* out,
@@ -254,6 +286,7 @@ int conv_sps_launch(const void* in, int S_in, const void* w, const float* scale,
   a.relu = relu;
   a.debug_flags = debug_flags;
   a.nstages = 0;
+  a.kpb = 1;
   if (impl == 1) {
     long long total = (long long)a.ntiles * 128 * n_out;
     int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
@@ -267,11 +300,20 @@ int conv_sps_launch(const void* in, int S_in, const void* w, const float* scale,
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  int nst = 8;
-  while (nst > 2 && conv_smem_bytes(S_in, ncta, ntaps, P, nst) > (size_t)max_smem) --nst;
-  const size_t smem = conv_smem_bytes(S_in, ncta, ntaps, P, nst);
+  // stage = kpb K-steps (fewer barrier round trips per MMA); keep at least 4 stages in flight
+  int kpb = (debug_flags >> 12) & 7 ? (debug_flags >> 12) & 7 : 2;
+  if (kpb > S_in / 2) kpb = S_in / 2;
+  int nst = (debug_flags >> 8) & 15 ? (debug_flags >> 8) & 15 : 6;
+  while (nst > 2 && conv_smem_bytes(S_in, ncta, ntaps, P, nst, kpb) > (size_t)max_smem) --nst;
+  if (nst < 4 && kpb > 1) {
+    kpb = 1;
+    nst = 8;
+    while (nst > 2 && conv_smem_bytes(S_in, ncta, ntaps, P, nst, kpb) > (size_t)max_smem) --nst;
+  }
+  const size_t smem = conv_smem_bytes(S_in, ncta, ntaps, P, nst, kpb);
   if (smem > (size_t)max_smem) return VC_ERR_UNSUPPORTED;
   a.nstages = nst;
+  a.kpb = kpb;
   if (cudaFuncSetAttribute(conv_sps_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return VC_ERR_CUDA;
   int gx = num_sms / nsplit;
