@@ -101,6 +101,20 @@ int vc_conv_sps(const void* in_sps, int32_t S_in, const void* w_packed, const fl
 int vc_tokens_forward(const void* f_sps, const void* tparams, int32_t n_patches, int32_t P, int32_t K, float* logits,
                       const int64_t* out_index, uint8_t* argmax_map, void* stream);
 
+/* ---- training building blocks ------------------------------------------------------------------
+ * Weight gradient of a 3x3 pad-1 conv (taps=9) or of a linear / 1x1 conv (taps=1) over SPS
+ * buffers, i.e. what autograd computes for Conv2d / Linear weights when loss.backward() runs
+ * (model_utils.py:936; the layers are those of SURVEY.md App. A):
+ *   dW[tap][m][n] = sum_rows A[row + sa(tap)][m] * B[row + sb(tap)][n],
+ * the tap's row shift applied to A (shift_on_a) or to B.  A: [SA][rows][8] (M <= SA*8 <= 128),
+ * B: [SB][rows][8] (SB even, N <= SB*8 <= 256).  Result scattered as out[m*sm + n*sn + tap*st]
+ * (= or +=); column bias_col (>= 0) of B goes to out_bias[m] (a constant-one channel in B makes
+ * it the bias gradient).  Deterministic (fixed-order split-K reduction through `workspace`). */
+int64_t vc_wgrad_workspace_bytes(int32_t SB, int32_t taps);
+int vc_wgrad_sps(const void* a_sps, int32_t SA, const void* b_sps, int32_t SB, int32_t n_patches, int32_t P, int32_t taps,
+                 int32_t shift_on_a, void* workspace, int64_t workspace_bytes, float* out, int32_t M, int32_t N,
+                 int64_t sm, int64_t sn, int64_t st, int32_t bias_col, float* out_bias, int32_t accumulate, void* stream);
+
 /* ---- model forward: replaces net(data, data2) at model_utils.py:921/1118/1144 (eval) ---------
  * hsi/lidar: f32 [n][C][P][P] with arbitrary element strides (sb, sc, si, sj) -- contiguous
  * NCHW from the DataLoader or the NHWC-memory view test() builds.  logits: f32 [n][K]. */

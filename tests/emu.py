@@ -48,6 +48,13 @@ def pack_sps(x, S):
     return flat.view(-1, S, 8).permute(1, 0, 2).contiguous()
 
 
+def unpack_sps(sps, n, P, C):
+    """SPS [S][RT][8] (any float dtype) -> [n, C, P, P] f32 (valid cells only)."""
+    S, RT, _ = sps.shape
+    flat = sps.float().permute(1, 0, 2).reshape(RT, S * 8)
+    return flat[row_index(n, P).reshape(-1), :C].reshape(n, P, P, C).permute(0, 3, 1, 2).contiguous()
+
+
 def conv_sps(sps_in, wpacked, scale, bias, n, P, relu=True):
     """sps_in [S_in][RT][8]; wpacked bf16 [ns][taps][S_in][ncta][8] -> [n_out/8][RT][8]."""
     S_in, RT, _ = sps_in.shape

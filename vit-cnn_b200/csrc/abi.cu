@@ -230,6 +230,18 @@ int vc_tokens_forward(const void* f_sps, const void* tparams, int32_t n_patches,
   return VC_OK;
 }
 
+int64_t vc_wgrad_workspace_bytes(int32_t SB, int32_t taps) { return (int64_t)vc::wgrad_workspace_bytes(SB, taps); }
+
+int vc_wgrad_sps(const void* a_sps, int32_t SA, const void* b_sps, int32_t SB, int32_t n_patches, int32_t P, int32_t taps,
+                 int32_t shift_on_a, void* workspace, int64_t workspace_bytes, float* out, int32_t M, int32_t N,
+                 int64_t sm, int64_t sn, int64_t st, int32_t bias_col, float* out_bias, int32_t accumulate, void* stream) {
+  if (!a_sps || !b_sps || !out || workspace_bytes < vc_wgrad_workspace_bytes(SB, taps))
+    return fail(VC_ERR_ARG, "vc_wgrad_sps: bad arguments");
+  VC_TRY(vc::wgrad_sps_launch(a_sps, SA, b_sps, SB, n_patches, P, taps, shift_on_a, workspace, out, M, N, sm, sn, st,
+                              bias_col, out_bias, accumulate, (cudaStream_t)stream));
+  return VC_OK;
+}
+
 int vc_forward_patches(const vc_model* m, const float* hsi, const int64_t hs[4], const float* lidar,
                        const int64_t ls[4], int32_t n, void* workspace, int64_t workspace_bytes, float* logits,
                        void* stream) {

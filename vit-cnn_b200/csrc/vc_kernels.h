@@ -26,4 +26,10 @@ size_t tparams_bytes(int P, int K);
 int transformer_fwd_launch(const void* f_sps, const void* tparams, int n_patches, int P, int K, float* logits,
                            const long long* out_index, unsigned char* argmax_map, cudaStream_t stream);
 
+// wgrad_tc.cu -- weight gradients (rows are the reduction axis; both operands MN-major)
+size_t wgrad_workspace_bytes(int SB, int ntaps);
+int wgrad_sps_launch(const void* A, int SA, const void* B, int SB, int n_patches, int P, int ntaps, int shift_on_a,
+                     void* workspace, float* out, int M, int Nr, long long sm, long long sn, long long st,
+                     int bias_col, float* out_bias, int accumulate, cudaStream_t stream);
+
 }  // namespace vc

@@ -104,3 +104,19 @@ def tokens_forward(f_sps, tparams, n, P, K, out_index=None, logits=None, argmax_
         _lib.check(_lib.lib().vc_tokens_forward(f_sps.data_ptr(), tparams.data_ptr(), n, P, K, logits.data_ptr(),
                                                 _ptr(out_index), _ptr(argmax_map), _stream()), "vc_tokens_forward")
     return logits
+
+
+def wgrad_sps(a_sps, b_sps, n, P, taps, shift_on_a, out, M, N, sm, sn, st, bias_col=-1, out_bias=None,
+              accumulate=False, workspace=None):
+    """dW[tap][m][n] = sum_rows A[row+sa][m] * B[row+sb][n] over SPS buffers (tcgen05, MN-major
+    operands); result scattered into ``out`` (fp32) with element strides (sm, sn, st)."""
+    L = _lib.lib()
+    SA, SB = a_sps.shape[0], b_sps.shape[0]
+    need = L.vc_wgrad_workspace_bytes(SB, taps)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=a_sps.device)
+    with torch.cuda.device(a_sps.device):
+        _lib.check(L.vc_wgrad_sps(a_sps.data_ptr(), SA, b_sps.data_ptr(), SB, n, P, taps, 1 if shift_on_a else 0,
+                                  workspace.data_ptr(), workspace.numel(), out.data_ptr(), M, N, sm, sn, st,
+                                  bias_col, _ptr(out_bias), 1 if accumulate else 0, _stream()), "vc_wgrad_sps")
+    return out
