@@ -51,8 +51,9 @@ const char* vc_last_error(void);
 /* ---- instrumentation (bench.py): kernels launched by this library so far in the process, and
  * per-kernel-class device time between vc_profile_begin/vc_profile_end on the calling thread
  * (CUDA events around each launch).  Classes: 0 window index, 1 pack (patch gather to SPS),
- * 2/3/4 HSI stem conv 1/2/3, 5 LiDAR stem convs, 6 token stage, 7 halo zeroing. */
-#define VC_KERNEL_CLASSES 8
+ * 2/3/4 HSI stem conv 1/2/3, 5 LiDAR stem convs, 6 token stage, 7 halo zeroing, 8 BatchNorm passes,
+ * 9 weight-gradient GEMMs, 10 data-gradient convs, 11 token-stage backward, 12 packing / loss / Adam. */
+#define VC_KERNEL_CLASSES 13
 int64_t vc_launch_count(void);
 int vc_profile_begin(void);
 int vc_profile_end(double* ms_per_class, int64_t* launches_per_class, int32_t n_classes);
@@ -114,6 +115,74 @@ int64_t vc_wgrad_workspace_bytes(int32_t SB, int32_t taps);
 int vc_wgrad_sps(const void* a_sps, int32_t SA, const void* b_sps, int32_t SB, int32_t n_patches, int32_t P, int32_t taps,
                  int32_t shift_on_a, void* workspace, int64_t workspace_bytes, float* out, int32_t M, int32_t N,
                  int64_t sm, int64_t sn, int64_t st, int32_t bias_col, float* out_bias, int32_t accumulate, void* stream);
+
+/* BatchNorm2d (training mode) + ReLU over an SPS buffer, forward and backward (the conv_bn_relu
+ * idiom of the stems as autograd differentiates it).  y: raw conv output bf16 [S][rows][8];
+ * sums: 2*S*8 doubles of scratch, zero on entry, left zero on exit; scale/shift/mean/rstd: fp32
+ * [S*8] saved for the backward.  Running statistics follow nn.BatchNorm2d (momentum, unbiased
+ * variance); pointers may be NULL. */
+int vc_bn_forward(const void* y, void* z, int32_t S, int32_t C, int32_t n_patches, int32_t P, const float* gamma,
+                  const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                  int64_t* num_batches_tracked, double* sums, float* scale, float* shift, float* mean, float* rstd,
+                  int32_t relu, void* stream);
+int vc_bn_backward(const void* dz, const void* y, void* dy, int32_t S, int32_t C, int32_t n_patches, int32_t P,
+                   const float* scale, const float* shift, const float* mean, const float* rstd, int32_t relu,
+                   double* sums, float* dgamma, float* dbeta, float* dbias, void* stream);
+/* torch conv weight fp32 [cout][cin][taps] -> bf16 operand of vc_conv_sps; transpose=1 gives the
+ * data-gradient operand (conv from cout back to cin channels with flipped taps). */
+int vc_pack_conv_weight(const float* w, int32_t cout, int32_t cin, int32_t taps, int32_t transpose, int32_t S_in,
+                        int32_t n_out, int32_t nsplit, void* dst, void* stream);
+/* table-driven fp32 -> packed blob copy: segs int64 [n][6] = src element offset, dst byte offset,
+ * rows, cols, dst pitch (elements), is_bf16 (device memory). */
+int vc_pack_segments(const float* flat, void* blob, const int64_t* segs, int32_t nsegs, void* stream);
+
+/* nn.CrossEntropyLoss(weight=w) (model_utils.py:63-66,216; applied at :929-936): loss_out[0] =
+ * weighted mean NLL, loss_out[1] = sum of weights; dlogits (nullable) = grad_scale * dloss/dlogits.
+ * labels int64 [n]; entries outside [0,K) are ignored (ignore_index semantics). */
+int vc_ce_loss(const float* logits, const int64_t* labels, const float* weight, int32_t n, int32_t K, float grad_scale,
+               float* loss_out, float* dlogits, void* stream);
+/* optim.Adam(lr) step (model_utils.py:214-215) on flat fp32 buffers; g is multiplied by
+ * grad_scale first (1/world_size after a summing all-reduce). */
+int vc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, int32_t step, float grad_scale, void* stream);
+
+/* ---- training: forward (batch statistics) / backward of the whole model -------------------------
+ * Replaces net(data, data2) in train mode and loss.backward() (model_utils.py:921-936).
+ * Parameters and gradients live in flat fp32 buffers; `off` gives the element offset of each
+ * tensor in the canonical order: conv layer i (0..6 = hsi_stem.0-2, lidar_stem.0-2, fusion):
+ * 4i+{0 conv.weight, 1 conv.bias, 2 bn.weight, 3 bn.bias}; 28 cls_token; 29 pos_embed; block l
+ * (0,1): 30+12l+{0 norm1.w, 1 norm1.b, 2 qkv.w, 3 qkv.b, 4 proj.w, 5 proj.b, 6 norm2.w, 7 norm2.b,
+ * 8 fc1.w, 9 fc1.b, 10 fc2.w, 11 fc2.b}; 54 norm.w; 55 norm.b; 56 head.w; 57 head.b. */
+#define VC_NPARAMS 58
+typedef struct vc_train {
+  int32_t C1, C2, P, K;
+  float* params;
+  float* grads;
+  int64_t off[VC_NPARAMS];
+  float* bn_running_mean[7];
+  float* bn_running_var[7];
+  int64_t* bn_num_batches[7];
+  float bn_eps, bn_momentum;
+  const int64_t* blob_segments;   /* device table for vc_pack_segments: token-stage blob from params */
+  int32_t n_blob_segments;
+} vc_train;
+
+int64_t vc_train_workspace_bytes(const vc_train* t, int32_t n);
+/* zero the workspace and write its constant parts; call once per (workspace, n) */
+int vc_train_workspace_init(const vc_train* t, int32_t n, void* workspace, int64_t workspace_bytes, void* stream);
+/* hsi/lidar: f32 [n][C][P][P] with element strides, as in vc_forward_patches */
+int vc_train_forward(const vc_train* t, const float* hsi, const int64_t hsi_strides[4], const float* lidar,
+                     const int64_t lidar_strides[4], int32_t n, void* workspace, int64_t workspace_bytes, float* logits,
+                     void* stream);
+/* same, patches gathered on the device from the rasters: xy int32 [n][2] patch centres
+ * (MultiModalX.__getitem__, datasets.py:550-556); labels (nullable, with gt) int64 [n] */
+int vc_train_forward_gather(const vc_train* t, const float* img1, const float* img2, const void* gt, int32_t gt_elem_bytes,
+                            int32_t H, int32_t W, const int32_t* xy, int32_t n, void* workspace, int64_t workspace_bytes,
+                            float* logits, int64_t* labels, void* stream);
+/* gradients of every parameter into t->grads (overwritten) for the batch of the last forward
+ * on this workspace */
+int vc_train_backward(const vc_train* t, const float* dlogits, int32_t n, void* workspace, int64_t workspace_bytes,
+                      void* stream);
 
 /* ---- model forward: replaces net(data, data2) at model_utils.py:921/1118/1144 (eval) ---------
  * hsi/lidar: f32 [n][C][P][P] with arbitrary element strides (sb, sc, si, sj) -- contiguous

@@ -54,6 +54,18 @@ class VcModel(ctypes.Structure):
     ]
 
 
+class VcTrain(ctypes.Structure):
+    """Mirror of ``struct vc_train`` (include/vitcnn.h)."""
+    _fields_ = [
+        ("C1", c_int32), ("C2", c_int32), ("P", c_int32), ("K", c_int32),
+        ("params", c_void_p), ("grads", c_void_p),
+        ("off", c_int64 * 58),
+        ("bn_running_mean", c_void_p * 7), ("bn_running_var", c_void_p * 7), ("bn_num_batches", c_void_p * 7),
+        ("bn_eps", c_float), ("bn_momentum", c_float),
+        ("blob_segments", c_void_p), ("n_blob_segments", c_int32),
+    ]
+
+
 _PROTOS = {
     "vc_abi_version": (c_int32, []),
     "vc_last_error": (c_char_p, []),
@@ -77,6 +89,24 @@ _PROTOS = {
     "vc_wgrad_sps": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                c_int64, c_void_p, c_int32, c_int32, c_int64, c_int64, c_int64, c_int32, c_void_p,
                                c_int32, c_void_p]),
+    "vc_bn_forward": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_float,
+                                c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_int32, c_void_p]),
+    "vc_bn_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vc_pack_conv_weight": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                      c_void_p, c_void_p]),
+    "vc_pack_segments": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
+    "vc_ce_loss": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p]),
+    "vc_adam_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
+                               c_float, c_int32, c_float, c_void_p]),
+    "vc_train_workspace_bytes": (c_int64, [POINTER(VcTrain), c_int32]),
+    "vc_train_workspace_init": (c_int32, [POINTER(VcTrain), c_int32, c_void_p, c_int64, c_void_p]),
+    "vc_train_forward": (c_int32, [POINTER(VcTrain), c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64), c_int32,
+                                   c_void_p, c_int64, c_void_p, c_void_p]),
+    "vc_train_forward_gather": (c_int32, [POINTER(VcTrain), c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                          c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "vc_train_backward": (c_int32, [POINTER(VcTrain), c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
     "vc_forward_patches": (c_int32, [POINTER(VcModel), c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64),
                                      c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
     "vc_scene_infer": (c_int32, [POINTER(VcModel), c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32,
@@ -113,7 +143,8 @@ def check(status: int, what: str) -> None:
         raise RuntimeError(f"{what} failed with status {status}: {msg.decode() if msg else ''}")
 
 
-KERNEL_CLASSES = ("index", "pack", "conv_h1", "conv_h2", "conv_h3", "conv_lidar", "tokens", "halo")
+KERNEL_CLASSES = ("index", "pack", "conv_h1", "conv_h2", "conv_h3", "conv_lidar", "tokens", "halo", "bn", "wgrad",
+                  "dgrad", "tokens_bwd", "misc")
 
 
 def profile_begin() -> None:

@@ -26,7 +26,8 @@ int fail(int code, const char* what) {
   } while (0)
 
 // ---- optional per-kernel-class timing (bench.py's roofline leg) ---------------------------------
-enum { KC_INDEX = 0, KC_PACK, KC_CONV_H1, KC_CONV_H2, KC_CONV_H3, KC_CONV_L, KC_TOKENS, KC_HALO, KC_COUNT };
+enum { KC_INDEX = 0, KC_PACK, KC_CONV_H1, KC_CONV_H2, KC_CONV_H3, KC_CONV_L, KC_TOKENS, KC_HALO, KC_BN, KC_WGRAD, KC_DGRAD,
+       KC_TOKENS_BWD, KC_MISC, KC_COUNT };
 struct ProfRec { int cls; cudaEvent_t e0, e1; };
 thread_local bool g_prof_on = false;
 thread_local std::vector<ProfRec>* g_prof = nullptr;
@@ -112,7 +113,7 @@ int forward_sps(const vc_model* m, const Workspace& w, int n, float* logits, con
                              0, st));
   VC_LAUNCH(KC_CONV_L, st, vc::conv_sps_launch(w.l2, 2, m->w_l[2], m->scale_l[2], m->bias_l[2], w.f, 4, 32, m->nsplit_l[2], n, P, 9, 1, 0,
                              0, st));
-  VC_LAUNCH(KC_TOKENS, st, vc::transformer_fwd_launch(w.f, m->tparams, n, P, m->K, logits, out_index, argmax_map, st));
+  VC_LAUNCH(KC_TOKENS, st, vc::transformer_fwd_launch(w.f, m->tparams, n, P, m->K, logits, out_index, argmax_map, 0, st));
   return VC_OK;
 }
 
@@ -226,7 +227,7 @@ int vc_conv_sps(const void* in_sps, int32_t S_in, const void* w_packed, const fl
 int vc_tokens_forward(const void* f_sps, const void* tparams, int32_t n_patches, int32_t P, int32_t K, float* logits,
                       const int64_t* out_index, uint8_t* argmax_map, void* stream) {
   VC_TRY(vc::transformer_fwd_launch(f_sps, tparams, n_patches, P, K, logits, (const long long*)out_index, argmax_map,
-                                    (cudaStream_t)stream));
+                                    0, (cudaStream_t)stream));
   return VC_OK;
 }
 
@@ -280,6 +281,342 @@ int vc_scene_infer(const vc_model* m, const float* img1, const float* img2, int3
   }
   (void)H;
   return VC_OK;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// Training: forward with batch statistics, backward of the whole model (see include/vitcnn.h)
+// =================================================================================================
+namespace {
+
+struct ConvPlan {
+  int cin, cout, taps, S_in, n_out, nsplit;     // forward operand
+  int has_dgrad, d_S_in, d_n_out, d_nsplit;     // data-gradient conv: n_out channels back to S_in*8
+  int shift_on_a;                               // weight-gradient orientation (A = layer input)
+};
+
+int choose_nsplit(int s_in, int n_out, int taps) {
+  for (int ns = 1; ns <= 8; ns *= 2) {
+    const int ncta = n_out / ns;
+    if (n_out % ns == 0 && ncta % 16 == 0 && ncta <= 128 && (long long)taps * s_in * ncta * 16 <= 180000) return ns;
+  }
+  return -1;
+}
+
+bool make_plans(const vc_train* t, ConvPlan pl[7]) {
+  const int hp[3] = {128, 64, 32}, lp[3] = {8, 16, 32};
+  int cin = t->C1;
+  for (int i = 0; i < 3; ++i) { pl[i].cin = cin; pl[i].cout = hp[i]; pl[i].taps = 9; cin = hp[i]; }
+  cin = t->C2;
+  for (int i = 0; i < 3; ++i) { pl[3 + i].cin = cin; pl[3 + i].cout = lp[i]; pl[3 + i].taps = 9; cin = lp[i]; }
+  pl[6].cin = 64; pl[6].cout = 32; pl[6].taps = 1;
+  for (int i = 0; i < 7; ++i) {
+    ConvPlan& p = pl[i];
+    p.S_in = slices_for(p.cin);
+    p.n_out = (p.cout + 15) / 16 * 16;
+    p.nsplit = choose_nsplit(p.S_in, p.n_out, p.taps);
+    p.has_dgrad = (i != 0 && i != 3);
+    p.d_S_in = p.n_out / 8;
+    p.d_n_out = p.S_in * 8;
+    p.d_nsplit = p.has_dgrad ? choose_nsplit(p.d_S_in, p.d_n_out, p.taps) : 1;
+    p.shift_on_a = (p.S_in * 8 <= 128 && p.S_in * 8 >= p.n_out) ? 1 : 0;
+    if (p.nsplit < 0 || p.d_nsplit < 0 || p.S_in > 32) return false;
+  }
+  return true;
+}
+
+const int kTokSlices[10] = {6, 12, 6, 4, 6, 16, 18, 4, 6, 12};   // xln1_0 dqkv_0 xo0 dxa0 xln2_0 dh0 xh0 dxb0 xln1_1 dqkv_1
+const int kClsSlices[8] = {6, 4, 6, 16, 18, 4, 6, 8};            // c_xo c_dxa c_xln2 c_dh c_xh c_dxb c_xc c_dlog
+const int kTokOnes[10] = {4, -1, 4, -1, 4, -1, 16, -1, 4, -1};    // slice holding the constant-one channel
+const int kClsOnes[8] = {4, -1, 4, -1, 16, -1, 4, -1};
+
+struct TrainWs {
+  uint8_t *a0, *l0, *f;
+  uint8_t *y[7], *z[7];
+  uint8_t *dzf, *df, *dzh2, *dzh1, *dzl2, *dzl1;
+  uint8_t *tok[10], *cls[8];
+  uint8_t *wf[7], *wd[7], *blob;
+  float *bias_pad[7], *ones, *zeros;
+  float *bn_scale[7], *bn_shift[7], *bn_mean[7], *bn_rstd[7];
+  double* sums;
+  uint8_t* wg;
+  long long wg_bytes;
+  long long *off1, *off2;
+  long long RT, RTt, RTc;
+  long long bytes;
+};
+
+TrainWs carve_train(void* base, const vc_train* t, const ConvPlan pl[7], int n) {
+  TrainWs w;
+  const int P = t->P, TP = (P * P + 1 + 15) / 16 * 16;
+  w.RT = vc::sps_rows(n, P);
+  w.RTt = ((long long)n * TP + 127) / 128 * 128;
+  w.RTc = ((long long)n + 127) / 128 * 128;
+  const long long sl = w.RT * 16;
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  auto take = [&](long long bytes) { uint8_t* r = p; p += (bytes + 255) & ~255LL; return r; };
+  w.a0 = take(sl * pl[0].S_in);
+  w.l0 = take(sl * pl[3].S_in);
+  w.f = take(sl * 8);
+  for (int i = 0; i < 7; ++i) w.y[i] = take(sl * (pl[i].n_out / 8));
+  w.z[0] = take(sl * 16); w.z[1] = take(sl * 8); w.z[2] = w.f;
+  w.z[3] = take(sl * 2); w.z[4] = take(sl * 2); w.z[5] = w.f + sl * 4;
+  w.z[6] = take(sl * 4);
+  w.dzf = take(sl * 4); w.df = take(sl * 8); w.dzh2 = take(sl * 8); w.dzh1 = take(sl * 16);
+  w.dzl2 = take(sl * 2); w.dzl1 = take(sl * 2);
+  for (int i = 0; i < 10; ++i) w.tok[i] = take(w.RTt * 16 * kTokSlices[i]);
+  for (int i = 0; i < 8; ++i) w.cls[i] = take(w.RTc * 16 * kClsSlices[i]);
+  for (int i = 0; i < 7; ++i) {
+    w.wf[i] = take((long long)pl[i].taps * pl[i].S_in * pl[i].n_out * 16);
+    w.wd[i] = take(pl[i].has_dgrad ? (long long)pl[i].taps * pl[i].d_S_in * pl[i].d_n_out * 16 : 0);
+  }
+  w.blob = take(vc::tlayout(P, t->K).total);
+  for (int i = 0; i < 7; ++i) w.bias_pad[i] = reinterpret_cast<float*>(take(128 * 4));
+  w.ones = reinterpret_cast<float*>(take(256 * 4));
+  w.zeros = reinterpret_cast<float*>(take(256 * 4));
+  for (int i = 0; i < 7; ++i) {
+    w.bn_scale[i] = reinterpret_cast<float*>(take(128 * 4));
+    w.bn_shift[i] = reinterpret_cast<float*>(take(128 * 4));
+    w.bn_mean[i] = reinterpret_cast<float*>(take(128 * 4));
+    w.bn_rstd[i] = reinterpret_cast<float*>(take(128 * 4));
+  }
+  w.sums = reinterpret_cast<double*>(take(256 * 8));
+  long long wg = 0;
+  for (int i = 0; i < 7; ++i) {
+    const int SB = pl[i].shift_on_a ? pl[i].n_out / 8 : pl[i].S_in;
+    const long long b = (long long)vc::wgrad_workspace_bytes(SB, pl[i].taps);
+    if (b > wg) wg = b;
+  }
+  const long long bt = (long long)vc::wgrad_workspace_bytes(18, 1);
+  if (bt > wg) wg = bt;
+  w.wg_bytes = wg;
+  w.wg = take(wg);
+  w.off1 = reinterpret_cast<long long*>(take(8LL * n));
+  w.off2 = reinterpret_cast<long long*>(take(8LL * n));
+  w.bytes = p - reinterpret_cast<uint8_t*>(base);
+  return w;
+}
+
+__global__ void fill_ones_slice_kernel(__nv_bfloat16* slice, long long rows) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
+    slice[r * 8] = __float2bfloat16_rn(1.f);
+}
+__global__ void fill_f32_kernel(float* p, int n, float v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+int check_train(const vc_train* t, ConvPlan pl[7]) {
+  if (!t || !t->params || !t->grads || t->P < 1 || t->P > 11 || t->K < 1 || t->K > 64 || t->C1 < 1 || t->C2 < 1 ||
+      !t->blob_segments || t->n_blob_segments <= 0)
+    return VC_ERR_ARG;
+  return make_plans(t, pl) ? VC_OK : VC_ERR_UNSUPPORTED;
+}
+
+int train_forward_core(const vc_train* t, const ConvPlan pl[7], const TrainWs& w, int n, float* logits, cudaStream_t st) {
+  const int P = t->P;
+  // bf16 operand forms of the current fp32 master weights
+  for (int i = 0; i < 7; ++i) {
+    const ConvPlan& c = pl[i];
+    VC_LAUNCH(KC_MISC, st, vc::pack_conv_w_launch(t->params + t->off[4 * i], c.cout, c.cin, c.taps, 0, c.S_in, c.n_out, c.nsplit,
+                                                 w.wf[i], st));
+    if (c.has_dgrad)
+      VC_LAUNCH(KC_MISC, st, vc::pack_conv_w_launch(t->params + t->off[4 * i], c.cout, c.cin, c.taps, 1, c.d_S_in, c.d_n_out,
+                                                   c.d_nsplit, w.wd[i], st));
+    if (cudaMemcpyAsync(w.bias_pad[i], t->params + t->off[4 * i + 1], sizeof(float) * c.cout, cudaMemcpyDeviceToDevice, st) !=
+        cudaSuccess)
+      return fail(VC_ERR_CUDA, "bias copy");
+  }
+  VC_LAUNCH(KC_MISC, st, vc::pack_segments_launch(t->params, w.blob, (const long long*)t->blob_segments, t->n_blob_segments, st));
+  // stems: conv (+bias) -> raw y -> BatchNorm with batch statistics -> ReLU -> z
+  for (int i = 0; i < 7; ++i) {
+    const ConvPlan& c = pl[i];
+    const uint8_t* in = (i == 0) ? w.a0 : (i == 3) ? w.l0 : (i == 6) ? w.f : w.z[i - 1];
+    const int cls = i == 0 ? KC_CONV_H1 : i == 1 ? KC_CONV_H2 : i == 2 ? KC_CONV_H3 : i < 6 ? KC_CONV_L : KC_TOKENS;
+    VC_LAUNCH(cls, st, vc::conv_sps_launch(in, c.S_in, w.wf[i], w.ones, w.bias_pad[i], w.y[i], 0, c.n_out, c.nsplit, n, P, c.taps,
+                                           0, 0, 0, st));
+    VC_LAUNCH(KC_BN, st, vc::bn_forward_launch(w.y[i], w.z[i], c.n_out / 8, c.cout, n, P, t->params + t->off[4 * i + 2],
+                                               t->params + t->off[4 * i + 3], t->bn_eps, t->bn_momentum, t->bn_running_mean[i],
+                                               t->bn_running_var[i], (long long*)t->bn_num_batches[i], w.sums, w.bn_scale[i],
+                                               w.bn_shift[i], w.bn_mean[i], w.bn_rstd[i], 1, st));
+  }
+  VC_LAUNCH(KC_TOKENS, st, vc::transformer_fwd_launch(w.z[6], w.blob, n, P, t->K, logits, nullptr, nullptr, 1, st));
+  return VC_OK;
+}
+
+int conv_wgrad(const vc_train* t, const ConvPlan& c, int i, const void* x, const void* dy, const TrainWs& w, int n,
+               cudaStream_t st) {
+  float* out = t->grads + t->off[4 * i];
+  const int P = t->P;
+  if (c.shift_on_a)
+    return vc::wgrad_sps_launch(x, c.S_in, dy, c.n_out / 8, n, P, c.taps, 1, w.wg, out, c.cin, c.cout, c.taps,
+                                (long long)c.cin * c.taps, 1, -1, nullptr, 0, st);
+  return vc::wgrad_sps_launch(dy, c.n_out / 8, x, c.S_in, n, P, c.taps, 0, w.wg, out, c.cout, c.cin, (long long)c.cin * c.taps,
+                              c.taps, 1, -1, nullptr, 0, st);
+}
+
+int linear_wgrad(const vc_train* t, const void* dy, int SA, const void* x, int SB, long long rows, int M, int N, int iw,
+                 const TrainWs& w, cudaStream_t st) {
+  return vc::wgrad_sps_launch(dy, SA, x, SB, (int)(rows / 128), 0, 1, 0, w.wg, t->grads + t->off[iw], M, N, N, 1, 0, N,
+                              t->grads + t->off[iw + 1], 0, st);
+}
+
+int train_backward_core(const vc_train* t, const ConvPlan pl[7], const TrainWs& w, int n, const float* dlogits,
+                        cudaStream_t st) {
+  const int P = t->P, K = t->K, T = P * P + 1;
+  float* G = t->grads;
+  // ---- token stage ----
+  const int small_idx[12] = {30, 31, 36, 37, 42, 43, 48, 49, 54, 55, 28, 29};
+  float* small[12];
+  for (int i = 0; i < 12; ++i) {
+    small[i] = G + t->off[small_idx[i]];
+    const size_t cnt = small_idx[i] == 29 ? (size_t)T * 32 : 32;
+    if (cudaMemsetAsync(small[i], 0, cnt * sizeof(float), st) != cudaSuccess) return fail(VC_ERR_CUDA, "memset");
+  }
+  VC_LAUNCH(KC_TOKENS_BWD, st, vc::transformer_bwd_launch(w.z[6], w.blob, dlogits, w.dzf, (void* const*)w.tok, (void* const*)w.cls,
+                                                         small, n, P, K, st));
+  // linear-layer weight / bias gradients: contraction over all token rows on the tensor cores
+  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, w.tok[1], 12, w.tok[0], 6, w.RTt, 96, 32, 32, w, st));    // block 0 qkv
+  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, w.tok[3], 4, w.tok[2], 6, w.RTt, 32, 32, 34, w, st));     //         proj
+  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, w.tok[5], 16, w.tok[4], 6, w.RTt, 128, 32, 38, w, st));   //         fc1
+  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, w.tok[7], 4, w.tok[6], 18, w.RTt, 32, 128, 40, w, st));   //         fc2
+  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, w.tok[9], 12, w.tok[8], 6, w.RTt, 96, 32, 44, w, st));    // block 1 qkv
+  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, w.cls[1], 4, w.cls[0], 6, w.RTc, 32, 32, 46, w, st));     //         proj (cls row)
+  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, w.cls[3], 16, w.cls[2], 6, w.RTc, 128, 32, 50, w, st));   //         fc1
+  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, w.cls[5], 4, w.cls[4], 18, w.RTc, 32, 128, 52, w, st));   //         fc2
+  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, w.cls[7], (K + 15) / 16 * 2, w.cls[6], 6, w.RTc, K, 32, 56, w, st));   // head
+  // ---- convolutions, last to first ----
+  const int order[7] = {6, 2, 1, 0, 5, 4, 3};
+  const long long sl = w.RT * 16;
+  for (int oi = 0; oi < 7; ++oi) {
+    const int i = order[oi];
+    const ConvPlan& c = pl[i];
+    uint8_t* dz = i == 6 ? w.dzf : i == 2 ? w.df : i == 1 ? w.dzh2 : i == 0 ? w.dzh1 : i == 5 ? w.df + 4 * sl : i == 4 ? w.dzl2 : w.dzl1;
+    const uint8_t* x = (i == 0) ? w.a0 : (i == 3) ? w.l0 : (i == 6) ? w.f : w.z[i - 1];
+    VC_LAUNCH(KC_BN, st, vc::bn_backward_launch(dz, w.y[i], dz, c.n_out / 8, c.cout, n, P, w.bn_scale[i], w.bn_shift[i], w.bn_mean[i],
+                                                w.bn_rstd[i], 1, w.sums, G + t->off[4 * i + 2], G + t->off[4 * i + 3],
+                                                G + t->off[4 * i + 1], 0, st));
+    VC_LAUNCH(KC_WGRAD, st, conv_wgrad(t, c, i, x, dz, w, n, st));
+    if (c.has_dgrad) {
+      uint8_t* dprev = i == 6 ? w.df : i == 2 ? w.dzh2 : i == 1 ? w.dzh1 : i == 5 ? w.dzl2 : w.dzl1;
+      VC_LAUNCH(KC_DGRAD, st, vc::conv_sps_launch(dz, c.d_S_in, w.wd[i], w.ones, w.zeros, dprev, 0, c.d_n_out, c.d_nsplit, n, P,
+                                                  c.taps, 0, 0, 0, st));
+    }
+  }
+  return VC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vc_bn_forward(const void* y, void* z, int32_t S, int32_t C, int32_t n_patches, int32_t P, const float* gamma,
+                  const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                  int64_t* num_batches_tracked, double* sums, float* scale, float* shift, float* mean, float* rstd,
+                  int32_t relu, void* stream) {
+  VC_TRY(vc::bn_forward_launch(y, z, S, C, n_patches, P, gamma, beta, eps, momentum, running_mean, running_var,
+                               (long long*)num_batches_tracked, sums, scale, shift, mean, rstd, relu, (cudaStream_t)stream));
+  return VC_OK;
+}
+
+int vc_bn_backward(const void* dz, const void* y, void* dy, int32_t S, int32_t C, int32_t n_patches, int32_t P,
+                   const float* scale, const float* shift, const float* mean, const float* rstd, int32_t relu,
+                   double* sums, float* dgamma, float* dbeta, float* dbias, void* stream) {
+  VC_TRY(vc::bn_backward_launch(dz, y, dy, S, C, n_patches, P, scale, shift, mean, rstd, relu, sums, dgamma, dbeta, dbias, 0,
+                                (cudaStream_t)stream));
+  return VC_OK;
+}
+
+int vc_pack_conv_weight(const float* w, int32_t cout, int32_t cin, int32_t taps, int32_t transpose, int32_t S_in,
+                        int32_t n_out, int32_t nsplit, void* dst, void* stream) {
+  VC_TRY(vc::pack_conv_w_launch(w, cout, cin, taps, transpose, S_in, n_out, nsplit, dst, (cudaStream_t)stream));
+  return VC_OK;
+}
+
+int vc_pack_segments(const float* flat, void* blob, const int64_t* segs, int32_t nsegs, void* stream) {
+  VC_TRY(vc::pack_segments_launch(flat, blob, (const long long*)segs, nsegs, (cudaStream_t)stream));
+  return VC_OK;
+}
+
+int vc_ce_loss(const float* logits, const int64_t* labels, const float* weight, int32_t n, int32_t K, float grad_scale,
+               float* loss_out, float* dlogits, void* stream) {
+  if (n == 0) return VC_OK;
+  VC_LAUNCH(KC_MISC, (cudaStream_t)stream, vc::ce_loss_launch(logits, (const long long*)labels, weight, n, K, grad_scale, loss_out,
+                                                              dlogits, (cudaStream_t)stream));
+  return VC_OK;
+}
+
+int vc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, int32_t step, float grad_scale, void* stream) {
+  VC_LAUNCH(KC_MISC, (cudaStream_t)stream,
+            vc::adam_launch(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, (cudaStream_t)stream));
+  return VC_OK;
+}
+
+int64_t vc_train_workspace_bytes(const vc_train* t, int32_t n) {
+  ConvPlan pl[7];
+  if (n <= 0 || check_train(t, pl) != VC_OK) return -1;
+  return carve_train(nullptr, t, pl, n).bytes + 256;
+}
+
+int vc_train_workspace_init(const vc_train* t, int32_t n, void* workspace, int64_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  ConvPlan pl[7];
+  VC_TRY(check_train(t, pl));
+  if (!workspace || workspace_bytes < vc_train_workspace_bytes(t, n)) return fail(VC_ERR_ARG, "workspace too small");
+  const TrainWs w = carve_train(workspace, t, pl, n);
+  if (cudaMemsetAsync(workspace, 0, (size_t)w.bytes, st) != cudaSuccess) return fail(VC_ERR_CUDA, "memset");
+  fill_f32_kernel<<<1, 256, 0, st>>>(w.ones, 256, 1.f);
+  for (int i = 0; i < 10; ++i)
+    if (kTokOnes[i] >= 0)
+      fill_ones_slice_kernel<<<148, 256, 0, st>>>((__nv_bfloat16*)w.tok[i] + (long long)kTokOnes[i] * w.RTt * 8, w.RTt);
+  for (int i = 0; i < 8; ++i)
+    if (kClsOnes[i] >= 0)
+      fill_ones_slice_kernel<<<16, 256, 0, st>>>((__nv_bfloat16*)w.cls[i] + (long long)kClsOnes[i] * w.RTc * 8, w.RTc);
+  return cudaGetLastError() == cudaSuccess ? VC_OK : fail(VC_ERR_CUDA, "workspace init");
+}
+
+int vc_train_forward(const vc_train* t, const float* hsi, const int64_t hs[4], const float* lidar, const int64_t ls[4],
+                     int32_t n, void* workspace, int64_t workspace_bytes, float* logits, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  ConvPlan pl[7];
+  VC_TRY(check_train(t, pl));
+  if (n <= 0 || !hsi || !lidar || !hs || !ls || !workspace || !logits) return fail(VC_ERR_ARG, "vc_train_forward: bad arguments");
+  if (workspace_bytes < vc_train_workspace_bytes(t, n)) return fail(VC_ERR_ARG, "workspace too small");
+  const TrainWs w = carve_train(workspace, t, pl, n);
+  VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(hsi, hs[0], hs[1], hs[2], hs[3], nullptr, n, t->C1, t->P, w.a0, pl[0].S_in, st));
+  VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(lidar, ls[0], ls[1], ls[2], ls[3], nullptr, n, t->C2, t->P, w.l0, pl[3].S_in, st));
+  return train_forward_core(t, pl, w, n, logits, st);
+}
+
+int vc_train_forward_gather(const vc_train* t, const float* img1, const float* img2, const void* gt, int32_t gt_elem_bytes,
+                            int32_t H, int32_t W, const int32_t* xy, int32_t n, void* workspace, int64_t workspace_bytes,
+                            float* logits, int64_t* labels, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  ConvPlan pl[7];
+  VC_TRY(check_train(t, pl));
+  if (n <= 0 || !img1 || !img2 || !xy || !workspace || !logits || H < t->P || W < t->P)
+    return fail(VC_ERR_ARG, "vc_train_forward_gather: bad arguments");
+  if (workspace_bytes < vc_train_workspace_bytes(t, n)) return fail(VC_ERR_ARG, "workspace too small");
+  const TrainWs w = carve_train(workspace, t, pl, n);
+  VC_LAUNCH(KC_INDEX, st, vc::center_offsets_launch(xy, n, W, t->C1, t->C2, t->P, w.off1, w.off2, st));
+  VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(img1, 0, 1, (long long)W * t->C1, t->C1, w.off1, n, t->C1, t->P, w.a0, pl[0].S_in, st));
+  VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(img2, 0, 1, (long long)W * t->C2, t->C2, w.off2, n, t->C2, t->P, w.l0, pl[3].S_in, st));
+  if (gt && labels)
+    VC_LAUNCH(KC_INDEX, st, vc::gather_labels_launch(gt, gt_elem_bytes, H, W, xy, n, t->P, 1, (long long*)labels, st));
+  return train_forward_core(t, pl, w, n, logits, st);
+}
+
+int vc_train_backward(const vc_train* t, const float* dlogits, int32_t n, void* workspace, int64_t workspace_bytes,
+                      void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  ConvPlan pl[7];
+  VC_TRY(check_train(t, pl));
+  if (n <= 0 || !dlogits || !workspace) return fail(VC_ERR_ARG, "vc_train_backward: bad arguments");
+  if (workspace_bytes < vc_train_workspace_bytes(t, n)) return fail(VC_ERR_ARG, "workspace too small");
+  const TrainWs w = carve_train(workspace, t, pl, n);
+  return train_backward_core(t, pl, w, n, dlogits, st);
 }
 
 }  // extern "C"

@@ -196,4 +196,21 @@ int scene_index_launch(const int* xs, const int* ys, int nx, int ny, int first, 
   return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
 }
 
+// Element offsets of the top-left corner of the P x P patch centred on (x, y) in the two rasters
+// (MultiModalX.__getitem__: x1 = x - P//2, y1 = y - P//2, datasets.py:551-556).
+__global__ void center_offsets_kernel(const int* xy, int n, int W, int C1, int C2, int P, long long* off1, long long* off2) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const long long pix = (long long)(xy[2 * t] - P / 2) * W + (xy[2 * t + 1] - P / 2);
+    off1[t] = pix * C1;
+    off2[t] = pix * C2;
+  }
+}
+
+int center_offsets_launch(const int* xy, int n, int W, int C1, int C2, int P, long long* off1, long long* off2,
+                          cudaStream_t stream) {
+  if (n <= 0) return VC_ERR_ARG;
+  center_offsets_kernel<<<(n + 255) / 256, 256, 0, stream>>>(xy, n, W, C1, C2, P, off1, off2);
+  return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
+}
+
 }  // namespace vc

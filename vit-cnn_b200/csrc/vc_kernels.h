@@ -21,15 +21,38 @@ int gather_labels_launch(const void* gt, int gt_elem_bytes, int H, int W, const 
 int scene_index_launch(const int* xs, const int* ys, int nx, int ny, int first, int count, int W, int C1, int C2, int P,
                        int K, long long* off1, long long* off2, long long* out_idx, int* xy, cudaStream_t stream);
 
+int center_offsets_launch(const int* xy, int n, int W, int C1, int C2, int P, long long* off1, long long* off2,
+                          cudaStream_t stream);
+
 // transformer.cu
 size_t tparams_bytes(int P, int K);
 int transformer_fwd_launch(const void* f_sps, const void* tparams, int n_patches, int P, int K, float* logits,
-                           const long long* out_index, unsigned char* argmax_map, cudaStream_t stream);
+                           const long long* out_index, unsigned char* argmax_map, int prefused, cudaStream_t stream);
 
 // wgrad_tc.cu -- weight gradients (rows are the reduction axis; both operands MN-major)
 size_t wgrad_workspace_bytes(int SB, int ntaps);
 int wgrad_sps_launch(const void* A, int SA, const void* B, int SB, int n_patches, int P, int ntaps, int shift_on_a,
                      void* workspace, float* out, int M, int Nr, long long sm, long long sn, long long st,
                      int bias_col, float* out_bias, int accumulate, cudaStream_t stream);
+
+
+// train.cu -- BatchNorm (training mode) forward / backward over SPS, loss, optimiser, weight packing
+int bn_forward_launch(const void* y, void* z, int S, int C, int n_patches, int P, const float* gamma, const float* beta,
+                      float eps, float momentum, float* running_mean, float* running_var, long long* nbt, double* sums,
+                      float* scale, float* shift, float* mean, float* rstd, int relu, cudaStream_t st);
+int bn_backward_launch(const void* dz, const void* y, void* dy, int S, int C, int n_patches, int P, const float* scale,
+                       const float* shift, const float* mean, const float* rstd, int relu, double* sums, float* dgamma,
+                       float* dbeta, float* dbias, int accumulate, cudaStream_t st);
+int ce_loss_launch(const float* logits, const long long* labels, const float* weight, int n, int K, float grad_scale,
+                   float* loss_out, float* dlogits, cudaStream_t st);
+int adam_launch(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                float wd, int step, float grad_scale, cudaStream_t st);
+int pack_conv_w_launch(const float* w, int cout, int cin, int taps, int transpose, int S_in, int n_out, int nsplit,
+                       void* dst, cudaStream_t st);
+int pack_segments_launch(const float* flat, void* blob, const long long* segs, int nsegs, cudaStream_t st);
+
+// tokens_bwd.cu
+int transformer_bwd_launch(const void* zf, const void* tparams, const float* dlogits, void* dzf, void* const* tok_dumps,
+                           void* const* cls_dumps, float* const* small, int n_patches, int P, int K, cudaStream_t stream);
 
 }  // namespace vc

@@ -23,7 +23,7 @@ struct WgradArgs {
   const __nv_bfloat16* B;   // [SB][RT][8]   N side (N = SB*8, multiple of 16, <= 256)
   float* part;              // [gridDim.x][ntaps][128][N]
   long long RT;
-  int SA, SB, ntaps, tpc, P, ntiles, shift_on_a, nstages;
+  int SA, SB, ntaps, tpc, halo, pw, ntiles, shift_on_a, nstages;
 };
 
 constexpr int kWgThreads = 192;    // warp0 producer, warp1 MMA issuer, warps 2..5 epilogue
@@ -42,7 +42,7 @@ __host__ __device__ inline uint32_t umma_idesc_bf16_mn(int M, int N) {
 __global__ void __launch_bounds__(kWgThreads) wgrad_sps_tc_kernel(WgradArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int HALO = sps_halo(a.P), PW = a.P + 1;
+  const int HALO = a.halo, PW = a.pw;
   const int N = a.SB * 8;
   const int rowsA = kWgStageRows + (a.shift_on_a ? 2 * HALO : 0);
   const int rowsB = kWgStageRows + (a.shift_on_a ? 0 : 2 * HALO);
@@ -196,8 +196,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int nparts, 
   }
 }
 
-static size_t wgrad_smem(int SA, int SB, int P, int shift_on_a, int nstages) {
-  const int HALO = sps_halo(P);
+static size_t wgrad_smem(int SA, int SB, int HALO, int shift_on_a, int nstages) {
   const size_t rowsA = kWgStageRows + (shift_on_a ? 2 * HALO : 0), rowsB = kWgStageRows + (shift_on_a ? 0 : 2 * HALO);
   (void)SA;
   return (size_t)nstages * (16 * rowsA * 16 + (size_t)SB * rowsB * 16) + (2 * nstages + 1) * 8 + 16;
@@ -216,22 +215,25 @@ size_t wgrad_workspace_bytes(int SB, int ntaps) {
   return (size_t)wgrad_grid_x(SB, ntaps) * ntaps * 128 * (SB * 8) * sizeof(float);
 }
 
+// rows mode (P == 0): plain [slice][ntiles*128][8] operands without halos (taps must be 1);
+// n_patches then carries the number of 128-row tiles.
 int wgrad_sps_launch(const void* A, int SA, const void* B, int SB, int n_patches, int P, int ntaps, int shift_on_a,
                      void* workspace, float* out, int M, int Nr, long long sm, long long sn, long long st,
                      int bias_col, float* out_bias, int accumulate, cudaStream_t stream) {
-  if (SA < 1 || SA > 16 || SB < 2 || (SB & 1) || SB > 32 || (ntaps != 1 && ntaps != 9) || n_patches <= 0 || P < 1 ||
-      M > SA * 8 || Nr > SB * 8 || !workspace)
+  if (SA < 1 || SA > 16 || SB < 2 || (SB & 1) || SB > 32 || (ntaps != 1 && ntaps != 9) || n_patches <= 0 || P < 0 ||
+      M > SA * 8 || Nr > SB * 8 || !workspace || (P == 0 && ntaps != 1))
     return VC_ERR_ARG;
   WgradArgs a;
   a.A = (const __nv_bfloat16*)A;
   a.B = (const __nv_bfloat16*)B;
   a.part = (float*)workspace;
-  a.RT = sps_rows(n_patches, P);
+  a.RT = P ? sps_rows(n_patches, P) : (long long)n_patches * 128;
   a.SA = SA;
   a.SB = SB;
   a.ntaps = ntaps;
-  a.P = P;
-  a.ntiles = sps_tiles(n_patches, P);
+  a.halo = P ? sps_halo(P) : 0;
+  a.pw = P + 1;
+  a.ntiles = P ? sps_tiles(n_patches, P) : n_patches;
   a.shift_on_a = shift_on_a;
   const int N = SB * 8;
   int tpc = 512 / N;
@@ -246,8 +248,8 @@ int wgrad_sps_launch(const void* A, int SA, const void* B, int SB, int n_patches
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   }
   int nst = 6;
-  while (nst > 2 && wgrad_smem(SA, SB, P, shift_on_a, nst) > (size_t)max_smem) --nst;
-  const size_t smem = wgrad_smem(SA, SB, P, shift_on_a, nst);
+  while (nst > 2 && wgrad_smem(SA, SB, a.halo, shift_on_a, nst) > (size_t)max_smem) --nst;
+  const size_t smem = wgrad_smem(SA, SB, a.halo, shift_on_a, nst);
   if (smem > (size_t)max_smem) return VC_ERR_UNSUPPORTED;
   a.nstages = nst;
   if (cudaFuncSetAttribute(wgrad_sps_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)

@@ -1,0 +1,319 @@
+"""Training side of the ViT-CNN module: what ``net(data, data2)`` in train mode, ``loss.backward()``
+and ``optimizer.step()`` do in the reference's loop (model_utils.py:908-945), computed by
+libvitcnn.so.
+
+* ``train_forward``  - autograd bridge used by ``ViTCNN.forward`` when ``model.training``: the
+  forward (BatchNorm with batch statistics) and the whole backward run in the library; torch
+  only routes the returned gradients to the ``nn.Parameter``s, so the reference's own loop
+  (criterion = nn.CrossEntropyLoss, optimizer = optim.Adam) works unchanged.
+* ``Trainer``        - the fast path: patches gathered on the device from the rasters, loss,
+  backward, (NCCL all-reduce of one flat fp32 gradient bucket), Adam - no torch operator on
+  the step except the collective.
+* ``train``          - the reference's ``train()`` signature on top of either.
+
+Parameters are kept in ONE flat fp32 buffer (the nn.Parameters are views into it, in the
+canonical order of include/vitcnn.h) so that packing, all-reduce and Adam are single launches.
+"""
+from __future__ import annotations
+
+import ctypes
+import warnings
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_BLOCK_KEYS = ("norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.qkv.bias", "attn.proj.weight", "attn.proj.bias",
+               "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias")
+
+
+def param_names() -> list:
+    """Canonical parameter order (include/vitcnn.h, struct vc_train)."""
+    names = []
+    for stem in ("hsi_stem.0", "hsi_stem.1", "hsi_stem.2", "lidar_stem.0", "lidar_stem.1", "lidar_stem.2", "fusion"):
+        names += [f"{stem}.conv.weight", f"{stem}.conv.bias", f"{stem}.bn.weight", f"{stem}.bn.bias"]
+    names += ["cls_token", "pos_embed"]
+    for l in (0, 1):
+        names += [f"blocks.{l}.{k}" for k in _BLOCK_KEYS]
+    names += ["norm.weight", "norm.bias", "head.weight", "head.bias"]
+    return names
+
+
+def _bn_layers(model):
+    return [model.hsi_stem[0].bn, model.hsi_stem[1].bn, model.hsi_stem[2].bn, model.lidar_stem[0].bn,
+            model.lidar_stem[1].bn, model.lidar_stem[2].bn, model.fusion.bn]
+
+
+class TrainState:
+    """Flat parameter / gradient buffers, the ``vc_train`` descriptor and per-batch-size
+    workspaces of one model on one device."""
+
+    def __init__(self, model):
+        self.model = model
+        self.names = param_names()
+        named = dict(model.named_parameters())
+        self.params = [named[k] for k in self.names]
+        assert len(self.params) == 58 and len(named) == 58
+        self.device = self.params[0].device
+        if self.device.type != "cuda":
+            raise RuntimeError("ViTCNN trains on a CUDA device only (no CPU path)")
+        self.offsets, o = [], 0
+        for p in self.params:
+            self.offsets.append(o)
+            o += (p.numel() + 3) // 4 * 4
+        self.numel = o
+        self.flat = torch.zeros(o, dtype=torch.float32, device=self.device)
+        self.grads = torch.zeros(o, dtype=torch.float32, device=self.device)
+        with torch.no_grad():
+            for p, off in zip(self.params, self.offsets):
+                view = self.flat[off:off + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+        P, K = model.patch_size, model.num_classes
+        self.segments = self._blob_segments(P, K)
+        st = _lib.VcTrain()
+        st.C1, st.C2, st.P, st.K = model.n_bands, model.n_bands2, P, K
+        st.params, st.grads = self.flat.data_ptr(), self.grads.data_ptr()
+        for i, off in enumerate(self.offsets):
+            st.off[i] = off
+        for i, bn in enumerate(_bn_layers(model)):
+            st.bn_running_mean[i] = bn.running_mean.data_ptr()
+            st.bn_running_var[i] = bn.running_var.data_ptr()
+            st.bn_num_batches[i] = bn.num_batches_tracked.data_ptr()
+        bn0 = model.hsi_stem[0].bn
+        st.bn_eps, st.bn_momentum = bn0.eps, bn0.momentum
+        st.blob_segments, st.n_blob_segments = self.segments.data_ptr(), self.segments.shape[0]
+        self.struct = st
+        self._bn_ptrs = [b.running_mean.data_ptr() for b in _bn_layers(model)]
+        self.ws = {}
+        self.pending = None     # batch size of a forward whose backward has not run yet
+
+    def __deepcopy__(self, memo):   # copies / pickles of the module rebuild their own state lazily
+        return None
+
+    def __reduce__(self):
+        return (type(None), ())
+
+    def _blob_segments(self, P, K):
+        lay = _lib.tparams_layout(P, K)
+        off = dict(zip(self.names, self.offsets))
+        T = P * P + 1
+        seg = [(off["cls_token"], lay["cls"], 1, 32, 32, 0), (off["pos_embed"], lay["pos"], 1, T * 32, T * 32, 0)]
+        for l, lo in enumerate(lay["layers"]):
+            b = f"blocks.{l}."
+            seg += [(off[b + "attn.qkv.weight"], lo["wqkv"], 96, 32, 40, 1),
+                    (off[b + "attn.proj.weight"], lo["wproj"], 32, 32, 40, 1),
+                    (off[b + "mlp.fc1.weight"], lo["wfc1"], 128, 32, 40, 1),
+                    (off[b + "mlp.fc2.weight"], lo["wfc2"], 32, 128, 136, 1)]
+            for key, name, n in (("ln1_g", "norm1.weight", 32), ("ln1_b", "norm1.bias", 32), ("bqkv", "attn.qkv.bias", 96),
+                                 ("bproj", "attn.proj.bias", 32), ("ln2_g", "norm2.weight", 32), ("ln2_b", "norm2.bias", 32),
+                                 ("bfc1", "mlp.fc1.bias", 128), ("bfc2", "mlp.fc2.bias", 32)):
+                seg.append((off[b + name], lo[key], 1, n, n, 0))
+        seg += [(off["norm.weight"], lay["lnf_g"], 1, 32, 32, 0), (off["norm.bias"], lay["lnf_b"], 1, 32, 32, 0),
+                (off["head.weight"], lay["whead"], 1, K * 32, K * 32, 0), (off["head.bias"], lay["bhead"], 1, K, K, 0)]
+        return torch.tensor(seg, dtype=torch.int64, device=self.device)
+
+    def valid(self) -> bool:
+        """Parameters still views into the flat buffer and BN buffers where we recorded them
+        (``.to()`` / ``load_state_dict(assign=True)`` replace storages)."""
+        base = self.flat.data_ptr()
+        if any(p.data_ptr() != base + 4 * off for p, off in zip(self.params, self.offsets)):
+            return False
+        return self._bn_ptrs == [b.running_mean.data_ptr() for b in _bn_layers(self.model)]
+
+    def workspace(self, n: int) -> torch.Tensor:
+        ws = self.ws.get(n)
+        if ws is None:
+            L = _lib.lib()
+            need = L.vc_train_workspace_bytes(ctypes.byref(self.struct), n)
+            if need <= 0:
+                raise RuntimeError("this configuration is not supported by the training kernels "
+                                   "(patch_size <= 11, n_classes <= 64)")
+            if len(self.ws) >= 4:
+                self.ws.pop(next(iter(self.ws)))
+            ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            _lib.check(L.vc_train_workspace_init(ctypes.byref(self.struct), n, ws.data_ptr(), ws.numel(),
+                                                 torch.cuda.current_stream().cuda_stream), "vc_train_workspace_init")
+            self.ws[n] = ws
+        return ws
+
+    # ---- one batch --------------------------------------------------------------------------------
+    def forward_patches(self, hsi, lidar):
+        n = hsi.shape[0]
+        logits = torch.empty(n, self.model.num_classes, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            ws = self.workspace(n)
+            hs = (ctypes.c_int64 * 4)(*hsi.stride())
+            ls = (ctypes.c_int64 * 4)(*lidar.stride())
+            _lib.check(_lib.lib().vc_train_forward(ctypes.byref(self.struct), hsi.data_ptr(), hs, lidar.data_ptr(), ls, n,
+                                                   ws.data_ptr(), ws.numel(), logits.data_ptr(),
+                                                   torch.cuda.current_stream().cuda_stream), "vc_train_forward")
+        self.pending = n
+        self.model._pack = None      # running statistics changed: eval-mode packing is stale
+        return logits
+
+    def forward_gather(self, img1, img2, gt, xy):
+        n = xy.shape[0]
+        H, W, _ = img1.shape
+        logits = torch.empty(n, self.model.num_classes, dtype=torch.float32, device=self.device)
+        labels = torch.empty(n, dtype=torch.int64, device=self.device) if gt is not None else None
+        with torch.cuda.device(self.device):
+            ws = self.workspace(n)
+            _lib.check(_lib.lib().vc_train_forward_gather(
+                ctypes.byref(self.struct), img1.data_ptr(), img2.data_ptr(), 0 if gt is None else gt.data_ptr(),
+                0 if gt is None else gt.element_size(), H, W, xy.data_ptr(), n, ws.data_ptr(), ws.numel(),
+                logits.data_ptr(), 0 if labels is None else labels.data_ptr(),
+                torch.cuda.current_stream().cuda_stream), "vc_train_forward_gather")
+        self.pending = n
+        self.model._pack = None
+        return logits, labels
+
+    def backward(self, dlogits):
+        n = dlogits.shape[0]
+        if self.pending != n:
+            raise RuntimeError("backward() without a matching training forward on this model")
+        with torch.cuda.device(self.device):
+            ws = self.workspace(n)
+            _lib.check(_lib.lib().vc_train_backward(ctypes.byref(self.struct), dlogits.data_ptr(), n, ws.data_ptr(),
+                                                    ws.numel(), torch.cuda.current_stream().cuda_stream),
+                       "vc_train_backward")
+        self.pending = None
+
+    def grad_views(self, flat):
+        return tuple(flat[off:off + p.numel()].view(p.shape) for p, off in zip(self.params, self.offsets))
+
+
+def train_state(model) -> TrainState:
+    st = getattr(model, "_train_state", None)
+    if st is None or not st.valid():
+        st = TrainState(model)
+        model._train_state = st
+        if model.dropout > 0 and not getattr(model, "_dropout_warned", False):
+            model._dropout_warned = True
+            warnings.warn("ViTCNN training kernels run without dropout (reference default p=0.01)")
+    return st
+
+
+class _TrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, state, hsi, lidar, *params):
+        ctx.state = state
+        return state.forward_patches(hsi, lidar)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        st = ctx.state
+        st.backward(dlogits.contiguous().float())
+        return (None, None, None) + st.grad_views(st.grads.clone())
+
+
+def train_forward(model, hsi, lidar):
+    """Training-mode forward of ``ViTCNN`` (called from ``ViTCNN.forward``)."""
+    st = train_state(model)
+    if hsi.shape[0] == 0:
+        return torch.empty(0, model.num_classes, dtype=torch.float32, device=hsi.device)
+    if not torch.is_grad_enabled():
+        return st.forward_patches(hsi, lidar)
+    return _TrainFn.apply(st, hsi, lidar, *st.params)
+
+
+# ----------------------------------------------------------------------------------------------------
+def ce_loss(logits, labels, weight=None, grad_scale=1.0, want_grad=True):
+    """nn.CrossEntropyLoss(weight) forward (+ gradient): returns (loss[2] = mean loss, weight sum;
+    dlogits or None)."""
+    n, K = logits.shape
+    out = torch.empty(2, dtype=torch.float32, device=logits.device)
+    d = torch.empty_like(logits) if want_grad else None
+    with torch.cuda.device(logits.device):
+        _lib.check(_lib.lib().vc_ce_loss(logits.data_ptr(), labels.data_ptr(), 0 if weight is None else weight.data_ptr(),
+                                         n, K, float(grad_scale), out.data_ptr(), 0 if d is None else d.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream), "vc_ce_loss")
+    return out, d
+
+
+def adam_step(p, g, m, v, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+    with torch.cuda.device(p.device):
+        _lib.check(_lib.lib().vc_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, betas[0],
+                                           betas[1], eps, weight_decay, step, grad_scale,
+                                           torch.cuda.current_stream().cuda_stream), "vc_adam_step")
+
+
+class Trainer:
+    """Data-parallel training step on device-resident rasters: gather -> forward -> weighted CE ->
+    backward -> all-reduce(sum) of the flat gradient bucket over NCCL -> Adam(grad / world).
+    One process per GPU; replicas start identical (same seed / broadcast state_dict)."""
+
+    def __init__(self, model, lr=1e-3, weights=None, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None):
+        import torch.distributed as dist
+        self.model = model.train()
+        self.state = train_state(model)
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.weights = None if weights is None else weights.to(self.state.device, torch.float32).contiguous()
+        self.m = torch.zeros_like(self.state.flat)
+        self.v = torch.zeros_like(self.state.flat)
+        self.t = 0
+        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.group = process_group
+        self.world = self.dist.get_world_size(process_group) if self.dist else 1
+
+    def step(self, img1, img2, gt, xy):
+        """One optimisation step on patches centred at xy (int32 [n,2], device).  Returns the
+        loss tensor [2] (mean loss of this rank, weight sum) without synchronising."""
+        st = self.state
+        if not st.valid():
+            raise RuntimeError("model parameters were moved after the Trainer was built")
+        logits, labels = st.forward_gather(img1, img2, gt, xy)
+        loss, dlogits = ce_loss(logits, labels, self.weights)
+        st.backward(dlogits)
+        if self.world > 1:
+            self.dist.all_reduce(st.grads, op=self.dist.ReduceOp.SUM, group=self.group)
+        self.t += 1
+        adam_step(st.flat, st.grads, self.m, self.v, self.t, self.lr, self.betas, self.eps, self.wd, 1.0 / self.world)
+        self.model._pack = None
+        return loss
+
+
+def train(net, optimizer, criterion, data_loader, epoch, scheduler=None, display_iter=100, device=torch.device("cpu"),
+          display=None, val_loader=None, supervision="full"):
+    """The reference's training loop (model_utils.py:854-1045) without its visdom plotting and
+    checkpoint writing: same iteration order, loss, optimiser and scheduler stepping, validation
+    after every epoch, returns the best ``state_dict`` by validation accuracy."""
+    import copy
+    from .model_utils import val
+    if criterion is None:
+        raise Exception("Missing criterion. You must specify a loss function.")
+    net.to(device)
+    best_acc, best_state = -1.0, None
+    losses = []
+    for e in range(1, epoch + 1):
+        net.train()
+        for data, data2, target in data_loader:
+            data, data2, target = data.to(device), data2.to(device), target.to(device)
+            optimizer.zero_grad()
+            if supervision == "full":
+                output = net(data, data2)
+                if isinstance(output, tuple):
+                    output = output[0]
+                loss = criterion(output, target)
+            else:
+                raise ValueError('supervision mode "{}" is unknown.'.format(supervision))
+            loss.backward()
+            optimizer.step()
+            losses.append(loss.detach())
+        if val_loader is not None:
+            net.eval()
+            acc = val(net, val_loader, device=device, supervision=supervision)
+            metric = acc
+        else:
+            metric = -float(torch.stack(losses[-len(data_loader):]).mean().item())
+            acc = metric
+        if scheduler is not None:
+            if isinstance(scheduler, torch.optim.lr_scheduler.ReduceLROnPlateau):
+                scheduler.step(metric)
+            else:
+                scheduler.step()
+        if acc > best_acc:
+            best_acc, best_state = acc, copy.deepcopy(net.state_dict())
+    return best_state
