@@ -112,6 +112,94 @@ def cpu_oracle_rate(seconds: float, threads: int):
     return done / dt * (H * W) / n_windows, done, dt   # pixels/s of a full scene at this window rate
 
 
+def train_flops_per_sample():
+    """Algorithmic FLOPs of one training sample: forward + data-gradient +
+    weight-gradient GEMMs = 3 x forward, minus the data gradient of the two input convs."""
+    from oracle.model_ref import forward_flops
+    f = forward_flops(C1, C2, P, K)
+    first = 2 * P * P * 9 * (C1 * 128 + C2 * 8)
+    return 3 * f["total"] - first
+
+
+def bench_train(args, rank, world, dev, dist, barrier):
+    """Training throughput, BASELINE.json configs[2]: batch data-parallel, global batch 4096
+    (4096 / N per GPU), patches gathered on the device from the resident raster, weighted CE,
+    backward, all-reduce of one flat fp32 bucket (NCCL), Adam.  samples/s = global batch / step."""
+    import vitcnn_b200
+    from vitcnn_b200 import _lib
+    from vitcnn_b200.train import Trainer
+    rng = np.random.default_rng(1)
+    img1 = torch.from_numpy(rng.random((H, W, C1), dtype=np.float32)).to(dev)
+    img2 = torch.from_numpy(rng.random((H, W, C2), dtype=np.float32)).to(dev)
+    gt_h = rng.integers(1, K, size=(H, W)).astype(np.int64)
+    gt = torch.from_numpy(gt_h).to(dev)
+    torch.manual_seed(0)
+    net = vitcnn_b200.ViTCNN(C1, C2, patch_size=P, num_classes=K, dropout=0.0).to(dev)
+    w = torch.ones(K)
+    w[0] = 0
+    tr = Trainer(net, lr=1e-3, weights=w)
+    per = args.train_batch // world
+    p = P // 2
+    nbatch = 8
+    xy_h = [torch.from_numpy(np.stack([rng.integers(p + 1, H - p - 1, per), rng.integers(p + 1, W - p - 1, per)], 1)
+                             .astype(np.int32)).pin_memory() for _ in range(nbatch)]
+    xy_d = [t.to(dev) for t in xy_h]
+    it = [0]
+
+    def step():
+        tr.step(img1, img2, gt, xy_d[it[0] % nbatch])
+        it[0] += 1
+
+    loss_h = torch.empty(2).pin_memory()
+
+    def e2e_step():
+        xy = xy_h[it[0] % nbatch].to(dev, non_blocking=True)
+        loss = tr.step(img1, img2, gt, xy)
+        loss_h.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        it[0] += 1
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    steps = max(args.steps, 5) * 4
+    for _ in range(max(args.warmup, 3)):
+        step()
+    l0 = _lib.lib().vc_launch_count()
+    ms = timed(step, steps)
+    launches = _lib.lib().vc_launch_count() - l0
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, steps)
+    _lib.profile_begin()
+    step()
+    prof = _lib.profile_end()
+    hbm, tf_burst, tf_sust, which = peaks()
+    fl = train_flops_per_sample() * per
+    total_ms = sum(v[0] for v in prof.values())
+    return {"metric": "train_samples_per_s", "value": args.train_batch * steps / (ms / 1e3), "unit": "samples/s",
+            "ms_per_step": ms / steps, "steps": steps, "global_batch": args.train_batch, "per_gpu_batch": per,
+            "parallelism": f"dp{world}", "scaling": "strong", "dtype": "bf16", "optimizer": "Adam(lr=1e-3)",
+            "loss": "CrossEntropy(weight)", "gpu_launches": int(launches),
+            "e2e": {"value": args.train_batch * steps / (ms_e2e / 1e3), "unit": "samples/s", "ms_per_step": ms_e2e / steps,
+                    "h2d_bytes_per_step": int(per * 8), "d2h_bytes_per_step": 8},
+            "roofline": {"bound": "tensor", "achieved": fl / (ms / steps / 1e3) / 1e12, "peak": tf_sust, "unit": "TFLOP/s",
+                         "frac": fl / (ms / steps / 1e3) / 1e12 / tf_sust, "peak_source": which + " bf16 sustained",
+                         "scope": "whole training step, algorithmic FLOPs (3 x forward - input-conv dgrad)",
+                         "breakdown_ms": {k: round(v[0], 3) for k, v in prof.items() if v[1]},
+                         "profiled_step_ms": total_ms}}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -147,6 +235,9 @@ def main():
     ap.add_argument("--windows", type=int, default=0, help="profiling aid: only the first N windows of the band")
     ap.add_argument("--no-cpu", action="store_true", help="profiling aid: skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the e2e leg")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-throughput leg")
+    ap.add_argument("--no-infer", action="store_true", help="profiling aid: training leg only")
+    ap.add_argument("--train-batch", type=int, default=4096, help="GLOBAL batch of the training leg (configs[2])")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -203,6 +294,16 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    train_line = None
+    if not args.no_train:
+        train_line = bench_train(args, rank, world, dev, dist, barrier)
+        torch.cuda.empty_cache()
+    if args.no_infer:
+        if rank == 0:
+            print(json.dumps({"train": train_line}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler(local_rank)
@@ -269,6 +370,8 @@ def main():
                 "cpu_baseline": {"value": cpu_v, "unit": "pixels/s", "cores": os.cpu_count() or 1, "kind": "port",
                                  "sample": f"{cpu_n} windows ({cpu_dt:.1f} s) of a {P + 3}-row band, batch 64, "
                                            "extrapolated to the scene"}}
+        if train_line is not None:
+            line["train"] = train_line
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -138,9 +138,9 @@ int vc_pack_segments(const float* flat, void* blob, const int64_t* segs, int32_t
 
 /* nn.CrossEntropyLoss(weight=w) (model_utils.py:63-66,216; applied at :929-936): loss_out[0] =
  * weighted mean NLL, loss_out[1] = sum of weights; dlogits (nullable) = grad_scale * dloss/dlogits.
- * labels int64 [n]; entries outside [0,K) are ignored (ignore_index semantics). */
+ * labels int64 [n]; entries outside [0,K) are ignored (ignore_index semantics); scratch: 2 doubles. */
 int vc_ce_loss(const float* logits, const int64_t* labels, const float* weight, int32_t n, int32_t K, float grad_scale,
-               float* loss_out, float* dlogits, void* stream);
+               float* loss_out, float* dlogits, double* scratch, void* stream);
 /* optim.Adam(lr) step (model_utils.py:214-215) on flat fp32 buffers; g is multiplied by
  * grad_scale first (1/world_size after a summing all-reduce). */
 int vc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,

@@ -97,7 +97,8 @@ _PROTOS = {
     "vc_pack_conv_weight": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                       c_void_p, c_void_p]),
     "vc_pack_segments": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
-    "vc_ce_loss": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p]),
+    "vc_ce_loss": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p,
+                             c_void_p]),
     "vc_adam_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
                                c_float, c_int32, c_float, c_void_p]),
     "vc_train_workspace_bytes": (c_int64, [POINTER(VcTrain), c_int32]),

@@ -540,10 +540,10 @@ int vc_pack_segments(const float* flat, void* blob, const int64_t* segs, int32_t
 }
 
 int vc_ce_loss(const float* logits, const int64_t* labels, const float* weight, int32_t n, int32_t K, float grad_scale,
-               float* loss_out, float* dlogits, void* stream) {
+               float* loss_out, float* dlogits, double* scratch, void* stream) {
   if (n == 0) return VC_OK;
   VC_LAUNCH(KC_MISC, (cudaStream_t)stream, vc::ce_loss_launch(logits, (const long long*)labels, weight, n, K, grad_scale, loss_out,
-                                                              dlogits, (cudaStream_t)stream));
+                                                              dlogits, scratch, (cudaStream_t)stream));
   return VC_OK;
 }
 

@@ -758,29 +758,26 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
       dump_afrag32(a.dxa0, a.RTt, trow, q, Adm);
       float dO[4][4];
       gemm_dgrad32<2>(Adm, wproj, LD, lane, dO);
-      uint32_t doa[kHeads][2];
 #pragma unroll
       for (int h = 0; h < kHeads; ++h) {
-        doa[h][0] = pack_bf16(dO[h][0], dO[h][1]);
-        doa[h][1] = pack_bf16(dO[h][2], dO[h][3]);
-        *reinterpret_cast<uint32_t*>(dOs + r0 * LD + 8 * h + 2 * q) = doa[h][0];
-        *reinterpret_cast<uint32_t*>(dOs + r1 * LD + 8 * h + 2 * q) = doa[h][1];
+        const uint32_t d0 = pack_bf16(dO[h][0], dO[h][1]), d1 = pack_bf16(dO[h][2], dO[h][3]);
+        *reinterpret_cast<uint32_t*>(dOs + r0 * LD + 8 * h + 2 * q) = d0;
+        *reinterpret_cast<uint32_t*>(dOs + r1 * LD + 8 * h + 2 * q) = d1;
         const uint32_t o0 = oa[h >> 1][(h & 1) * 2 + 0], o1 = oa[h >> 1][(h & 1) * 2 + 1];
         const float dl0 = quad_sum(dO[h][0] * bf_lo(o0) + dO[h][1] * bf_hi(o0));
         const float dl1 = quad_sum(dO[h][2] * bf_lo(o1) + dO[h][3] * bf_hi(o1));
         if (q == 0) { st_dl[h * TP + r0] = dl0; st_dl[h * TP + r1] = dl1; }
       }
       __syncthreads();
-      float dqkv[12][4];
-#pragma unroll
-      for (int j = 0; j < 12; ++j)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) dqkv[j][e] = 0.f;
+      // per head: dQ / dK / dV tiles of this warp's rows, staged (bf16) in the dead block-1 arrays
+      // K1s (dq), V1s (dk), dV1s (dv) so that nothing is indexed dynamically in registers
 #pragma unroll 1
       for (int h = 0; h < kHeads; ++h) {
+        float dq[4] = {0.f, 0.f, 0.f, 0.f}, dk[4] = {0.f, 0.f, 0.f, 0.f}, dv[4] = {0.f, 0.f, 0.f, 0.f};
         // ---- sweep A: this warp's rows as queries -> dQ ----
         {
           const uint32_t qa0 = lds32(Qs + r0 * LD + 8 * h + 2 * q), qa1 = lds32(Qs + r1 * LD + 8 * h + 2 * q);
+          const uint32_t da0 = lds32(dOs + r0 * LD + 8 * h + 2 * q), da1 = lds32(dOs + r1 * LD + 8 * h + 2 * q);
           const float m0 = st_m[h * TP + r0], m1 = st_m[h * TP + r1];
           const float il0 = st_il[h * TP + r0], il1 = st_il[h * TP + r1];
           const float dl0 = st_dl[h * TP + r0], dl1 = st_dl[h * TP + r1];
@@ -792,7 +789,7 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
               const int t = 2 * kk + u;
               float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
               mma1688(s, qa0, qa1, lds32(Ks + (8 * t + g) * LD + 8 * h + 2 * q));
-              mma1688(dp, doa[h][0], doa[h][1], lds32(Vs + (8 * t + g) * LD + 8 * h + 2 * q));
+              mma1688(dp, da0, da1, lds32(Vs + (8 * t + g) * LD + 8 * h + 2 * q));
               const int kc = 8 * t + 2 * q;
               const float p0 = kc < T ? ex2(s[0] - m0) * il0 : 0.f, p1 = kc + 1 < T ? ex2(s[1] - m0) * il0 : 0.f;
               const float p2 = kc < T ? ex2(s[2] - m1) * il1 : 0.f, p3 = kc + 1 < T ? ex2(s[3] - m1) * il1 : 0.f;
@@ -802,7 +799,7 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
             uint32_t Ads[4], b0, b1;
             acc2_to_afrag(ds[0], ds[1], Ads);
             ldsm_x2_trans(b0, b1, Ks + (16 * kk + (lane & 15)) * LD + 8 * h);
-            mma16816(dqkv[h], Ads, b0, b1);
+            mma16816(dq, Ads, b0, b1);
           }
         }
         // ---- sweep B: this warp's rows as keys -> dK, dV ----
@@ -832,21 +829,27 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
             acc2_to_afrag(ds[0], ds[1], Ads);
             acc2_to_afrag(pt[0], pt[1], Apt);
             ldsm_x2_trans(b0, b1, Qs + (16 * kk + (lane & 15)) * LD + 8 * h);
-            mma16816(dqkv[4 + h], Ads, b0, b1);
+            mma16816(dk, Ads, b0, b1);
             ldsm_x2_trans(b0, b1, dOs + (16 * kk + (lane & 15)) * LD + 8 * h);
-            mma16816(dqkv[8 + h], Apt, b0, b1);
+            mma16816(dv, Apt, b0, b1);
           }
         }
+        // scale: dq = scale * dS K ; dk = dS^T qhat / log2(e)
+        const int col = 8 * h + 2 * q;
+        *reinterpret_cast<uint32_t*>(K1s + r0 * LD + col) = pack_bf16(dq[0] * kScale, dq[1] * kScale);
+        *reinterpret_cast<uint32_t*>(K1s + r1 * LD + col) = pack_bf16(dq[2] * kScale, dq[3] * kScale);
+        *reinterpret_cast<uint32_t*>(V1s + r0 * LD + col) = pack_bf16(dk[0] * kLn2, dk[1] * kLn2);
+        *reinterpret_cast<uint32_t*>(V1s + r1 * LD + col) = pack_bf16(dk[2] * kLn2, dk[3] * kLn2);
+        *reinterpret_cast<uint32_t*>(dV1s + r0 * LD + col) = pack_bf16(dv[0], dv[1]);
+        *reinterpret_cast<uint32_t*>(dV1s + r1 * LD + col) = pack_bf16(dv[2], dv[3]);
       }
-      // scale: dq = scale * dS K ; dk = dS^T qhat / log2(e)
-#pragma unroll
-      for (int h = 0; h < kHeads; ++h)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { dqkv[h][e] *= kScale; dqkv[4 + h][e] *= kLn2; }
+      __syncwarp();
       uint32_t Aq[6][4];
 #pragma unroll
       for (int kk = 0; kk < 6; ++kk) {
-        acc2_to_afrag(dqkv[2 * kk], dqkv[2 * kk + 1], Aq[kk]);
+        const __nv_bfloat16* src = (kk < 2 ? K1s : kk < 4 ? V1s : dV1s) + 16 * (kk & 1) + 2 * q;
+        Aq[kk][0] = lds32(src + r0 * LD); Aq[kk][1] = lds32(src + r1 * LD);
+        Aq[kk][2] = lds32(src + r0 * LD + 8); Aq[kk][3] = lds32(src + r1 * LD + 8);
         dump2(a.dqkv[0], a.RTt, trow, 16 * kk + 2 * q, Aq[kk][0]);
         dump2(a.dqkv[0], a.RTt, trow + 8, 16 * kk + 2 * q, Aq[kk][1]);
         dump2(a.dqkv[0], a.RTt, trow, 16 * kk + 8 + 2 * q, Aq[kk][2]);

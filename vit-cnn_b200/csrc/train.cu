@@ -246,24 +246,30 @@ int bn_backward_launch(const void* dz, const void* y, void* dy, int S, int C, in
 
 // ---- weighted cross entropy ----------------------------------------------------------------------
 // loss = sum_i w[y_i] * nll_i / sum_i w[y_i]   (nn.CrossEntropyLoss(weight=w), reduction 'mean',
-// ignore_index -100); dlogits = grad_scale * w[y_i] * (softmax - onehot) / sum w.  One block.
-__global__ void __launch_bounds__(1024) ce_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
-                                                       const float* __restrict__ weight, int n, int K, float grad_scale,
-                                                       float* __restrict__ loss_out, float* __restrict__ dlogits) {
-  __shared__ double s_num[32], s_den[32];
-  __shared__ double tot_num, tot_den;
+// ignore_index -100); dlogits = grad_scale * w[y_i] * (softmax - onehot) / sum w.
+// Pass 1: per-sample softmax (kept unnormalised in dlogits) + block sums -> double atomics;
+// pass 2: scale by 1 / sum w.  acc: 2 doubles, zero on entry, zeroed again by pass 2.
+__global__ void __launch_bounds__(256) ce_loss_pass1_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
+                                                            const float* __restrict__ weight, int n, int K,
+                                                            float* __restrict__ dlogits, double* __restrict__ acc) {
+  __shared__ double s_num[8], s_den[8];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double num = 0.0, den = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  if (i < n) {
     const long long yl = labels[i];
-    if (yl < 0 || yl >= K) continue;
-    const float w = weight ? weight[yl] : 1.f;
+    const bool ok = yl >= 0 && yl < K;
+    const float w = ok ? (weight ? weight[yl] : 1.f) : 0.f;
     const float* l = logits + (long long)i * K;
     float m = l[0];
     for (int k = 1; k < K; ++k) m = fmaxf(m, l[k]);
     float se = 0.f;
     for (int k = 0; k < K; ++k) se += expf(l[k] - m);
-    num += (double)(w * (logf(se) + m - l[yl]));
-    den += (double)w;
+    if (ok) { num = (double)(w * (logf(se) + m - l[yl])); den = (double)w; }
+    if (dlogits) {
+      const float is = w / se;
+      float* d = dlogits + (long long)i * K;
+      for (int k = 0; k < K; ++k) d[k] = is * expf(l[k] - m) - (k == yl ? w : 0.f);
+    }
   }
   for (int o = 16; o > 0; o >>= 1) {
     num += __shfl_xor_sync(0xffffffffu, num, o);
@@ -273,32 +279,29 @@ __global__ void __launch_bounds__(1024) ce_loss_kernel(const float* __restrict__
   __syncthreads();
   if (threadIdx.x == 0) {
     double a = 0.0, b = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += s_num[w]; b += s_den[w]; }
-    tot_num = a; tot_den = b;
-    if (loss_out) { loss_out[0] = (float)(a / b); loss_out[1] = (float)b; }
-  }
-  __syncthreads();
-  if (!dlogits) return;
-  const float inv = (float)(grad_scale / tot_den);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const long long yl = labels[i];
-    float* d = dlogits + (long long)i * K;
-    if (yl < 0 || yl >= K) { for (int k = 0; k < K; ++k) d[k] = 0.f; continue; }
-    const float w = (weight ? weight[yl] : 1.f) * inv;
-    const float* l = logits + (long long)i * K;
-    float m = l[0];
-    for (int k = 1; k < K; ++k) m = fmaxf(m, l[k]);
-    float se = 0.f;
-    for (int k = 0; k < K; ++k) se += expf(l[k] - m);
-    const float is = 1.f / se;
-    for (int k = 0; k < K; ++k) d[k] = w * (expf(l[k] - m) * is - (k == yl ? 1.f : 0.f));
+    for (int w = 0; w < 8; ++w) { a += s_num[w]; b += s_den[w]; }
+    atomicAdd(acc, a);
+    atomicAdd(acc + 1, b);
   }
 }
+__global__ void __launch_bounds__(256) ce_loss_pass2_kernel(int total, float grad_scale, float* __restrict__ loss_out,
+                                                            float* __restrict__ dlogits, const double* __restrict__ acc) {
+  const double den = acc[1];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && loss_out) { loss_out[0] = (float)(acc[0] / den); loss_out[1] = (float)den; }
+  if (!dlogits) return;
+  const float inv = (float)((double)grad_scale / den);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) dlogits[i] *= inv;
+}
+__global__ void ce_loss_clear_kernel(double* acc) { acc[0] = 0.0; acc[1] = 0.0; }
 
 int ce_loss_launch(const float* logits, const long long* labels, const float* weight, int n, int K, float grad_scale,
-                   float* loss_out, float* dlogits, cudaStream_t st) {
-  if (n <= 0 || K < 1) return VC_ERR_ARG;
-  ce_loss_kernel<<<1, 1024, 0, st>>>(logits, labels, weight, n, K, grad_scale, loss_out, dlogits);
+                   float* loss_out, float* dlogits, double* acc, cudaStream_t st) {
+  if (n <= 0 || K < 1 || !acc) return VC_ERR_ARG;
+  ce_loss_clear_kernel<<<1, 1, 0, st>>>(acc);
+  ce_loss_pass1_kernel<<<(n + 255) / 256, 256, 0, st>>>(logits, labels, weight, n, K, dlogits, acc);
+  int blocks = (n * K + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  ce_loss_pass2_kernel<<<dlogits ? blocks : 1, 256, 0, st>>>(n * K, grad_scale, loss_out, dlogits, acc);
   return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
 }
 

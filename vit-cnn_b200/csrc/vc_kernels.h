@@ -44,7 +44,7 @@ int bn_backward_launch(const void* dz, const void* y, void* dy, int S, int C, in
                        const float* shift, const float* mean, const float* rstd, int relu, double* sums, float* dgamma,
                        float* dbeta, float* dbias, int accumulate, cudaStream_t st);
 int ce_loss_launch(const float* logits, const long long* labels, const float* weight, int n, int K, float grad_scale,
-                   float* loss_out, float* dlogits, cudaStream_t st);
+                   float* loss_out, float* dlogits, double* acc, cudaStream_t st);
 int adam_launch(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                 float wd, int step, float grad_scale, cudaStream_t st);
 int pack_conv_w_launch(const float* w, int cout, int cin, int taps, int transpose, int S_in, int n_out, int nsplit,

@@ -90,23 +90,30 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_sps_tc_kernel(WgradArgs a) {
   const int nsteps = my_tiles * (128 / kWgStageRows);
 
   if (warp == 0) {
-    if (lane == 0) {
-      int st = 0;
-      uint32_t ph = 0;
-      for (int s = 0; s < nsteps; ++s) {
-        const int tile = blockIdx.x + (s / (128 / kWgStageRows)) * gridDim.x;
-        // first row of this stage, as an index into the buffer WITH the lead halo
-        const long long R = HALO + (long long)tile * 128 + (long long)(s % (128 / kWgStageRows)) * kWgStageRows;
-        const long long RA = a.shift_on_a ? R - HALO : R, RB = a.shift_on_a ? R : R - HALO;
+    // ===== producer: every lane issues its share of the per-slice bulk copies (a single issuing
+    // thread was the bottleneck: up to 34 copies of 1-1.5 KB per stage) =====
+    int st = 0;
+    uint32_t ph = 0;
+    const int ncopies = a.SA + a.SB;
+    for (int s = 0; s < nsteps; ++s) {
+      const int tile = blockIdx.x + (s / (128 / kWgStageRows)) * gridDim.x;
+      // first row of this stage, as an index into the buffer WITH the lead halo
+      const long long R = HALO + (long long)tile * 128 + (long long)(s % (128 / kWgStageRows)) * kWgStageRows;
+      const long long RA = a.shift_on_a ? R - HALO : R, RB = a.shift_on_a ? R : R - HALO;
+      if (lane == 0) {
         mbar_wait(&empty[st], ph ^ 1u);
         mbar_arrive_expect_tx(&full[st], (uint32_t)a.SA * sliceA + bytesB);
-        uint8_t* dst = stage_s + (size_t)st * stage_bytes;
-        for (int sl = 0; sl < a.SA; ++sl)
-          bulk_g2s(dst + (size_t)sl * sliceA, a.A + ((long long)sl * a.RT + RA) * 8, sliceA, &full[st]);
-        for (int sl = 0; sl < a.SB; ++sl)
-          bulk_g2s(dst + bytesA + (size_t)sl * sliceB, a.B + ((long long)sl * a.RT + RB) * 8, sliceB, &full[st]);
-        if (++st == a.nstages) { st = 0; ph ^= 1u; }
       }
+      __syncwarp();
+      uint8_t* dst = stage_s + (size_t)st * stage_bytes;
+      for (int c = lane; c < ncopies; c += 32) {
+        if (c < a.SA)
+          bulk_g2s(dst + (size_t)c * sliceA, a.A + ((long long)c * a.RT + RA) * 8, sliceA, &full[st]);
+        else
+          bulk_g2s(dst + bytesA + (size_t)(c - a.SA) * sliceB, a.B + ((long long)(c - a.SA) * a.RT + RB) * 8, sliceB,
+                   &full[st]);
+      }
+      if (++st == a.nstages) { st = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
     const uint32_t idesc = umma_idesc_bf16_mn(128, N);
@@ -123,16 +130,17 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_sps_tc_kernel(WgradArgs a) {
       tc_fence_after();
       if (elect_one()) {
         const uint32_t so = (uint32_t)st * (stage_bytes >> 4);
+        const uint32_t acc = s != 0 ? 1u : 0u;
 #pragma unroll 1
-        for (int k = 0; k < kWgStageRows / 16; ++k) {
-          for (int t = 0; t < ntap; ++t) {
-            const int tap = tap0 + t;
-            const int shift = (a.ntaps == 9) ? ((tap / 3 - 1) * PW + (tap % 3 - 1)) : 0;
-            const uint32_t a_lo = a_lo0 + so + (uint32_t)(k * 16) + (uint32_t)(a.shift_on_a ? shift : 0);
-            const uint32_t b_lo = b_lo0 + so + (uint32_t)(k * 16) + (uint32_t)(a.shift_on_a ? 0 : shift);
-            umma_bf16(tmem_base + (uint32_t)(t * N), a_hi | (uint64_t)a_lo, b_hi | (uint64_t)b_lo, idesc,
-                      (s | k) != 0 ? 1u : 0u);
-          }
+        for (int t = 0; t < ntap; ++t) {
+          const int tap = tap0 + t;
+          const int shift = (a.ntaps == 9) ? ((tap / 3 - 1) * PW + (tap % 3 - 1)) : 0;
+          const uint32_t a_lo = a_lo0 + so + (uint32_t)(a.shift_on_a ? shift : 0);
+          const uint32_t b_lo = b_lo0 + so + (uint32_t)(a.shift_on_a ? 0 : shift);
+          const uint32_t d = tmem_base + (uint32_t)(t * N);
+#pragma unroll
+          for (int k = 0; k < kWgStageRows / 16; ++k)
+            umma_bf16(d, a_hi | (uint64_t)(a_lo + 16u * k), b_hi | (uint64_t)(b_lo + 16u * k), idesc, k ? 1u : acc);
         }
         umma_commit(&empty[st]);
         if (s == nsteps - 1) umma_commit(done);
@@ -140,15 +148,21 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_sps_tc_kernel(WgradArgs a) {
       __syncwarp();
       if (++st == a.nstages) { st = 0; ph ^= 1u; }
     }
+    if (nsteps > 0) {
+      if (lane == 0) mbar_wait(done, 0);
+      __syncwarp();
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, 160;" ::: "memory");
   } else {
     // ===== epilogue (once): TMEM -> registers -> partial workspace =====
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
     float* dst = a.part + ((long long)blockIdx.x * a.ntaps + tap0) * 128 * N + (long long)m * N;
-    if (nsteps > 0) {
-      mbar_wait(done, 0);
-      tc_fence_after();
-    }
+    // block on a hardware barrier (no issue slots burnt while the main loop runs): the MMA warp
+    // joins it once the last commit has landed
+    asm volatile("bar.sync 1, 160;" ::: "memory");
+    tc_fence_after();
     for (int t = 0; t < ntap; ++t) {
       for (int c0 = 0; c0 < N; c0 += 16) {
         uint32_t v[16];
@@ -175,24 +189,40 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_sps_tc_kernel(WgradArgs a) {
 
 // out[m*sm + n*sn + tap*st] (+)= sum_p part[p][tap][m][n]   for m < M, n < Nr;
 // column n == bias_col (if >= 0) goes to out_bias[m] instead (the "ones" slice of the B operand).
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int ntaps, int N, int M, int Nr,
-                                    float* __restrict__ out, long long sm, long long sn, long long st, int bias_col,
-                                    float* __restrict__ out_bias, int accumulate) {
+// A block owns 32 consecutive (tap, m, n) elements; its 8 warps sum interleaved subsets of the
+// partials and are combined in a fixed order (deterministic, coalesced 128-byte reads).
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int ntaps, int N, int M,
+                                                           int Nr, float* __restrict__ out, long long sm, long long sn,
+                                                           long long st, int bias_col, float* __restrict__ out_bias,
+                                                           int accumulate) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long total = (long long)ntaps * M * N;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int n = (int)(idx % N);
-    const int m = (int)((idx / N) % M);
-    const int tap = (int)(idx / ((long long)N * M));
-    const bool is_bias = (n == bias_col);
-    if (n >= Nr && !is_bias) continue;
+  const long long pstride = (long long)ntaps * 128 * N;
+  for (long long base = (long long)blockIdx.x * 32; base < total; base += (long long)gridDim.x * 32) {
+    const long long idx = base + lane;
+    int n = 0, m = 0, tap = 0;
     float s = 0.f;
-    const float* p = part + ((long long)tap * 128 + m) * N + n;
-    const long long pstride = (long long)ntaps * 128 * N;
-    for (int k = 0; k < nparts; ++k) s += p[k * pstride];
-    float* o = is_bias ? (out_bias ? out_bias + m : nullptr) : out + m * sm + n * sn + tap * st;
-    if (!o) continue;
-    *o = accumulate ? *o + s : s;
+    if (idx < total) {
+      n = (int)(idx % N);
+      m = (int)((idx / N) % M);
+      tap = (int)(idx / ((long long)N * M));
+      const float* p = part + ((long long)tap * 128 + m) * N + n;
+      for (int k = w; k < nparts; k += 8) s += p[k * pstride];
+    }
+    red[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && idx < total) {
+      float t = red[0][lane];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) t += red[k][lane];
+      const bool is_bias = (n == bias_col);
+      if (n < Nr || is_bias) {
+        float* o = is_bias ? (out_bias ? out_bias + m : nullptr) : out + m * sm + n * sn + tap * st;
+        if (o) *o = accumulate ? *o + t : t;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -259,7 +289,7 @@ int wgrad_sps_launch(const void* A, int SA, const void* B, int SB, int n_patches
   wgrad_sps_tc_kernel<<<grid, kWgThreads, smem, stream>>>(a);
   if (cudaGetLastError() != cudaSuccess) return VC_ERR_CUDA;
   const long long total = (long long)ntaps * M * N;
-  int blocks = (int)((total + 255) / 256);
+  int blocks = (int)((total + 31) / 32);
   if (blocks > 148 * 8) blocks = 148 * 8;
   wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(a.part, gx, ntaps, N, M, Nr, out, sm, sn, st, bias_col, out_bias,
                                                   accumulate);

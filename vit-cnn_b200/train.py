@@ -220,16 +220,22 @@ def train_forward(model, hsi, lidar):
 
 
 # ----------------------------------------------------------------------------------------------------
+_CE_SCRATCH = {}
+
+
 def ce_loss(logits, labels, weight=None, grad_scale=1.0, want_grad=True):
     """nn.CrossEntropyLoss(weight) forward (+ gradient): returns (loss[2] = mean loss, weight sum;
     dlogits or None)."""
     n, K = logits.shape
     out = torch.empty(2, dtype=torch.float32, device=logits.device)
     d = torch.empty_like(logits) if want_grad else None
+    scratch = _CE_SCRATCH.get(logits.device)
+    if scratch is None:
+        scratch = _CE_SCRATCH[logits.device] = torch.zeros(2, dtype=torch.float64, device=logits.device)
     with torch.cuda.device(logits.device):
         _lib.check(_lib.lib().vc_ce_loss(logits.data_ptr(), labels.data_ptr(), 0 if weight is None else weight.data_ptr(),
                                          n, K, float(grad_scale), out.data_ptr(), 0 if d is None else d.data_ptr(),
-                                         torch.cuda.current_stream().cuda_stream), "vc_ce_loss")
+                                         scratch.data_ptr(), torch.cuda.current_stream().cuda_stream), "vc_ce_loss")
     return out, d
 
 
