@@ -159,7 +159,8 @@ __device__ __forceinline__ void gemm_dgrad32(const uint32_t (*A)[4], const __nv_
 
 // scratch of the cls-only path (one warp)
 struct ClsScratch {
-  float q[kD], o[kD], doo[kD], dq[kD], dxres[kD], h[kHidden], du[kHidden];
+  float q[kD], doo[kD], dq[kD], dxres[kD], dlt[kHeads], h[kHidden], du[kHidden];
+  float part[16][kD];
   float p[kHeads][256], ds[kHeads][256];
 };
 
@@ -252,7 +253,6 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
       uint32_t A1[2][4];
       ln_to_afrag(x, f32 + O0.ln1_g / 4, f32 + O0.ln1_b / 4, q, A1);
       dump_afrag32(a.xln1[0], a.RTt, trow, q, A1);
-      uint32_t qa[kHeads][2];
 #pragma unroll
       for (int jn = 0; jn < 12; ++jn) {
         float c[4] = {0.f, 0.f, 0.f, 0.f};
@@ -265,10 +265,8 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
         c[0] += bb.x; c[1] += bb.y; c[2] += bb.x; c[3] += bb.y;
         const int col = 8 * (jn & 3) + 2 * q;
         if (jn < 4) {
-          qa[jn][0] = pack_bf16(c[0] * qscale, c[1] * qscale);
-          qa[jn][1] = pack_bf16(c[2] * qscale, c[3] * qscale);
-          *reinterpret_cast<uint32_t*>(Qs + r0 * LD + col) = qa[jn][0];
-          *reinterpret_cast<uint32_t*>(Qs + r1 * LD + col) = qa[jn][1];
+          *reinterpret_cast<uint32_t*>(Qs + r0 * LD + col) = pack_bf16(c[0] * qscale, c[1] * qscale);
+          *reinterpret_cast<uint32_t*>(Qs + r1 * LD + col) = pack_bf16(c[2] * qscale, c[3] * qscale);
         } else {
           __nv_bfloat16* dst = jn < 8 ? Ks : Vs;
           *reinterpret_cast<uint32_t*>(dst + r0 * LD + col) = pack_bf16(c[0], c[1]);
@@ -278,14 +276,15 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
       __syncthreads();
       // attention forward: all keys at once per head (scores in registers), stats saved
       uint32_t oa[2][4];
-#pragma unroll
+#pragma unroll 1
       for (int h = 0; h < kHeads; ++h) {
         float s[NT][4];
         float mx0 = -INFINITY, mx1 = -INFINITY;
+        const uint32_t qa0 = lds32(Qs + r0 * LD + 8 * h + 2 * q), qa1 = lds32(Qs + r1 * LD + 8 * h + 2 * q);
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
           s[t][0] = s[t][1] = s[t][2] = s[t][3] = 0.f;
-          mma1688(s[t], qa[h][0], qa[h][1], lds32(Ks + (8 * t + g) * LD + 8 * h + 2 * q));
+          mma1688(s[t], qa0, qa1, lds32(Ks + (8 * t + g) * LD + 8 * h + 2 * q));
           if (t >= NT - 2) {
             const int kc = 8 * t + 2 * q;
             if (kc >= T) { s[t][0] = -INFINITY; s[t][2] = -INFINITY; }
@@ -317,16 +316,17 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
           ldsm_x2_trans(b0, b1, Vs + (16 * kk + (lane & 15)) * LD + 8 * h);
           mma16816(oh, Pa, b0, b1);
         }
-        oa[h >> 1][(h & 1) * 2 + 0] = pack_bf16(oh[0] * il0, oh[1] * il0);
-        oa[h >> 1][(h & 1) * 2 + 1] = pack_bf16(oh[2] * il1, oh[3] * il1);
+        // save O (bf16) for the backward of this block
+        *reinterpret_cast<uint32_t*>(Os + r0 * LD + 8 * h + 2 * q) = pack_bf16(oh[0] * il0, oh[1] * il0);
+        *reinterpret_cast<uint32_t*>(Os + r1 * LD + 8 * h + 2 * q) = pack_bf16(oh[2] * il1, oh[3] * il1);
       }
-      // save O (bf16) for the backward of this block
+      __syncwarp();
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
-        *reinterpret_cast<uint32_t*>(Os + r0 * LD + 16 * kk + 2 * q) = oa[kk][0];
-        *reinterpret_cast<uint32_t*>(Os + r1 * LD + 16 * kk + 2 * q) = oa[kk][1];
-        *reinterpret_cast<uint32_t*>(Os + r0 * LD + 16 * kk + 8 + 2 * q) = oa[kk][2];
-        *reinterpret_cast<uint32_t*>(Os + r1 * LD + 16 * kk + 8 + 2 * q) = oa[kk][3];
+        oa[kk][0] = lds32(Os + r0 * LD + 16 * kk + 2 * q);
+        oa[kk][1] = lds32(Os + r1 * LD + 16 * kk + 2 * q);
+        oa[kk][2] = lds32(Os + r0 * LD + 16 * kk + 8 + 2 * q);
+        oa[kk][3] = lds32(Os + r1 * LD + 16 * kk + 8 + 2 * q);
       }
       dump_afrag32(a.xo0, a.RTt, trow, q, oa);
       // proj (+bias, +residual)
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
       for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc2[j][e] = 0.f;
-#pragma unroll
+#pragma unroll 2
       for (int hk = 0; hk < kHidden / 16; ++hk) {
         float h0[4] = {0.f, 0.f, 0.f, 0.f}, h1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -411,214 +411,216 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
     }
     __syncthreads();
 
-    // ====================== cls path of block 1 + head: forward and backward (warp 0) ============
-    if (warp == 0) {
+    // ====================== cls path of block 1 + head: forward and backward =======================
+    // Vector-matrix steps run on warp 0 (lane = channel); everything that is "per key" (scores,
+    // P.V, dP, dK / dV, dQ) is spread over all warps between CTA barriers.
+    {
       const __nv_bfloat16* wqkv = reinterpret_cast<const __nv_bfloat16*>(smem + O1.wqkv);
       const __nv_bfloat16* wproj = reinterpret_cast<const __nv_bfloat16*>(smem + O1.wproj);
       const __nv_bfloat16* wfc1 = reinterpret_cast<const __nv_bfloat16*>(smem + O1.wfc1);
       const __nv_bfloat16* wfc2 = reinterpret_cast<const __nv_bfloat16*>(smem + O1.wfc2);
       const int hd = lane >> 3;                       // head of channel `lane`
-      const float x10 = cs->dxres[lane];
-      // LN1 -> q
-      float mean = warp_sum(x10) * (1.f / kD);
-      float d = x10 - mean;
-      float rstd = rsqrtf(warp_sum(d * d) * (1.f / kD) + 1e-6f);
-      const float y1 = __bfloat162float(__float2bfloat16_rn(d * rstd * f32[O1.ln1_g / 4 + lane] + f32[O1.ln1_b / 4 + lane]));
-      float qv = f32[O1.bqkv / 4 + lane];
+      const int nthr = NW * 32;
+      float x10 = 0.f;
+      // ---- C1 (warp 0): LN1 -> q ----
+      if (warp == 0) {
+        x10 = cs->dxres[lane];
+        const float mean = warp_sum(x10) * (1.f / kD);
+        const float d = x10 - mean;
+        const float rstd = rsqrtf(warp_sum(d * d) * (1.f / kD) + 1e-6f);
+        const float y1 = __bfloat162float(__float2bfloat16_rn(d * rstd * f32[O1.ln1_g / 4 + lane] + f32[O1.ln1_b / 4 + lane]));
+        float qv = f32[O1.bqkv / 4 + lane];
 #pragma unroll
-      for (int k2 = 0; k2 < kD / 2; ++k2) {
-        const uint32_t wv = lds32(wqkv + lane * LD + 2 * k2);
-        qv = fmaf(bf_lo(wv), __shfl_sync(0xffffffffu, y1, 2 * k2), qv);
-        qv = fmaf(bf_hi(wv), __shfl_sync(0xffffffffu, y1, 2 * k2 + 1), qv);
-      }
-      const float qhat = qv * qscale;
-      cs->q[lane] = qhat;
-      __syncwarp();
-      // scores / softmax over all keys, 4 heads; key = lane + 32 * kk
-      constexpr int KK = (TP + 31) / 32;
-      float sc[KK][kHeads];
-      float mxh[kHeads] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int kk = 0; kk < KK; ++kk) {
-        const int key = lane + 32 * kk;
-#pragma unroll
-        for (int h = 0; h < kHeads; ++h) {
-          float s = -INFINITY;
-          if (key < T) {
-            s = 0.f;
-#pragma unroll
-            for (int dd = 0; dd < kHd; dd += 2) {
-              const uint32_t kv = lds32(K1s + key * LD + 8 * h + dd);
-              s = fmaf(cs->q[8 * h + dd], bf_lo(kv), s);
-              s = fmaf(cs->q[8 * h + dd + 1], bf_hi(kv), s);
-            }
-          }
-          sc[kk][h] = s;
-          mxh[h] = fmaxf(mxh[h], s);
+        for (int k2 = 0; k2 < kD / 2; ++k2) {
+          const uint32_t wv = lds32(wqkv + lane * LD + 2 * k2);
+          qv = fmaf(bf_lo(wv), __shfl_sync(0xffffffffu, y1, 2 * k2), qv);
+          qv = fmaf(bf_hi(wv), __shfl_sync(0xffffffffu, y1, 2 * k2 + 1), qv);
         }
+        cs->q[lane] = qv * qscale;
       }
-      float lh[kHeads];
+      __syncthreads();
+      // ---- C2 (all): scores of the cls query against every key, log2 domain ----
+      for (int i = threadIdx.x; i < kHeads * TP; i += nthr) {
+        const int h = i / TP, key = i - h * TP;
+        float sv = -INFINITY;
+        if (key < T) {
+          const uint4 kv = *reinterpret_cast<const uint4*>(K1s + key * LD + 8 * h);
+          const float* qq = cs->q + 8 * h;
+          sv = qq[0] * bf_lo(kv.x) + qq[1] * bf_hi(kv.x) + qq[2] * bf_lo(kv.y) + qq[3] * bf_hi(kv.y) +
+               qq[4] * bf_lo(kv.z) + qq[5] * bf_hi(kv.z) + qq[6] * bf_lo(kv.w) + qq[7] * bf_hi(kv.w);
+        }
+        cs->p[h][key] = sv;
+      }
+      __syncthreads();
+      // ---- C3 (one warp per head): softmax ----
+      for (int h = warp; h < kHeads; h += NW) {
+        float mx = -INFINITY;
+        for (int key = lane; key < TP; key += 32) mx = fmaxf(mx, cs->p[h][key]);
 #pragma unroll
-      for (int h = 0; h < kHeads; ++h) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mxh[h] = fmaxf(mxh[h], __shfl_xor_sync(0xffffffffu, mxh[h], o));
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         float l = 0.f;
-#pragma unroll
-        for (int kk = 0; kk < KK; ++kk) { sc[kk][h] = ex2(sc[kk][h] - mxh[h]); l += sc[kk][h]; }
-        lh[h] = 1.f / warp_sum(l);
-#pragma unroll
-        for (int kk = 0; kk < KK; ++kk) {
-          sc[kk][h] *= lh[h];
-          if (lane + 32 * kk < TP) cs->p[h][lane + 32 * kk] = sc[kk][h];
+        for (int key = lane; key < TP; key += 32) {
+          const float e = ex2(cs->p[h][key] - mx);
+          cs->p[h][key] = e;
+          l += e;
         }
+        const float il = 1.f / warp_sum(l);
+        for (int key = lane; key < TP; key += 32) cs->p[h][key] *= il;
       }
-      __syncwarp();
-      // o = sum_key p * V   (lane = channel)
-      float ov = 0.f;
-      for (int key = 0; key < T; ++key) ov = fmaf(cs->p[hd][key], __bfloat162float(V1s[key * LD + lane]), ov);
-      // proj (+bias, +residual)
-      float y = f32[O1.bproj / 4 + lane];
-#pragma unroll
-      for (int k2 = 0; k2 < kD / 2; ++k2) {
-        const uint32_t wv = lds32(wproj + lane * LD + 2 * k2);
-        y = fmaf(bf_lo(wv), __shfl_sync(0xffffffffu, ov, 2 * k2), y);
-        y = fmaf(bf_hi(wv), __shfl_sync(0xffffffffu, ov, 2 * k2 + 1), y);
+      __syncthreads();
+      // ---- C4 (all): o = sum_key p * V, keys split over the warps ----
+      {
+        float part = 0.f;
+        for (int key = warp; key < T; key += NW) part = fmaf(cs->p[hd][key], __bfloat162float(V1s[key * LD + lane]), part);
+        cs->part[warp][lane] = part;
       }
-      const float xm = x10 + y;
-      // LN2 -> fc1 -> GELU -> fc2
-      const float mean2 = warp_sum(xm) * (1.f / kD);
-      const float d2 = xm - mean2;
-      const float rstd2 = rsqrtf(warp_sum(d2 * d2) * (1.f / kD) + 1e-6f);
-      const float xh2 = d2 * rstd2;
-      const float y2 = xh2 * f32[O1.ln2_g / 4 + lane] + f32[O1.ln2_b / 4 + lane];
-      float u[4], hv[4], hder[4];
+      __syncthreads();
+      // ---- C5 (warp 0): rest of the block for the cls row, head, and their backward ----
+      if (warp == 0) {
+        float ov = 0.f;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) u[i] = f32[O1.bfc1 / 4 + lane + 32 * i];
+        for (int w = 0; w < NW; ++w) ov += cs->part[w][lane];
+        float y = f32[O1.bproj / 4 + lane];
 #pragma unroll
-      for (int k2 = 0; k2 < kD / 2; ++k2) {
-        const float ya = __shfl_sync(0xffffffffu, y2, 2 * k2), yb = __shfl_sync(0xffffffffu, y2, 2 * k2 + 1);
+        for (int k2 = 0; k2 < kD / 2; ++k2) {
+          const uint32_t wv = lds32(wproj + lane * LD + 2 * k2);
+          y = fmaf(bf_lo(wv), __shfl_sync(0xffffffffu, ov, 2 * k2), y);
+          y = fmaf(bf_hi(wv), __shfl_sync(0xffffffffu, ov, 2 * k2 + 1), y);
+        }
+        const float xm = x10 + y;
+        const float mean2 = warp_sum(xm) * (1.f / kD);
+        const float d2 = xm - mean2;
+        const float rstd2 = rsqrtf(warp_sum(d2 * d2) * (1.f / kD) + 1e-6f);
+        const float xh2 = d2 * rstd2;
+        const float y2 = xh2 * f32[O1.ln2_g / 4 + lane] + f32[O1.ln2_b / 4 + lane];
+        float u[4], hv[4], hder[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) u[i] = f32[O1.bfc1 / 4 + lane + 32 * i];
+#pragma unroll
+        for (int k2 = 0; k2 < kD / 2; ++k2) {
+          const float ya = __shfl_sync(0xffffffffu, y2, 2 * k2), yb = __shfl_sync(0xffffffffu, y2, 2 * k2 + 1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t wv = lds32(wfc1 + (lane + 32 * i) * LD + 2 * k2);
+            u[i] = fmaf(bf_lo(wv), ya, fmaf(bf_hi(wv), yb, u[i]));
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const uint32_t wv = lds32(wfc1 + (lane + 32 * i) * LD + 2 * k2);
-          u[i] = fmaf(bf_lo(wv), ya, fmaf(bf_hi(wv), yb, u[i]));
+          gelu_erf_grad(u[i], hv[i], hder[i]);
+          cs->h[lane + 32 * i] = hv[i];
         }
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        gelu_erf_grad(u[i], hv[i], hder[i]);
-        cs->h[lane + 32 * i] = hv[i];
-      }
-      __syncwarp();
-      float z = f32[O1.bfc2 / 4 + lane];
+        __syncwarp();
+        float z0 = f32[O1.bfc2 / 4 + lane], z1 = 0.f;
 #pragma unroll 8
-      for (int k2 = 0; k2 < kHidden / 2; ++k2) {
-        const uint32_t wv = lds32(wfc2 + lane * kLdHid + 2 * k2);
-        const float2 hh = *reinterpret_cast<const float2*>(cs->h + 2 * k2);
-        z = fmaf(bf_lo(wv), hh.x, fmaf(bf_hi(wv), hh.y, z));
-      }
-      const float x2 = xm + z;
-      // final LayerNorm
-      const float meanf = warp_sum(x2) * (1.f / kD);
-      const float df = x2 - meanf;
-      const float rstdf = rsqrtf(warp_sum(df * df) * (1.f / kD) + 1e-6f);
-      const float xhf = df * rstdf;
-      const float cfin = xhf * f32[L.lnf_g / 4 + lane] + f32[L.lnf_b / 4 + lane];
-
-      // ---------------- backward ----------------
-      const float* dl = a.dlogits + (long long)b * K;
-      float dc = 0.f;
-      for (int k = 0; k < K; ++k) dc = fmaf(__ldg(dl + k), f32[L.whead / 4 + k * kD + lane], dc);
-      // head operands (compact space): X = final-LN output, dY = dlogits
-      a.c_xc[((long long)(lane >> 3) * a.RTc + b) * 8 + (lane & 7)] = __float2bfloat16_rn(cfin);
-      for (int k = lane; k < ((K + 15) / 16) * 16; k += 32)
-        a.c_dlog[((long long)(k >> 3) * a.RTc + b) * 8 + (k & 7)] = __float2bfloat16_rn(k < K ? __ldg(dl + k) : 0.f);
-      // final LN backward
-      gcls_lnf[0] += dc * xhf;
-      gcls_lnf[1] += dc;
-      float dgm = dc * f32[L.lnf_g / 4 + lane];
-      float c1 = warp_sum(dgm) * (1.f / kD), c2 = warp_sum(dgm * xhf) * (1.f / kD);
-      const float dx2 = rstdf * (dgm - c1 - xhf * c2);
-      // fc2 backward: dh[j] = sum_o W2[o][j] dx2[o]; du = dh * gelu'(u)
-      float dh[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 8
-      for (int o = 0; o < kD; ++o) {
-        const float dv = __shfl_sync(0xffffffffu, dx2, o);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dh[i] = fmaf(__bfloat162float(wfc2[o * kLdHid + lane + 32 * i]), dv, dh[i]);
-      }
-      float du[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        du[i] = dh[i] * hder[i];
-        cs->du[lane + 32 * i] = du[i];
-        const int j = lane + 32 * i;
-        a.c_xh[((long long)(j >> 3) * a.RTc + b) * 8 + (j & 7)] = __float2bfloat16_rn(hv[i]);
-        a.c_dh[((long long)(j >> 3) * a.RTc + b) * 8 + (j & 7)] = __float2bfloat16_rn(du[i]);
-      }
-      a.c_dxb[((long long)(lane >> 3) * a.RTc + b) * 8 + (lane & 7)] = __float2bfloat16_rn(dx2);
-      a.c_xln2[((long long)(lane >> 3) * a.RTc + b) * 8 + (lane & 7)] = __float2bfloat16_rn(y2);
-      __syncwarp();
-      // fc1 backward: dy2[i] = sum_j W1[j][i] du[j]
-      float dy2 = 0.f;
-#pragma unroll 8
-      for (int j = 0; j < kHidden; ++j) dy2 = fmaf(__bfloat162float(wfc1[j * LD + lane]), cs->du[j], dy2);
-      gcls_ln2[0] += dy2 * xh2;
-      gcls_ln2[1] += dy2;
-      dgm = dy2 * f32[O1.ln2_g / 4 + lane];
-      c1 = warp_sum(dgm) * (1.f / kD);
-      c2 = warp_sum(dgm * xh2) * (1.f / kD);
-      const float dxm = dx2 + rstd2 * (dgm - c1 - xh2 * c2);
-      a.c_dxa[((long long)(lane >> 3) * a.RTc + b) * 8 + (lane & 7)] = __float2bfloat16_rn(dxm);
-      a.c_xo[((long long)(lane >> 3) * a.RTc + b) * 8 + (lane & 7)] = __float2bfloat16_rn(ov);
-      // proj backward: do[i] = sum_o Wp[o][i] dxm[o]
-      float dov = 0.f;
-#pragma unroll 8
-      for (int o = 0; o < kD; ++o)
-        dov = fmaf(__bfloat162float(wproj[o * LD + lane]), __shfl_sync(0xffffffffu, dxm, o), dov);
-      cs->doo[lane] = dov;
-      float delta = dov * ov;   // per head: sum over its 8 channels
-      delta += __shfl_xor_sync(0xffffffffu, delta, 1);
-      delta += __shfl_xor_sync(0xffffffffu, delta, 2);
-      delta += __shfl_xor_sync(0xffffffffu, delta, 4);
-      float dlt[kHeads];
-#pragma unroll
-      for (int h = 0; h < kHeads; ++h) dlt[h] = __shfl_sync(0xffffffffu, delta, 8 * h);
-      __syncwarp();
-      // single-query attention backward: ds, dK, dV per key (key = lane + 32 kk)
-#pragma unroll
-      for (int kk = 0; kk < KK; ++kk) {
-        const int key = lane + 32 * kk;
-        if (key < TP) {
-#pragma unroll
-          for (int h = 0; h < kHeads; ++h) {
-            float dp = 0.f;
-            uint32_t vv[4];
-#pragma unroll
-            for (int dd = 0; dd < 4; ++dd) {
-              vv[dd] = lds32(V1s + key * LD + 8 * h + 2 * dd);
-              dp = fmaf(cs->doo[8 * h + 2 * dd], bf_lo(vv[dd]), dp);
-              dp = fmaf(cs->doo[8 * h + 2 * dd + 1], bf_hi(vv[dd]), dp);
-            }
-            const float pk = key < T ? sc[kk][h] : 0.f;
-            const float dsv = pk * (dp - dlt[h]);
-            cs->ds[h][key] = dsv;
-            const float dsk = dsv * kLn2;   // dK = ds * scale * q = ds * qhat / log2(e)
-#pragma unroll
-            for (int dd = 0; dd < 4; ++dd) {
-              *reinterpret_cast<uint32_t*>(dK1s + key * LD + 8 * h + 2 * dd) =
-                  pack_bf16(dsk * cs->q[8 * h + 2 * dd], dsk * cs->q[8 * h + 2 * dd + 1]);
-              *reinterpret_cast<uint32_t*>(dV1s + key * LD + 8 * h + 2 * dd) =
-                  pack_bf16(pk * cs->doo[8 * h + 2 * dd], pk * cs->doo[8 * h + 2 * dd + 1]);
-            }
-          }
+        for (int k2 = 0; k2 < kHidden / 2; k2 += 2) {
+          const uint2 wv = *reinterpret_cast<const uint2*>(wfc2 + lane * kLdHid + 2 * k2);
+          const float4 hh = *reinterpret_cast<const float4*>(cs->h + 2 * k2);
+          z0 = fmaf(bf_lo(wv.x), hh.x, fmaf(bf_hi(wv.x), hh.y, z0));
+          z1 = fmaf(bf_lo(wv.y), hh.z, fmaf(bf_hi(wv.y), hh.w, z1));
         }
+        const float x2 = xm + z0 + z1;
+        const float meanf = warp_sum(x2) * (1.f / kD);
+        const float df = x2 - meanf;
+        const float rstdf = rsqrtf(warp_sum(df * df) * (1.f / kD) + 1e-6f);
+        const float xhf = df * rstdf;
+        const float cfin = xhf * f32[L.lnf_g / 4 + lane] + f32[L.lnf_b / 4 + lane];
+        // ---------------- backward ----------------
+        const float* dl = a.dlogits + (long long)b * K;
+        float dc = 0.f;
+        for (int k = 0; k < K; ++k) dc = fmaf(__ldg(dl + k), f32[L.whead / 4 + k * kD + lane], dc);
+        a.c_xc[((long long)(lane >> 3) * a.RTc + b) * 8 + (lane & 7)] = __float2bfloat16_rn(cfin);
+        for (int k = lane; k < ((K + 15) / 16) * 16; k += 32)
+          a.c_dlog[((long long)(k >> 3) * a.RTc + b) * 8 + (k & 7)] = __float2bfloat16_rn(k < K ? __ldg(dl + k) : 0.f);
+        gcls_lnf[0] += dc * xhf;
+        gcls_lnf[1] += dc;
+        float dgm = dc * f32[L.lnf_g / 4 + lane];
+        float c1 = warp_sum(dgm) * (1.f / kD), c2 = warp_sum(dgm * xhf) * (1.f / kD);
+        const float dx2 = rstdf * (dgm - c1 - xhf * c2);
+        // fc2 backward: dh[j] = sum_o W2[o][j] dx2[o]; du = dh * gelu'(u)
+        float dh[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+        for (int o = 0; o < kD; ++o) {
+          const float dv = __shfl_sync(0xffffffffu, dx2, o);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dh[i] = fmaf(__bfloat162float(wfc2[o * kLdHid + lane + 32 * i]), dv, dh[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float du = dh[i] * hder[i];
+          cs->du[lane + 32 * i] = du;
+          const int j = lane + 32 * i;
+          a.c_xh[((long long)(j >> 3) * a.RTc + b) * 8 + (j & 7)] = __float2bfloat16_rn(hv[i]);
+          a.c_dh[((long long)(j >> 3) * a.RTc + b) * 8 + (j & 7)] = __float2bfloat16_rn(du);
+        }
+        a.c_dxb[((long long)(lane >> 3) * a.RTc + b) * 8 + (lane & 7)] = __float2bfloat16_rn(dx2);
+        a.c_xln2[((long long)(lane >> 3) * a.RTc + b) * 8 + (lane & 7)] = __float2bfloat16_rn(y2);
+        __syncwarp();
+        // fc1 backward: dy2[i] = sum_j W1[j][i] du[j]  (four independent chains)
+        float dy2a = 0.f, dy2b = 0.f, dy2c = 0.f, dy2d = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < kHidden; j += 4) {
+          dy2a = fmaf(__bfloat162float(wfc1[j * LD + lane]), cs->du[j], dy2a);
+          dy2b = fmaf(__bfloat162float(wfc1[(j + 1) * LD + lane]), cs->du[j + 1], dy2b);
+          dy2c = fmaf(__bfloat162float(wfc1[(j + 2) * LD + lane]), cs->du[j + 2], dy2c);
+          dy2d = fmaf(__bfloat162float(wfc1[(j + 3) * LD + lane]), cs->du[j + 3], dy2d);
+        }
+        const float dy2 = (dy2a + dy2b) + (dy2c + dy2d);
+        gcls_ln2[0] += dy2 * xh2;
+        gcls_ln2[1] += dy2;
+        dgm = dy2 * f32[O1.ln2_g / 4 + lane];
+        c1 = warp_sum(dgm) * (1.f / kD);
+        c2 = warp_sum(dgm * xh2) * (1.f / kD);
+        const float dxm = dx2 + rstd2 * (dgm - c1 - xh2 * c2);
+        a.c_dxa[((long long)(lane >> 3) * a.RTc + b) * 8 + (lane & 7)] = __float2bfloat16_rn(dxm);
+        a.c_xo[((long long)(lane >> 3) * a.RTc + b) * 8 + (lane & 7)] = __float2bfloat16_rn(ov);
+        // proj backward: do[i] = sum_o Wp[o][i] dxm[o]
+        float dov = 0.f;
+#pragma unroll 8
+        for (int o = 0; o < kD; ++o)
+          dov = fmaf(__bfloat162float(wproj[o * LD + lane]), __shfl_sync(0xffffffffu, dxm, o), dov);
+        cs->doo[lane] = dov;
+        float delta = dov * ov;   // per head: sum over its 8 channels
+        delta += __shfl_xor_sync(0xffffffffu, delta, 1);
+        delta += __shfl_xor_sync(0xffffffffu, delta, 2);
+        delta += __shfl_xor_sync(0xffffffffu, delta, 4);
+        if ((lane & 7) == 0) cs->dlt[hd] = delta;
+        cs->dxres[lane] = dxm;      // residual gradient reaching x1[cls]
       }
-      __syncwarp();
-      // dq[d] = scale * sum_key ds[h(d)][key] * K[key][d]
-      float dqv = 0.f;
-      for (int key = 0; key < T; ++key) dqv = fmaf(cs->ds[hd][key], __bfloat162float(K1s[key * LD + lane]), dqv);
-      cs->dq[lane] = dqv * kScale;
-      cs->dxres[lane] = dxm;      // residual gradient reaching x1[cls]
+      __syncthreads();
+      // ---- C6 (all): single-query attention backward per (head, key): ds, dK, dV ----
+      for (int i = threadIdx.x; i < kHeads * TP; i += nthr) {
+        const int h = i / TP, key = i - h * TP;
+        const uint4 vv = *reinterpret_cast<const uint4*>(V1s + key * LD + 8 * h);
+        const float* dd = cs->doo + 8 * h;
+        const float* qq = cs->q + 8 * h;
+        const float dp = dd[0] * bf_lo(vv.x) + dd[1] * bf_hi(vv.x) + dd[2] * bf_lo(vv.y) + dd[3] * bf_hi(vv.y) +
+                         dd[4] * bf_lo(vv.z) + dd[5] * bf_hi(vv.z) + dd[6] * bf_lo(vv.w) + dd[7] * bf_hi(vv.w);
+        const float pk = key < T ? cs->p[h][key] : 0.f;
+        const float dsv = pk * (dp - cs->dlt[h]);
+        cs->ds[h][key] = dsv;
+        const float dsk = dsv * kLn2;   // dK = ds * scale * q = ds * qhat / log2(e)
+        *reinterpret_cast<uint4*>(dK1s + key * LD + 8 * h) =
+            make_uint4(pack_bf16(dsk * qq[0], dsk * qq[1]), pack_bf16(dsk * qq[2], dsk * qq[3]),
+                       pack_bf16(dsk * qq[4], dsk * qq[5]), pack_bf16(dsk * qq[6], dsk * qq[7]));
+        *reinterpret_cast<uint4*>(dV1s + key * LD + 8 * h) =
+            make_uint4(pack_bf16(pk * dd[0], pk * dd[1]), pack_bf16(pk * dd[2], pk * dd[3]),
+                       pack_bf16(pk * dd[4], pk * dd[5]), pack_bf16(pk * dd[6], pk * dd[7]));
+      }
+      __syncthreads();
+      // ---- C7 (all): dq[d] = scale * sum_key ds[h(d)][key] * K[key][d], keys split over the warps ----
+      {
+        float part = 0.f;
+        for (int key = warp; key < T; key += NW) part = fmaf(cs->ds[hd][key], __bfloat162float(K1s[key * LD + lane]), part);
+        cs->part[warp][lane] = part;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        float dqv = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) dqv += cs->part[w][lane];
+        cs->dq[lane] = dqv * kScale;
+      }
     }
     __syncthreads();
 
