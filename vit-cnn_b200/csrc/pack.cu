@@ -12,38 +12,42 @@
 namespace vc {
 
 // ------------------------------------------------------------------------------------------
-__global__ void pack_sps_kernel(const float* __restrict__ src, long long sb, long long sc, long long si, long long sj,
-                                const long long* __restrict__ patch_off, int n_patches, int C, int P,
-                                __nv_bfloat16* __restrict__ sps, int S, long long RT, int vec) {
+// One thread owns one SPS row (= one pixel of one patch, or a pad / halo row) and walks its
+// channel slices: row decode and source address are computed once per row instead of once per
+// 16 bytes, a warp writes 32 consecutive rows of a slice (512 contiguous bytes), and its reads
+// are whole 32-byte sectors of the pixel's channel vector.
+__global__ void __launch_bounds__(256) pack_sps_kernel(const float* __restrict__ src, long long sb, long long sc,
+                                                       long long si, long long sj, const long long* __restrict__ patch_off,
+                                                       int n_patches, int C, int P, __nv_bfloat16* __restrict__ sps, int S,
+                                                       long long RT, int vec) {
   const int HALO = sps_halo(P), PP = sps_pp(P), PW = P + 1;
-  const long long total = (long long)S * RT;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int s = (int)(idx / RT);
-    const long long R = idx - (long long)s * RT;
+  for (long long R = (long long)blockIdx.x * blockDim.x + threadIdx.x; R < RT; R += (long long)gridDim.x * blockDim.x) {
     const long long r = R - HALO;
-    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    const float* p = nullptr;
     if (r >= 0) {
       const long long b = r / PP;
       const int q = (int)(r - b * PP);
       const int i = q / PW, j = q - i * PW;
-      if (b < n_patches && i < P && j < P) {
-        const float* p = src + (patch_off ? patch_off[b] : b * sb) + i * si + j * sj;
-        const int c0 = s * 8;
-        float v[8];
-        if (vec && c0 + 8 <= C) {
-          const float4 lo = __ldg(reinterpret_cast<const float4*>(p + c0));
-          const float4 hi = __ldg(reinterpret_cast<const float4*>(p + c0 + 4));
-          v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
-          v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-        } else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = (c0 + k < C) ? __ldg(p + (long long)(c0 + k) * sc) : 0.f;
-        }
-        o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-      }
+      if (b < n_patches && i < P && j < P) p = src + (patch_off ? patch_off[b] : b * sb) + i * si + j * sj;
     }
-    *reinterpret_cast<uint4*>(sps + idx * 8) = o;
+    uint4* dst = reinterpret_cast<uint4*>(sps) + R;
+    if (!p) {
+      for (int s = 0; s < S; ++s) dst[(long long)s * RT] = make_uint4(0u, 0u, 0u, 0u);
+      continue;
+    }
+    const int full = vec ? C / 8 : 0;     // slices that are two aligned float4 loads
+#pragma unroll 6
+    for (int s = 0; s < full; ++s) {
+      const float4 lo = __ldg(reinterpret_cast<const float4*>(p + s * 8));
+      const float4 hi = __ldg(reinterpret_cast<const float4*>(p + s * 8 + 4));
+      dst[(long long)s * RT] = make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
+    }
+    for (int s = full; s < S; ++s) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = (s * 8 + k < C) ? __ldg(p + (long long)(s * 8 + k) * sc) : 0.f;
+      dst[(long long)s * RT] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
   }
 }
 
@@ -51,15 +55,13 @@ int pack_sps_launch(const float* src, long long sb, long long sc, long long si, 
                     int n_patches, int C, int P, void* sps, int S, cudaStream_t stream) {
   if (n_patches <= 0 || C <= 0 || S * 8 < C || P < 1) return VC_ERR_ARG;
   const long long RT = sps_rows(n_patches, P);
-  const int vec = (sc == 1 && C % 8 == 0 && si % 4 == 0 && sj % 4 == 0 && sb % 4 == 0 &&
-                   (reinterpret_cast<uintptr_t>(src) & 15) == 0)
+  const int vec = (sc == 1 && si % 4 == 0 && sj % 4 == 0 && sb % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0)
                       ? 1
-                      : 0;  // patch_off entries are multiples of C in raster mode
-  const long long total = (long long)S * RT;
-  long long blocks = (total + 255) / 256;
+                      : 0;  // patch_off entries are multiples of C in raster mode: 16-byte aligned iff C % 4 == 0
+  long long blocks = (RT + 255) / 256;
   if (blocks > 148LL * 32) blocks = 148LL * 32;
   pack_sps_kernel<<<(int)blocks, 256, 0, stream>>>(src, sb, sc, si, sj, patch_off, n_patches, C, P,
-                                                   (__nv_bfloat16*)sps, S, RT, vec);
+                                                   (__nv_bfloat16*)sps, S, RT, vec && (C % 4 == 0 || !patch_off));
   return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
 }
 

@@ -45,7 +45,7 @@ struct TailBuf {
 // warp finishes the cls row (proj, MLP, final LN, head) while the token warps already work
 // on the next patch.
 template <int NW>
-__global__ void __launch_bounds__((NW + 1) * 32) transformer_fwd_kernel(TArgs a) {
+__global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_fwd_kernel(TArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr int TP = 16 * NW;    // padded token count
   constexpr int LDV = TP + 8;    // pitch of V^T rows

@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import torch
 
-from .utils import row_band_ranges, window_starts
+from .utils import band_geometry
 
 
 @torch.no_grad()
@@ -24,17 +24,15 @@ def predict_scene_host(net, img1: torch.Tensor, img2: torch.Tensor, stride: int 
         logits_out = torch.zeros(H, W, K, dtype=torch.float32)
     if argmax_out is None:
         argmax_out = torch.zeros(H, W, dtype=torch.uint8)
-    xs, ys = window_starts(H, P, stride), window_starts(W, P, stride)
-    first, count = row_band_ranges(len(xs), len(ys), world)[rank]
-    if count == 0:
+    geo = band_geometry(H, W, P, stride, rank, world)
+    if geo["count"] == 0:
         return logits_out, argmax_out
-    r0, r1 = first // len(ys), (first + count - 1) // len(ys)       # window rows of the band
-    x0, x1 = int(xs[r0]), int(xs[r1]) + P                           # raster rows incl. halo
+    x0, x1 = geo["x0"], geo["x1"]
     with torch.cuda.device(dev):
         b1 = img1[x0:x1].to(dev, non_blocking=True)
         b2 = img2[x0:x1].to(dev, non_blocking=True)
-        lg, am = net.predict_scene(b1, b2, stride=stride, chunk=chunk, xs=xs[r0:r1 + 1] - x0)
-        o0, o1 = x0 + P // 2, x1 - P + P // 2 + 1                   # rows with window centres
+        lg, am = net.predict_scene(b1, b2, stride=stride, chunk=chunk, xs=geo["xs"])
+        o0, o1 = geo["o0"], geo["o1"]                               # rows with window centres
         logits_out[o0:o1].copy_(lg[P // 2:P // 2 + (o1 - o0)], non_blocking=True)
         argmax_out[o0:o1].copy_(am[P // 2:P // 2 + (o1 - o0)], non_blocking=True)
         torch.cuda.current_stream().synchronize()

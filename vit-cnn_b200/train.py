@@ -41,6 +41,48 @@ def param_names() -> list:
     return names
 
 
+def flat_offsets(numels) -> tuple:
+    """Element offset of every tensor in the flat parameter / gradient bucket (each tensor
+    starts on a 16-byte boundary) and the bucket length."""
+    offs, o = [], 0
+    for n in numels:
+        offs.append(o)
+        o += (int(n) + 3) // 4 * 4
+    return offs, o
+
+
+def flatten_grads(model, device=None) -> torch.Tensor:
+    """Gradients of ``model`` (any module with this package's state_dict keys) as one flat fp32
+    bucket in the canonical order -- the layout the all-reduce and the Adam kernel work on."""
+    named = dict(model.named_parameters())
+    ps = [named[k] for k in param_names()]
+    offs, total = flat_offsets([p.numel() for p in ps])
+    flat = torch.zeros(total, dtype=torch.float32, device=device or ps[0].device)
+    for p, o in zip(ps, offs):
+        if p.grad is not None:
+            flat[o:o + p.numel()] = p.grad.reshape(-1)
+    return flat
+
+
+def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum the flat bucket over the ranks (NCCL on GPUs, gloo in the CPU tests) and divide by the
+    world size: the data-parallel gradient of the mean of the per-rank losses."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        world = dist.get_world_size(group)
+        if world > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            flat.div_(world)
+    return flat
+
+
+def shard_batch(n_global: int, rank: int, world: int) -> slice:
+    """Contiguous shard of a global batch for one rank (sizes differ by at most one)."""
+    base, rem = divmod(n_global, world)
+    start = rank * base + min(rank, rem)
+    return slice(start, start + base + (1 if rank < rem else 0))
+
+
 def _bn_layers(model):
     return [model.hsi_stem[0].bn, model.hsi_stem[1].bn, model.hsi_stem[2].bn, model.lidar_stem[0].bn,
             model.lidar_stem[1].bn, model.lidar_stem[2].bn, model.fusion.bn]
@@ -59,10 +101,7 @@ class TrainState:
         self.device = self.params[0].device
         if self.device.type != "cuda":
             raise RuntimeError("ViTCNN trains on a CUDA device only (no CPU path)")
-        self.offsets, o = [], 0
-        for p in self.params:
-            self.offsets.append(o)
-            o += (p.numel() + 3) // 4 * 4
+        self.offsets, o = flat_offsets([p.numel() for p in self.params])
         self.numel = o
         self.flat = torch.zeros(o, dtype=torch.float32, device=self.device)
         self.grads = torch.zeros(o, dtype=torch.float32, device=self.device)
@@ -263,6 +302,15 @@ class Trainer:
         self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
         self.group = process_group
         self.world = self.dist.get_world_size(process_group) if self.dist else 1
+
+    def step_lr(self, epoch: int, step_size: int = 30, gamma: float = 0.9, base_lr: float = None) -> float:
+        """StepLR(step_size, gamma) as the reference schedules Adam (model_utils.py:498): call once
+        per epoch with the number of finished epochs."""
+        if base_lr is None:
+            base_lr = getattr(self, "_base_lr", self.lr)
+        self._base_lr = base_lr
+        self.lr = base_lr * gamma ** (epoch // step_size)
+        return self.lr
 
     def step(self, img1, img2, gt, xy):
         """One optimisation step on patches centred at xy (int32 [n,2], device).  Returns the

@@ -58,3 +58,35 @@ def row_band_ranges(n_rows: int, n_cols: int, world_size: int):
         out.append((r0 * n_cols, rows * n_cols))
         r0 += rows
     return out
+
+
+def band_geometry(H: int, W: int, P: int, stride: int, rank: int, world: int) -> dict:
+    """What rank ``rank`` of ``world`` needs for its row band of the scene:
+    ``first`` / ``count`` = its windows in the reference's order, ``x0:x1`` = raster rows to
+    upload (band + halo), ``o0:o1`` = map rows it owns (window centres), ``xs`` = window-row
+    starts relative to ``x0``.  ``count == 0`` when there are more ranks than window rows."""
+    xs, ys = window_starts(H, P, stride), window_starts(W, P, stride)
+    first, count = row_band_ranges(len(xs), len(ys), world)[rank]
+    if count == 0:
+        return dict(first=first, count=0, x0=0, x1=0, o0=0, o1=0, xs=xs[:0], ys=ys)
+    r0, r1 = first // len(ys), (first + count - 1) // len(ys)
+    x0, x1 = int(xs[r0]), int(xs[r1]) + P
+    return dict(first=first, count=count, x0=x0, x1=x1, o0=x0 + P // 2, o1=x1 - P + P // 2 + 1,
+                xs=xs[r0:r1 + 1] - x0, ys=ys)
+
+
+def seed_torch(seed: int = 1029) -> None:
+    """utils.py:887-895: seed Python, numpy and torch RNGs (the determinism contract of the
+    sample shuffle, datasets.py:506, and of weight initialisation)."""
+    import os
+    import random
+    import torch
+    random.seed(seed)
+    os.environ["PYTHONHASHSEED"] = str(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed(seed)
+        torch.cuda.manual_seed_all(seed)
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.deterministic = True
