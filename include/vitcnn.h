@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VC_ABI_VERSION 1
+#define VC_ABI_VERSION 2
 
 /* Parameters of one model instance in kernel-ready form (built by vc-side packing, see
  * vitcnn_b200/model.py::pack_for_inference).  Conv weights: bf16 [nsplit][taps][S_in][N/nsplit][8]
@@ -43,9 +43,16 @@ typedef struct vc_model {
   const float* scale_l[3];
   const float* bias_l[3];
   const void* tparams;         /* fusion 1x1 + cls/pos + 2 blocks + norm + head           */
+  const void* lidar_blob;      /* nullable: operands of the fused LiDAR-stem kernel (C2 <= 8),
+                                  vc_lidar_blob_bytes() bytes: bf16 rows of 24 elements --
+                                  [5 tap pairs][8][k: tap 2p ch 0-7 | tap 2p+1 ch 0-7],
+                                  [5][16][same], [9 taps][32][16 ch] -- then fp32 scale/bias
+                                  of the three layers (8+8, 16+16, 32+32); NULL = three
+                                  tensor-core conv launches through w_l / scale_l / bias_l   */
 } vc_model;
 
 int vc_abi_version(void);
+int64_t vc_lidar_blob_bytes(void);
 const char* vc_last_error(void);
 
 /* ---- instrumentation (bench.py): kernels launched by this library so far in the process, and

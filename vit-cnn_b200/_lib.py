@@ -13,7 +13,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_uint8, c_void
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libvitcnn.so")
-SOURCES = ["abi.cu", "conv_tc.cu", "pack.cu", "transformer.cu", "wgrad_tc.cu", "train.cu", "tokens_bwd.cu"]
+SOURCES = ["abi.cu", "conv_tc.cu", "pack.cu", "transformer.cu", "lidar_stem.cu", "wgrad_tc.cu", "train.cu", "tokens_bwd.cu"]
 HEADERS = ["vc_common.cuh", "vc_kernels.h", "vc_tparams.h", os.path.join("..", "..", "include", "vitcnn.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -51,6 +51,7 @@ class VcModel(ctypes.Structure):
         ("w_h", c_void_p * 3), ("scale_h", c_void_p * 3), ("bias_h", c_void_p * 3),
         ("w_l", c_void_p * 3), ("scale_l", c_void_p * 3), ("bias_l", c_void_p * 3),
         ("tparams", c_void_p),
+        ("lidar_blob", c_void_p),
     ]
 
 
@@ -68,6 +69,7 @@ class VcTrain(ctypes.Structure):
 
 _PROTOS = {
     "vc_abi_version": (c_int32, []),
+    "vc_lidar_blob_bytes": (c_int64, []),
     "vc_last_error": (c_char_p, []),
     "vc_sps_rows": (c_int64, [c_int32, c_int32]),
     "vc_launch_count": (c_int64, []),
@@ -132,7 +134,7 @@ def lib() -> ctypes.CDLL:
         for name, (res, args) in _PROTOS.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        if L.vc_abi_version() != 1:
+        if L.vc_abi_version() != 2:
             raise RuntimeError("libvitcnn.so ABI version mismatch")
         _lib = L
     return _lib

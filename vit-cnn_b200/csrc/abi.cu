@@ -107,12 +107,21 @@ int forward_sps(const vc_model* m, const Workspace& w, int n, float* logits, con
                              0, 0, st));
   VC_LAUNCH(KC_CONV_H3, st, vc::conv_sps_launch(w.a2, 8, m->w_h[2], m->scale_h[2], m->bias_h[2], w.f, 0, 32, m->nsplit_h[2], n, P, 9, 1, 0,
                              0, st));
-  VC_LAUNCH(KC_CONV_L, st, vc::conv_sps_launch(w.l0, m->S2, m->w_l[0], m->scale_l[0], m->bias_l[0], w.l1, 0, 16, m->nsplit_l[0], n, P, 9,
-                             1, 0, 0, st));
-  VC_LAUNCH(KC_CONV_L, st, vc::conv_sps_launch(w.l1, 2, m->w_l[1], m->scale_l[1], m->bias_l[1], w.l2, 0, 16, m->nsplit_l[1], n, P, 9, 1, 0,
-                             0, st));
-  VC_LAUNCH(KC_CONV_L, st, vc::conv_sps_launch(w.l2, 2, m->w_l[2], m->scale_l[2], m->bias_l[2], w.f, 4, 32, m->nsplit_l[2], n, P, 9, 1, 0,
-                             0, st));
+  bool lidar_done = false;
+  if (m->lidar_blob && m->C2 <= 8) {   // one fused launch instead of three latency-bound ones
+    Scope sc(KC_CONV_L, st);
+    const int rc = vc::lidar_stem_launch(w.l0, m->lidar_blob, w.f, 4, n, P, st);
+    if (rc == VC_OK) lidar_done = true;
+    else if (rc != VC_ERR_UNSUPPORTED) return fail(rc, "lidar_stem_launch");
+  }
+  if (!lidar_done) {
+    VC_LAUNCH(KC_CONV_L, st, vc::conv_sps_launch(w.l0, m->S2, m->w_l[0], m->scale_l[0], m->bias_l[0], w.l1, 0, 16, m->nsplit_l[0], n, P,
+                                                 9, 1, 0, 0, st));
+    VC_LAUNCH(KC_CONV_L, st, vc::conv_sps_launch(w.l1, 2, m->w_l[1], m->scale_l[1], m->bias_l[1], w.l2, 0, 16, m->nsplit_l[1], n, P, 9, 1,
+                                                 0, 0, st));
+    VC_LAUNCH(KC_CONV_L, st, vc::conv_sps_launch(w.l2, 2, m->w_l[2], m->scale_l[2], m->bias_l[2], w.f, 4, 32, m->nsplit_l[2], n, P, 9, 1,
+                                                 0, 0, st));
+  }
   VC_LAUNCH(KC_TOKENS, st, vc::transformer_fwd_launch(w.f, m->tparams, n, P, m->K, logits, out_index, argmax_map, 0, st));
   return VC_OK;
 }
@@ -131,6 +140,7 @@ int check_model(const vc_model* m) {
 extern "C" {
 
 int vc_abi_version(void) { return VC_ABI_VERSION; }
+int64_t vc_lidar_blob_bytes(void) { return (int64_t)vc::lidar_blob_bytes(); }
 const char* vc_last_error(void) { return g_err; }
 
 int64_t vc_sps_rows(int32_t n_patches, int32_t P) { return vc::sps_rows(n_patches, P); }

@@ -24,6 +24,11 @@ int scene_index_launch(const int* xs, const int* ys, int nx, int ny, int first, 
 int center_offsets_launch(const int* xy, int n, int W, int C1, int C2, int P, long long* off1, long long* off2,
                           cudaStream_t stream);
 
+// lidar_stem.cu -- fused eval-mode LiDAR stem (C2 <= 8)
+size_t lidar_blob_bytes();
+int lidar_stem_launch(const void* in_sps, const void* blob, void* out_sps, int out_slice_off, int n_patches, int P,
+                      cudaStream_t stream);
+
 // transformer.cu
 size_t tparams_bytes(int P, int K);
 int transformer_fwd_launch(const void* f_sps, const void* tparams, int n_patches, int P, int K, float* logits,

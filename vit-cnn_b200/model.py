@@ -135,6 +135,35 @@ def pack_tparams(model: "ViTCNN", layout: dict) -> torch.Tensor:
     return blob
 
 
+def pack_lidar_blob(model: "ViTCNN") -> torch.Tensor:
+    """Operands of the fused LiDAR-stem kernel (csrc/lidar_stem.cu; layout in include/vitcnn.h):
+    bf16 weight rows of 24 elements (conv 1 / 2 with two taps per K=16 step, conv 3 tap-major),
+    then the folded-BN affine of the three layers in fp32."""
+    dev = model.cls_token.device
+    l1, l2, l3 = model.lidar_stem
+    c2 = model.n_bands2
+    assert c2 <= 8
+    rows = torch.zeros(5 * 8 + 5 * 16 + 9 * 32, 24, dtype=torch.float32, device=dev)
+    w1 = l1.conv.weight.detach().float().reshape(8, c2, 9)
+    w2 = l2.conv.weight.detach().float().reshape(16, 8, 9)
+    w3 = l3.conv.weight.detach().float().reshape(32, 16, 9)
+    for p in range(5):
+        for half, tap in ((0, 2 * p), (1, 2 * p + 1)):
+            if tap > 8:
+                continue
+            rows[p * 8:p * 8 + 8, 8 * half:8 * half + c2] = w1[:, :, tap]
+            rows[40 + p * 16:40 + p * 16 + 16, 8 * half:8 * half + 8] = w2[:, :, tap]
+    for tap in range(9):
+        rows[120 + tap * 32:120 + tap * 32 + 32, :16] = w3[:, :, tap]
+    aff = []
+    for layer, n in ((l1, 8), (l2, 16), (l3, 32)):
+        s, b = fold_bn(layer.conv, layer.bn, n)
+        aff += [s, b]
+    blob = torch.cat([rows.to(torch.bfloat16).reshape(-1).view(torch.uint8), torch.cat(aff).view(torch.uint8)])
+    assert blob.numel() == _lib.lib().vc_lidar_blob_bytes()
+    return blob.contiguous()
+
+
 def stem_plan(c_in: int, planes) -> list:
     """(S_in, n_out_padded, nsplit) per conv of a 3-layer stem; channels are padded to 16."""
     plan, s_in = [], slices_for(c_in)
@@ -222,6 +251,10 @@ class ViTCNN(nn.Module):
         blob = pack_tparams(self, _lib.tparams_layout(P, K))
         pk["keep"].append(blob)
         st.tparams = blob.data_ptr()
+        if self.n_bands2 <= 8:
+            lb = pack_lidar_blob(self)
+            pk["keep"].append(lb)
+            st.lidar_blob = lb.data_ptr()
         pk["struct"] = st
         self._pack, self._pack_key = pk, key
         return pk
