@@ -346,9 +346,15 @@ def main():
     hbm, tf_burst, tf_sust, which = peaks()
     flops_c1 = 2.0 * P * P * 128 * C1 * 9 * count * scenes            # algorithmic (App. D), this rank
     achieved = flops_c1 / (c1_ms / 1e3) / 1e12 if c1_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_conv1_traffic.json")
+    if os.path.isfile(tpath):       # dram bytes per launch from the committed ncu capture (same chunk size only)
+        tj = json.load(open(tpath))
+        if tj.get("chunk_windows") == min(args.chunk, count):
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     roofline = {"kernel": "conv_sps_tc_kernel (HSI stem conv1, tcgen05)", "bound": "tensor",
                 "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s", "frac": achieved / tf_sust,
-                "peak_source": which + " bf16 sustained", "traffic": None,
+                "peak_source": which + " bf16 sustained", "traffic": traffic,
                 "launches": c1_n, "avg_launch_ms": c1_ms / max(c1_n, 1),
                 "share_of_step": c1_ms / total_ms if total_ms else None,
                 "breakdown_ms": {k: round(v[0], 3) for k, v in prof.items()}}

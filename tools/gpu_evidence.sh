@@ -1,19 +1,24 @@
 #!/bin/bash
-# Round evidence for the inference path: gpu tests, bench (both arms), ncu launch list and
-# full captures of the two dominant kernels (B200_PROFILING.md recipe).
+# Round evidence: all gpu tests, smoke, bench (both arms), ncu launch lists and full captures of the
+# dominant kernels of the inference scene and of the training step (B200_PROFILING.md recipe).
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" | tail -1
 timeout 900 python -m pytest tests -m gpu -x -q -p no:cacheprovider 2>&1 | tail -3
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; cat gpurun_out/bench_ref.json
-PROF="python bench.py --steps 1 --warmup 3 --windows 16384 --no-cpu --no-e2e"
+PROF="python bench.py --steps 1 --warmup 3 --windows 65536 --no-cpu --no-e2e --no-train"
 $PROF > gpurun_out/prof_plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $PROF > gpurun_out/ncu_list.log 2>&1
-echo "ncu list rc=$?"; tail -2 gpurun_out/ncu_list.log
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $PROF > gpurun_out/ncu_list.log 2>&1
+echo "ncu list rc=$?"
 $PROF > gpurun_out/prof_plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:conv_sps_tc -s 12 -c 6 -o gpurun_out/prof_conv $PROF > gpurun_out/ncu_full.log 2>&1
-echo "ncu conv rc=$?"; tail -2 gpurun_out/ncu_full.log
-$PROF > gpurun_out/prof_plain3.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"transformer_fwd|pack_sps" -s 6 -c 3 -o gpurun_out/prof_tokens $PROF > gpurun_out/ncu_tokens.log 2>&1
-echo "ncu tokens rc=$?"; tail -2 gpurun_out/ncu_tokens.log
-ls -la gpurun_out
+ncu --set full --clock-control none --import-source on -k regex:"conv_sps_tc|transformer_fwd|pack_strip|lidar_stem" -s 12 -c 7 -o gpurun_out/prof_infer $PROF > gpurun_out/ncu_full.log 2>&1
+echo "ncu infer rc=$?"; tail -1 gpurun_out/ncu_full.log
+TPROF="python bench.py --no-infer --steps 1 --warmup 3"
+$TPROF > gpurun_out/train_plain1.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 400 --csv --log-file gpurun_out/train_launches.csv $TPROF > gpurun_out/ncu_train_list.log 2>&1
+echo "ncu train list rc=$?"
+$TPROF > gpurun_out/train_plain2.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:"wgrad_sps_tc|transformer_bwd|bn_bwd_apply" -s 18 -c 19 -o gpurun_out/prof_train $TPROF > gpurun_out/ncu_train_full.log 2>&1
+echo "ncu train rc=$?"; tail -1 gpurun_out/ncu_train_full.log
+ls -la gpurun_out | head -40

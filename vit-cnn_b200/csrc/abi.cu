@@ -285,8 +285,20 @@ int vc_scene_infer(const vc_model* m, const float* img1, const float* img2, int3
     if (done == 0 || n != chunk) VC_TRY(zero_halos(w, n, m->P, st));
     VC_LAUNCH(KC_INDEX, st, vc::scene_index_launch(xs, ys, nx, ny, (int)(first_window + done), n, W, m->C1, m->C2, m->P,
                                                    m->K, w.off1, w.off2, w.oidx, nullptr, st));
-    VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(img1, 0, 1, s1, m->C1, w.off1, n, m->C1, m->P, w.a0, m->S1, st));
-    VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(img2, 0, 1, s2, m->C2, w.off2, n, m->C2, m->P, w.l0, m->S2, st));
+    // strip-staged gather (stride-1 runs reuse the overlap of consecutive windows); the generic
+    // per-row gather is the fallback for geometries the strip kernel does not take
+    {
+      Scope sc(KC_PACK, st);
+      int rc = vc::pack_scene_launch(img1, W, m->C1, xs, ys, nx, ny, (int)(first_window + done), n, m->P, w.a0, m->S1, st);
+      if (rc == VC_ERR_UNSUPPORTED) rc = vc::pack_sps_launch(img1, 0, 1, s1, m->C1, w.off1, n, m->C1, m->P, w.a0, m->S1, st);
+      if (rc != VC_OK) return fail(rc, "scene gather (hsi)");
+    }
+    {
+      Scope sc(KC_PACK, st);
+      int rc = vc::pack_scene_launch(img2, W, m->C2, xs, ys, nx, ny, (int)(first_window + done), n, m->P, w.l0, m->S2, st);
+      if (rc == VC_ERR_UNSUPPORTED) rc = vc::pack_sps_launch(img2, 0, 1, s2, m->C2, w.off2, n, m->C2, m->P, w.l0, m->S2, st);
+      if (rc != VC_OK) return fail(rc, "scene gather (lidar)");
+    }
     VC_TRY(forward_sps(m, w, n, logits_map, w.oidx, argmax_map, st));
   }
   (void)H;

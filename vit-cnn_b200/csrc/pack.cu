@@ -65,6 +65,168 @@ int pack_sps_launch(const float* src, long long sb, long long sc, long long si, 
   return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
 }
 
+// ------------------------------------------------------------------------------------------
+// Scene gather for stride-1 sliding windows (test(), model_utils.py:1086-1112): consecutive
+// windows of one window row overlap in P-1 of their P columns, so a CTA stages the raster strip
+// under `ws` consecutive windows (P rows x (ws+P-1) pixels x a part of the channels, fp32) in
+// shared memory ONCE -- one bulk async copy (TMA unit) per pixel, padded pixel pitch so the
+// 32-byte reads below are bank-conflict free -- and emits all ws patches from it.  Each raster
+// pixel is then fetched from L2 ~(ws+P-1)/ws times per window row instead of P times, which
+// leaves the kernel bound by its bf16 SPS writes.
+struct StripArgs {
+  const float* img;          // [H][W][C]
+  const int* xs;             // window-row starts [nx]
+  const int* ys;             // window-column starts [ny]
+  __nv_bfloat16* sps;        // [S][RT][8]
+  long long RT;
+  int W, C, P, S, ny, first, count, ws, strips_per_row, gs_first, nparts, part_slices;
+};
+
+__global__ void __launch_bounds__(256) pack_strip_kernel(StripArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ int s_fallback;
+  const int P = a.P, PW = P + 1, PP = sps_pp(P), HALO = sps_halo(P);
+  const int part = blockIdx.y;
+  const int sl0 = part * a.part_slices;
+  const int nsl = (a.S - sl0) < a.part_slices ? (a.S - sl0) : a.part_slices;     // slices of this part
+  const int c0 = sl0 * 8;
+  const int cn = (a.C - c0) < nsl * 8 ? (a.C - c0) : nsl * 8;                    // real channels of this part (may be <= 0)
+  const int pitch = nsl * 32 + 16;                                              // bytes per staged pixel
+  const int SW = a.ws + P - 1;                                                   // staged pixels per row
+  const bool aligned = (a.C % 4 == 0) && cn == nsl * 8 && ((reinterpret_cast<uintptr_t>(a.img) & 15) == 0);
+  short* rowtab = reinterpret_cast<short*>(smem);                                // [PP] pixel index i*SW+j or -1
+  uint8_t* strip = smem + ((PP * 2 + 127) & ~127);
+  for (int r = threadIdx.x; r < PP; r += blockDim.x) {
+    const int i = r / PW, j = r - i * PW;
+    rowtab[r] = (i < P && j < P) ? (short)(i * SW + j) : (short)-1;
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  const int nstrips = gridDim.x;   // one strip per block in x; loop kept for generality
+  for (int gs = a.gs_first + blockIdx.x; gs < a.gs_first + nstrips; gs += gridDim.x) {
+    const int xr = gs / a.strips_per_row, m = gs - xr * a.strips_per_row;
+    int w0 = xr * a.ny + m * a.ws, w1 = w0 + a.ws;                               // window index range of the strip
+    const int row_end = (xr + 1) * a.ny;
+    if (w1 > row_end) w1 = row_end;
+    if (w0 < a.first) w0 = a.first;
+    if (w1 > a.first + a.count) w1 = a.first + a.count;
+    const int nw = w1 - w0;
+    if (nw <= 0) continue;
+    const int x = a.xs[xr], yi0 = w0 - xr * a.ny, y0 = a.ys[yi0];
+    if (threadIdx.x == 0) s_fallback = (a.ys[yi0 + nw - 1] - y0 != nw - 1) ? 1 : 0;   // stride > 1: not contiguous
+    __syncthreads();
+    const bool fallback = s_fallback != 0;
+    const int npx = nw + P - 1;
+    if (!fallback && cn > 0) {
+      if (aligned) {
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(&bar, (uint32_t)(P * npx) * (uint32_t)(cn * 4));
+        __syncthreads();
+        for (int t = threadIdx.x; t < P * npx; t += blockDim.x) {
+          const int i = t / npx, j = t - i * npx;
+          bulk_g2s(strip + (size_t)(i * SW + j) * pitch, a.img + ((long long)(x + i) * a.W + y0 + j) * a.C + c0,
+                   (uint32_t)(cn * 4), &bar);
+        }
+        mbar_wait(&bar, phase);
+        phase ^= 1u;
+      } else {
+        for (int t = threadIdx.x; t < P * npx * nsl * 8; t += blockDim.x) {
+          const int c = t % (nsl * 8), pix = t / (nsl * 8);
+          const int i = pix / npx, j = pix - i * npx;
+          float v = 0.f;
+          if (c < cn) v = __ldg(a.img + ((long long)(x + i) * a.W + y0 + j) * a.C + c0 + c);
+          *reinterpret_cast<float*>(strip + (size_t)(i * SW + j) * pitch + c * 4) = v;
+        }
+        __syncthreads();
+      }
+    }
+    // emit: one warp per (slice, window) pair, lanes walk the patch rows -> 512-byte contiguous
+    // stores, no per-element index division
+    const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int pair = threadIdx.x >> 5; pair < nsl * nw; pair += nwarps) {
+      const int s = pair / nw, w = pair - s * nw;
+      uint4* dst = reinterpret_cast<uint4*>(a.sps + ((long long)(sl0 + s) * a.RT + HALO + (long long)(w0 - a.first + w) * PP) * 8);
+      const uint8_t* sbase = strip + (size_t)w * pitch + s * 32;
+      for (int r = lane; r < PP; r += 32) {
+        const int pix = rowtab[r];
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (pix >= 0 && cn > 0) {
+          float4 lo, hi;
+          if (!fallback) {
+            const uint8_t* src = sbase + (size_t)pix * pitch;
+            lo = *reinterpret_cast<const float4*>(src);
+            hi = *reinterpret_cast<const float4*>(src + 16);
+          } else {
+            const int i = pix / SW, j = pix - i * SW;
+            const float* src = a.img + ((long long)(x + i) * a.W + a.ys[yi0 + w] + j) * a.C + c0 + s * 8;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = (s * 8 + k < cn) ? __ldg(src + k) : 0.f;
+            lo = make_float4(v[0], v[1], v[2], v[3]);
+            hi = make_float4(v[4], v[5], v[6], v[7]);
+          }
+          o = make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
+        }
+        dst[r] = o;
+      }
+    }
+    __syncthreads();   // the strip is overwritten by the next iteration
+  }
+}
+
+// rows outside the patches (lead halo, tile padding, trailing halo) of every slice
+__global__ void pack_strip_tail_kernel(__nv_bfloat16* sps, int S, long long RT, long long first_pad, int HALO) {
+  const long long per = HALO + (RT - first_pad);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < per * S; idx += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(idx / per);
+    const long long k = idx - (long long)s * per;
+    const long long R = k < HALO ? k : first_pad + (k - HALO);
+    *reinterpret_cast<uint4*>(sps + ((long long)s * RT + R) * 8) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+int pack_scene_launch(const float* img, int W, int C, const int* xs, const int* ys, int nx, int ny, int first, int count,
+                      int P, void* sps, int S, cudaStream_t stream) {
+  if (count <= 0 || first < 0 || (long long)first + count > (long long)nx * ny || S * 8 < C || P < 1) return VC_ERR_ARG;
+  static int max_smem = 0;
+  if (!max_smem) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  }
+  StripArgs a;
+  a.img = img; a.xs = xs; a.ys = ys; a.sps = (__nv_bfloat16*)sps;
+  a.RT = sps_rows(count, P);
+  a.W = W; a.C = C; a.P = P; a.S = S; a.ny = ny; a.first = first; a.count = count;
+  // two CTAs per SM: split the channel slices into parts of <= 9 slices, 16 windows per strip
+  a.part_slices = S <= 9 ? S : (S + 1) / 2 <= 9 ? (S + 1) / 2 : 9;
+  a.nparts = (S + a.part_slices - 1) / a.part_slices;
+  const int budget = 100 * 1024;
+  const int pitch = a.part_slices * 32 + 16;
+  int ws = budget / (P * pitch) - (P - 1);
+  if (ws > 16) ws = 16;
+  if (ws < 2) return VC_ERR_UNSUPPORTED;
+  a.ws = ws;
+  a.strips_per_row = (ny + ws - 1) / ws;
+  const int xr0 = first / ny, xr1 = (first + count - 1) / ny;
+  a.gs_first = xr0 * a.strips_per_row + (first - xr0 * ny) / ws;
+  const int gs_last = xr1 * a.strips_per_row + (first + count - 1 - xr1 * ny) / ws;
+  const size_t smem = ((sps_pp(P) * 2 + 127) & ~127) + (size_t)P * (ws + P - 1) * pitch;
+  if (smem > (size_t)max_smem) return VC_ERR_UNSUPPORTED;
+  if (cudaFuncSetAttribute(pack_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return VC_ERR_CUDA;
+  dim3 grid(gs_last - a.gs_first + 1, a.nparts);
+  pack_strip_kernel<<<grid, 256, smem, stream>>>(a);
+  const int HALO = sps_halo(P);
+  const long long first_pad = HALO + (long long)count * sps_pp(P);
+  pack_strip_tail_kernel<<<8, 256, 0, stream>>>((__nv_bfloat16*)sps, S, a.RT, first_pad, HALO);
+  return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
+}
+
 // Zero the lead / trailing halo rows of an SPS buffer (the conv epilogue writes the rest).
 __global__ void zero_halo_kernel(__nv_bfloat16* sps, int S, long long RT, int HALO) {
   const int per = 2 * HALO;
