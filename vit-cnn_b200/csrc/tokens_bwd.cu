@@ -67,21 +67,6 @@ __device__ __forceinline__ void dump_afrag32(__nv_bfloat16* buf, long long rows,
     dump2(buf, rows, row0 + 8, 16 * kk + 8 + 2 * q, A[kk][3]);
   }
 }
-// GELU (erf form) value and derivative, same erf approximation as the forward kernel
-__device__ __forceinline__ void gelu_erf_grad(float v, float& val, float& der) {
-  const float z = fabsf(v) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float ez = ex2(-1.44269504088896340736f * z * z);   // exp(-v^2/2)
-  const float half_erfc = 0.5f * p * t * ez;
-  const float Phi = v >= 0.f ? 1.f - half_erfc : half_erfc;
-  val = v * Phi;
-  der = fmaf(v * ez, 0.39894228040143267794f, Phi);
-}
-
 // LayerNorm statistics of the two rows this thread shares with its quad
 __device__ __forceinline__ void ln_stats(const float (&x)[4][4], float& m0, float& rs0, float& m1, float& rs1) {
   float s0 = 0.f, s1 = 0.f;

@@ -23,18 +23,26 @@ __device__ __forceinline__ float ex2(float v) {  // 2^v, one MUFU (flush-to-zero
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
   return r;
 }
-// exact-erf GELU (nn.GELU default, mlp.py:21) with erf from Abramowitz-Stegun 7.1.26
-// (|error| <= 1.5e-7, far below bf16 resolution): one RCP + one EX2 + a few FMAs.
+__device__ __forceinline__ float tanh_fast(float v) {   // one MUFU, max relative error 2^-11
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+// GELU (nn.GELU default = erf form, mlp.py:21) evaluated in its tanh form with the hardware tanh:
+// |gelu_tanh - gelu_erf| <= 4.8e-4 for every x, 1/16 of a bf16 ulp of the stored activation near
+// its maximum, for 6 instructions instead of ~20 (the erf polynomial was 25 % of the kernel).
 __device__ __forceinline__ float gelu_erf(float v) {
-  const float z = fabsf(v) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = p * t * ex2(-1.44269504088896340736f * z * z);   // 1 - erf(z)
-  const float half_erfc = 0.5f * e;                                  // v>=0: Phi = 1 - e/2, v<0: Phi = e/2
-  return v * (v >= 0.f ? 1.f - half_erfc : half_erfc);
+  const float u = v * fmaf(0.0356774081f, v * v, 0.7978845608f);
+  const float hv = 0.5f * v;
+  return fmaf(hv, tanh_fast(u), hv);
+}
+// value and derivative (backward kernel); same approximation so forward and backward agree
+__device__ __forceinline__ void gelu_erf_grad(float v, float& val, float& der) {
+  const float v2 = v * v;
+  const float t = tanh_fast(v * fmaf(0.0356774081f, v2, 0.7978845608f));
+  const float hv = 0.5f * v;
+  val = fmaf(hv, t, hv);
+  der = fmaf(hv * (1.f - t * t), fmaf(0.1070322243f, v2, 0.7978845608f), fmaf(0.5f, t, 0.5f));
 }
 
 // LayerNorm (eps 1e-6) of the two token rows this thread shares with its quad; result as the
