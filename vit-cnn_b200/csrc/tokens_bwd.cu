@@ -279,20 +279,12 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
           mx1 = fmaxf(mx1, fmaxf(s[t][2], s[t][3]));
         }
         mx0 = quad_max(mx0); mx1 = quad_max(mx1);
-        float l0 = 0.f, l1 = 0.f;
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
           s[t][0] = ex2(s[t][0] - mx0); s[t][1] = ex2(s[t][1] - mx0);
           s[t][2] = ex2(s[t][2] - mx1); s[t][3] = ex2(s[t][3] - mx1);
-          l0 += s[t][0] + s[t][1];
-          l1 += s[t][2] + s[t][3];
         }
-        const float il0 = 1.f / quad_sum(l0), il1 = 1.f / quad_sum(l1);
-        if (q == 0) {
-          st_m[h * TP + r0] = mx0; st_m[h * TP + r1] = mx1;
-          st_il[h * TP + r0] = il0; st_il[h * TP + r1] = il1;
-        }
-        float oh[4] = {0.f, 0.f, 0.f, 0.f};
+        float oh[4] = {0.f, 0.f, 0.f, 0.f}, lacc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int kk = 0; kk < NW; ++kk) {
           uint32_t Pa[4];
@@ -300,6 +292,12 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
           uint32_t b0, b1;
           ldsm_x2_trans(b0, b1, Vs + (16 * kk + (lane & 15)) * LD + 8 * h);
           mma16816(oh, Pa, b0, b1);
+          mma16816(lacc, Pa, 0x3F803F80u, 0x3F803F80u);   // row sums of (bf16) P on the tensor core
+        }
+        const float il0 = 1.f / lacc[0], il1 = 1.f / lacc[2];
+        if (q == 0) {
+          st_m[h * TP + r0] = mx0; st_m[h * TP + r1] = mx1;
+          st_il[h * TP + r0] = il0; st_il[h * TP + r1] = il1;
         }
         // save O (bf16) for the backward of this block
         *reinterpret_cast<uint32_t*>(Os + r0 * LD + 8 * h + 2 * q) = pack_bf16(oh[0] * il0, oh[1] * il0);

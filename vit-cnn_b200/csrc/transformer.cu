@@ -243,14 +243,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
       uint32_t qa[kHeads][2];
 #pragma unroll
       for (int jn = 0; jn < 12; ++jn) {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        const float2 bb = *reinterpret_cast<const float2*>(bqkv + 8 * jn + 2 * q);
+        float c[4] = {bb.x, bb.y, bb.x, bb.y};      // bias = accumulator init
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) {
           const __nv_bfloat16* w = wqkv + (8 * jn + g) * kLdD + 16 * kk + 2 * q;
           mma16816(c, A1[kk], lds32(w), lds32(w + 8));
         }
-        const float2 bb = *reinterpret_cast<const float2*>(bqkv + 8 * jn + 2 * q);
-        c[0] += bb.x; c[1] += bb.y; c[2] += bb.x; c[3] += bb.y;
         if (jn < 4) {
           qa[jn][0] = pack_bf16(c[0] * qscale, c[1] * qscale);
           qa[jn][1] = pack_bf16(c[2] * qscale, c[3] * qscale);
@@ -272,7 +271,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
       uint32_t oa[2][4];  // attention output as the two K=16 A fragments of the proj GEMM
 #pragma unroll
       for (int h = 0; h < kHeads; ++h) {
-        float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+        float m0 = -INFINITY, m1 = -INFINITY;
+        float lacc[4] = {0.f, 0.f, 0.f, 0.f};   // softmax denominators from the tensor core: P x ones
         float oh[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int kb = 0; kb < NKB; ++kb) {
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
           const float mn0 = fmaxf(m0, quad_max(bm0)), mn1 = fmaxf(m1, quad_max(bm1));
           if (kb > 0) {
             const float al0 = ex2(m0 - mn0), al1 = ex2(m1 - mn1);
-            l0 *= al0; l1 *= al1;
+            lacc[0] *= al0; lacc[2] *= al1;
             oh[0] *= al0; oh[1] *= al0; oh[2] *= al1; oh[3] *= al1;
           }
           m0 = mn0; m1 = mn1;
@@ -311,8 +311,6 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
             if (t < ntile) {
               s[t][0] = ex2(s[t][0] - mn0); s[t][1] = ex2(s[t][1] - mn0);
               s[t][2] = ex2(s[t][2] - mn1); s[t][3] = ex2(s[t][3] - mn1);
-              l0 += s[t][0] + s[t][1];
-              l1 += s[t][2] + s[t][3];
             }
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
@@ -324,37 +322,39 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
               Pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
               const __nv_bfloat16* v = Vt + (8 * h + g) * LDV + (8 * kb + 2 * kk) * 8 + 2 * q;
               mma16816(oh, Pa, lds32(v), lds32(v + 8));
+              mma16816(lacc, Pa, 0x3F803F80u, 0x3F803F80u);   // every column = row sum of (bf16) P
             }
         }
-        const float il0 = 1.f / quad_sum(l0), il1 = 1.f / quad_sum(l1);
+        const float il0 = 1.f / lacc[0], il1 = 1.f / lacc[2];
         oa[h >> 1][(h & 1) * 2 + 0] = pack_bf16(oh[0] * il0, oh[1] * il0);
         oa[h >> 1][(h & 1) * 2 + 1] = pack_bf16(oh[2] * il1, oh[3] * il1);
       }
 
       // ---- proj GEMM, bias + residual epilogue ----
 #pragma unroll
-      for (int jn = 0; jn < 4; ++jn) {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int jn = 0; jn < 4; ++jn) {   // the residual stream is the accumulator
+        const float2 bb = *reinterpret_cast<const float2*>(bproj + 8 * jn + 2 * q);
+        x[jn][0] += bb.x; x[jn][1] += bb.y; x[jn][2] += bb.x; x[jn][3] += bb.y;
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) {
           const __nv_bfloat16* w = wproj + (8 * jn + g) * kLdD + 16 * kk + 2 * q;
-          mma16816(c, oa[kk], lds32(w), lds32(w + 8));
+          mma16816(x[jn], oa[kk], lds32(w), lds32(w + 8));
         }
-        const float2 bb = *reinterpret_cast<const float2*>(bproj + 8 * jn + 2 * q);
-        x[jn][0] += c[0] + bb.x; x[jn][1] += c[1] + bb.y; x[jn][2] += c[2] + bb.x; x[jn][3] += c[3] + bb.y;
       }
 
       // ---- LN2 -> fc1 (+bias, GELU) -> fc2 (+bias, +residual), 16 hidden units at a time ----
       uint32_t A2[2][4];
       ln_to_afrag(x, reinterpret_cast<const float*>(smem + O.ln2_g), reinterpret_cast<const float*>(smem + O.ln2_b), q, A2);
-      float acc2[4][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc2[j][e] = 0.f;
+      for (int jn = 0; jn < 4; ++jn) {   // fc2 accumulates straight into the residual stream
+        const float2 bb = *reinterpret_cast<const float2*>(bfc2 + 8 * jn + 2 * q);
+        x[jn][0] += bb.x; x[jn][1] += bb.y; x[jn][2] += bb.x; x[jn][3] += bb.y;
+      }
 #pragma unroll
       for (int hk = 0; hk < kHidden / 16; ++hk) {
-        float h0[4] = {0.f, 0.f, 0.f, 0.f}, h1[4] = {0.f, 0.f, 0.f, 0.f};
+        const float2 b0 = *reinterpret_cast<const float2*>(bfc1 + 16 * hk + 2 * q);
+        const float2 b1 = *reinterpret_cast<const float2*>(bfc1 + 16 * hk + 8 + 2 * q);
+        float h0[4] = {b0.x, b0.y, b0.x, b0.y}, h1[4] = {b1.x, b1.y, b1.x, b1.y};
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) {
           const __nv_bfloat16* w0 = wfc1 + (16 * hk + g) * kLdD + 16 * kk + 2 * q;
@@ -362,24 +362,16 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
           mma16816(h0, A2[kk], lds32(w0), lds32(w0 + 8));
           mma16816(h1, A2[kk], lds32(w1), lds32(w1 + 8));
         }
-        const float2 b0 = *reinterpret_cast<const float2*>(bfc1 + 16 * hk + 2 * q);
-        const float2 b1 = *reinterpret_cast<const float2*>(bfc1 + 16 * hk + 8 + 2 * q);
         uint32_t Ha[4];
-        Ha[0] = pack_bf16(gelu_erf(h0[0] + b0.x), gelu_erf(h0[1] + b0.y));
-        Ha[1] = pack_bf16(gelu_erf(h0[2] + b0.x), gelu_erf(h0[3] + b0.y));
-        Ha[2] = pack_bf16(gelu_erf(h1[0] + b1.x), gelu_erf(h1[1] + b1.y));
-        Ha[3] = pack_bf16(gelu_erf(h1[2] + b1.x), gelu_erf(h1[3] + b1.y));
+        Ha[0] = pack_bf16(gelu_erf(h0[0]), gelu_erf(h0[1]));
+        Ha[1] = pack_bf16(gelu_erf(h0[2]), gelu_erf(h0[3]));
+        Ha[2] = pack_bf16(gelu_erf(h1[0]), gelu_erf(h1[1]));
+        Ha[3] = pack_bf16(gelu_erf(h1[2]), gelu_erf(h1[3]));
 #pragma unroll
         for (int jn = 0; jn < 4; ++jn) {
           const __nv_bfloat16* w = wfc2 + (8 * jn + g) * kLdHid + 16 * hk + 2 * q;
-          mma16816(acc2[jn], Ha, lds32(w), lds32(w + 8));
+          mma16816(x[jn], Ha, lds32(w), lds32(w + 8));
         }
-      }
-#pragma unroll
-      for (int jn = 0; jn < 4; ++jn) {
-        const float2 bb = *reinterpret_cast<const float2*>(bfc2 + 8 * jn + 2 * q);
-        x[jn][0] += acc2[jn][0] + bb.x; x[jn][1] += acc2[jn][1] + bb.y;
-        x[jn][2] += acc2[jn][2] + bb.x; x[jn][3] += acc2[jn][3] + bb.y;
       }
       bar_sync(BAR_MAIN, NMAIN);  // every warp is done with this layer's K / V^T
     }
