@@ -137,7 +137,7 @@ def bench_train(args, rank, world, dev, dist, barrier):
     net = vitcnn_b200.ViTCNN(C1, C2, patch_size=P, num_classes=K, dropout=0.0).to(dev)
     w = torch.ones(K)
     w[0] = 0
-    tr = Trainer(net, lr=1e-3, weights=w)
+    tr = Trainer(net, lr=1e-3, weights=w, use_graph=not args.no_graph)
     per = args.train_batch // world
     p = P // 2
     nbatch = 8
@@ -173,14 +173,18 @@ def bench_train(args, rank, world, dev, dist, barrier):
         return float(ms.item())
 
     steps = max(args.steps, 5) * 4
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 3) + 4):      # includes the eager steps before the graph capture
         step()
     l0 = _lib.lib().vc_launch_count()
     ms = timed(step, steps)
     launches = _lib.lib().vc_launch_count() - l0
+    if tr.use_graph and tr.launches_per_step:      # replays do not pass through the library's counter
+        launches = tr.launches_per_step * steps
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, steps)
+    tr.use_graph = False                          # per-kernel-class events need eager launches
+    step()
     _lib.profile_begin()
     step()
     prof = _lib.profile_end()
@@ -190,7 +194,7 @@ def bench_train(args, rank, world, dev, dist, barrier):
     return {"metric": "train_samples_per_s", "value": args.train_batch * steps / (ms / 1e3), "unit": "samples/s",
             "ms_per_step": ms / steps, "steps": steps, "global_batch": args.train_batch, "per_gpu_batch": per,
             "parallelism": f"dp{world}", "scaling": "strong", "dtype": "bf16", "optimizer": "Adam(lr=1e-3)",
-            "loss": "CrossEntropy(weight)", "gpu_launches": int(launches),
+            "loss": "CrossEntropy(weight)", "gpu_launches": int(launches), "cuda_graph": not args.no_graph,
             "e2e": {"value": args.train_batch * steps / (ms_e2e / 1e3), "unit": "samples/s", "ms_per_step": ms_e2e / steps,
                     "h2d_bytes_per_step": int(per * 8), "d2h_bytes_per_step": 8},
             "roofline": {"bound": "tensor", "achieved": fl / (ms / steps / 1e3) / 1e12, "peak": tf_sust, "unit": "TFLOP/s",
@@ -236,6 +240,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="profiling aid: skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the e2e leg")
     ap.add_argument("--no-train", action="store_true", help="skip the training-throughput leg")
+    ap.add_argument("--no-graph", action="store_true", help="training leg: eager launches instead of one CUDA graph per step")
     ap.add_argument("--no-infer", action="store_true", help="profiling aid: training leg only")
     ap.add_argument("--train-batch", type=int, default=4096, help="GLOBAL batch of the training leg (configs[2])")
     args = ap.parse_args()

@@ -94,6 +94,13 @@ int vc_scene_index(const int32_t* xs, const int32_t* ys, int32_t nx, int32_t ny,
                    int32_t W, int32_t C1, int32_t C2, int32_t P, int64_t* off1, int64_t* off2, int64_t* out_idx,
                    int32_t* xy, void* stream);
 
+/* ---- prediction post-processing: confusion matrix of metrics() (utils.py:585-663) ------------
+ * cm int64 [K][K] (row = target, column = prediction) += counts over the n elements whose target is
+ * not in the ignored set (bit l of ignored_mask = label l ignored, utils.py:595-601) and whose
+ * labels lie in range(K) (sklearn's labels=range(n_classes)).  Element sizes 1 / 4 / 8 bytes. */
+int vc_confusion_matrix(const void* prediction, int32_t pred_elem_bytes, const void* target, int32_t target_elem_bytes, int64_t n,
+                        int32_t n_classes, uint64_t ignored_mask, int64_t* cm, void* stream);
+
 /* ---- building blocks (exposed for tests and profiling) --------------------------------------- */
 /* fp32 patches (any strides, in elements) or raster windows (patch_off != NULL: per-patch
  * element offset, sb ignored) -> bf16 SPS buffer [S][rows][8]. */
@@ -152,6 +159,12 @@ int vc_ce_loss(const float* logits, const int64_t* labels, const float* weight, 
  * grad_scale first (1/world_size after a summing all-reduce). */
 int vc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                  float weight_decay, int32_t step, float grad_scale, void* stream);
+
+/* Same step with the hyper-parameters and the step counter in DEVICE memory, so that a captured
+ * CUDA graph of the training step replays correctly: hyper f32 [8] = lr, beta1, beta2, eps,
+ * weight_decay, then 3 scratch floats; step int32 (incremented by the call). */
+int vc_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float* hyper, int32_t* step, float grad_scale,
+                     void* stream);
 
 /* ---- training: forward (batch statistics) / backward of the whole model -------------------------
  * Replaces net(data, data2) in train mode and loss.backward() (model_utils.py:921-936).

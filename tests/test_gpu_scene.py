@@ -56,3 +56,22 @@ def test_scene_equals_batched_forward_and_row_bands():
         for first, count in row_band_ranges(nx, ny, world):
             ours.predict_scene(t1, t2, chunk=300, window_range=(first, count), logits_map=acc, argmax_map=am)
         assert torch.equal(acc, full) and torch.equal(am, amax)
+
+
+def test_device_metrics_match_reference_formulas():
+    """metrics() (utils.py:585-663) with the confusion matrix counted on the device: integers
+    bit-exact, derived floats equal to the oracle's restatement (pinned to the reference)."""
+    from vitcnn_b200.utils import metrics
+    rng = np.random.default_rng(3)
+    H, W, K = 61, 83, 16
+    gt = rng.integers(0, K, size=(H, W)).astype(np.int64)
+    pred = np.where(rng.random((H, W)) < 0.7, gt, rng.integers(0, K, size=(H, W))).astype(np.int64)
+    for ignored, n_classes in (([0], K), ([0, 3], K), ([], None)):
+        want = R.metrics(pred, gt, ignored_labels=ignored, n_classes=n_classes)
+        got = metrics(torch.from_numpy(pred.astype(np.uint8)).to(DEV), torch.from_numpy(gt).to(DEV),
+                      ignored_labels=ignored, n_classes=n_classes)
+        assert np.array_equal(got["Confusion matrix"], want["Confusion matrix"])
+        for k in ("Accuracy", "AA", "Kappa"):
+            assert got[k] == want[k], k
+        for k in ("F1 scores", "Precisions"):
+            assert np.array_equal(got[k], want[k], equal_nan=True), k

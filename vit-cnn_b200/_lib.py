@@ -13,7 +13,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_uint8, c_void
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libvitcnn.so")
-SOURCES = ["abi.cu", "conv_tc.cu", "pack.cu", "transformer.cu", "lidar_stem.cu", "wgrad_tc.cu", "train.cu", "tokens_bwd.cu"]
+SOURCES = ["abi.cu", "conv_tc.cu", "pack.cu", "transformer.cu", "lidar_stem.cu", "metrics.cu", "wgrad_tc.cu", "train.cu", "tokens_bwd.cu"]
 HEADERS = ["vc_common.cuh", "vc_kernels.h", "vc_tparams.h", os.path.join("..", "..", "include", "vitcnn.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -81,6 +81,8 @@ _PROTOS = {
                                         c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vc_scene_index": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                  c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vc_confusion_matrix": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_int32, ctypes.c_uint64, c_void_p,
+                                      c_void_p]),
     "vc_pack_sps": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int32, c_int32, c_int32,
                               c_void_p, c_int32, c_void_p]),
     "vc_conv_sps": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
@@ -103,6 +105,7 @@ _PROTOS = {
                              c_void_p]),
     "vc_adam_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
                                c_float, c_int32, c_float, c_void_p]),
+    "vc_adam_step_dev": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_float, c_void_p]),
     "vc_train_workspace_bytes": (c_int64, [POINTER(VcTrain), c_int32]),
     "vc_train_workspace_init": (c_int32, [POINTER(VcTrain), c_int32, c_void_p, c_int64, c_void_p]),
     "vc_train_forward": (c_int32, [POINTER(VcTrain), c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64), c_int32,

@@ -219,6 +219,13 @@ int vc_scene_index(const int32_t* xs, const int32_t* ys, int32_t nx, int32_t ny,
   return VC_OK;
 }
 
+int vc_confusion_matrix(const void* prediction, int32_t pred_elem_bytes, const void* target, int32_t target_elem_bytes, int64_t n,
+                        int32_t n_classes, uint64_t ignored_mask, int64_t* cm, void* stream) {
+  VC_LAUNCH(KC_MISC, (cudaStream_t)stream, vc::confusion_launch(prediction, pred_elem_bytes, target, target_elem_bytes, n, n_classes,
+                                                               ignored_mask, (long long*)cm, (cudaStream_t)stream));
+  return VC_OK;
+}
+
 int vc_pack_sps(const float* src, int64_t sb, int64_t sc, int64_t si, int64_t sj, const int64_t* patch_off,
                 int32_t n_patches, int32_t C, int32_t P, void* sps, int32_t S, void* stream) {
   VC_TRY(vc::pack_sps_launch(src, sb, sc, si, sj, (const long long*)patch_off, n_patches, C, P, sps, S,
@@ -573,6 +580,12 @@ int vc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float 
                  float weight_decay, int32_t step, float grad_scale, void* stream) {
   VC_LAUNCH(KC_MISC, (cudaStream_t)stream,
             vc::adam_launch(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, (cudaStream_t)stream));
+  return VC_OK;
+}
+
+int vc_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float* hyper, int32_t* step, float grad_scale,
+                     void* stream) {
+  VC_LAUNCH(KC_MISC, (cudaStream_t)stream, vc::adam_dev_launch(p, g, m, v, n, hyper, step, grad_scale, (cudaStream_t)stream));
   return VC_OK;
 }
 

@@ -330,6 +330,36 @@ int adam_launch(float* p, const float* g, float* m, float* v, long long n, float
   return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
 }
 
+// Graph-safe variant: hyper-parameters and the step counter live in device memory so that a
+// captured CUDA graph replays correctly.  hyper: [lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, -]
+__global__ void adam_prep_kernel(float* hyper, int* step) {
+  const int t = *step + 1;
+  *step = t;
+  hyper[5] = 1.f - powf(hyper[1], (float)t);
+  hyper[6] = sqrtf(1.f - powf(hyper[2], (float)t));
+}
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                long long n, const float* __restrict__ hyper, float grad_scale) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], bc1 = hyper[5], bc2s = hyper[6];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] * grad_scale;
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi - (lr / bc1) * (mi / (sqrtf(vi) / bc2s + eps));
+  }
+}
+int adam_dev_launch(float* p, const float* g, float* m, float* v, long long n, float* hyper, int* step, float grad_scale,
+                    cudaStream_t st) {
+  if (n <= 0 || !hyper || !step) return VC_ERR_ARG;
+  adam_prep_kernel<<<1, 1, 0, st>>>(hyper, step);
+  adam_dev_kernel<<<flat_grid(n), 256, 0, st>>>(p, g, m, v, n, hyper, grad_scale);
+  return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
+}
+
 // ---- weight packing ------------------------------------------------------------------------------
 // torch conv weight fp32 [cout][cin][taps] -> bf16 [nsplit][taps][S_in][ncta][8] of conv_sps_tc.
 // transpose = 0: the forward operand (in = cin, out = cout).

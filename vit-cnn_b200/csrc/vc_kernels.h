@@ -31,6 +31,10 @@ size_t lidar_blob_bytes();
 int lidar_stem_launch(const void* in_sps, const void* blob, void* out_sps, int out_slice_off, int n_patches, int P,
                       cudaStream_t stream);
 
+// metrics.cu
+int confusion_launch(const void* pred, int peb, const void* target, int teb, long long n, int K, unsigned long long ignored_mask,
+                     long long* cm, cudaStream_t stream);
+
 // transformer.cu
 size_t tparams_bytes(int P, int K);
 int transformer_fwd_launch(const void* f_sps, const void* tparams, int n_patches, int P, int K, float* logits,
@@ -54,6 +58,8 @@ int ce_loss_launch(const float* logits, const long long* labels, const float* we
                    float* loss_out, float* dlogits, double* acc, cudaStream_t st);
 int adam_launch(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                 float wd, int step, float grad_scale, cudaStream_t st);
+int adam_dev_launch(float* p, const float* g, float* m, float* v, long long n, float* hyper, int* step, float grad_scale,
+                    cudaStream_t st);
 int pack_conv_w_launch(const float* w, int cout, int cin, int taps, int transpose, int S_in, int n_out, int nsplit,
                        void* dst, cudaStream_t st);
 int pack_segments_launch(const float* flat, void* blob, const long long* segs, int nsegs, cudaStream_t st);

@@ -288,20 +288,39 @@ def adam_step(p, g, m, v, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_de
 class Trainer:
     """Data-parallel training step on device-resident rasters: gather -> forward -> weighted CE ->
     backward -> all-reduce(sum) of the flat gradient bucket over NCCL -> Adam(grad / world).
-    One process per GPU; replicas start identical (same seed / broadcast state_dict)."""
+    One process per GPU; replicas start identical (same seed / broadcast state_dict).
 
-    def __init__(self, model, lr=1e-3, weights=None, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None):
+    ``use_graph=True`` captures the whole step (every kernel of this library, the collective and
+    the optimiser) in one CUDA graph after ``graph_warmup`` eager steps: the step is ~65 short
+    launches, so at small per-GPU batches the CPU launch rate, not the GPU, sets the pace."""
+
+    def __init__(self, model, lr=1e-3, weights=None, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None,
+                 use_graph=False, graph_warmup=3):
         import torch.distributed as dist
         self.model = model.train()
         self.state = train_state(model)
-        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
-        self.weights = None if weights is None else weights.to(self.state.device, torch.float32).contiguous()
+        dev = self.state.device
+        self.weights = None if weights is None else weights.to(dev, torch.float32).contiguous()
         self.m = torch.zeros_like(self.state.flat)
         self.v = torch.zeros_like(self.state.flat)
-        self.t = 0
+        self.hyper = torch.tensor([lr, betas[0], betas[1], eps, weight_decay, 0.0, 0.0, 0.0], dtype=torch.float32, device=dev)
+        self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.lr = lr
         self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
         self.group = process_group
         self.world = self.dist.get_world_size(process_group) if self.dist else 1
+        self.use_graph, self.graph_warmup = use_graph, graph_warmup
+        self._graphs = {}       # batch size -> (graph, static xy, static loss)
+        self.launches_per_step = 0
+        self._eager_steps = 0
+
+    @property
+    def t(self) -> int:
+        return int(self.step_count.item())
+
+    def set_lr(self, lr: float) -> None:
+        self.lr = float(lr)
+        self.hyper[0:1].fill_(self.lr)
 
     def step_lr(self, epoch: int, step_size: int = 30, gamma: float = 0.9, base_lr: float = None) -> float:
         """StepLR(step_size, gamma) as the reference schedules Adam (model_utils.py:498): call once
@@ -309,8 +328,22 @@ class Trainer:
         if base_lr is None:
             base_lr = getattr(self, "_base_lr", self.lr)
         self._base_lr = base_lr
-        self.lr = base_lr * gamma ** (epoch // step_size)
+        self.set_lr(base_lr * gamma ** (epoch // step_size))
         return self.lr
+
+    def _step_impl(self, img1, img2, gt, xy):
+        st = self.state
+        logits, labels = st.forward_gather(img1, img2, gt, xy)
+        loss, dlogits = ce_loss(logits, labels, self.weights)
+        st.backward(dlogits)
+        if self.world > 1:
+            self.dist.all_reduce(st.grads, op=self.dist.ReduceOp.SUM, group=self.group)
+        with torch.cuda.device(st.device):
+            _lib.check(_lib.lib().vc_adam_step_dev(st.flat.data_ptr(), st.grads.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                                   st.flat.numel(), self.hyper.data_ptr(), self.step_count.data_ptr(),
+                                                   1.0 / self.world, torch.cuda.current_stream().cuda_stream),
+                       "vc_adam_step_dev")
+        return loss
 
     def step(self, img1, img2, gt, xy):
         """One optimisation step on patches centred at xy (int32 [n,2], device).  Returns the
@@ -318,15 +351,29 @@ class Trainer:
         st = self.state
         if not st.valid():
             raise RuntimeError("model parameters were moved after the Trainer was built")
-        logits, labels = st.forward_gather(img1, img2, gt, xy)
-        loss, dlogits = ce_loss(logits, labels, self.weights)
-        st.backward(dlogits)
-        if self.world > 1:
-            self.dist.all_reduce(st.grads, op=self.dist.ReduceOp.SUM, group=self.group)
-        self.t += 1
-        adam_step(st.flat, st.grads, self.m, self.v, self.t, self.lr, self.betas, self.eps, self.wd, 1.0 / self.world)
         self.model._pack = None
-        return loss
+        n = xy.shape[0]
+        if not self.use_graph:
+            return self._step_impl(img1, img2, gt, xy)
+        entry = self._graphs.get(n)
+        if entry is not None and entry[3] == (img1.data_ptr(), img2.data_ptr(), gt.data_ptr()):
+            graph, xy_s, loss_s, _ = entry
+            xy_s.copy_(xy, non_blocking=True)
+            graph.replay()
+            return loss_s
+        if self._eager_steps < self.graph_warmup:
+            self._eager_steps += 1
+            return self._step_impl(img1, img2, gt, xy)
+        xy_s = xy.clone()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        l0 = _lib.lib().vc_launch_count()
+        with torch.cuda.graph(graph):
+            loss_s = self._step_impl(img1, img2, gt, xy_s)
+        self.launches_per_step = int(_lib.lib().vc_launch_count() - l0)   # kernels of this library in one replay
+        self._graphs[n] = (graph, xy_s, loss_s, (img1.data_ptr(), img2.data_ptr(), gt.data_ptr()))
+        graph.replay()      # capturing records the step without running it
+        return loss_s
 
 
 def train(net, optimizer, criterion, data_loader, epoch, scheduler=None, display_iter=100, device=torch.device("cpu"),

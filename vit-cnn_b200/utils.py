@@ -90,3 +90,52 @@ def seed_torch(seed: int = 1029) -> None:
         torch.cuda.manual_seed_all(seed)
     torch.backends.cudnn.benchmark = False
     torch.backends.cudnn.deterministic = True
+
+
+def confusion_matrix(prediction, target, n_classes: int, ignored_labels=()):
+    """K x K confusion matrix (rows = target) on the device: what metrics() feeds to sklearn
+    (utils.py:595-611).  prediction / target: CUDA integer tensors of equal numel."""
+    import torch
+    from . import _lib
+    if not (prediction.is_cuda and target.is_cuda):
+        raise RuntimeError("confusion_matrix needs CUDA tensors (no CPU path)")
+    prediction, target = prediction.contiguous(), target.contiguous()
+    if prediction.numel() != target.numel():
+        raise ValueError("prediction and target differ in size")
+    mask = 0
+    for l in ignored_labels:
+        if 0 <= int(l) < 64:
+            mask |= 1 << int(l)
+    cm = torch.zeros(n_classes, n_classes, dtype=torch.int64, device=target.device)
+    with torch.cuda.device(target.device):
+        _lib.check(_lib.lib().vc_confusion_matrix(prediction.data_ptr(), prediction.element_size(), target.data_ptr(),
+                                                  target.element_size(), target.numel(), n_classes, mask, cm.data_ptr(),
+                                                  torch.cuda.current_stream().cuda_stream), "vc_confusion_matrix")
+    return cm
+
+
+def metrics(prediction, target, ignored_labels=[], n_classes=None):
+    """utils.py:585-663 with the same keys and formulas; the confusion matrix is counted on the
+    device (CUDA tensors in), the K x K arithmetic stays on the host in float64 like the
+    reference's.  Returns the reference's dict: "Confusion matrix", "Accuracy", "F1 scores",
+    "Precisions", "AA", "Kappa"."""
+    import torch
+    if n_classes is None:
+        keep = torch.ones_like(target, dtype=torch.bool)
+        for l in ignored_labels:
+            keep &= target != l
+        n_classes = int(target[keep].max().item()) + 1
+    cm = confusion_matrix(prediction, target, n_classes, ignored_labels).cpu().numpy()
+    results = {"Confusion matrix": cm}
+    total = np.sum(cm)
+    results["Accuracy"] = sum(cm[x][x] for x in range(len(cm))) * (100 / float(total))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rs, cs, dg = cm.sum(1), cm.sum(0), np.diag(cm)
+        results["F1 scores"] = 2.0 * dg / (rs + cs)
+        results["Precisions"] = 1.0 * dg / rs
+        rec = dg / rs
+        results["AA"] = np.mean(rec[~np.isnan(rec)])
+        pa = np.trace(cm) / float(total)
+        pe = np.sum(cs * rs) / float(total * total)
+        results["Kappa"] = (pa - pe) / (1 - pe)
+    return results
