@@ -192,7 +192,8 @@ def _autocast_grads(ref, hsi, lid, y, w):
     return floor
 
 
-@pytest.mark.parametrize("cfg", [(16, 1, 5, 4, 6), (64, 2, 7, 12, 9), (144, 1, 11, 16, 8)])
+@pytest.mark.parametrize("cfg", [(16, 1, 5, 4, 6), (64, 2, 7, 12, 9), (144, 1, 11, 16, 8), (180, 1, 11, 8, 5),
+                                 (24, 1, 9, 6, 7), (16, 1, 13, 4, 4), (20, 2, 15, 5, 3)])
 def test_model_gradients_vs_oracle_autograd(cfg):
     C1, C2, P, K, B = cfg
     ref, ours = _pair(C1, C2, P, K)
@@ -212,7 +213,7 @@ def test_model_gradients_vs_oracle_autograd(cfg):
     floor = _autocast_grads(ref, hsi, lid, y, w)
     rows = [r for r in rows if not r[0].endswith("conv.bias") and r[3] > 1e-7]
     bad = [(k, round(e, 4), round(c, 5), floor[k]) for k, e, c, s in rows
-           if e > max(GRAD_TOL, 3.0 * floor[k][0]) or c < min(0.98, floor[k][1] - 0.02)]
+           if e > max(GRAD_TOL, 4.0 * floor[k][0]) or c < min(0.98, floor[k][1] - 0.02)]
     assert not bad, bad
     # no systematic excess over the bf16 floor, and the whole gradient points the same way
     ratios = sorted(e / max(floor[k][0], 1e-3) for k, e, c, s in rows)

@@ -437,7 +437,7 @@ __global__ void fill_f32_kernel(float* p, int n, float v) {
 }
 
 int check_train(const vc_train* t, ConvPlan pl[7]) {
-  if (!t || !t->params || !t->grads || t->P < 1 || t->P > 11 || t->K < 1 || t->K > 64 || t->C1 < 1 || t->C2 < 1 ||
+  if (!t || !t->params || !t->grads || t->P < 1 || (t->P > 11 && t->P != 13 && t->P != 15) || t->K < 1 || t->K > 64 || t->C1 < 1 || t->C2 < 1 ||
       !t->blob_segments || t->n_blob_segments <= 0)
     return VC_ERR_ARG;
   return make_plans(t, pl) ? VC_OK : VC_ERR_UNSUPPORTED;

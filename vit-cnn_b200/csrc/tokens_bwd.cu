@@ -56,6 +56,9 @@ __device__ __forceinline__ void acc2_to_afrag(const float (&t0)[4], const float 
 __device__ __forceinline__ void dump2(__nv_bfloat16* buf, long long rows, long long row, int c, uint32_t v) {
   *reinterpret_cast<uint32_t*>(buf + ((long long)(c >> 3) * rows + row) * 8 + (c & 7)) = v;
 }
+__device__ __forceinline__ uint32_t load2(const __nv_bfloat16* buf, long long rows, long long row, int c) {
+  return *reinterpret_cast<const volatile uint32_t*>(buf + ((long long)(c >> 3) * rows + row) * 8 + (c & 7));
+}
 // dump the K=32 A fragments of this thread (rows r0 / r1 of the patch)
 __device__ __forceinline__ void dump_afrag32(__nv_bfloat16* buf, long long rows, long long row0, int q,
                                              const uint32_t (&A)[2][4]) {
@@ -157,16 +160,18 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
   constexpr int NT = 2 * NW;               // 8-wide key / query tiles
   const TLayout& L = a.L;
   const int PB = L.pos;                    // parameter bytes kept in shared memory (pos stays in L2)
+  // five [TP][40] bf16 arrays; the block-1 arrays reuse the block-0 ones (Q/K/V of block 0 are
+  // recomputed at the start of its backward: 24 MMAs per warp for 3 arrays less shared memory)
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem + PB);
   __nv_bfloat16* Ks = Qs + TP * LD;
   __nv_bfloat16* Vs = Ks + TP * LD;
   __nv_bfloat16* Os = Vs + TP * LD;
-  __nv_bfloat16* K1s = Os + TP * LD;
-  __nv_bfloat16* V1s = K1s + TP * LD;
-  __nv_bfloat16* dK1s = V1s + TP * LD;     // also dO of block 0 (dead before it is needed)
-  __nv_bfloat16* dV1s = dK1s + TP * LD;
-  __nv_bfloat16* dOs = dK1s;
-  float* st_m = reinterpret_cast<float*>(dV1s + TP * LD);   // [4][TP]
+  __nv_bfloat16* dOs = Os + TP * LD;
+  __nv_bfloat16* K1s = Qs;
+  __nv_bfloat16* V1s = Ks;
+  __nv_bfloat16* dK1s = Vs;
+  __nv_bfloat16* dV1s = dOs;
+  float* st_m = reinterpret_cast<float*>(dOs + TP * LD);   // [4][TP]
   float* st_il = st_m + kHeads * TP;
   float* st_dl = st_il + kHeads * TP;
   ClsScratch* cs = reinterpret_cast<ClsScratch*>(st_dl + kHeads * TP);
@@ -228,16 +233,12 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
     };
     float x[4][4];
     load_x0(x);
-
-    // =============================== F1: block 0 forward (with saves) ===========================
-    {
+    // LN1 -> qkv of block 0: Q (scaled, log2 domain), K, V of this warp's rows into shared memory
+    auto qkv0 = [&](const float (&xin)[4][4], bool dump) {
       const __nv_bfloat16* wqkv = reinterpret_cast<const __nv_bfloat16*>(smem + O0.wqkv);
-      const __nv_bfloat16* wproj = reinterpret_cast<const __nv_bfloat16*>(smem + O0.wproj);
-      const __nv_bfloat16* wfc1 = reinterpret_cast<const __nv_bfloat16*>(smem + O0.wfc1);
-      const __nv_bfloat16* wfc2 = reinterpret_cast<const __nv_bfloat16*>(smem + O0.wfc2);
       uint32_t A1[2][4];
-      ln_to_afrag(x, f32 + O0.ln1_g / 4, f32 + O0.ln1_b / 4, q, A1);
-      dump_afrag32(a.xln1[0], a.RTt, trow, q, A1);
+      ln_to_afrag(xin, f32 + O0.ln1_g / 4, f32 + O0.ln1_b / 4, q, A1);
+      if (dump) dump_afrag32(a.xln1[0], a.RTt, trow, q, A1);
 #pragma unroll
       for (int jn = 0; jn < 12; ++jn) {
         float c[4] = {0.f, 0.f, 0.f, 0.f};
@@ -258,6 +259,15 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
           *reinterpret_cast<uint32_t*>(dst + r1 * LD + col) = pack_bf16(c[2], c[3]);
         }
       }
+    };
+
+    // =============================== F1: block 0 forward (with saves) ===========================
+    {
+      const __nv_bfloat16* wqkv = reinterpret_cast<const __nv_bfloat16*>(smem + O0.wqkv);
+      const __nv_bfloat16* wproj = reinterpret_cast<const __nv_bfloat16*>(smem + O0.wproj);
+      const __nv_bfloat16* wfc1 = reinterpret_cast<const __nv_bfloat16*>(smem + O0.wfc1);
+      const __nv_bfloat16* wfc2 = reinterpret_cast<const __nv_bfloat16*>(smem + O0.wfc2);
+      qkv0(x, true);
       __syncthreads();
       // attention forward: all keys at once per head (scores in registers), stats saved
       uint32_t oa[2][4];
@@ -365,6 +375,7 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
     // x = x1: output of block 0 (rows >= T hold finite garbage; they never reach a valid row)
 
     // =============================== F2: block 1, K / V for every token =========================
+    __syncthreads();   // K1s / V1s alias Qs / Ks: every warp must be done with block 0's attention
     {
       const __nv_bfloat16* wqkv = reinterpret_cast<const __nv_bfloat16*>(smem + O1.wqkv);
       uint32_t A1[2][4];
@@ -655,8 +666,9 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
       const __nv_bfloat16* wproj = reinterpret_cast<const __nv_bfloat16*>(smem + O0.wproj);
       const __nv_bfloat16* wfc1 = reinterpret_cast<const __nv_bfloat16*>(smem + O0.wfc1);
       const __nv_bfloat16* wfc2 = reinterpret_cast<const __nv_bfloat16*>(smem + O0.wfc2);
-      // recompute x_mid = x0 + proj(O) + b
+      // recompute Q / K / V of block 0 (their arrays were reused by block 1) and x_mid = x0 + proj(O) + b
       load_x0(x);
+      qkv0(x, false);
       uint32_t oa[2][4];
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
@@ -754,8 +766,7 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
         if (q == 0) { st_dl[h * TP + r0] = dl0; st_dl[h * TP + r1] = dl1; }
       }
       __syncthreads();
-      // per head: dQ / dK / dV tiles of this warp's rows, staged (bf16) in the dead block-1 arrays
-      // K1s (dq), V1s (dk), dV1s (dv) so that nothing is indexed dynamically in registers
+      // per head: dQ / dK / dV tiles of this warp's rows (nothing indexed dynamically in registers)
 #pragma unroll 1
       for (int h = 0; h < kHeads; ++h) {
         float dq[4] = {0.f, 0.f, 0.f, 0.f}, dk[4] = {0.f, 0.f, 0.f, 0.f}, dv[4] = {0.f, 0.f, 0.f, 0.f};
@@ -821,24 +832,22 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
         }
         // scale: dq = scale * dS K ; dk = dS^T qhat / log2(e)
         const int col = 8 * h + 2 * q;
-        *reinterpret_cast<uint32_t*>(K1s + r0 * LD + col) = pack_bf16(dq[0] * kScale, dq[1] * kScale);
-        *reinterpret_cast<uint32_t*>(K1s + r1 * LD + col) = pack_bf16(dq[2] * kScale, dq[3] * kScale);
-        *reinterpret_cast<uint32_t*>(V1s + r0 * LD + col) = pack_bf16(dk[0] * kLn2, dk[1] * kLn2);
-        *reinterpret_cast<uint32_t*>(V1s + r1 * LD + col) = pack_bf16(dk[2] * kLn2, dk[3] * kLn2);
-        *reinterpret_cast<uint32_t*>(dV1s + r0 * LD + col) = pack_bf16(dv[0], dv[1]);
-        *reinterpret_cast<uint32_t*>(dV1s + r1 * LD + col) = pack_bf16(dv[2], dv[3]);
+        // straight into the operand dump of the qkv weight gradient; each thread re-reads its own
+        // writes below (same-thread global RAW), so no staging array is needed
+        dump2(a.dqkv[0], a.RTt, trow, col, pack_bf16(dq[0] * kScale, dq[1] * kScale));
+        dump2(a.dqkv[0], a.RTt, trow + 8, col, pack_bf16(dq[2] * kScale, dq[3] * kScale));
+        dump2(a.dqkv[0], a.RTt, trow, 32 + col, pack_bf16(dk[0] * kLn2, dk[1] * kLn2));
+        dump2(a.dqkv[0], a.RTt, trow + 8, 32 + col, pack_bf16(dk[2] * kLn2, dk[3] * kLn2));
+        dump2(a.dqkv[0], a.RTt, trow, 64 + col, pack_bf16(dv[0], dv[1]));
+        dump2(a.dqkv[0], a.RTt, trow + 8, 64 + col, pack_bf16(dv[2], dv[3]));
       }
-      __syncwarp();
       uint32_t Aq[6][4];
 #pragma unroll
       for (int kk = 0; kk < 6; ++kk) {
-        const __nv_bfloat16* src = (kk < 2 ? K1s : kk < 4 ? V1s : dV1s) + 16 * (kk & 1) + 2 * q;
-        Aq[kk][0] = lds32(src + r0 * LD); Aq[kk][1] = lds32(src + r1 * LD);
-        Aq[kk][2] = lds32(src + r0 * LD + 8); Aq[kk][3] = lds32(src + r1 * LD + 8);
-        dump2(a.dqkv[0], a.RTt, trow, 16 * kk + 2 * q, Aq[kk][0]);
-        dump2(a.dqkv[0], a.RTt, trow + 8, 16 * kk + 2 * q, Aq[kk][1]);
-        dump2(a.dqkv[0], a.RTt, trow, 16 * kk + 8 + 2 * q, Aq[kk][2]);
-        dump2(a.dqkv[0], a.RTt, trow + 8, 16 * kk + 8 + 2 * q, Aq[kk][3]);
+        Aq[kk][0] = load2(a.dqkv[0], a.RTt, trow, 16 * kk + 2 * q);
+        Aq[kk][1] = load2(a.dqkv[0], a.RTt, trow + 8, 16 * kk + 2 * q);
+        Aq[kk][2] = load2(a.dqkv[0], a.RTt, trow, 16 * kk + 8 + 2 * q);
+        Aq[kk][3] = load2(a.dqkv[0], a.RTt, trow + 8, 16 * kk + 8 + 2 * q);
       }
       float dy[4][4];
       gemm_dgrad32<6>(Aq, wqkv, LD, lane, dy);
@@ -887,7 +896,7 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
 template <int NW>
 static int launch_bwd(const TBArgs& a, cudaStream_t stream) {
   constexpr int TP = 16 * NW;
-  const size_t smem = (size_t)a.L.pos + 8 * (size_t)TP * kLdD * 2 + 3 * (size_t)kHeads * TP * 4 + sizeof(ClsScratch) + 16;
+  const size_t smem = (size_t)a.L.pos + 5 * (size_t)TP * kLdD * 2 + 3 * (size_t)kHeads * TP * 4 + sizeof(ClsScratch) + 16;
   int dev = 0, max_smem = 0, num_sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -932,8 +941,9 @@ int transformer_bwd_launch(const void* zf, const void* tparams, const float* dlo
   switch (NW) {
 #define VC_CASE(N) case N: return launch_bwd<N>(a, stream);
     VC_CASE(1) VC_CASE(2) VC_CASE(3) VC_CASE(4) VC_CASE(5) VC_CASE(6) VC_CASE(7) VC_CASE(8)
+    VC_CASE(11) VC_CASE(15)   // P = 13, 15 (odd patch sizes: the centre pixel is classified)
 #undef VC_CASE
-    default: return VC_ERR_UNSUPPORTED;   // P > 11: the per-patch working set no longer fits (round-2 item)
+    default: return VC_ERR_UNSUPPORTED;   // even P > 11
   }
 }
 

@@ -169,7 +169,7 @@ class TrainState:
             need = L.vc_train_workspace_bytes(ctypes.byref(self.struct), n)
             if need <= 0:
                 raise RuntimeError("this configuration is not supported by the training kernels "
-                                   "(patch_size <= 11, n_classes <= 64)")
+                                   "(patch_size <= 11 or 13 / 15, n_classes <= 64)")
             if len(self.ws) >= 4:
                 self.ws.pop(next(iter(self.ws)))
             ws = torch.empty(need, dtype=torch.uint8, device=self.device)
