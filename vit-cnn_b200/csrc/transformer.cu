@@ -245,11 +245,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
       for (int jn = 0; jn < 12; ++jn) {
         const float2 bb = *reinterpret_cast<const float2*>(bqkv + 8 * jn + 2 * q);
         float c[4] = {bb.x, bb.y, bb.x, bb.y};      // bias = accumulator init
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-          const __nv_bfloat16* w = wqkv + (8 * jn + g) * kLdD + 16 * kk + 2 * q;
-          mma16816(c, A1[kk], lds32(w), lds32(w + 8));
-        }
+        uint32_t B[4];   // B fragments of both K=16 steps in one ldmatrix
+        ldsm4(B, wqkv + (8 * jn + (lane & 7)) * kLdD + 8 * (lane >> 3));
+        mma16816(c, A1[0], B[0], B[1]);
+        mma16816(c, A1[1], B[2], B[3]);
         if (jn < 4) {
           qa[jn][0] = pack_bf16(c[0] * qscale, c[1] * qscale);
           qa[jn][1] = pack_bf16(c[2] * qscale, c[3] * qscale);
@@ -279,12 +278,16 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
           constexpr int kFull = 8;
           const int ntile = (2 * NW - 8 * kb) < kFull ? (2 * NW - 8 * kb) : kFull;
           float s[8][4];
+          uint32_t kfr[4];
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
             if (t < ntile) {
               s[t][0] = s[t][1] = s[t][2] = s[t][3] = 0.f;
               const int key0 = (8 * kb + t) * 8;
-              mma1688(s[t], qa[h][0], qa[h][1], lds32(Ks + (key0 + g) * kLdD + 8 * h + 2 * q));
+              if ((t & 3) == 0 && t + 3 < ntile)     // K fragments of four key tiles in one ldmatrix
+                ldsm4(kfr, Ks + (key0 + 8 * (lane >> 3) + (lane & 7)) * kLdD + 8 * h);
+              const uint32_t kb0 = ((t & ~3) + 3 < ntile) ? kfr[t & 3] : lds32(Ks + (key0 + g) * kLdD + 8 * h + 2 * q);
+              mma1688(s[t], qa[h][0], qa[h][1], kb0);
               if (8 * kb + t >= 2 * NW - 2) {   // only the last 16 keys can be padding (T > 16(NW-1))
                 const int kc = key0 + 2 * q;
                 if (kc >= T) { s[t][0] = -INFINITY; s[t][2] = -INFINITY; }
@@ -312,6 +315,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
               s[t][0] = ex2(s[t][0] - mn0); s[t][1] = ex2(s[t][1] - mn0);
               s[t][2] = ex2(s[t][2] - mn1); s[t][3] = ex2(s[t][3] - mn1);
             }
+          uint32_t vfr[4];
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             if (2 * kk < ntile) {
@@ -320,8 +324,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
               Pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
               Pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
               Pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+              if ((kk & 1) == 0 && 2 * kk + 2 < ntile)
+                ldsm4(vfr, Vt + (8 * h + (lane & 7)) * LDV + (8 * kb + 2 * kk) * 8 + 8 * (lane >> 3));
               const __nv_bfloat16* v = Vt + (8 * h + g) * LDV + (8 * kb + 2 * kk) * 8 + 2 * q;
-              mma16816(oh, Pa, lds32(v), lds32(v + 8));
+              const bool pair = 2 * (kk & ~1) + 2 < ntile;
+              const uint32_t vb0 = pair ? vfr[2 * (kk & 1)] : lds32(v), vb1 = pair ? vfr[2 * (kk & 1) + 1] : lds32(v + 8);
+              mma16816(oh, Pa, vb0, vb1);
               mma16816(lacc, Pa, 0x3F803F80u, 0x3F803F80u);   // every column = row sum of (bf16) P
             }
         }
@@ -335,11 +343,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
       for (int jn = 0; jn < 4; ++jn) {   // the residual stream is the accumulator
         const float2 bb = *reinterpret_cast<const float2*>(bproj + 8 * jn + 2 * q);
         x[jn][0] += bb.x; x[jn][1] += bb.y; x[jn][2] += bb.x; x[jn][3] += bb.y;
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-          const __nv_bfloat16* w = wproj + (8 * jn + g) * kLdD + 16 * kk + 2 * q;
-          mma16816(x[jn], oa[kk], lds32(w), lds32(w + 8));
-        }
+        uint32_t B[4];
+        ldsm4(B, wproj + (8 * jn + (lane & 7)) * kLdD + 8 * (lane >> 3));
+        mma16816(x[jn], oa[0], B[0], B[1]);
+        mma16816(x[jn], oa[1], B[2], B[3]);
       }
 
       // ---- LN2 -> fc1 (+bias, GELU) -> fc2 (+bias, +residual), 16 hidden units at a time ----
@@ -355,12 +362,14 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
         const float2 b0 = *reinterpret_cast<const float2*>(bfc1 + 16 * hk + 2 * q);
         const float2 b1 = *reinterpret_cast<const float2*>(bfc1 + 16 * hk + 8 + 2 * q);
         float h0[4] = {b0.x, b0.y, b0.x, b0.y}, h1[4] = {b1.x, b1.y, b1.x, b1.y};
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-          const __nv_bfloat16* w0 = wfc1 + (16 * hk + g) * kLdD + 16 * kk + 2 * q;
-          const __nv_bfloat16* w1 = w0 + 8 * kLdD;
-          mma16816(h0, A2[kk], lds32(w0), lds32(w0 + 8));
-          mma16816(h1, A2[kk], lds32(w1), lds32(w1 + 8));
+        {
+          uint32_t B0[4], B1[4];
+          ldsm4(B0, wfc1 + (16 * hk + (lane & 7)) * kLdD + 8 * (lane >> 3));
+          ldsm4(B1, wfc1 + (16 * hk + 8 + (lane & 7)) * kLdD + 8 * (lane >> 3));
+          mma16816(h0, A2[0], B0[0], B0[1]);
+          mma16816(h0, A2[1], B0[2], B0[3]);
+          mma16816(h1, A2[0], B1[0], B1[1]);
+          mma16816(h1, A2[1], B1[2], B1[3]);
         }
         uint32_t Ha[4];
         Ha[0] = pack_bf16(gelu_erf(h0[0]), gelu_erf(h0[1]));
@@ -368,9 +377,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
         Ha[2] = pack_bf16(gelu_erf(h1[0]), gelu_erf(h1[1]));
         Ha[3] = pack_bf16(gelu_erf(h1[2]), gelu_erf(h1[3]));
 #pragma unroll
-        for (int jn = 0; jn < 4; ++jn) {
-          const __nv_bfloat16* w = wfc2 + (8 * jn + g) * kLdHid + 16 * hk + 2 * q;
-          mma16816(x[jn], Ha, lds32(w), lds32(w + 8));
+        for (int jn = 0; jn < 4; jn += 2) {   // one ldmatrix = B fragments of two output tiles
+          uint32_t B[4];
+          ldsm4(B, wfc2 + (8 * (jn + (lane >> 4)) + (lane & 7)) * kLdHid + 16 * hk + 8 * ((lane >> 3) & 1));
+          mma16816(x[jn], Ha, B[0], B[1]);
+          mma16816(x[jn + 1], Ha, B[2], B[3]);
         }
       }
       bar_sync(BAR_MAIN, NMAIN);  // every warp is done with this layer's K / V^T
