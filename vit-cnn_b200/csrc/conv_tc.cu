@@ -10,6 +10,7 @@
 // per 8-channel slice, so one resident stage [2 slices][128+2*halo rows][16 B] serves all
 // nine taps by moving the descriptor start address.  Weights stay resident in shared memory
 // for the life of the (persistent) CTA.
+#include <stdlib.h>
 #include "vc_common.cuh"
 #include "vc_kernels.h"
 
@@ -224,6 +225,214 @@ __global__ void __launch_bounds__(kConvThreads) conv_sps_tc_kernel(ConvArgs a) {
   }
 }
 
+// ---- CTA-pair variant (cta_group::2) for 128-channel layers whose weights do not fit one CTA ----
+// conv 1 of the HSI stem has 9 x 144 x 128 bf16 = 332 KB of weights.  The single-CTA kernel splits
+// the output channels over two CTAs (N = 64 per instruction), which leaves the tensor pipe
+// operand-fetch bound (A: 4 KB + B: 2 KB per 32-cycle instruction).  Here a cluster of two CTAs
+// works as ONE M = 256, N = 128 tile: each CTA stages its own 128 rows (A) and holds HALF of the
+// weights (64 of the 128 output channels, exactly the per-half packing of the split kernel); the
+// hardware reads the B halves from both shared memories, every instruction does N = 128 per CTA,
+// and each CTA's TMEM receives its own 128 rows x all 128 channels.  The leader CTA issues; the
+// peer forwards "my stage is full" / "my accumulator is drained" with remote mbarrier arrives;
+// tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads) conv_sps_tc2_kernel(ConvArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HALO = sps_halo(a.P), ROWS = 128 + 2 * HALO, PP = sps_pp(a.P), PW = a.P + 1;
+  const int KPB = a.kpb;
+  const uint32_t slice_bytes = (uint32_t)ROWS * 16u, kstep_bytes = 2u * slice_bytes, stage_bytes = (uint32_t)KPB * kstep_bytes;
+  const uint32_t wbytes = (uint32_t)a.ntaps * a.S_in * a.ncta * 16u;     // this CTA's half (ncta = 64 channels)
+  const int KS = a.S_in / 2;
+  const uint32_t rank = cluster_ctarank();
+  const int NOUT = 2 * a.ncta;                                           // 128
+  const int npairs = gridDim.x / 2, pair = blockIdx.x / 2;
+  const int nsuper = (a.ntiles + 1) / 2;                                 // 256-row super tiles
+
+  uint8_t* w_s = smem;
+  uint8_t* stage_s = smem + ((wbytes + 127u) & ~127u);
+  uint8_t* tail = stage_s + (size_t)a.nstages * stage_bytes;
+  float* sc_s = reinterpret_cast<float*>(tail);
+  float* bi_s = sc_s + NOUT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bi_s + NOUT) + 7) & ~uintptr_t(7));
+  uint64_t* full = bars;
+  uint64_t* empty = bars + a.nstages;
+  uint64_t* pfull = bars + 2 * a.nstages;      // leader: the peer's stage is full
+  uint64_t* wfull = bars + 3 * a.nstages;
+  uint64_t* pwfull = wfull + 1;                // leader: the peer's weights are resident
+  uint64_t* tfull = wfull + 2;                 // [2]
+  uint64_t* tempty = wfull + 4;                // [2] leader: both CTAs' epilogues are done with the buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 6);
+
+  for (int i = threadIdx.x; i < NOUT; i += blockDim.x) {
+    sc_s[i] = a.scale[i];
+    bi_s[i] = a.bias[i];
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.nstages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+      mbar_init(&pfull[s], 1);
+    }
+    mbar_init(wfull, 1);
+    mbar_init(pwfull, 1);
+    mbar_init(&tfull[0], 1);
+    mbar_init(&tfull[1], 1);
+    mbar_init(&tempty[0], 256);
+    mbar_init(&tempty[1], 256);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(tmem_slot, 256);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer (both CTAs): own weight half once, then own 128 rows per stage =====
+    if (lane == 0) {
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) + (size_t)rank * wbytes;
+      mbar_arrive_expect_tx(wfull, wbytes);
+      for (uint32_t off = 0; off < wbytes; off += 32768u) {
+        uint32_t n = wbytes - off < 32768u ? wbytes - off : 32768u;
+        bulk_g2s(w_s + off, wsrc + off, n, wfull);
+      }
+      int st = 0;
+      uint32_t ph = 0;
+      for (int u = pair; u < nsuper; u += npairs) {
+        int tile = 2 * u + (int)rank;
+        if (tile >= a.ntiles) tile = a.ntiles - 1;     // odd tile count: the peer re-reads the last tile, stores nothing
+        const long long row0 = (long long)tile * 128;
+        for (int ks0 = 0; ks0 < KS; ks0 += KPB) {
+          const int nk = KS - ks0 < KPB ? KS - ks0 : KPB;
+          mbar_wait(&empty[st], ph ^ 1u);
+          mbar_arrive_expect_tx(&full[st], (uint32_t)nk * kstep_bytes);
+          uint8_t* dst = stage_s + (size_t)st * stage_bytes;
+          for (int sl = 0; sl < 2 * nk; ++sl)
+            bulk_g2s(dst + (size_t)sl * slice_bytes, a.in + ((long long)(2 * ks0 + sl) * a.RT + row0) * 8, slice_bytes, &full[st]);
+          if (++st == a.nstages) { st = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 1) {
+    // ===== peer relay: tell the leader when this CTA's weights / stages have landed =====
+    if (lane == 0) {
+      mbar_wait(wfull, 0);
+      mbar_arrive_remote(pwfull, 0);
+      int st = 0;
+      uint32_t ph = 0;
+      for (int u = pair; u < nsuper; u += npairs) {
+        for (int ks0 = 0; ks0 < KS; ks0 += KPB) {
+          mbar_wait(&full[st], ph);
+          mbar_arrive_remote(&pfull[st], 0);
+          if (++st == a.nstages) { st = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== leader MMA issuer: one instruction = 256 rows (both CTAs) x 128 channels x K=16 =====
+    const uint32_t idesc = umma_idesc_bf16(256, NOUT);
+    const uint64_t a_hi = umma_desc(0, slice_bytes, 128) & 0xFFFFFFFF00000000ull;
+    const uint64_t b_hi = umma_desc(0, (uint32_t)a.ncta * 16u, 128) & 0xFFFFFFFF00000000ull;
+    const uint32_t a_lbo_lo = (uint32_t)(umma_desc(0, slice_bytes, 128) & 0xFFFF0000u);
+    const uint32_t b_lbo_lo = (uint32_t)(umma_desc(0, (uint32_t)a.ncta * 16u, 128) & 0xFFFF0000u);
+    const uint32_t w_lo = b_lbo_lo | ((smem_u32(w_s) & 0x3FFFFu) >> 4);
+    const uint32_t a_lo0 = a_lbo_lo | (((smem_u32(stage_s) & 0x3FFFFu) >> 4) + (uint32_t)HALO);
+    const uint32_t a_stage = stage_bytes >> 4;
+    const uint32_t b_tap = (uint32_t)(a.S_in * a.ncta);
+    const uint32_t b_ks = (uint32_t)(2 * a.ncta);
+    const bool nine = a.ntaps == 9;
+    mbar_wait(wfull, 0);
+    mbar_wait(pwfull, 0);
+    int st = 0;
+    uint32_t ph = 0;
+    int acc = 0;
+    uint32_t accph = 0;
+    for (int u = pair; u < nsuper; u += npairs) {
+      mbar_wait(&tempty[acc], accph ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NOUT);
+      for (int ks0 = 0; ks0 < KS; ks0 += KPB) {
+        const int nk = KS - ks0 < KPB ? KS - ks0 : KPB;
+        mbar_wait(&full[st], ph);
+        mbar_wait(&pfull[st], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          for (int kl = 0; kl < nk; ++kl) {
+            const int ks = ks0 + kl;
+            const uint32_t a_lo = a_lo0 + (uint32_t)st * a_stage + (uint32_t)kl * (kstep_bytes >> 4);
+            const uint32_t b_lo = w_lo + (uint32_t)ks * b_ks;
+            if (nine) {
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                const int shift = (tap / 3 - 1) * PW + (tap % 3 - 1);
+                umma_bf16_2(d_tmem, a_hi | (uint64_t)(a_lo + (uint32_t)shift), b_hi | (uint64_t)(b_lo + (uint32_t)tap * b_tap),
+                            idesc, (ks | tap) != 0 ? 1u : 0u);
+              }
+            } else {
+              umma_bf16_2(d_tmem, a_hi | (uint64_t)a_lo, b_hi | (uint64_t)b_lo, idesc, ks != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit2(&empty[st], 3);
+          if (ks0 + nk == KS) umma_commit2(&tfull[acc], 3);
+        }
+        __syncwarp();
+        if (++st == a.nstages) { st = 0; ph ^= 1u; }
+      }
+      if (++acc == 2) { acc = 0; accph ^= 1u; }
+    }
+  } else {
+    // ===== epilogue (both CTAs): own 128 rows x 128 channels =====
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t accph = 0;
+    for (int u = pair; u < nsuper; u += npairs) {
+      const int tile = 2 * u + (int)rank;
+      const bool have = tile < a.ntiles;
+      const long long r = (long long)tile * 128 + row_in_tile;
+      const long long R = r + HALO;
+      const long long b = r / PP;
+      const int q = (int)(r - b * PP);
+      const int i = q / PW, j = q - i * PW;
+      const bool valid = (b < a.n_patches) && (i < a.P) && (j < a.P);
+      mbar_wait(&tfull[acc], accph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * NOUT);
+      for (int c0 = 0; c0 < NOUT; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        tc_wait_ld();
+        uint32_t pk[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float y0 = __uint_as_float(v[2 * k]) * sc_s[c0 + 2 * k] + bi_s[c0 + 2 * k];
+          float y1 = __uint_as_float(v[2 * k + 1]) * sc_s[c0 + 2 * k + 1] + bi_s[c0 + 2 * k + 1];
+          if (a.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+          if (!valid) { y0 = 0.f; y1 = 0.f; }
+          pk[k] = pack_bf16(y0, y1);
+        }
+        if (have) {
+          const int slice = a.out_slice_off + c0 / 8;
+          *reinterpret_cast<uint4*>(a.out + ((long long)slice * a.RT + R) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(a.out + ((long long)(slice + 1) * a.RT + R) * 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      tc_fence_before();
+      if (rank == 0) mbar_arrive(&tempty[acc]);
+      else mbar_arrive_remote(&tempty[acc], 0);
+      if (++acc == 2) { acc = 0; accph ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc2(tmem_base, 256);
+}
+
 // ---- plain SIMT twin (tests / bring-up cross-check only; same arguments, same layouts) ------
 __global__ void conv_sps_simt_kernel(ConvArgs a, int nsplit) {
   const int HALO = sps_halo(a.P), PP = sps_pp(a.P), PW = a.P + 1;
@@ -319,6 +528,26 @@ int conv_sps_launch(const void* in, int S_in, const void* w, const float* scale,
     }
   }
   if (nst == 0) return VC_ERR_UNSUPPORTED;
+  // CTA-pair kernel: 128 output channels split over two CTAs (impl 3 forces the split kernel)
+  static int pair_ok = -1;
+  if (pair_ok < 0) {
+    const char* e = getenv("VC_CONV_PAIR");
+    pair_ok = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (impl == 0 && pair_ok && nsplit == 2 && ncta == 64 && a.ntiles >= 2) {
+    const size_t smem2 = conv_smem_bytes(S_in, ncta, ntaps, P, nst, kpb) + (size_t)nst * 8 + 64 + 2 * 128 * 4;
+    if (smem2 <= (size_t)max_smem) {
+      a.nstages = nst;
+      a.kpb = kpb;
+      if (cudaFuncSetAttribute(conv_sps_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2) != cudaSuccess)
+        return VC_ERR_CUDA;
+      int npairs = num_sms / 2;
+      const int nsuper = (a.ntiles + 1) / 2;
+      if (npairs > nsuper) npairs = nsuper;
+      conv_sps_tc2_kernel<<<2 * npairs, kConvThreads, smem2, stream>>>(a);
+      return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
+    }
+  }
   const size_t smem = conv_smem_bytes(S_in, ncta, ntaps, P, nst, kpb);
   a.nstages = nst;
   a.kpb = kpb;
