@@ -12,9 +12,9 @@ $PROF > gpurun_out/prof_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $PROF > gpurun_out/ncu_list.log 2>&1
 echo "ncu list rc=$?"
 $PROF > gpurun_out/prof_plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"conv_sps_tc|transformer_fwd|pack_strip|lidar_stem" -s 12 -c 7 -o gpurun_out/prof_infer $PROF > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"conv_sps_tc|transformer_fwd|pack_strip_kernel|lidar_stem" -s 6 -c 7 -o gpurun_out/prof_infer $PROF > gpurun_out/ncu_full.log 2>&1
 echo "ncu infer rc=$?"; tail -1 gpurun_out/ncu_full.log
-TPROF="python bench.py --no-infer --steps 1 --warmup 3"
+TPROF="python bench.py --no-infer --no-graph --steps 1 --warmup 3"
 $TPROF > gpurun_out/train_plain1.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 400 --csv --log-file gpurun_out/train_launches.csv $TPROF > gpurun_out/ncu_train_list.log 2>&1
 echo "ncu train list rc=$?"

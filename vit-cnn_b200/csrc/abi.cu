@@ -419,6 +419,7 @@ TrainWs carve_train(void* base, const vc_train* t, const ConvPlan pl[7], int n) 
   }
   const long long bt = (long long)vc::wgrad_workspace_bytes(18, 1);
   if (bt > wg) wg = bt;
+  if ((long long)vc::wgrad_small_workspace_bytes() > wg) wg = (long long)vc::wgrad_small_workspace_bytes();
   w.wg_bytes = wg;
   w.wg = take(wg);
   w.off1 = reinterpret_cast<long long*>(take(8LL * n));
@@ -478,6 +479,10 @@ int conv_wgrad(const vc_train* t, const ConvPlan& c, int i, const void* x, const
                cudaStream_t st) {
   float* out = t->grads + t->off[4 * i];
   const int P = t->P;
+  if (c.taps == 9 && c.n_out <= 32 && c.S_in == 2) {   // thin LiDAR layers: mma.sync kernel
+    const int rc = vc::wgrad_small_launch(dy, c.n_out / 8, x, c.S_in, n, P, w.wg, out, c.cout, c.cin, st);
+    if (rc != VC_ERR_UNSUPPORTED) return rc;
+  }
   if (c.shift_on_a)
     return vc::wgrad_sps_launch(x, c.S_in, dy, c.n_out / 8, n, P, c.taps, 1, w.wg, out, c.cin, c.cout, c.taps,
                                 (long long)c.cin * c.taps, 1, -1, nullptr, 0, st);

@@ -47,6 +47,13 @@ int wgrad_sps_launch(const void* A, int SA, const void* B, int SB, int n_patches
                      int bias_col, float* out_bias, int accumulate, cudaStream_t stream);
 
 
+int wgrad_reduce_launch(const float* part, int nparts, int ntaps, int N, int M, int Nr, float* out, long long sm, long long sn,
+                        long long st, int bias_col, float* out_bias, int accumulate, cudaStream_t stream);
+// wgrad_small.cu -- thin 3x3 convs (<= 32 x <= 16 channels) on mma.sync
+size_t wgrad_small_workspace_bytes();
+int wgrad_small_launch(const void* dy, int SA, const void* x, int SB, int n_patches, int P, void* workspace, float* out,
+                       int cout, int cin, cudaStream_t stream);
+
 // train.cu -- BatchNorm (training mode) forward / backward over SPS, loss, optimiser, weight packing
 int bn_forward_launch(const void* y, void* z, int S, int C, int n_patches, int P, const float* gamma, const float* beta,
                       float eps, float momentum, float* running_mean, float* running_var, long long* nbt, double* sums,

@@ -227,6 +227,15 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   }
 }
 
+int wgrad_reduce_launch(const float* part, int nparts, int ntaps, int N, int M, int Nr, float* out, long long sm, long long sn,
+                        long long st, int bias_col, float* out_bias, int accumulate, cudaStream_t stream) {
+  const long long total = (long long)ntaps * M * N;
+  int blocks = (int)((total + 31) / 32);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(part, nparts, ntaps, N, M, Nr, out, sm, sn, st, bias_col, out_bias, accumulate);
+  return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
+}
+
 static size_t wgrad_smem(int SA, int SB, int HALO, int shift_on_a, int nstages, int srows) {
   const size_t rowsA = srows + (shift_on_a ? 2 * HALO : 0), rowsB = srows + (shift_on_a ? 0 : 2 * HALO);
   (void)SA;
