@@ -98,28 +98,34 @@ __global__ void bn_finalize_kernel(double* sums, double count, int C, int Cp, co
   sums[Cp + c] = 0.0;
 }
 
-// z = relu(y * scale + shift) on valid cells, 0 elsewhere
+// z = relu(y * scale + shift) on valid cells, 0 elsewhere.  One thread per SPS row walking the
+// slices: the row's validity is decoded once, per-channel constants come from shared memory.
 __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ z,
                                                        int S, long long RT, const float* __restrict__ scale,
                                                        const float* __restrict__ shift, int relu, int P, int n) {
+  __shared__ float sc_s[256], sh_s[256];
+  for (int i = threadIdx.x; i < S * 8; i += blockDim.x) { sc_s[i] = scale[i]; sh_s[i] = shift[i]; }
+  __syncthreads();
   const int HALO = sps_halo(P), PP = sps_pp(P), PW = P + 1;
-  const long long total = (long long)S * RT;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int s = (int)(idx / RT);
-    const int R = (int)(idx - (long long)s * RT);
-    uint4 o = make_uint4(0u, 0u, 0u, 0u);
-    if (sps_row_valid(R, HALO, PP, PW, P, n)) {
+  for (long long R = (long long)blockIdx.x * blockDim.x + threadIdx.x; R < RT; R += (long long)gridDim.x * blockDim.x) {
+    const bool valid = sps_row_valid((int)R, HALO, PP, PW, P, n);
+    const uint4* src = reinterpret_cast<const uint4*>(y) + R;
+    uint4* dst = reinterpret_cast<uint4*>(z) + R;
+    if (!valid) {
+      for (int s = 0; s < S; ++s) dst[(long long)s * RT] = make_uint4(0u, 0u, 0u, 0u);
+      continue;
+    }
+#pragma unroll 4
+    for (int s = 0; s < S; ++s) {
       float v[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(y) + idx), v);
+      unpack8(__ldg(src + (long long)s * RT), v);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        v[k] = fmaf(v[k], scale[s * 8 + k], shift[s * 8 + k]);
+        v[k] = fmaf(v[k], sc_s[s * 8 + k], sh_s[s * 8 + k]);
         if (relu) v[k] = fmaxf(v[k], 0.f);
       }
-      o = pack8(v);
+      dst[(long long)s * RT] = pack8(v);
     }
-    reinterpret_cast<uint4*>(z)[idx] = o;
   }
 }
 
@@ -153,35 +159,49 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
   block_reduce16_atomic(acc, sums + s * 8, sums + Cp + s * 8);
 }
 
-// dy = scale * (g - mean(g) - xhat * mean(g*xhat)) on valid cells (0 elsewhere); may run in place
+// dy = scale * (g - mean(g) - xhat * mean(g*xhat)) on valid cells (0 elsewhere); may run in place.
+// One thread per SPS row walking the slices; per-channel constants (fp32) staged in shared memory:
+//   dy = k0 * g - k1 - k2 * y   with  k0 = scale, k2 = scale * rstd * mean(g xhat),
+//                                    k1 = scale * mean(g) - k2 * mean
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* dz, const __nv_bfloat16* __restrict__ y,
                                                            __nv_bfloat16* dy, int S, long long RT, int Cp,
                                                            const float* __restrict__ scale, const float* __restrict__ shift,
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
                                                            int relu, const double* __restrict__ sums, double inv_count,
                                                            int P, int n) {
+  __shared__ float sc_s[256], sh_s[256], k1_s[256], k2_s[256];
+  for (int c = threadIdx.x; c < S * 8; c += blockDim.x) {
+    const float sc = scale[c];
+    const float k2 = sc * rstd[c] * (float)(sums[Cp + c] * inv_count);
+    sc_s[c] = sc;
+    sh_s[c] = shift[c];
+    k2_s[c] = k2;
+    k1_s[c] = sc * (float)(sums[c] * inv_count) - k2 * mean[c];
+  }
+  __syncthreads();
   const int HALO = sps_halo(P), PP = sps_pp(P), PW = P + 1;
-  const long long total = (long long)S * RT;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int s = (int)(idx / RT);
-    const int R = (int)(idx - (long long)s * RT);
-    uint4 o = make_uint4(0u, 0u, 0u, 0u);
-    if (sps_row_valid(R, HALO, PP, PW, P, n)) {
+  for (long long R = (long long)blockIdx.x * blockDim.x + threadIdx.x; R < RT; R += (long long)gridDim.x * blockDim.x) {
+    const bool valid = sps_row_valid((int)R, HALO, PP, PW, P, n);
+    const uint4* pdz = reinterpret_cast<const uint4*>(dz) + R;
+    const uint4* py = reinterpret_cast<const uint4*>(y) + R;
+    uint4* pdy = reinterpret_cast<uint4*>(dy) + R;
+    if (!valid) {
+      for (int s = 0; s < S; ++s) pdy[(long long)s * RT] = make_uint4(0u, 0u, 0u, 0u);
+      continue;
+    }
+#pragma unroll 4
+    for (int s = 0; s < S; ++s) {
       float g[8], v[8];
-      unpack8(reinterpret_cast<const uint4*>(dz)[idx], g);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(y) + idx), v);
+      unpack8(pdz[(long long)s * RT], g);
+      unpack8(__ldg(py + (long long)s * RT), v);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int c = s * 8 + k;
-        const float sc = scale[c];
-        const float gg = (!relu || fmaf(v[k], sc, shift[c]) > 0.f) ? g[k] : 0.f;
-        const float xh = (v[k] - mean[c]) * rstd[c];
-        g[k] = sc * (gg - (float)(sums[c] * inv_count) - xh * (float)(sums[Cp + c] * inv_count));
+        const float gg = (!relu || fmaf(v[k], sc_s[c], sh_s[c]) > 0.f) ? g[k] : 0.f;
+        g[k] = fmaf(sc_s[c], gg, -fmaf(k2_s[c], v[k], k1_s[c]));
       }
-      o = pack8(g);
+      pdy[(long long)s * RT] = pack8(g);
     }
-    reinterpret_cast<uint4*>(dy)[idx] = o;
   }
 }
 
@@ -222,7 +242,7 @@ int bn_forward_launch(const void* y, void* z, int S, int C, int n_patches, int P
   bn_stats_kernel<<<dim3(rows_grid(RT, S), S), 256, 0, st>>>((const __nv_bfloat16*)y, RT, Cp, sums);
   bn_finalize_kernel<<<(Cp + 127) / 128, 128, 0, st>>>(sums, (double)n_patches * P * P, C, Cp, gamma, beta, eps, momentum,
                                                       running_mean, running_var, nbt, scale, shift, mean, rstd);
-  bn_apply_kernel<<<flat_grid((long long)S * RT), 256, 0, st>>>((const __nv_bfloat16*)y, (__nv_bfloat16*)z, S, RT, scale,
+  bn_apply_kernel<<<flat_grid(RT), 256, 0, st>>>((const __nv_bfloat16*)y, (__nv_bfloat16*)z, S, RT, scale,
                                                                  shift, relu, P, n_patches);
   return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
 }
@@ -235,7 +255,7 @@ int bn_backward_launch(const void* dz, const void* y, void* dy, int S, int C, in
   const int Cp = S * 8;
   bn_bwd_reduce_kernel<<<dim3(rows_grid(RT, S), S), 256, 0, st>>>((const __nv_bfloat16*)dz, (const __nv_bfloat16*)y, RT, Cp,
                                                                    scale, shift, mean, rstd, relu, sums);
-  bn_bwd_apply_kernel<<<flat_grid((long long)S * RT), 256, 0, st>>>((const __nv_bfloat16*)dz, (const __nv_bfloat16*)y,
+  bn_bwd_apply_kernel<<<flat_grid(RT), 256, 0, st>>>((const __nv_bfloat16*)dz, (const __nv_bfloat16*)y,
                                                                      (__nv_bfloat16*)dy, S, RT, Cp, scale, shift, mean, rstd,
                                                                      relu, sums, 1.0 / ((double)n_patches * P * P), P,
                                                                      n_patches);
