@@ -134,7 +134,7 @@ def bench_train(args, rank, world, dev, dist, barrier):
     gt_h = rng.integers(1, K, size=(H, W)).astype(np.int64)
     gt = torch.from_numpy(gt_h).to(dev)
     torch.manual_seed(0)
-    net = vitcnn_b200.ViTCNN(C1, C2, patch_size=P, num_classes=K, dropout=0.0).to(dev)
+    net = vitcnn_b200.ViTCNN(C1, C2, patch_size=P, num_classes=K, dropout=0.01).to(dev)   # reference default (model_utils.py:213)
     w = torch.ones(K)
     w[0] = 0
     tr = Trainer(net, lr=1e-3, weights=w, use_graph=not args.no_graph)
@@ -194,7 +194,7 @@ def bench_train(args, rank, world, dev, dist, barrier):
     return {"metric": "train_samples_per_s", "value": args.train_batch * steps / (ms / 1e3), "unit": "samples/s",
             "ms_per_step": ms / steps, "steps": steps, "global_batch": args.train_batch, "per_gpu_batch": per,
             "parallelism": f"dp{world}", "scaling": "strong", "dtype": "bf16", "optimizer": "Adam(lr=1e-3)",
-            "loss": "CrossEntropy(weight)", "gpu_launches": int(launches), "cuda_graph": not args.no_graph,
+            "loss": "CrossEntropy(weight)", "dropout": 0.01, "gpu_launches": int(launches), "cuda_graph": not args.no_graph,
             "e2e": {"value": args.train_batch * steps / (ms_e2e / 1e3), "unit": "samples/s", "ms_per_step": ms_e2e / steps,
                     "h2d_bytes_per_step": int(per * 8), "d2h_bytes_per_step": 8},
             "roofline": {"bound": "tensor", "achieved": fl / (ms / steps / 1e3) / 1e12, "peak": tf_sust, "unit": "TFLOP/s",

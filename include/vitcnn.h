@@ -185,6 +185,10 @@ typedef struct vc_train {
   float bn_eps, bn_momentum;
   const int64_t* blob_segments;   /* device table for vc_pack_segments: token-stage blob from params */
   int32_t n_blob_segments;
+  float dropout;                  /* p of pos_drop / proj_drop / MLP drops (vision_transformer.py:598-629,
+                                     mlp.py:41-47); masks are a stateless hash of (seed, sample, site, element) */
+  uint32_t* drop_seed;            /* device: seed word, advanced by every vc_train_forward* call (graph-safe);
+                                     required when dropout > 0 */
 } vc_train;
 
 int64_t vc_train_workspace_bytes(const vc_train* t, int32_t n);

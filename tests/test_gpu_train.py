@@ -316,3 +316,58 @@ def test_trainer_cuda_graph_matches_eager():
     # Adam moves a parameter by up to lr per step whatever the gradient's size, so atomics-order noise on
     # near-zero gradients shows as differences of a few lr; the bulk of the parameters agree closely
     assert (fa - fb).abs().max().item() <= 8e-3 and (fa - fb).abs().mean().item() <= 1e-4
+
+
+@pytest.mark.parametrize("p_drop", [0.0, 0.3])
+def test_dropout_masks_consistent_between_forward_and_backward(p_drop):
+    """Dropout masks are a stateless hash of (seed, sample, site, element) evaluated by the forward,
+    the recompute and the backward: (1) the same seed gives the same logits, another seed different
+    ones; (2) with the seed pinned, the directional derivative of the loss along our gradient
+    matches a central finite difference (a mask mismatch anywhere would break this; p = 0 is the
+    control for the bf16 noise of the method)."""
+    import vitcnn_b200
+    from vitcnn_b200.train import train_state
+    C1, C2, P, K, B = 16, 1, 7, 5, 48
+    torch.manual_seed(0)
+    net = vitcnn_b200.ViTCNN(C1, C2, patch_size=P, num_classes=K, dropout=p_drop)
+    with torch.no_grad():
+        for blk in net.blocks:
+            blk.attn.qkv.weight.mul_(8.0)
+        net.cls_token.normal_(std=0.02)
+    net = net.to(DEV).train()
+    g = torch.Generator().manual_seed(2)
+    hsi, lid = torch.rand(B, C1, P, P, generator=g).to(DEV), torch.rand(B, C2, P, P, generator=g).to(DEV)
+    y = torch.randint(1, K, (B,), generator=g).to(DEV)
+    st = train_state(net)
+    seed0 = 12345
+
+    def loss_at():
+        st.drop_seed.fill_(seed0)
+        with torch.no_grad():
+            return F.cross_entropy(net(hsi, lid).double(), y).item()
+
+    st.drop_seed.fill_(seed0)
+    out1 = net(hsi, lid)
+    F.cross_entropy(out1, y).backward()
+    grad = torch.cat([p.grad.reshape(-1) for p in st.params]).double()
+    st.drop_seed.fill_(seed0)
+    with torch.no_grad():
+        out2 = net(hsi, lid)
+        st.drop_seed.fill_(seed0 + 1)
+        out3 = net(hsi, lid)
+    assert torch.equal(out1.detach(), out2)
+    assert (not torch.equal(out2, out3)) == (p_drop > 0)
+    gn = grad.norm().item()
+    dirs = [(p_.grad / gn).clone() for p_ in st.params]
+    eps = 0.04 / gn
+    with torch.no_grad():
+        def shift(scale):
+            for p_, d_ in zip(st.params, dirs):
+                p_.add_(scale * d_)
+        shift(eps)
+        lp = loss_at()
+        shift(-2 * eps)
+        lm = loss_at()
+        shift(eps)
+    fd = (lp - lm) / (2 * eps)
+    assert abs(fd - gn) <= 0.15 * gn, (fd, gn, p_drop)

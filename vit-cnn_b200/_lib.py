@@ -64,6 +64,7 @@ class VcTrain(ctypes.Structure):
         ("bn_running_mean", c_void_p * 7), ("bn_running_var", c_void_p * 7), ("bn_num_batches", c_void_p * 7),
         ("bn_eps", c_float), ("bn_momentum", c_float),
         ("blob_segments", c_void_p), ("n_blob_segments", c_int32),
+        ("dropout", c_float), ("drop_seed", c_void_p),
     ]
 
 

@@ -122,7 +122,7 @@ int forward_sps(const vc_model* m, const Workspace& w, int n, float* logits, con
     VC_LAUNCH(KC_CONV_L, st, vc::conv_sps_launch(w.l2, 2, m->w_l[2], m->scale_l[2], m->bias_l[2], w.f, 4, 32, m->nsplit_l[2], n, P, 9, 1,
                                                  0, 0, st));
   }
-  VC_LAUNCH(KC_TOKENS, st, vc::transformer_fwd_launch(w.f, m->tparams, n, P, m->K, logits, out_index, argmax_map, 0, st));
+  VC_LAUNCH(KC_TOKENS, st, vc::transformer_fwd_launch(w.f, m->tparams, n, P, m->K, logits, out_index, argmax_map, 0, 0, nullptr, st));
   return VC_OK;
 }
 
@@ -244,7 +244,7 @@ int vc_conv_sps(const void* in_sps, int32_t S_in, const void* w_packed, const fl
 int vc_tokens_forward(const void* f_sps, const void* tparams, int32_t n_patches, int32_t P, int32_t K, float* logits,
                       const int64_t* out_index, uint8_t* argmax_map, void* stream) {
   VC_TRY(vc::transformer_fwd_launch(f_sps, tparams, n_patches, P, K, logits, (const long long*)out_index, argmax_map,
-                                    0, (cudaStream_t)stream));
+                                    0, 0, nullptr, (cudaStream_t)stream));
   return VC_OK;
 }
 
@@ -428,6 +428,13 @@ TrainWs carve_train(void* base, const vc_train* t, const ConvPlan pl[7], int n) 
   return w;
 }
 
+__global__ void bump_seed_kernel(uint32_t* seed) { *seed = *seed * 747796405u + 2891336453u; }
+inline unsigned int drop_threshold(const vc_train* t) {
+  if (!(t->dropout > 0.f) || !t->drop_seed) return 0u;
+  const float v = t->dropout * 65536.f + 0.5f;
+  return v >= 65535.f ? 65535u : (unsigned int)v;
+}
+
 __global__ void fill_ones_slice_kernel(__nv_bfloat16* slice, long long rows) {
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
     slice[r * 8] = __float2bfloat16_rn(1.f);
@@ -439,7 +446,7 @@ __global__ void fill_f32_kernel(float* p, int n, float v) {
 
 int check_train(const vc_train* t, ConvPlan pl[7]) {
   if (!t || !t->params || !t->grads || t->P < 1 || (t->P > 11 && t->P != 13 && t->P != 15) || t->K < 1 || t->K > 64 || t->C1 < 1 || t->C2 < 1 ||
-      !t->blob_segments || t->n_blob_segments <= 0)
+      !t->blob_segments || t->n_blob_segments <= 0 || t->dropout < 0.f || t->dropout >= 1.f || (t->dropout > 0.f && !t->drop_seed))
     return VC_ERR_ARG;
   return make_plans(t, pl) ? VC_OK : VC_ERR_UNSUPPORTED;
 }
@@ -471,7 +478,9 @@ int train_forward_core(const vc_train* t, const ConvPlan pl[7], const TrainWs& w
                                                t->bn_running_var[i], (long long*)t->bn_num_batches[i], w.sums, w.bn_scale[i],
                                                w.bn_shift[i], w.bn_mean[i], w.bn_rstd[i], 1, st));
   }
-  VC_LAUNCH(KC_TOKENS, st, vc::transformer_fwd_launch(w.z[6], w.blob, n, P, t->K, logits, nullptr, nullptr, 1, st));
+  const unsigned int thr = drop_threshold(t);
+  if (thr) bump_seed_kernel<<<1, 1, 0, st>>>(t->drop_seed);     // a fresh mask set for this step
+  VC_LAUNCH(KC_TOKENS, st, vc::transformer_fwd_launch(w.z[6], w.blob, n, P, t->K, logits, nullptr, nullptr, 1, thr, t->drop_seed, st));
   return VC_OK;
 }
 
@@ -509,7 +518,7 @@ int train_backward_core(const vc_train* t, const ConvPlan pl[7], const TrainWs& 
     if (cudaMemsetAsync(small[i], 0, cnt * sizeof(float), st) != cudaSuccess) return fail(VC_ERR_CUDA, "memset");
   }
   VC_LAUNCH(KC_TOKENS_BWD, st, vc::transformer_bwd_launch(w.z[6], w.blob, dlogits, w.dzf, (void* const*)w.tok, (void* const*)w.cls,
-                                                         small, n, P, K, st));
+                                                         small, n, P, K, drop_threshold(t), t->drop_seed, st));
   // linear-layer weight / bias gradients: contraction over all token rows on the tensor cores
   VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, w.tok[1], 12, w.tok[0], 6, w.RTt, 96, 32, 32, w, st));    // block 0 qkv
   VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, w.tok[3], 4, w.tok[2], 6, w.RTt, 32, 32, 34, w, st));     //         proj

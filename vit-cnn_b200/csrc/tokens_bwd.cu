@@ -39,6 +39,8 @@ struct TBArgs {
   float *g_cls, *g_pos;      // fp32 [32], [T][32] (atomics; caller zeroes all of these)
   long long RT, RTt, RTc;
   int n, P, K, T;
+  uint32_t drop_thr;            // dropout of the forward pass being differentiated (0 = off)
+  const uint32_t* drop_seed;    // device: seed of this step
   TLayout L;
 };
 
@@ -152,7 +154,7 @@ struct ClsScratch {
   float p[kHeads][256], ds[kHeads][256];
 };
 
-template <int NW>
+template <int NW, bool DROP>
 __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr int TP = 16 * NW;
@@ -191,6 +193,10 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
   const float* posg = reinterpret_cast<const float*>(a.blob + L.pos);
   const float qscale = 0.35355339059327376220f * 1.44269504088896340736f;  // hd^-0.5 * log2(e)
   const float kLn2 = 0.69314718055994530942f, kScale = 0.35355339059327376220f;
+  DropCfg dcfg;
+  dcfg.thr = DROP ? a.drop_thr : 0u;
+  dcfg.seed = DROP ? __ldg(a.drop_seed) : 0u;
+  dcfg.inv_keep = 65536.f / (65536.f - (float)dcfg.thr);
   const TLayerOff& O0 = L.layer[0];
   const TLayerOff& O1 = L.layer[1];
 
@@ -229,6 +235,10 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
         if (r0 == 0) { x[jn][0] = f32[L.cls / 4 + col] + p0.x; x[jn][1] = f32[L.cls / 4 + col + 1] + p0.y; }
         if (r0 >= T) { x[jn][0] = 0.f; x[jn][1] = 0.f; }
         if (r1 >= T) { x[jn][2] = 0.f; x[jn][3] = 0.f; }
+        if (DROP) {   // pos_drop
+          drop2(x[jn][0], x[jn][1], drop_key(b, 0, r0, 4 * jn + q), dcfg);
+          drop2(x[jn][2], x[jn][3], drop_key(b, 0, r1, 4 * jn + q), dcfg);
+        }
       }
     };
     float x[4][4];
@@ -332,7 +342,12 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
           mma16816(c, oa[kk], lds32(w), lds32(w + 8));
         }
         const float2 bb = *reinterpret_cast<const float2*>(f32 + O0.bproj / 4 + 8 * jn + 2 * q);
-        x[jn][0] += c[0] + bb.x; x[jn][1] += c[1] + bb.y; x[jn][2] += c[2] + bb.x; x[jn][3] += c[3] + bb.y;
+        c[0] += bb.x; c[1] += bb.y; c[2] += bb.x; c[3] += bb.y;
+        if (DROP) {
+          drop2(c[0], c[1], drop_key(b, 1, r0, 4 * jn + q), dcfg);
+          drop2(c[2], c[3], drop_key(b, 1, r1, 4 * jn + q), dcfg);
+        }
+        x[jn][0] += c[0]; x[jn][1] += c[1]; x[jn][2] += c[2]; x[jn][3] += c[3];
       }
       // MLP
       uint32_t A2[2][4];
@@ -354,11 +369,19 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
         }
         const float2 b0 = *reinterpret_cast<const float2*>(f32 + O0.bfc1 / 4 + 16 * hk + 2 * q);
         const float2 b1 = *reinterpret_cast<const float2*>(f32 + O0.bfc1 / 4 + 16 * hk + 8 + 2 * q);
+        h0[0] = gelu_erf(h0[0] + b0.x); h0[1] = gelu_erf(h0[1] + b0.y); h0[2] = gelu_erf(h0[2] + b0.x); h0[3] = gelu_erf(h0[3] + b0.y);
+        h1[0] = gelu_erf(h1[0] + b1.x); h1[1] = gelu_erf(h1[1] + b1.y); h1[2] = gelu_erf(h1[2] + b1.x); h1[3] = gelu_erf(h1[3] + b1.y);
+        if (DROP) {
+          drop2(h0[0], h0[1], drop_key(b, 2, r0, 8 * hk + q), dcfg);
+          drop2(h0[2], h0[3], drop_key(b, 2, r1, 8 * hk + q), dcfg);
+          drop2(h1[0], h1[1], drop_key(b, 2, r0, 8 * hk + 4 + q), dcfg);
+          drop2(h1[2], h1[3], drop_key(b, 2, r1, 8 * hk + 4 + q), dcfg);
+        }
         uint32_t Ha[4];
-        Ha[0] = pack_bf16(gelu_erf(h0[0] + b0.x), gelu_erf(h0[1] + b0.y));
-        Ha[1] = pack_bf16(gelu_erf(h0[2] + b0.x), gelu_erf(h0[3] + b0.y));
-        Ha[2] = pack_bf16(gelu_erf(h1[0] + b1.x), gelu_erf(h1[1] + b1.y));
-        Ha[3] = pack_bf16(gelu_erf(h1[2] + b1.x), gelu_erf(h1[3] + b1.y));
+        Ha[0] = pack_bf16(h0[0], h0[1]);
+        Ha[1] = pack_bf16(h0[2], h0[3]);
+        Ha[2] = pack_bf16(h1[0], h1[1]);
+        Ha[3] = pack_bf16(h1[2], h1[3]);
 #pragma unroll
         for (int jn = 0; jn < 4; ++jn) {
           const __nv_bfloat16* w = wfc2 + (8 * jn + g) * kLdHid + 16 * hk + 2 * q;
@@ -368,8 +391,12 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
 #pragma unroll
       for (int jn = 0; jn < 4; ++jn) {
         const float2 bb = *reinterpret_cast<const float2*>(f32 + O0.bfc2 / 4 + 8 * jn + 2 * q);
-        x[jn][0] += acc2[jn][0] + bb.x; x[jn][1] += acc2[jn][1] + bb.y;
-        x[jn][2] += acc2[jn][2] + bb.x; x[jn][3] += acc2[jn][3] + bb.y;
+        acc2[jn][0] += bb.x; acc2[jn][1] += bb.y; acc2[jn][2] += bb.x; acc2[jn][3] += bb.y;
+        if (DROP) {
+          drop2(acc2[jn][0], acc2[jn][1], drop_key(b, 3, r0, 4 * jn + q), dcfg);
+          drop2(acc2[jn][2], acc2[jn][3], drop_key(b, 3, r1, 4 * jn + q), dcfg);
+        }
+        x[jn][0] += acc2[jn][0]; x[jn][1] += acc2[jn][1]; x[jn][2] += acc2[jn][2]; x[jn][3] += acc2[jn][3];
       }
     }
     // x = x1: output of block 0 (rows >= T hold finite garbage; they never reach a valid row)
@@ -481,6 +508,7 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
           y = fmaf(bf_lo(wv), __shfl_sync(0xffffffffu, ov, 2 * k2), y);
           y = fmaf(bf_hi(wv), __shfl_sync(0xffffffffu, ov, 2 * k2 + 1), y);
         }
+        if (DROP) y = drop1(y, drop_key(b, 4, 0, lane >> 1), lane & 1, dcfg);
         const float xm = x10 + y;
         const float mean2 = warp_sum(xm) * (1.f / kD);
         const float d2 = xm - mean2;
@@ -502,6 +530,10 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           gelu_erf_grad(u[i], hv[i], hder[i]);
+          if (DROP) {   // post-dropout activation; the mask (0 or 1/keep) also multiplies the derivative
+            hv[i] = drop1(hv[i], drop_key(b, 5, 0, (lane + 32 * i) >> 1), lane & 1, dcfg);
+            hder[i] = drop1(hder[i], drop_key(b, 5, 0, (lane + 32 * i) >> 1), lane & 1, dcfg);
+          }
           cs->h[lane + 32 * i] = hv[i];
         }
         __syncwarp();
@@ -513,7 +545,9 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
           z0 = fmaf(bf_lo(wv.x), hh.x, fmaf(bf_hi(wv.x), hh.y, z0));
           z1 = fmaf(bf_lo(wv.y), hh.z, fmaf(bf_hi(wv.y), hh.w, z1));
         }
-        const float x2 = xm + z0 + z1;
+        float zz = z0 + z1;
+        if (DROP) zz = drop1(zz, drop_key(b, 6, 0, lane >> 1), lane & 1, dcfg);
+        const float x2 = xm + zz;
         const float meanf = warp_sum(x2) * (1.f / kD);
         const float df = x2 - meanf;
         const float rstdf = rsqrtf(warp_sum(df * df) * (1.f / kD) + 1e-6f);
@@ -531,11 +565,12 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
         float dgm = dc * f32[L.lnf_g / 4 + lane];
         float c1 = warp_sum(dgm) * (1.f / kD), c2 = warp_sum(dgm * xhf) * (1.f / kD);
         const float dx2 = rstdf * (dgm - c1 - xhf * c2);
+        const float dz2 = DROP ? drop1(dx2, drop_key(b, 6, 0, lane >> 1), lane & 1, dcfg) : dx2;   // d(fc2 output)
         // fc2 backward: dh[j] = sum_o W2[o][j] dx2[o]; du = dh * gelu'(u)
         float dh[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 8
         for (int o = 0; o < kD; ++o) {
-          const float dv = __shfl_sync(0xffffffffu, dx2, o);
+          const float dv = __shfl_sync(0xffffffffu, dz2, o);
 #pragma unroll
           for (int i = 0; i < 4; ++i) dh[i] = fmaf(__bfloat162float(wfc2[o * kLdHid + lane + 32 * i]), dv, dh[i]);
         }
@@ -547,7 +582,7 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
           a.c_xh[((long long)(j >> 3) * a.RTc + b) * 8 + (j & 7)] = __float2bfloat16_rn(hv[i]);
           a.c_dh[((long long)(j >> 3) * a.RTc + b) * 8 + (j & 7)] = __float2bfloat16_rn(du);
         }
-        a.c_dxb[((long long)(lane >> 3) * a.RTc + b) * 8 + (lane & 7)] = __float2bfloat16_rn(dx2);
+        a.c_dxb[((long long)(lane >> 3) * a.RTc + b) * 8 + (lane & 7)] = __float2bfloat16_rn(dz2);
         a.c_xln2[((long long)(lane >> 3) * a.RTc + b) * 8 + (lane & 7)] = __float2bfloat16_rn(y2);
         __syncwarp();
         // fc1 backward: dy2[i] = sum_j W1[j][i] du[j]  (four independent chains)
@@ -566,13 +601,14 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
         c1 = warp_sum(dgm) * (1.f / kD);
         c2 = warp_sum(dgm * xh2) * (1.f / kD);
         const float dxm = dx2 + rstd2 * (dgm - c1 - xh2 * c2);
-        a.c_dxa[((long long)(lane >> 3) * a.RTc + b) * 8 + (lane & 7)] = __float2bfloat16_rn(dxm);
+        const float dpo = DROP ? drop1(dxm, drop_key(b, 4, 0, lane >> 1), lane & 1, dcfg) : dxm;   // d(proj output)
+        a.c_dxa[((long long)(lane >> 3) * a.RTc + b) * 8 + (lane & 7)] = __float2bfloat16_rn(dpo);
         a.c_xo[((long long)(lane >> 3) * a.RTc + b) * 8 + (lane & 7)] = __float2bfloat16_rn(ov);
         // proj backward: do[i] = sum_o Wp[o][i] dxm[o]
         float dov = 0.f;
 #pragma unroll 8
         for (int o = 0; o < kD; ++o)
-          dov = fmaf(__bfloat162float(wproj[o * LD + lane]), __shfl_sync(0xffffffffu, dxm, o), dov);
+          dov = fmaf(__bfloat162float(wproj[o * LD + lane]), __shfl_sync(0xffffffffu, dpo, o), dov);
         cs->doo[lane] = dov;
         float delta = dov * ov;   // per head: sum over its 8 channels
         delta += __shfl_xor_sync(0xffffffffu, delta, 1);
@@ -687,15 +723,32 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
           mma16816(c, oa[kk], lds32(w), lds32(w + 8));
         }
         const float2 bb = *reinterpret_cast<const float2*>(f32 + O0.bproj / 4 + 8 * jn + 2 * q);
-        xm[jn][0] = x[jn][0] + c[0] + bb.x; xm[jn][1] = x[jn][1] + c[1] + bb.y;
-        xm[jn][2] = x[jn][2] + c[2] + bb.x; xm[jn][3] = x[jn][3] + c[3] + bb.y;
+        c[0] += bb.x; c[1] += bb.y; c[2] += bb.x; c[3] += bb.y;
+        if (DROP) {
+          drop2(c[0], c[1], drop_key(b, 1, r0, 4 * jn + q), dcfg);
+          drop2(c[2], c[3], drop_key(b, 1, r1, 4 * jn + q), dcfg);
+        }
+        xm[jn][0] = x[jn][0] + c[0]; xm[jn][1] = x[jn][1] + c[1];
+        xm[jn][2] = x[jn][2] + c[2]; xm[jn][3] = x[jn][3] + c[3];
       }
       // ---- MLP backward ----
       uint32_t A2[2][4], Adx[2][4];
       ln_to_afrag(xm, f32 + O0.ln2_g / 4, f32 + O0.ln2_b / 4, q, A2);
       dump_afrag32(a.xln2_0, a.RTt, trow, q, A2);
-      acc2_to_afrag(dx[0], dx[1], Adx[0]);
-      acc2_to_afrag(dx[2], dx[3], Adx[1]);
+      {
+        float d3[4][4];    // d(fc2 output) = dropout mask (site 3) applied to d x1
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) d3[jn][e] = dx[jn][e];
+          if (DROP) {
+            drop2(d3[jn][0], d3[jn][1], drop_key(b, 3, r0, 4 * jn + q), dcfg);
+            drop2(d3[jn][2], d3[jn][3], drop_key(b, 3, r1, 4 * jn + q), dcfg);
+          }
+        }
+        acc2_to_afrag(d3[0], d3[1], Adx[0]);
+        acc2_to_afrag(d3[2], d3[3], Adx[1]);
+      }
       dump_afrag32(a.dxb0, a.RTt, trow, q, Adx);
       float dln2[4][4];
 #pragma unroll
@@ -729,6 +782,14 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
           gelu_erf_grad(h1[e] + ((e & 1) ? b1.y : b1.x), hv1[e], der);
           du1[e] = e1[e] * der;
         }
+        if (DROP) {
+          const uint32_t k00 = drop_key(b, 2, r0, 8 * hk + q), k01 = drop_key(b, 2, r1, 8 * hk + q);
+          const uint32_t k10 = drop_key(b, 2, r0, 8 * hk + 4 + q), k11 = drop_key(b, 2, r1, 8 * hk + 4 + q);
+          drop2(hv0[0], hv0[1], k00, dcfg); drop2(hv0[2], hv0[3], k01, dcfg);
+          drop2(hv1[0], hv1[1], k10, dcfg); drop2(hv1[2], hv1[3], k11, dcfg);
+          drop2(du0[0], du0[1], k00, dcfg); drop2(du0[2], du0[3], k01, dcfg);
+          drop2(du1[0], du1[1], k10, dcfg); drop2(du1[2], du1[3], k11, dcfg);
+        }
         uint32_t Ah[4], Ad[4];
         acc2_to_afrag(hv0, hv1, Ah);
         acc2_to_afrag(du0, du1, Ad);
@@ -750,8 +811,20 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
       ln_backward(xm, dln2, f32 + O0.ln2_g / 4, q, dx, true, gln[1]);   // dx = d x_mid
       // ---- attention block backward ----
       uint32_t Adm[2][4];
-      acc2_to_afrag(dx[0], dx[1], Adm[0]);
-      acc2_to_afrag(dx[2], dx[3], Adm[1]);
+      {
+        float d1[4][4];    // d(proj output) = dropout mask (site 1) applied to d x_mid
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) d1[jn][e] = dx[jn][e];
+          if (DROP) {
+            drop2(d1[jn][0], d1[jn][1], drop_key(b, 1, r0, 4 * jn + q), dcfg);
+            drop2(d1[jn][2], d1[jn][3], drop_key(b, 1, r1, 4 * jn + q), dcfg);
+          }
+        }
+        acc2_to_afrag(d1[0], d1[1], Adm[0]);
+        acc2_to_afrag(d1[2], d1[3], Adm[1]);
+      }
       dump_afrag32(a.dxa0, a.RTt, trow, q, Adm);
       float dO[4][4];
       gemm_dgrad32<2>(Adm, wproj, LD, lane, dO);
@@ -859,6 +932,10 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
     for (int jn = 0; jn < 4; ++jn) {
       if (r0 >= T) { dx[jn][0] = 0.f; dx[jn][1] = 0.f; }
       if (r1 >= T) { dx[jn][2] = 0.f; dx[jn][3] = 0.f; }
+      if (DROP) {   // back through pos_drop: d(tokens + pos)
+        drop2(dx[jn][0], dx[jn][1], drop_key(b, 0, r0, 4 * jn + q), dcfg);
+        drop2(dx[jn][2], dx[jn][3], drop_key(b, 0, r1, 4 * jn + q), dcfg);
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) gpos[jn][e] += dx[jn][e];
       __nv_bfloat16* sl = a.dzf + (long long)jn * a.RT * 8 + 2 * q;
@@ -893,7 +970,7 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
   }
 }
 
-template <int NW>
+template <int NW, bool DROP>
 static int launch_bwd(const TBArgs& a, cudaStream_t stream) {
   constexpr int TP = 16 * NW;
   const size_t smem = (size_t)a.L.pos + 5 * (size_t)TP * kLdD * 2 + 3 * (size_t)kHeads * TP * 4 + sizeof(ClsScratch) + 16;
@@ -902,10 +979,10 @@ static int launch_bwd(const TBArgs& a, cudaStream_t stream) {
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   if (smem > (size_t)max_smem || TP > 256) return VC_ERR_UNSUPPORTED;
-  if (cudaFuncSetAttribute(transformer_bwd_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+  if (cudaFuncSetAttribute(transformer_bwd_kernel<NW, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return VC_ERR_CUDA;
   int blocks = num_sms < a.n ? num_sms : a.n;
-  transformer_bwd_kernel<NW><<<blocks, NW * 32, smem, stream>>>(a);
+  transformer_bwd_kernel<NW, DROP><<<blocks, NW * 32, smem, stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
 }
 
@@ -913,8 +990,9 @@ static int launch_bwd(const TBArgs& a, cudaStream_t stream) {
 // cls_dumps[8]: c_xo, c_dxa, c_xln2, c_dh, c_xh, c_dxb, c_xc, c_dlog (compact space);
 // small[12]: gamma / beta grads of ln1_0, ln2_0, ln1_1, ln2_1, final norm, then cls, pos.
 int transformer_bwd_launch(const void* zf, const void* tparams, const float* dlogits, void* dzf, void* const* tok_dumps,
-                           void* const* cls_dumps, float* const* small, int n_patches, int P, int K, cudaStream_t stream) {
-  if (n_patches <= 0 || P < 1 || K < 1 || K > 64) return VC_ERR_ARG;
+                           void* const* cls_dumps, float* const* small, int n_patches, int P, int K, unsigned int drop_thr,
+                           const unsigned int* drop_seed, cudaStream_t stream) {
+  if (n_patches <= 0 || P < 1 || K < 1 || K > 64 || (drop_thr && !drop_seed) || drop_thr >= 65536u) return VC_ERR_ARG;
   const int T = P * P + 1, NW = (T + 15) / 16, TP = 16 * NW;
   TBArgs a;
   a.zf = (const __nv_bfloat16*)zf;
@@ -937,9 +1015,19 @@ int transformer_bwd_launch(const void* zf, const void* tparams, const float* dlo
   a.P = P;
   a.K = K;
   a.T = T;
+  a.drop_thr = drop_thr;
+  a.drop_seed = drop_seed;
   a.L = tlayout(P, K);
+  if (drop_thr) {
+    switch (NW) {
+#define VC_CASE(N) case N: return launch_bwd<N, true>(a, stream);
+      VC_CASE(1) VC_CASE(2) VC_CASE(3) VC_CASE(4) VC_CASE(5) VC_CASE(6) VC_CASE(7) VC_CASE(8) VC_CASE(11) VC_CASE(15)
+#undef VC_CASE
+      default: return VC_ERR_UNSUPPORTED;
+    }
+  }
   switch (NW) {
-#define VC_CASE(N) case N: return launch_bwd<N>(a, stream);
+#define VC_CASE(N) case N: return launch_bwd<N, false>(a, stream);
     VC_CASE(1) VC_CASE(2) VC_CASE(3) VC_CASE(4) VC_CASE(5) VC_CASE(6) VC_CASE(7) VC_CASE(8)
     VC_CASE(11) VC_CASE(15)   // P = 13, 15 (odd patch sizes: the centre pixel is classified)
 #undef VC_CASE

@@ -28,6 +28,8 @@ struct TArgs {
   unsigned char* argmax_map;   // nullable: argmax written at out_index[b]
   long long RT;
   int n_patches, P, K, T;
+  uint32_t drop_thr;            // training-mode dropout (0 = off): see DropCfg
+  const uint32_t* drop_seed;    // device: seed of this step
   TLayout L;  // parameter-blob offsets (kernel-argument space: constant-bank reads)
 };
 
@@ -44,7 +46,7 @@ struct TailBuf {
 // warps only produce K / V for every token and the cls query's attention partials; the tail
 // warp finishes the cls row (proj, MLP, final LN, head) while the token warps already work
 // on the next patch.
-template <int NW>
+template <int NW, bool DROP>
 __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_fwd_kernel(TArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr int TP = 16 * NW;    // padded token count
@@ -70,6 +72,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
   const int T = a.T, P = a.P;
+  DropCfg dc;
+  dc.thr = DROP ? a.drop_thr : 0u;
+  dc.seed = DROP ? __ldg(a.drop_seed) : 0u;
+  dc.inv_keep = 65536.f / (65536.f - (float)dc.thr);
   const int my_patches = (a.n_patches - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const TLayerOff& OL = L.layer[kLayers - 1];   // the cls-only block
 
@@ -97,6 +103,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
         y = fmaf(bf_lo(wv), __shfl_sync(0xffffffffu, att, 2 * k2), y);
         y = fmaf(bf_hi(wv), __shfl_sync(0xffffffffu, att, 2 * k2 + 1), y);
       }
+      if (DROP) y = drop1(y, drop_key(b, 4, 0, lane >> 1), lane & 1, dc);
       x0 += y;
       // LN2
       float mean = warp_sum(x0) * (1.f / kD);
@@ -117,7 +124,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
         }
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) h_s[lane + 32 * i] = gelu_erf(hacc[i]);
+      for (int i = 0; i < 4; ++i) {
+        float hv = gelu_erf(hacc[i]);
+        if (DROP) hv = drop1(hv, drop_key(b, 5, 0, (lane + 32 * i) >> 1), lane & 1, dc);
+        h_s[lane + 32 * i] = hv;
+      }
       __syncwarp();
       // fc2 (+bias, +residual)
       float z = f32[OL.bfc2 / 4 + lane];
@@ -128,6 +139,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
         z = fmaf(bf_lo(wv), hh.x, fmaf(bf_hi(wv), hh.y, z));
       }
       __syncwarp();
+      if (DROP) z = drop1(z, drop_key(b, 6, 0, lane >> 1), lane & 1, dc);
       x0 += z;
       // final LayerNorm + head
       mean = warp_sum(x0) * (1.f / kD);
@@ -220,6 +232,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
           if (r == 0) v = cls[c] + pos[c];
           else if (r < T) v = (a.prefused ? acc[jn][e] : fmaxf(acc[jn][e] * fus_scale[c] + fus_bias[c], 0.f)) + pos[r * kD + c];
           x[jn][e] = v;
+        }
+        if (DROP) {   // pos_drop
+          drop2(x[jn][0], x[jn][1], drop_key(b, 0, r0, 4 * jn + q), dc);
+          drop2(x[jn][2], x[jn][3], drop_key(b, 0, r1, 4 * jn + q), dc);
         }
       }
     }
@@ -342,20 +358,31 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
 #pragma unroll
       for (int jn = 0; jn < 4; ++jn) {   // the residual stream is the accumulator
         const float2 bb = *reinterpret_cast<const float2*>(bproj + 8 * jn + 2 * q);
-        x[jn][0] += bb.x; x[jn][1] += bb.y; x[jn][2] += bb.x; x[jn][3] += bb.y;
         uint32_t B[4];
         ldsm4(B, wproj + (8 * jn + (lane & 7)) * kLdD + 8 * (lane >> 3));
-        mma16816(x[jn], oa[0], B[0], B[1]);
-        mma16816(x[jn], oa[1], B[2], B[3]);
+        if (!DROP) {
+          x[jn][0] += bb.x; x[jn][1] += bb.y; x[jn][2] += bb.x; x[jn][3] += bb.y;
+          mma16816(x[jn], oa[0], B[0], B[1]);
+          mma16816(x[jn], oa[1], B[2], B[3]);
+        } else {     // proj_drop acts on the branch output before the residual add
+          float c[4] = {bb.x, bb.y, bb.x, bb.y};
+          mma16816(c, oa[0], B[0], B[1]);
+          mma16816(c, oa[1], B[2], B[3]);
+          drop2(c[0], c[1], drop_key(b, 1 + 3 * l, r0, 4 * jn + q), dc);
+          drop2(c[2], c[3], drop_key(b, 1 + 3 * l, r1, 4 * jn + q), dc);
+          x[jn][0] += c[0]; x[jn][1] += c[1]; x[jn][2] += c[2]; x[jn][3] += c[3];
+        }
       }
 
       // ---- LN2 -> fc1 (+bias, GELU) -> fc2 (+bias, +residual), 16 hidden units at a time ----
       uint32_t A2[2][4];
       ln_to_afrag(x, reinterpret_cast<const float*>(smem + O.ln2_g), reinterpret_cast<const float*>(smem + O.ln2_b), q, A2);
+      float acc2[DROP ? 4 : 1][4];        // dropout needs the branch output separate from the residual
 #pragma unroll
       for (int jn = 0; jn < 4; ++jn) {   // fc2 accumulates straight into the residual stream
         const float2 bb = *reinterpret_cast<const float2*>(bfc2 + 8 * jn + 2 * q);
-        x[jn][0] += bb.x; x[jn][1] += bb.y; x[jn][2] += bb.x; x[jn][3] += bb.y;
+        if (!DROP) { x[jn][0] += bb.x; x[jn][1] += bb.y; x[jn][2] += bb.x; x[jn][3] += bb.y; }
+        else { acc2[DROP ? jn : 0][0] = bb.x; acc2[DROP ? jn : 0][1] = bb.y; acc2[DROP ? jn : 0][2] = bb.x; acc2[DROP ? jn : 0][3] = bb.y; }
       }
 #pragma unroll
       for (int hk = 0; hk < kHidden / 16; ++hk) {
@@ -371,17 +398,39 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
           mma16816(h1, A2[0], B1[0], B1[1]);
           mma16816(h1, A2[1], B1[2], B1[3]);
         }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { h0[e] = gelu_erf(h0[e]); h1[e] = gelu_erf(h1[e]); }
+        if (DROP) {
+          drop2(h0[0], h0[1], drop_key(b, 2 + 3 * l, r0, 8 * hk + q), dc);
+          drop2(h0[2], h0[3], drop_key(b, 2 + 3 * l, r1, 8 * hk + q), dc);
+          drop2(h1[0], h1[1], drop_key(b, 2 + 3 * l, r0, 8 * hk + 4 + q), dc);
+          drop2(h1[2], h1[3], drop_key(b, 2 + 3 * l, r1, 8 * hk + 4 + q), dc);
+        }
         uint32_t Ha[4];
-        Ha[0] = pack_bf16(gelu_erf(h0[0]), gelu_erf(h0[1]));
-        Ha[1] = pack_bf16(gelu_erf(h0[2]), gelu_erf(h0[3]));
-        Ha[2] = pack_bf16(gelu_erf(h1[0]), gelu_erf(h1[1]));
-        Ha[3] = pack_bf16(gelu_erf(h1[2]), gelu_erf(h1[3]));
+        Ha[0] = pack_bf16(h0[0], h0[1]);
+        Ha[1] = pack_bf16(h0[2], h0[3]);
+        Ha[2] = pack_bf16(h1[0], h1[1]);
+        Ha[3] = pack_bf16(h1[2], h1[3]);
 #pragma unroll
         for (int jn = 0; jn < 4; jn += 2) {   // one ldmatrix = B fragments of two output tiles
           uint32_t B[4];
           ldsm4(B, wfc2 + (8 * (jn + (lane >> 4)) + (lane & 7)) * kLdHid + 16 * hk + 8 * ((lane >> 3) & 1));
-          mma16816(x[jn], Ha, B[0], B[1]);
-          mma16816(x[jn + 1], Ha, B[2], B[3]);
+          if (!DROP) {
+            mma16816(x[jn], Ha, B[0], B[1]);
+            mma16816(x[jn + 1], Ha, B[2], B[3]);
+          } else {
+            mma16816(acc2[DROP ? jn : 0], Ha, B[0], B[1]);
+            mma16816(acc2[DROP ? jn + 1 : 0], Ha, B[2], B[3]);
+          }
+        }
+      }
+      if (DROP) {
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) {
+          float* c = acc2[DROP ? jn : 0];
+          drop2(c[0], c[1], drop_key(b, 3 + 3 * l, r0, 4 * jn + q), dc);
+          drop2(c[2], c[3], drop_key(b, 3 + 3 * l, r1, 4 * jn + q), dc);
+          x[jn][0] += c[0]; x[jn][1] += c[1]; x[jn][2] += c[2]; x[jn][3] += c[3];
         }
       }
       bar_sync(BAR_MAIN, NMAIN);  // every warp is done with this layer's K / V^T
@@ -468,7 +517,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
 
 size_t tparams_bytes(int P, int K) { return (size_t)tlayout(P, K).total; }
 
-template <int NW>
+template <int NW, bool DROP>
 static int launch_nw(const TArgs& a, cudaStream_t stream) {
   const TLayout L = tlayout(a.P, a.K);
   const size_t smem = (size_t)L.total + (size_t)(16 * NW) * kLdD * 2 + (size_t)kD * (16 * NW + 8) * 2 + kD * 4 +
@@ -478,21 +527,22 @@ static int launch_nw(const TArgs& a, cudaStream_t stream) {
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   if (smem > (size_t)max_smem) return VC_ERR_UNSUPPORTED;
-  if (cudaFuncSetAttribute(transformer_fwd_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+  if (cudaFuncSetAttribute(transformer_fwd_kernel<NW, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
       cudaSuccess)
     return VC_ERR_CUDA;
   int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, transformer_fwd_kernel<NW>, (NW + 1) * 32, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, transformer_fwd_kernel<NW, DROP>, (NW + 1) * 32, smem);
   if (occ < 1) occ = 1;
   long long blocks = (long long)num_sms * occ;
   if (blocks > a.n_patches) blocks = a.n_patches;
-  transformer_fwd_kernel<NW><<<(int)blocks, (NW + 1) * 32, smem, stream>>>(a);
+  transformer_fwd_kernel<NW, DROP><<<(int)blocks, (NW + 1) * 32, smem, stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
 }
 
 int transformer_fwd_launch(const void* f_sps, const void* tparams, int n_patches, int P, int K, float* logits,
-                           const long long* out_index, unsigned char* argmax_map, int prefused, cudaStream_t stream) {
-  if (n_patches <= 0 || P < 1 || K < 1 || K > 64) return VC_ERR_ARG;
+                           const long long* out_index, unsigned char* argmax_map, int prefused, unsigned int drop_thr,
+                           const unsigned int* drop_seed, cudaStream_t stream) {
+  if (n_patches <= 0 || P < 1 || K < 1 || K > 64 || (drop_thr && !drop_seed) || drop_thr >= 65536u) return VC_ERR_ARG;
   TArgs a;
   a.f = (const __nv_bfloat16*)f_sps;
   a.blob = (const uint8_t*)tparams;
@@ -505,10 +555,20 @@ int transformer_fwd_launch(const void* f_sps, const void* tparams, int n_patches
   a.P = P;
   a.K = K;
   a.T = P * P + 1;
+  a.drop_thr = drop_thr;
+  a.drop_seed = drop_seed;
   a.L = tlayout(P, K);
   const int NW = (a.T + 15) / 16;
+  if (drop_thr) {   // training-mode dropout: the patch sizes the training kernels cover
+    switch (NW) {
+#define VC_CASE(N) case N: return launch_nw<N, true>(a, stream);
+      VC_CASE(1) VC_CASE(2) VC_CASE(3) VC_CASE(4) VC_CASE(5) VC_CASE(6) VC_CASE(7) VC_CASE(8) VC_CASE(11) VC_CASE(15)
+#undef VC_CASE
+      default: return VC_ERR_UNSUPPORTED;
+    }
+  }
   switch (NW) {
-#define VC_CASE(N) case N: return launch_nw<N>(a, stream);
+#define VC_CASE(N) case N: return launch_nw<N, false>(a, stream);
     VC_CASE(1) VC_CASE(2) VC_CASE(3) VC_CASE(4) VC_CASE(5) VC_CASE(6) VC_CASE(7) VC_CASE(8)
     VC_CASE(9) VC_CASE(10) VC_CASE(11) VC_CASE(12) VC_CASE(13) VC_CASE(14) VC_CASE(15)
 #undef VC_CASE

@@ -38,7 +38,8 @@ int confusion_launch(const void* pred, int peb, const void* target, int teb, lon
 // transformer.cu
 size_t tparams_bytes(int P, int K);
 int transformer_fwd_launch(const void* f_sps, const void* tparams, int n_patches, int P, int K, float* logits,
-                           const long long* out_index, unsigned char* argmax_map, int prefused, cudaStream_t stream);
+                           const long long* out_index, unsigned char* argmax_map, int prefused, unsigned int drop_thr,
+                           const unsigned int* drop_seed, cudaStream_t stream);
 
 // wgrad_tc.cu -- weight gradients (rows are the reduction axis; both operands MN-major)
 size_t wgrad_workspace_bytes(int SB, int ntaps);
@@ -73,6 +74,7 @@ int pack_segments_launch(const float* flat, void* blob, const long long* segs, i
 
 // tokens_bwd.cu
 int transformer_bwd_launch(const void* zf, const void* tparams, const float* dlogits, void* dzf, void* const* tok_dumps,
-                           void* const* cls_dumps, float* const* small, int n_patches, int P, int K, cudaStream_t stream);
+                           void* const* cls_dumps, float* const* small, int n_patches, int P, int K, unsigned int drop_thr,
+                           const unsigned int* drop_seed, cudaStream_t stream);
 
 }  // namespace vc

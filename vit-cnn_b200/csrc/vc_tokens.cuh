@@ -52,6 +52,40 @@ __device__ __forceinline__ void gelu_erf_grad(float v, float& val, float& der) {
   der = fmaf(hv * (1.f - t * t), fmaf(0.1070322243f, v2, 0.7978845608f), fmaf(0.5f, t, 0.5f));
 }
 
+// ---- dropout (training only; vision_transformer.py:598-629 pos_drop, :57-105 proj_drop,
+// mlp.py:41-47 drop after GELU and after fc2) -----------------------------------------------------
+// Stateless masks: a 32-bit hash of (seed of this step, sample, site, token row, column pair) yields
+// two 16-bit draws, an element is kept iff its draw >= thr = round(p * 65536) and scaled by 1/(1-p').
+// Forward, recompute and backward evaluate the same function, so no mask is stored.
+// Sites: 0 pos_drop; block l: 1+3l proj_drop, 2+3l drop after GELU, 3+3l drop after fc2.
+struct DropCfg {
+  uint32_t thr;       // 0 = dropout off
+  uint32_t seed;
+  float inv_keep;     // 65536 / (65536 - thr)
+};
+__device__ __forceinline__ uint32_t drop_key(int b, int site, int row, int colpair) {
+  return (((uint32_t)b * 8u + (uint32_t)site) * 256u + (uint32_t)row) * 64u + (uint32_t)colpair;
+}
+__device__ __forceinline__ uint32_t drop_hash(uint32_t key, uint32_t seed) {   // two multiply-xorshift rounds
+  uint32_t h = (key ^ seed) * 0x9E3779B1u;
+  h ^= h >> 16;
+  h *= 0x85EBCA77u;
+  h ^= h >> 15;
+  return h;
+}
+// columns (2 * colpair, 2 * colpair + 1) of one row
+__device__ __forceinline__ void drop2(float& a, float& b, uint32_t key, const DropCfg& d) {
+  const uint32_t h = drop_hash(key, d.seed);
+  a = ((h & 0xFFFFu) >= d.thr) ? a * d.inv_keep : 0.f;
+  b = ((h >> 16) >= d.thr) ? b * d.inv_keep : 0.f;
+}
+// one column (lane = column layouts): `odd` selects the column's half of its pair's hash
+__device__ __forceinline__ float drop1(float a, uint32_t key, int odd, const DropCfg& d) {
+  const uint32_t h = drop_hash(key, d.seed);
+  const uint32_t draw = odd ? (h >> 16) : (h & 0xFFFFu);
+  return (draw >= d.thr) ? a * d.inv_keep : 0.f;
+}
+
 // LayerNorm (eps 1e-6) of the two token rows this thread shares with its quad; result as the
 // two K=16 A fragments of the following GEMM.
 __device__ __forceinline__ void ln_to_afrag(const float (&x)[4][4], const float* gam, const float* bet, int q,

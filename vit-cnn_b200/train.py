@@ -17,7 +17,6 @@ canonical order of include/vitcnn.h) so that packing, all-reduce and Adam are si
 from __future__ import annotations
 
 import ctypes
-import warnings
 
 import numpy as np
 import torch
@@ -124,6 +123,9 @@ class TrainState:
         bn0 = model.hsi_stem[0].bn
         st.bn_eps, st.bn_momentum = bn0.eps, bn0.momentum
         st.blob_segments, st.n_blob_segments = self.segments.data_ptr(), self.segments.shape[0]
+        # dropout masks are a hash of (seed word, sample, site, element); the word advances on the device
+        self.drop_seed = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int64).to(torch.int32).to(self.device)
+        st.dropout, st.drop_seed = float(model.dropout), self.drop_seed.data_ptr()
         self.struct = st
         self._bn_ptrs = [b.running_mean.data_ptr() for b in _bn_layers(model)]
         self.ws = {}
@@ -229,9 +231,8 @@ def train_state(model) -> TrainState:
     if st is None or not st.valid():
         st = TrainState(model)
         model._train_state = st
-        if model.dropout > 0 and not getattr(model, "_dropout_warned", False):
-            model._dropout_warned = True
-            warnings.warn("ViTCNN training kernels run without dropout (reference default p=0.01)")
+    if st.struct.dropout != float(model.dropout):       # model.dropout may be changed between steps
+        st.struct.dropout = float(model.dropout)
     return st
 
 
@@ -355,8 +356,9 @@ class Trainer:
         n = xy.shape[0]
         if not self.use_graph:
             return self._step_impl(img1, img2, gt, xy)
+        st = train_state(self.model)                      # picks up a changed model.dropout
         entry = self._graphs.get(n)
-        if entry is not None and entry[3] == (img1.data_ptr(), img2.data_ptr(), gt.data_ptr()):
+        if entry is not None and entry[3] == (img1.data_ptr(), img2.data_ptr(), gt.data_ptr(), st.struct.dropout):
             graph, xy_s, loss_s, _ = entry
             xy_s.copy_(xy, non_blocking=True)
             graph.replay()
@@ -371,7 +373,7 @@ class Trainer:
         with torch.cuda.graph(graph):
             loss_s = self._step_impl(img1, img2, gt, xy_s)
         self.launches_per_step = int(_lib.lib().vc_launch_count() - l0)   # kernels of this library in one replay
-        self._graphs[n] = (graph, xy_s, loss_s, (img1.data_ptr(), img2.data_ptr(), gt.data_ptr()))
+        self._graphs[n] = (graph, xy_s, loss_s, (img1.data_ptr(), img2.data_ptr(), gt.data_ptr(), st.struct.dropout))
         graph.replay()      # capturing records the step without running it
         return loss_s
 
