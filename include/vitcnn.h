@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VC_ABI_VERSION 2
+#define VC_ABI_VERSION 3
 
 /* Parameters of one model instance in kernel-ready form (built by vc-side packing, see
  * vitcnn_b200/model.py::pack_for_inference).  Conv weights: bf16 [nsplit][taps][S_in][N/nsplit][8]
@@ -81,9 +81,12 @@ int32_t vc_tparams_layout(int32_t P, int32_t K, int64_t* out, int32_t n);
  * 1112, windows from utils.sliding_window) when center_mode=0 (xy = top-left corners).
  * img1/img2: f32 [H][W][C] rasters; xy: int32 [n][2]; hsi: f32 [n][C1][P][P]; lidar: f32
  * [n][C2][P][P]; labels (nullable with gt): int64 [n] = gt[centre]; gt element size 1/4/8 B.
+ * ops (nullable): uint8 [n], the spatial augmentation of each sample as the host drew it with the
+ * reference's RNG calls (datasets.py:510-526, 559-564): 0 identity, 1 fliplr, 2 flipud, 3 both,
+ * 4/5/6 np.rot90 k = 1/2/3 -- applied as an index remap to data, LiDAR and label alike.
  * Bit-exact copies. */
 int vc_gather_patches_f32(const float* img1, const float* img2, const void* gt, int32_t gt_elem_bytes, int32_t H,
-                          int32_t W, int32_t C1, int32_t C2, const int32_t* xy, int32_t n, int32_t P,
+                          int32_t W, int32_t C1, int32_t C2, const int32_t* xy, const uint8_t* ops, int32_t n, int32_t P,
                           int32_t center_mode, float* hsi, float* lidar, int64_t* labels, void* stream);
 
 /* Window enumeration of utils.sliding_window (utils.py:374-397) for windows [first, first+count)
@@ -199,10 +202,11 @@ int vc_train_forward(const vc_train* t, const float* hsi, const int64_t hsi_stri
                      const int64_t lidar_strides[4], int32_t n, void* workspace, int64_t workspace_bytes, float* logits,
                      void* stream);
 /* same, patches gathered on the device from the rasters: xy int32 [n][2] patch centres
- * (MultiModalX.__getitem__, datasets.py:550-556); labels (nullable, with gt) int64 [n] */
+ * (MultiModalX.__getitem__, datasets.py:550-556); ops (nullable) uint8 [n] flip / rot90 codes as in
+ * vc_gather_patches_f32; labels (nullable, with gt) int64 [n] */
 int vc_train_forward_gather(const vc_train* t, const float* img1, const float* img2, const void* gt, int32_t gt_elem_bytes,
-                            int32_t H, int32_t W, const int32_t* xy, int32_t n, void* workspace, int64_t workspace_bytes,
-                            float* logits, int64_t* labels, void* stream);
+                            int32_t H, int32_t W, const int32_t* xy, const uint8_t* ops, int32_t n, void* workspace,
+                            int64_t workspace_bytes, float* logits, int64_t* labels, void* stream);
 /* gradients of every parameter into t->grads (overwritten) for the batch of the last forward
  * on this workspace */
 int vc_train_backward(const vc_train* t, const float* dlogits, int32_t n, void* workspace, int64_t workspace_bytes,

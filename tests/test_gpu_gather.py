@@ -7,6 +7,7 @@ import torch
 from oracle import data_ref as R
 
 pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
 
 
 def _dev():
@@ -80,3 +81,61 @@ def test_empty_batch():
     h, l, _ = ops.gather_patches(torch.rand(12, 12, 4, device=d), torch.rand(12, 12, 1, device=d),
                                  torch.zeros(0, 2, dtype=torch.int32, device=d), 5)
     assert h.shape == (0, 4, 5, 5) and l.shape == (0, 1, 5, 5)
+
+
+def test_flip_rotate_augmentation_matches_reference_golden(data_golden):
+    """flip_augmentation on: the dataset mirror draws the reference's RNG decisions and the gather
+    kernel applies them as an index remap -- bit-exact with what the reference's own
+    MultiModalX.__getitem__ returned (tests/golden/make_golden.py), labels included."""
+    import vitcnn_b200
+    g = data_golden
+    for ci, (H, W, C1, C2, P, n) in enumerate(g["ds_cases"]):
+        img1, img2, gt = g[f"ds{ci}_img1"], g[f"ds{ci}_img2"], g[f"ds{ci}_gt"]
+        hp = dict(dataset="synthetic", patch_size=int(P), ignored_labels=[0], flip_augmentation=True,
+                  radiation_augmentation=False, mixture_augmentation=False, center_pixel=True,
+                  supervision="full", applyPCA=False, device=DEV)
+        np.random.seed(100 + ci)                     # seed_torch(100 + ci) of make_golden.py
+        ds = vitcnn_b200.MultiModalX(img1, img2, gt, **hp)
+        h, l, y = ds.batch(np.arange(int(n)))        # the draws of n consecutive __getitem__ calls
+        assert h.cpu().numpy().tobytes() == g[f"ds{ci}_aug_hsi"].tobytes(), ci
+        assert l.cpu().numpy().tobytes() == g[f"ds{ci}_aug_lidar"].tobytes(), ci
+        assert np.array_equal(y.cpu().numpy(), g[f"ds{ci}_aug_label"]), ci
+
+
+def test_all_dihedral_ops_and_radiation_noise_vs_oracle():
+    from vitcnn_b200 import ops
+    import vitcnn_b200
+    for P in (5, 8, 11):       # even P: the label moves with the transform
+        img1, img2, gt = R.synthetic_scene(30, 34, 12, 2, 6, seed=P)
+        idx = R.train_indices(gt, [0], P)[:21]
+        codes = np.arange(21, dtype=np.uint8) % 7
+        h, l, y = ops.gather_patches(torch.from_numpy(img1).to(DEV), torch.from_numpy(img2).to(DEV),
+                                     torch.from_numpy(idx.astype(np.int32)).to(DEV), P, center_mode=True,
+                                     gt=torch.from_numpy(gt).to(DEV), ops=torch.from_numpy(codes).to(DEV))
+        for i, (x, yy) in enumerate(idx):
+            wh, wl, wy = R.augmented_sample(img1, img2, gt, int(x), int(yy), P, int(codes[i]))
+            assert h[i].cpu().numpy().tobytes() == wh.tobytes() and l[i].cpu().numpy().tobytes() == wl.tobytes()
+            assert int(y[i]) == int(wy)
+    # radiation noise: same draws, float64 arithmetic like numpy (datasets.py:528-532)
+    P = 7
+    img1, img2, gt = R.synthetic_scene(30, 34, 12, 2, 6, seed=1)
+    hp = dict(dataset="synthetic", patch_size=P, ignored_labels=[0], flip_augmentation=False,
+              radiation_augmentation=True, mixture_augmentation=False, center_pixel=True,
+              supervision="full", applyPCA=False, device=DEV)
+    np.random.seed(5)
+    ds = vitcnn_b200.MultiModalX(img1, img2, gt, **hp)
+    state = np.random.get_state()
+    h, l, y = ds.batch(np.arange(60))
+    np.random.set_state(state)
+    hit = 0
+    for i in range(60):
+        x, yy = ds.indices[i]
+        wh, wl, wy = R.augmented_sample(img1, img2, gt, int(x), int(yy), P, 0)
+        if np.random.random() < 0.1:
+            alpha = np.random.uniform(0.9, 1.1)
+            noise = np.random.normal(loc=0.0, scale=1.0, size=(P, P, 12))
+            d = R.radiation_noise(img1[x - P // 2:x - P // 2 + P, yy - P // 2:yy - P // 2 + P], alpha, noise)
+            wh = np.asarray(np.copy(d).transpose((2, 0, 1)), dtype="float32")
+            hit += 1
+        assert h[i].cpu().numpy().tobytes() == wh.tobytes(), i
+    assert hit > 0

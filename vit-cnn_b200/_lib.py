@@ -79,7 +79,8 @@ _PROTOS = {
     "vc_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
     "vc_tparams_layout": (c_int32, [c_int32, c_int32, POINTER(c_int64), c_int32]),
     "vc_gather_patches_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
-                                        c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                        c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                        c_void_p]),
     "vc_scene_index": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                  c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vc_confusion_matrix": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_int32, ctypes.c_uint64, c_void_p,
@@ -112,7 +113,7 @@ _PROTOS = {
     "vc_train_forward": (c_int32, [POINTER(VcTrain), c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64), c_int32,
                                    c_void_p, c_int64, c_void_p, c_void_p]),
     "vc_train_forward_gather": (c_int32, [POINTER(VcTrain), c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
-                                          c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+                                          c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "vc_train_backward": (c_int32, [POINTER(VcTrain), c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
     "vc_forward_patches": (c_int32, [POINTER(VcModel), c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64),
                                      c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
@@ -138,7 +139,7 @@ def lib() -> ctypes.CDLL:
         for name, (res, args) in _PROTOS.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        if L.vc_abi_version() != 2:
+        if L.vc_abi_version() != 3:
             raise RuntimeError("libvitcnn.so ABI version mismatch")
         _lib = L
     return _lib

@@ -198,15 +198,15 @@ int32_t vc_tparams_layout(int32_t P, int32_t K, int64_t* out, int32_t n) {
 }
 
 int vc_gather_patches_f32(const float* img1, const float* img2, const void* gt, int32_t gt_elem_bytes, int32_t H,
-                          int32_t W, int32_t C1, int32_t C2, const int32_t* xy, int32_t n, int32_t P,
+                          int32_t W, int32_t C1, int32_t C2, const int32_t* xy, const uint8_t* ops, int32_t n, int32_t P,
                           int32_t center_mode, float* hsi, float* lidar, int64_t* labels, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) return VC_OK;
   if (!xy || n < 0) return fail(VC_ERR_ARG, "vc_gather_patches_f32: bad arguments");
-  if (img1 && hsi) VC_TRY(vc::gather_f32_launch(img1, H, W, C1, xy, n, P, center_mode, hsi, st));
-  if (img2 && lidar) VC_TRY(vc::gather_f32_launch(img2, H, W, C2, xy, n, P, center_mode, lidar, st));
+  if (img1 && hsi) VC_TRY(vc::gather_f32_launch(img1, H, W, C1, xy, ops, n, P, center_mode, hsi, st));
+  if (img2 && lidar) VC_TRY(vc::gather_f32_launch(img2, H, W, C2, xy, ops, n, P, center_mode, lidar, st));
   if (gt && labels)
-    VC_TRY(vc::gather_labels_launch(gt, gt_elem_bytes, H, W, xy, n, P, center_mode, (long long*)labels, st));
+    VC_TRY(vc::gather_labels_launch(gt, gt_elem_bytes, H, W, xy, ops, n, P, center_mode, (long long*)labels, st));
   return VC_OK;
 }
 
@@ -228,7 +228,7 @@ int vc_confusion_matrix(const void* prediction, int32_t pred_elem_bytes, const v
 
 int vc_pack_sps(const float* src, int64_t sb, int64_t sc, int64_t si, int64_t sj, const int64_t* patch_off,
                 int32_t n_patches, int32_t C, int32_t P, void* sps, int32_t S, void* stream) {
-  VC_TRY(vc::pack_sps_launch(src, sb, sc, si, sj, (const long long*)patch_off, n_patches, C, P, sps, S,
+  VC_TRY(vc::pack_sps_launch(src, sb, sc, si, sj, (const long long*)patch_off, nullptr, n_patches, C, P, sps, S,
                              (cudaStream_t)stream));
   return VC_OK;
 }
@@ -269,8 +269,8 @@ int vc_forward_patches(const vc_model* m, const float* hsi, const int64_t hs[4],
     return fail(VC_ERR_ARG, "vc_forward_patches: bad arguments");
   if (workspace_bytes < vc_workspace_bytes(n, m->P, m->C1, m->C2)) return fail(VC_ERR_ARG, "workspace too small");
   const Workspace w = carve(workspace, n, m->P, m->S1, m->S2);
-  VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(hsi, hs[0], hs[1], hs[2], hs[3], nullptr, n, m->C1, m->P, w.a0, m->S1, st));
-  VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(lidar, ls[0], ls[1], ls[2], ls[3], nullptr, n, m->C2, m->P, w.l0, m->S2, st));
+  VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(hsi, hs[0], hs[1], hs[2], hs[3], nullptr, nullptr, n, m->C1, m->P, w.a0, m->S1, st));
+  VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(lidar, ls[0], ls[1], ls[2], ls[3], nullptr, nullptr, n, m->C2, m->P, w.l0, m->S2, st));
   VC_TRY(zero_halos(w, n, m->P, st));
   return forward_sps(m, w, n, logits, nullptr, nullptr, st);
 }
@@ -297,13 +297,13 @@ int vc_scene_infer(const vc_model* m, const float* img1, const float* img2, int3
     {
       Scope sc(KC_PACK, st);
       int rc = vc::pack_scene_launch(img1, W, m->C1, xs, ys, nx, ny, (int)(first_window + done), n, m->P, w.a0, m->S1, st);
-      if (rc == VC_ERR_UNSUPPORTED) rc = vc::pack_sps_launch(img1, 0, 1, s1, m->C1, w.off1, n, m->C1, m->P, w.a0, m->S1, st);
+      if (rc == VC_ERR_UNSUPPORTED) rc = vc::pack_sps_launch(img1, 0, 1, s1, m->C1, w.off1, nullptr, n, m->C1, m->P, w.a0, m->S1, st);
       if (rc != VC_OK) return fail(rc, "scene gather (hsi)");
     }
     {
       Scope sc(KC_PACK, st);
       int rc = vc::pack_scene_launch(img2, W, m->C2, xs, ys, nx, ny, (int)(first_window + done), n, m->P, w.l0, m->S2, st);
-      if (rc == VC_ERR_UNSUPPORTED) rc = vc::pack_sps_launch(img2, 0, 1, s2, m->C2, w.off2, n, m->C2, m->P, w.l0, m->S2, st);
+      if (rc == VC_ERR_UNSUPPORTED) rc = vc::pack_sps_launch(img2, 0, 1, s2, m->C2, w.off2, nullptr, n, m->C2, m->P, w.l0, m->S2, st);
       if (rc != VC_OK) return fail(rc, "scene gather (lidar)");
     }
     VC_TRY(forward_sps(m, w, n, logits_map, w.oidx, argmax_map, st));
@@ -634,14 +634,14 @@ int vc_train_forward(const vc_train* t, const float* hsi, const int64_t hs[4], c
   if (n <= 0 || !hsi || !lidar || !hs || !ls || !workspace || !logits) return fail(VC_ERR_ARG, "vc_train_forward: bad arguments");
   if (workspace_bytes < vc_train_workspace_bytes(t, n)) return fail(VC_ERR_ARG, "workspace too small");
   const TrainWs w = carve_train(workspace, t, pl, n);
-  VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(hsi, hs[0], hs[1], hs[2], hs[3], nullptr, n, t->C1, t->P, w.a0, pl[0].S_in, st));
-  VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(lidar, ls[0], ls[1], ls[2], ls[3], nullptr, n, t->C2, t->P, w.l0, pl[3].S_in, st));
+  VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(hsi, hs[0], hs[1], hs[2], hs[3], nullptr, nullptr, n, t->C1, t->P, w.a0, pl[0].S_in, st));
+  VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(lidar, ls[0], ls[1], ls[2], ls[3], nullptr, nullptr, n, t->C2, t->P, w.l0, pl[3].S_in, st));
   return train_forward_core(t, pl, w, n, logits, st);
 }
 
 int vc_train_forward_gather(const vc_train* t, const float* img1, const float* img2, const void* gt, int32_t gt_elem_bytes,
-                            int32_t H, int32_t W, const int32_t* xy, int32_t n, void* workspace, int64_t workspace_bytes,
-                            float* logits, int64_t* labels, void* stream) {
+                            int32_t H, int32_t W, const int32_t* xy, const uint8_t* ops, int32_t n, void* workspace,
+                            int64_t workspace_bytes, float* logits, int64_t* labels, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   ConvPlan pl[7];
   VC_TRY(check_train(t, pl));
@@ -650,10 +650,10 @@ int vc_train_forward_gather(const vc_train* t, const float* img1, const float* i
   if (workspace_bytes < vc_train_workspace_bytes(t, n)) return fail(VC_ERR_ARG, "workspace too small");
   const TrainWs w = carve_train(workspace, t, pl, n);
   VC_LAUNCH(KC_INDEX, st, vc::center_offsets_launch(xy, n, W, t->C1, t->C2, t->P, w.off1, w.off2, st));
-  VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(img1, 0, 1, (long long)W * t->C1, t->C1, w.off1, n, t->C1, t->P, w.a0, pl[0].S_in, st));
-  VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(img2, 0, 1, (long long)W * t->C2, t->C2, w.off2, n, t->C2, t->P, w.l0, pl[3].S_in, st));
+  VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(img1, 0, 1, (long long)W * t->C1, t->C1, w.off1, ops, n, t->C1, t->P, w.a0, pl[0].S_in, st));
+  VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(img2, 0, 1, (long long)W * t->C2, t->C2, w.off2, ops, n, t->C2, t->P, w.l0, pl[3].S_in, st));
   if (gt && labels)
-    VC_LAUNCH(KC_INDEX, st, vc::gather_labels_launch(gt, gt_elem_bytes, H, W, xy, n, t->P, 1, (long long*)labels, st));
+    VC_LAUNCH(KC_INDEX, st, vc::gather_labels_launch(gt, gt_elem_bytes, H, W, xy, ops, n, t->P, 1, (long long*)labels, st));
   return train_forward_core(t, pl, w, n, logits, st);
 }
 

@@ -18,8 +18,8 @@ namespace vc {
 // are whole 32-byte sectors of the pixel's channel vector.
 __global__ void __launch_bounds__(256) pack_sps_kernel(const float* __restrict__ src, long long sb, long long sc,
                                                        long long si, long long sj, const long long* __restrict__ patch_off,
-                                                       int n_patches, int C, int P, __nv_bfloat16* __restrict__ sps, int S,
-                                                       long long RT, int vec) {
+                                                       const unsigned char* __restrict__ ops, int n_patches, int C, int P,
+                                                       __nv_bfloat16* __restrict__ sps, int S, long long RT, int vec) {
   const int HALO = sps_halo(P), PP = sps_pp(P), PW = P + 1;
   for (long long R = (long long)blockIdx.x * blockDim.x + threadIdx.x; R < RT; R += (long long)gridDim.x * blockDim.x) {
     const long long r = R - HALO;
@@ -28,7 +28,11 @@ __global__ void __launch_bounds__(256) pack_sps_kernel(const float* __restrict__
       const long long b = r / PP;
       const int q = (int)(r - b * PP);
       const int i = q / PW, j = q - i * PW;
-      if (b < n_patches && i < P && j < P) p = src + (patch_off ? patch_off[b] : b * sb) + i * si + j * sj;
+      if (b < n_patches && i < P && j < P) {
+        int ii = i, jj = j;
+        if (ops) dihedral_src(ops[b], P, i, j, ii, jj);     // flip / rot90 augmentation = index remap
+        p = src + (patch_off ? patch_off[b] : b * sb) + ii * si + jj * sj;
+      }
     }
     uint4* dst = reinterpret_cast<uint4*>(sps) + R;
     if (!p) {
@@ -52,7 +56,7 @@ __global__ void __launch_bounds__(256) pack_sps_kernel(const float* __restrict__
 }
 
 int pack_sps_launch(const float* src, long long sb, long long sc, long long si, long long sj, const long long* patch_off,
-                    int n_patches, int C, int P, void* sps, int S, cudaStream_t stream) {
+                    const unsigned char* ops, int n_patches, int C, int P, void* sps, int S, cudaStream_t stream) {
   if (n_patches <= 0 || C <= 0 || S * 8 < C || P < 1) return VC_ERR_ARG;
   const long long RT = sps_rows(n_patches, P);
   const int vec = (sc == 1 && si % 4 == 0 && sj % 4 == 0 && sb % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0)
@@ -60,7 +64,7 @@ int pack_sps_launch(const float* src, long long sb, long long sc, long long si, 
                       : 0;  // patch_off entries are multiples of C in raster mode: 16-byte aligned iff C % 4 == 0
   long long blocks = (RT + 255) / 256;
   if (blocks > 148LL * 32) blocks = 148LL * 32;
-  pack_sps_kernel<<<(int)blocks, 256, 0, stream>>>(src, sb, sc, si, sj, patch_off, n_patches, C, P,
+  pack_sps_kernel<<<(int)blocks, 256, 0, stream>>>(src, sb, sc, si, sj, patch_off, ops, n_patches, C, P,
                                                    (__nv_bfloat16*)sps, S, RT, vec && (C % 4 == 0 || !patch_off));
   return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
 }
@@ -247,8 +251,9 @@ int zero_halo_launch(void* sps, int S, int n_patches, int P, cudaStream_t stream
 
 // ------------------------------------------------------------------------------------------
 // Exact fp32 gather: out[b][c][i][j] = img[x0+i][y0+j][c].
-__global__ void gather_f32_kernel(const float* __restrict__ img, int H, int W, int C, const int* __restrict__ xy, int n,
-                                  int P, int center_mode, float* __restrict__ out, int pitch, int vec_in, int vec_out) {
+__global__ void gather_f32_kernel(const float* __restrict__ img, int H, int W, int C, const int* __restrict__ xy,
+                                  const unsigned char* __restrict__ ops, int n, int P, int center_mode,
+                                  float* __restrict__ out, int pitch, int vec_in, int vec_out) {
   extern __shared__ float tile[];  // [P*P][pitch], pitch odd -> conflict-free transposed reads
   const int PP2 = P * P;
   const int rowlen = P * C;  // one patch row is contiguous in the raster
@@ -275,7 +280,15 @@ __global__ void gather_f32_kernel(const float* __restrict__ img, int H, int W, i
     __syncthreads();
     float* o = out + (long long)b * C * PP2;
     const int total = C * PP2;
-    if (vec_out) {
+    const int op = ops ? ops[b] : 0;
+    if (op) {           // augmented sample: output pixel (i, j) reads its source pixel from the staged patch
+      for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        const int c = t / PP2, pix = t - c * PP2;
+        int si_, sj_;
+        dihedral_src(op, P, pix / P, pix % P, si_, sj_);
+        o[t] = tile[(si_ * P + sj_) * pitch + c];
+      }
+    } else if (vec_out) {
       for (int t = threadIdx.x * 4; t < total; t += blockDim.x * 4) {
         float v[4];
 #pragma unroll
@@ -294,8 +307,8 @@ __global__ void gather_f32_kernel(const float* __restrict__ img, int H, int W, i
   }
 }
 
-int gather_f32_launch(const float* img, int H, int W, int C, const int* xy, int n, int P, int center_mode, float* out,
-                      cudaStream_t stream) {
+int gather_f32_launch(const float* img, int H, int W, int C, const int* xy, const unsigned char* ops, int n, int P,
+                      int center_mode, float* out, cudaStream_t stream) {
   if (n <= 0 || P < 1 || C < 1 || P > H || P > W) return VC_ERR_ARG;
   const int pitch = C | 1;
   const size_t smem = (size_t)P * P * pitch * sizeof(float);
@@ -311,16 +324,22 @@ int gather_f32_launch(const float* img, int H, int W, int C, const int* xy, int 
   const int vec_in = (C % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0) ? 1 : 0;
   const int vec_out = (((long long)C * P * P) % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
   int blocks = n < 148 * 8 ? n : 148 * 8;
-  gather_f32_kernel<<<blocks, 256, smem, stream>>>(img, H, W, C, xy, n, P, center_mode, out, pitch, vec_in, vec_out);
+  gather_f32_kernel<<<blocks, 256, smem, stream>>>(img, H, W, C, xy, ops, n, P, center_mode, out, pitch, vec_in, vec_out);
   return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
 }
 
 // Centre labels: labels[b] = int64(gt[x][y]) (datasets.py:573-581); gt is uint8 / int32 / int64.
-__global__ void gather_labels_kernel(const void* gt, int eb, int H, int W, const int* xy, int n, int P, int center_mode,
-                                     long long* labels) {
+__global__ void gather_labels_kernel(const void* gt, int eb, int H, int W, const int* xy, const unsigned char* ops, int n, int P,
+                                     int center_mode, long long* labels) {
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) {
     int x = xy[2 * b], y = xy[2 * b + 1];
     if (!center_mode) { x += P / 2; y += P / 2; }
+    if (ops && ops[b]) {      // label = transformed label window at [P/2, P/2] (datasets.py:557-581; matters for even P)
+      int si_, sj_;
+      dihedral_src(ops[b], P, P / 2, P / 2, si_, sj_);
+      x += si_ - P / 2;
+      y += sj_ - P / 2;
+    }
     const long long e = (long long)x * W + y;
     long long v;
     if (eb == 1) v = reinterpret_cast<const unsigned char*>(gt)[e];
@@ -330,10 +349,10 @@ __global__ void gather_labels_kernel(const void* gt, int eb, int H, int W, const
   }
 }
 
-int gather_labels_launch(const void* gt, int eb, int H, int W, const int* xy, int n, int P, int center_mode,
-                         long long* labels, cudaStream_t stream) {
+int gather_labels_launch(const void* gt, int eb, int H, int W, const int* xy, const unsigned char* ops, int n, int P,
+                         int center_mode, long long* labels, cudaStream_t stream) {
   if (n <= 0 || (eb != 1 && eb != 4 && eb != 8)) return VC_ERR_ARG;
-  gather_labels_kernel<<<(n + 255) / 256, 256, 0, stream>>>(gt, eb, H, W, xy, n, P, center_mode, labels);
+  gather_labels_kernel<<<(n + 255) / 256, 256, 0, stream>>>(gt, eb, H, W, xy, ops, n, P, center_mode, labels);
   return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
 }
 

@@ -26,6 +26,19 @@ __host__ __device__ inline long long sps_rows(int n, int P) {
   return (long long)sps_halo(P) * 2 + (long long)sps_tiles(n, P) * 128;
 }
 
+// Source pixel of output pixel (i, j) of a P x P patch under the reference's spatial augmentations
+// (datasets.py:510-526): op 0 identity, 1 fliplr, 2 flipud, 3 both, 4/5/6 np.rot90 with k = 1/2/3.
+__host__ __device__ inline void dihedral_src(int op, int P, int i, int j, int& si, int& sj) {
+  switch (op) {
+    case 1: si = i; sj = P - 1 - j; break;
+    case 2: si = P - 1 - i; sj = j; break;
+    case 3: case 5: si = P - 1 - i; sj = P - 1 - j; break;
+    case 4: si = j; sj = P - 1 - i; break;
+    case 6: si = P - 1 - j; sj = i; break;
+    default: si = i; sj = j; break;
+  }
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }

@@ -12,14 +12,14 @@ int conv_sps_launch(const void* in, int S_in, const void* w, const float* scale,
 
 // pack.cu
 int pack_sps_launch(const float* src, long long sb, long long sc, long long si, long long sj, const long long* patch_off,
-                    int n_patches, int C, int P, void* sps, int S, cudaStream_t stream);
+                    const unsigned char* ops, int n_patches, int C, int P, void* sps, int S, cudaStream_t stream);
 int pack_scene_launch(const float* img, int W, int C, const int* xs, const int* ys, int nx, int ny, int first, int count,
                       int P, void* sps, int S, cudaStream_t stream);
 int zero_halo_launch(void* sps, int S, int n_patches, int P, cudaStream_t stream);
-int gather_f32_launch(const float* img, int H, int W, int C, const int* xy, int n, int P, int center_mode, float* out,
-                      cudaStream_t stream);
-int gather_labels_launch(const void* gt, int gt_elem_bytes, int H, int W, const int* xy, int n, int P, int center_mode,
-                         long long* labels, cudaStream_t stream);
+int gather_f32_launch(const float* img, int H, int W, int C, const int* xy, const unsigned char* ops, int n, int P,
+                      int center_mode, float* out, cudaStream_t stream);
+int gather_labels_launch(const void* gt, int gt_elem_bytes, int H, int W, const int* xy, const unsigned char* ops, int n, int P,
+                         int center_mode, long long* labels, cudaStream_t stream);
 int scene_index_launch(const int* xs, const int* ys, int nx, int ny, int first, int count, int W, int C1, int C2, int P,
                        int K, long long* off1, long long* off2, long long* out_idx, int* xy, cudaStream_t stream);
 

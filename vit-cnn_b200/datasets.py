@@ -23,9 +23,9 @@ class MultiModalX(torch.utils.data.Dataset):
         self.radiation_augmentation = hyperparams["radiation_augmentation"]
         self.mixture_augmentation = hyperparams["mixture_augmentation"]
         self.center_pixel = hyperparams["center_pixel"]
-        if self.flip_augmentation or self.radiation_augmentation or self.mixture_augmentation:
-            raise NotImplementedError("augmentations are not implemented on the device path yet "
-                                      "(mixture_augmentation is broken upstream: SURVEY.md App. C rule 2)")
+        if self.mixture_augmentation:
+            raise NotImplementedError("mixture_augmentation is broken upstream (its label lookup compares a list with "
+                                      "a scalar and raises, SURVEY.md App. C rule 2) and is not implemented")
         if hyperparams.get("applyPCA", False) == True:  # noqa: E712
             raise ValueError("ViT-CNN runs on the full band set: applyPCA must be False")
         if not self.center_pixel or self.patch_size < 2:
@@ -59,11 +59,43 @@ class MultiModalX(torch.utils.data.Dataset):
     def __len__(self):
         return len(self.indices)
 
+    def draw_augmentation(self, n: int):
+        """The numpy RNG draws of n consecutive ``__getitem__`` calls (datasets.py:559-566, 510-532), in
+        the reference's order: per item the flip / rotate decision, then the radiation-noise decision with
+        its alpha and its [P,P,C1] normal noise.  Returns (ops uint8 [n], list of (item, alpha, noise))."""
+        P, C1 = self.patch_size, self.data.shape[2]
+        codes, rad = np.zeros(n, dtype=np.uint8), []
+        for i in range(n):
+            if self.flip_augmentation and P > 1:
+                if np.random.random() > 0.5:                       # flip(): horizontal, then vertical draw
+                    horizontal = np.random.random() > 0.5
+                    vertical = np.random.random() > 0.5
+                    codes[i] = int(horizontal) + 2 * int(vertical)
+                elif np.random.random() > 0.5:                     # rotate()
+                    codes[i] = 3 + int(np.random.choice([1, 2, 3]))
+            if self.radiation_augmentation and np.random.random() < 0.1:
+                alpha = np.random.uniform(0.9, 1.1)
+                rad.append((i, alpha, np.random.normal(loc=0.0, scale=1.0, size=(P, P, C1))))
+        return codes, rad
+
     def batch(self, idx):
-        """(data [B,C1,P,P] f32, data2 [B,C2,P,P] f32, target int64 [B]) for sample numbers idx."""
+        """(data [B,C1,P,P] f32, data2 [B,C2,P,P] f32, target int64 [B]) for sample numbers idx; with the
+        augmentation flags on, the RNG decisions are drawn on the host exactly as the reference's
+        ``__getitem__`` would for these items in this order, flips / rot90 are applied by the gather
+        kernel (index remap), radiation noise as alpha * x (float32) + noise / 25 (float64) like numpy."""
         idx = torch.as_tensor(idx, dtype=torch.int64, device=self.device).reshape(-1)
         xy = self._xy[idx].contiguous()
-        return ops.gather_patches(self.data, self.data2, xy, self.patch_size, center_mode=True, gt=self.label)
+        codes, rad = None, []
+        if self.flip_augmentation or self.radiation_augmentation:
+            c, rad = self.draw_augmentation(idx.numel())
+            codes = torch.from_numpy(c).to(self.device) if c.any() else None
+        data, data2, target = ops.gather_patches(self.data, self.data2, xy, self.patch_size, center_mode=True,
+                                                 gt=self.label, ops=codes)
+        for i, alpha, noise in rad:                                   # datasets.py:528-532
+            nz = torch.from_numpy(noise).to(self.device).permute(2, 0, 1)
+            # numpy: python-float alpha times a float32 array stays float32; the float64 noise term promotes the sum
+            data[i] = ((data[i] * float(alpha)).double() + (1 / 25) * nz).float()
+        return data, data2, target
 
     def centres(self, idx):
         idx = torch.as_tensor(idx, dtype=torch.int64, device=self.device).reshape(-1)

@@ -20,10 +20,11 @@ def sps_rows(n: int, P: int) -> int:
     return int(_lib.lib().vc_sps_rows(n, P))
 
 
-def gather_patches(img1, img2, xy, P, center_mode=True, gt=None):
+def gather_patches(img1, img2, xy, P, center_mode=True, gt=None, ops=None):
     """Exact fp32 patch extraction.  img1 [H,W,C1] f32, img2 [H,W,C2] f32 (CUDA, contiguous),
     xy int32 [n,2] centres (center_mode) or top-left corners.  Returns (hsi [n,C1,P,P],
-    lidar [n,C2,P,P], labels int64 [n] or None)."""
+    lidar [n,C2,P,P], labels int64 [n] or None).  ``ops`` (uint8 [n], optional): flip / rot90 code of each
+    sample (0 identity, 1 fliplr, 2 flipud, 3 both, 4/5/6 rot90 k=1/2/3), applied as an index remap."""
     if not img1.is_cuda:
         raise RuntimeError("gather_patches needs CUDA tensors (no CPU path)")
     assert img1.dtype == torch.float32 and img2.dtype == torch.float32
@@ -42,8 +43,10 @@ def gather_patches(img1, img2, xy, P, center_mode=True, gt=None):
             raise ValueError("gt must be uint8, int32 or int64")
         labels = torch.empty(n, dtype=torch.int64, device=img1.device)
     with torch.cuda.device(img1.device):
+        if ops is not None:
+            ops = ops.to(device=img1.device, dtype=torch.uint8).contiguous()
         _lib.check(_lib.lib().vc_gather_patches_f32(img1.data_ptr(), img2.data_ptr(), _ptr(gt), eb, H, W, C1, C2,
-                                                    xy.data_ptr(), n, P, 1 if center_mode else 0, hsi.data_ptr(),
+                                                    xy.data_ptr(), _ptr(ops), n, P, 1 if center_mode else 0, hsi.data_ptr(),
                                                     lid.data_ptr(), _ptr(labels), _stream()), "vc_gather_patches_f32")
     return hsi, lid, labels
 

@@ -195,7 +195,7 @@ class TrainState:
         self.model._pack = None      # running statistics changed: eval-mode packing is stale
         return logits
 
-    def forward_gather(self, img1, img2, gt, xy):
+    def forward_gather(self, img1, img2, gt, xy, ops=None):
         n = xy.shape[0]
         H, W, _ = img1.shape
         logits = torch.empty(n, self.model.num_classes, dtype=torch.float32, device=self.device)
@@ -204,7 +204,8 @@ class TrainState:
             ws = self.workspace(n)
             _lib.check(_lib.lib().vc_train_forward_gather(
                 ctypes.byref(self.struct), img1.data_ptr(), img2.data_ptr(), 0 if gt is None else gt.data_ptr(),
-                0 if gt is None else gt.element_size(), H, W, xy.data_ptr(), n, ws.data_ptr(), ws.numel(),
+                0 if gt is None else gt.element_size(), H, W, xy.data_ptr(), 0 if ops is None else ops.data_ptr(), n,
+                ws.data_ptr(), ws.numel(),
                 logits.data_ptr(), 0 if labels is None else labels.data_ptr(),
                 torch.cuda.current_stream().cuda_stream), "vc_train_forward_gather")
         self.pending = n
@@ -332,9 +333,9 @@ class Trainer:
         self.set_lr(base_lr * gamma ** (epoch // step_size))
         return self.lr
 
-    def _step_impl(self, img1, img2, gt, xy):
+    def _step_impl(self, img1, img2, gt, xy, ops=None):
         st = self.state
-        logits, labels = st.forward_gather(img1, img2, gt, xy)
+        logits, labels = st.forward_gather(img1, img2, gt, xy, ops)
         loss, dlogits = ce_loss(logits, labels, self.weights)
         st.backward(dlogits)
         if self.world > 1:
@@ -346,16 +347,17 @@ class Trainer:
                        "vc_adam_step_dev")
         return loss
 
-    def step(self, img1, img2, gt, xy):
-        """One optimisation step on patches centred at xy (int32 [n,2], device).  Returns the
+    def step(self, img1, img2, gt, xy, ops=None):
+        """One optimisation step on patches centred at xy (int32 [n,2], device); ``ops`` (uint8 [n],
+        device, optional) = flip / rot90 augmentation code per sample, drawn by the host.  Returns the
         loss tensor [2] (mean loss of this rank, weight sum) without synchronising."""
         st = self.state
         if not st.valid():
             raise RuntimeError("model parameters were moved after the Trainer was built")
         self.model._pack = None
         n = xy.shape[0]
-        if not self.use_graph:
-            return self._step_impl(img1, img2, gt, xy)
+        if not self.use_graph or ops is not None:
+            return self._step_impl(img1, img2, gt, xy, ops)
         st = train_state(self.model)                      # picks up a changed model.dropout
         entry = self._graphs.get(n)
         if entry is not None and entry[3] == (img1.data_ptr(), img2.data_ptr(), gt.data_ptr(), st.struct.dropout):
