@@ -104,6 +104,11 @@ int vc_scene_index(const int32_t* xs, const int32_t* ys, int32_t nx, int32_t ny,
 int vc_confusion_matrix(const void* prediction, int32_t pred_elem_bytes, const void* target, int32_t target_elem_bytes, int64_t n,
                         int32_t n_classes, uint64_t ignored_mask, int64_t* cm, void* stream);
 
+/* ---- raster ingest: min-max normalisation to [0,1] in place (datasets.py:124-133) ----------------
+ * img f32 [n_pixels][C]; per_band = 1: each band by its own min / max (the HSI cube), 0: one min / max
+ * for the whole array (the LiDAR raster); scratch: 2*C floats.  Bit-exact with numpy's float32 form. */
+int vc_minmax_normalise(float* img, int64_t n_pixels, int32_t C, int32_t per_band, float* scratch, void* stream);
+
 /* ---- building blocks (exposed for tests and profiling) --------------------------------------- */
 /* fp32 patches (any strides, in elements) or raster windows (patch_off != NULL: per-patch
  * element offset, sb ignored) -> bf16 SPS buffer [S][rows][8]. */

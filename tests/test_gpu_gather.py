@@ -139,3 +139,18 @@ def test_all_dihedral_ops_and_radiation_noise_vs_oracle():
             hit += 1
         assert h[i].cpu().numpy().tobytes() == wh.tobytes(), i
     assert hit > 0
+
+
+def test_minmax_normalise_bit_exact():
+    """Raster ingest (datasets.py:124-133): per-band (HSI) and whole-array (LiDAR) min-max to [0,1]."""
+    from vitcnn_b200.utils import minmax_normalise_
+    rng = np.random.default_rng(4)
+    for H, W, C in ((37, 53, 144), (20, 31, 1), (19, 23, 5)):
+        raw = (rng.random((H, W, C), dtype=np.float32) * 4000 - 300).astype(np.float32)
+        want = R.minmax_normalise(raw)
+        got = minmax_normalise_(torch.from_numpy(raw.copy()).to(DEV)).cpu().numpy()
+        assert got.tobytes() == want.tobytes()
+        lo, hi = raw.min(), raw.max()
+        want_g = (raw - lo) / (hi - lo)
+        got_g = minmax_normalise_(torch.from_numpy(raw.copy()).to(DEV), per_band=False).cpu().numpy()
+        assert got_g.tobytes() == want_g.tobytes()

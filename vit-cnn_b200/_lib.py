@@ -85,6 +85,7 @@ _PROTOS = {
                                  c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vc_confusion_matrix": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_int32, ctypes.c_uint64, c_void_p,
                                       c_void_p]),
+    "vc_minmax_normalise": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "vc_pack_sps": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int32, c_int32, c_int32,
                               c_void_p, c_int32, c_void_p]),
     "vc_conv_sps": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,

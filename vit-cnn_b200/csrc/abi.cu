@@ -226,6 +226,11 @@ int vc_confusion_matrix(const void* prediction, int32_t pred_elem_bytes, const v
   return VC_OK;
 }
 
+int vc_minmax_normalise(float* img, int64_t n_pixels, int32_t C, int32_t per_band, float* scratch, void* stream) {
+  VC_LAUNCH(KC_MISC, (cudaStream_t)stream, vc::minmax_normalise_launch(img, n_pixels, C, per_band, scratch, (cudaStream_t)stream));
+  return VC_OK;
+}
+
 int vc_pack_sps(const float* src, int64_t sb, int64_t sc, int64_t si, int64_t sj, const int64_t* patch_off,
                 int32_t n_patches, int32_t C, int32_t P, void* sps, int32_t S, void* stream) {
   VC_TRY(vc::pack_sps_launch(src, sb, sc, si, sj, (const long long*)patch_off, nullptr, n_patches, C, P, sps, S,

@@ -43,3 +43,78 @@ int confusion_launch(const void* pred, int peb, const void* target, int teb, lon
 }
 
 }  // namespace vc
+
+// ------------------------------------------------------------------------------------------------
+// Raster ingest: per-band min-max normalisation to [0, 1] (datasets.py:124-133 for the HSI cube, and
+// the whole-array form used for the LiDAR raster), in place on the pixel-interleaved fp32 raster:
+//   x <- (x - min_band) / (max_band - min_band)      (float32 subtract and divide: bit-exact with numpy)
+namespace vc {
+
+__device__ __forceinline__ void atomic_min_f(float* addr, float v) {
+  int* a = reinterpret_cast<int*>(addr);
+  int old = *a;
+  while (__int_as_float(old) > v) {
+    const int assumed = old;
+    old = atomicCAS(a, assumed, __float_as_int(v));
+    if (old == assumed) break;
+  }
+}
+__device__ __forceinline__ void atomic_max_f(float* addr, float v) {
+  int* a = reinterpret_cast<int*>(addr);
+  int old = *a;
+  while (__int_as_float(old) < v) {
+    const int assumed = old;
+    old = atomicCAS(a, assumed, __float_as_int(v));
+    if (old == assumed) break;
+  }
+}
+
+// mm[c] = min, mm[Cs + c] = max over all pixels (Cs = C per band, 1 when global)
+__global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ img, long long npix, int C, int per_band,
+                                                     float* __restrict__ mm) {
+  const int Cb = C < 256 ? C : 256;               // channels handled side by side
+  const int lanes = 256 / Cb;                     // pixels handled side by side
+  const int tc = threadIdx.x % Cb, tp = threadIdx.x / Cb;
+  if (tp >= lanes) return;
+  for (int c0 = 0; c0 < C; c0 += Cb) {
+    const int c = c0 + tc;
+    if (c >= C) continue;
+    float lo = INFINITY, hi = -INFINITY;
+    for (long long p = (long long)blockIdx.x * lanes + tp; p < npix; p += (long long)gridDim.x * lanes) {
+      const float v = __ldg(img + p * C + c);
+      lo = fminf(lo, v);
+      hi = fmaxf(hi, v);
+    }
+    const int slot = per_band ? c : 0, Cs = per_band ? C : 1;
+    if (lo <= hi) {
+      atomic_min_f(mm + slot, lo);
+      atomic_max_f(mm + Cs + slot, hi);
+    }
+  }
+}
+__global__ void minmax_init_kernel(float* mm, int Cs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Cs) { mm[i] = INFINITY; mm[Cs + i] = -INFINITY; }
+}
+__global__ void __launch_bounds__(256) minmax_apply_kernel(float* __restrict__ img, long long total, int C, int per_band,
+                                                           const float* __restrict__ mm) {
+  const int Cs = per_band ? C : 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = per_band ? (int)(i % C) : 0;
+    const float lo = mm[c], hi = mm[Cs + c];
+    img[i] = (img[i] - lo) / (hi - lo);
+  }
+}
+
+int minmax_normalise_launch(float* img, long long npix, int C, int per_band, float* scratch, cudaStream_t stream) {
+  if (npix <= 0 || C < 1 || !img || !scratch) return VC_ERR_ARG;
+  const int Cs = per_band ? C : 1;
+  minmax_init_kernel<<<(Cs + 255) / 256, 256, 0, stream>>>(scratch, Cs);
+  minmax_kernel<<<148 * 4, 256, 0, stream>>>(img, npix, C, per_band, scratch);
+  long long blocks = (npix * C + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  minmax_apply_kernel<<<(int)blocks, 256, 0, stream>>>(img, npix * C, C, per_band, scratch);
+  return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
+}
+
+}  // namespace vc

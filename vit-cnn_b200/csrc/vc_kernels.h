@@ -35,6 +35,8 @@ int lidar_stem_launch(const void* in_sps, const void* blob, void* out_sps, int o
 int confusion_launch(const void* pred, int peb, const void* target, int teb, long long n, int K, unsigned long long ignored_mask,
                      long long* cm, cudaStream_t stream);
 
+int minmax_normalise_launch(float* img, long long npix, int C, int per_band, float* scratch, cudaStream_t stream);
+
 // transformer.cu
 size_t tparams_bytes(int P, int K);
 int transformer_fwd_launch(const void* f_sps, const void* tparams, int n_patches, int P, int K, float* logits,

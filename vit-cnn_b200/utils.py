@@ -139,3 +139,20 @@ def metrics(prediction, target, ignored_labels=[], n_classes=None):
         pe = np.sum(cs * rs) / float(total * total)
         results["Kappa"] = (pa - pe) / (1 - pe)
     return results
+
+
+def minmax_normalise_(img, per_band: bool = True):
+    """Min-max normalisation to [0, 1] of a CUDA raster f32 [H, W, C], in place (datasets.py:124-133:
+    per band for the HSI cube; ``per_band=False`` = one min / max for the whole array, as the reference
+    does for the LiDAR raster).  Bit-exact with numpy's float32 arithmetic."""
+    import torch
+    from . import _lib
+    if not img.is_cuda or img.dtype != torch.float32 or not img.is_contiguous():
+        raise RuntimeError("minmax_normalise_ needs a contiguous CUDA float32 raster (no CPU path)")
+    C = img.shape[-1]
+    scratch = torch.empty(2 * C, dtype=torch.float32, device=img.device)
+    with torch.cuda.device(img.device):
+        _lib.check(_lib.lib().vc_minmax_normalise(img.data_ptr(), img.numel() // C, C, 1 if per_band else 0,
+                                                  scratch.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                   "vc_minmax_normalise")
+    return img
