@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
       for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc2[j][e] = 0.f;
-#pragma unroll 2
+#pragma unroll 1
       for (int hk = 0; hk < kHidden / 16; ++hk) {
         float h0[4] = {0.f, 0.f, 0.f, 0.f}, h1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -755,7 +755,7 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
       for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int e = 0; e < 4; ++e) dln2[j][e] = 0.f;
-#pragma unroll 2
+#pragma unroll 1
       for (int hk = 0; hk < kHidden / 16; ++hk) {
         float h0[4] = {0.f, 0.f, 0.f, 0.f}, h1[4] = {0.f, 0.f, 0.f, 0.f};
         float e0[4] = {0.f, 0.f, 0.f, 0.f}, e1[4] = {0.f, 0.f, 0.f, 0.f};
@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
           const float m0 = st_m[h * TP + r0], m1 = st_m[h * TP + r1];
           const float il0 = st_il[h * TP + r0], il1 = st_il[h * TP + r1];
           const float dl0 = st_dl[h * TP + r0], dl1 = st_dl[h * TP + r1];
-#pragma unroll
+#pragma unroll 2
           for (int kk = 0; kk < NW; ++kk) {
             float ds[2][4];
 #pragma unroll
@@ -876,7 +876,7 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
           const uint32_t ka0 = lds32(Ks + r0 * LD + 8 * h + 2 * q), ka1 = lds32(Ks + r1 * LD + 8 * h + 2 * q);
           const uint32_t va0 = lds32(Vs + r0 * LD + 8 * h + 2 * q), va1 = lds32(Vs + r1 * LD + 8 * h + 2 * q);
           const bool kv0 = r0 < T, kv1 = r1 < T;
-#pragma unroll
+#pragma unroll 2
           for (int kk = 0; kk < NW; ++kk) {
             float ds[2][4], pt[2][4];
 #pragma unroll
