@@ -204,6 +204,40 @@ def bench_train(args, rank, world, dev, dist, barrier):
                          "profiled_step_ms": total_ms}}
 
 
+def cpu_train_rate(seconds: float, threads: int, batch: int = 64):
+    """Training throughput of the fp32 oracle on the host cores: the reference's own loop body
+    (model_utils.py:908-945: forward, weighted CE, backward, Adam) at its default batch size 64 on
+    patches cut from a synthetic Houston-shaped raster, for about `seconds` of work."""
+    from oracle import data_ref as R
+    from oracle.model_ref import ViTCNNRef
+    import torch.nn.functional as F
+    torch.set_num_threads(threads)
+    rng = np.random.default_rng(2)
+    rows = 3 * P
+    img1 = rng.random((rows, W, C1), dtype=np.float32)
+    img2 = rng.random((rows, W, C2), dtype=np.float32)
+    gt = rng.integers(1, K, size=(rows, W)).astype(np.int64)
+    torch.manual_seed(0)
+    ref = ViTCNNRef(C1, C2, patch_size=P, num_classes=K).train()
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    w = torch.ones(K)
+    w[0] = 0
+    p = P // 2
+    done, t0 = 0, time.perf_counter()
+    while True:
+        xy = np.stack([rng.integers(p + 1, rows - p - 1, batch), rng.integers(p + 1, W - p - 1, batch)], 1)
+        h, l, y = R.gather_centers(img1, img2, gt, xy, P)
+        loss = F.cross_entropy(ref(torch.from_numpy(h), torch.from_numpy(l)), torch.from_numpy(y), w)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        done += batch
+        if time.perf_counter() - t0 > seconds:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, done, dt
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -218,13 +252,16 @@ def run_reference(args, rank):
         samples += n
     dt = time.perf_counter() - t0
     v = float(np.mean(vals))
+    tv, tn, tdt = cpu_train_rate(8.0, threads)
     line = {"impl": "reference", "metric": "full_scene_inference_pixels_per_s", "value": v, "unit": "pixels/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "fp32 oracle port on host cores (reference ships no ViT-CNN source)"},
             "cpu_baseline": {"value": v, "unit": "pixels/s", "cores": threads, "kind": "port",
                              "sample": f"{samples} windows of a {P + 3}-row band, batch 64, extrapolated to the scene"},
-            "e2e": {"value": v, "unit": "pixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": v, "unit": "pixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "train": {"metric": "train_samples_per_s", "value": tv, "unit": "samples/s", "cores": threads, "kind": "port",
+                      "sample": f"{tn} samples ({tdt:.1f} s), batch 64 (the reference's default), fp32 oracle + torch Adam"}}
     print(json.dumps(line), flush=True)
 
 
@@ -402,6 +439,10 @@ def main():
                                  "sample": f"{cpu_n} windows ({cpu_dt:.1f} s) of a {P + 3}-row band, batch 64, "
                                            "extrapolated to the scene"}}
         if train_line is not None:
+            if not args.no_cpu:
+                tv, tn, tdt = cpu_train_rate(min(args.cpu_seconds, 8.0), os.cpu_count() or 1)
+                train_line["cpu_baseline"] = {"value": tv, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                              "sample": f"{tn} samples ({tdt:.1f} s), batch 64, fp32 oracle + torch Adam"}
             line["train"] = train_line
         print(json.dumps(line), flush=True)
     if world > 1:
