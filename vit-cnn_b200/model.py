@@ -340,7 +340,9 @@ class ViTCNN(nn.Module):
             L = _lib.lib()
             with torch.cuda.device(dev):
                 pk = self.pack_for_inference()
-                chunk = int(min(chunk, count))
+                # equal-sized chunks (no short tail launch): ceil(count / ceil(count / chunk))
+                n_chunks = -(-count // int(chunk))
+                chunk = -(-count // n_chunks)
                 ws = self._workspace(chunk, dev)
                 stream = torch.cuda.current_stream().cuda_stream
                 _lib.check(L.vc_scene_infer(ctypes.byref(pk["struct"]), img1.data_ptr(), img2.data_ptr(), H, W,
