@@ -123,6 +123,13 @@ int vc_conv_sps(const void* in_sps, int32_t S_in, const void* w_packed, const fl
  * out_index[b] when given); argmax_map (nullable, uint8) receives argmax at out_index[b]. */
 int vc_tokens_forward(const void* f_sps, const void* tparams, int32_t n_patches, int32_t P, int32_t K, float* logits,
                       const int64_t* out_index, uint8_t* argmax_map, void* stream);
+/* The same token stage on the tcgen05 tensor cores (eval mode; the token set of a patch must fit one
+ * M = 128 tile: P*P + 1 <= 128, else VC_ERR_UNSUPPORTED).  scratch: caller-owned device buffer of
+ * vc_tokens_tc_scratch_bytes(n_patches) bytes.  vc_forward_patches / vc_scene_infer pick this kernel
+ * themselves when it applies (scratch = a dead part of their workspace). */
+int64_t vc_tokens_tc_scratch_bytes(int32_t n_patches);
+int vc_tokens_forward_tc(const void* f_sps, const void* tparams, int32_t n_patches, int32_t P, int32_t K, float* logits,
+                         const int64_t* out_index, uint8_t* argmax_map, void* scratch, int64_t scratch_bytes, void* stream);
 
 /* ---- training building blocks ------------------------------------------------------------------
  * Weight gradient of a 3x3 pad-1 conv (taps=9) or of a linear / 1x1 conv (taps=1) over SPS

@@ -98,6 +98,15 @@ int zero_halos(const Workspace& w, int n, int P, cudaStream_t st) {
   return VC_OK;
 }
 
+// bring-up / A-B knob: VITCNN_TOKENS_IMPL=0 selects the mma.sync token kernel for every patch size
+int tokens_impl() {
+  static const int impl = [] {
+    const char* e = getenv("VITCNN_TOKENS_IMPL");
+    return e ? atoi(e) : 1;
+  }();
+  return impl;
+}
+
 int forward_sps(const vc_model* m, const Workspace& w, int n, float* logits, const long long* out_index,
                 uint8_t* argmax_map, cudaStream_t st) {
   const int P = m->P;
@@ -122,7 +131,12 @@ int forward_sps(const vc_model* m, const Workspace& w, int n, float* logits, con
     VC_LAUNCH(KC_CONV_L, st, vc::conv_sps_launch(w.l2, 2, m->w_l[2], m->scale_l[2], m->bias_l[2], w.f, 4, 32, m->nsplit_l[2], n, P, 9, 1,
                                                  0, 0, st));
   }
-  VC_LAUNCH(KC_TOKENS, st, vc::transformer_fwd_launch(w.f, m->tparams, n, P, m->K, logits, out_index, argmax_map, 0, 0, nullptr, st));
+  // token stage: tcgen05 kernel when the token set fits one M = 128 tile (P <= 11), the mma.sync kernel
+  // otherwise.  conv 1's output (w.a1) is dead by now and serves as the cls-record scratch.
+  if (tokens_impl() == 1 && vc::tokens_tc_supported(P, m->K))
+    VC_LAUNCH(KC_TOKENS, st, vc::tokens_tc_launch(w.f, m->tparams, n, P, m->K, logits, out_index, argmax_map, w.a1, st));
+  else
+    VC_LAUNCH(KC_TOKENS, st, vc::transformer_fwd_launch(w.f, m->tparams, n, P, m->K, logits, out_index, argmax_map, 0, 0, nullptr, st));
   return VC_OK;
 }
 
@@ -250,6 +264,18 @@ int vc_tokens_forward(const void* f_sps, const void* tparams, int32_t n_patches,
                       const int64_t* out_index, uint8_t* argmax_map, void* stream) {
   VC_TRY(vc::transformer_fwd_launch(f_sps, tparams, n_patches, P, K, logits, (const long long*)out_index, argmax_map,
                                     0, 0, nullptr, (cudaStream_t)stream));
+  return VC_OK;
+}
+
+int64_t vc_tokens_tc_scratch_bytes(int32_t n_patches) { return (int64_t)vc::tokens_tc_scratch_bytes(n_patches); }
+
+int vc_tokens_forward_tc(const void* f_sps, const void* tparams, int32_t n_patches, int32_t P, int32_t K, float* logits,
+                         const int64_t* out_index, uint8_t* argmax_map, void* scratch, int64_t scratch_bytes, void* stream) {
+  if (!f_sps || !tparams || !logits || !scratch || scratch_bytes < vc_tokens_tc_scratch_bytes(n_patches))
+    return fail(VC_ERR_ARG, "vc_tokens_forward_tc: bad argument / scratch too small");
+  if (!vc::tokens_tc_supported(P, K)) return fail(VC_ERR_UNSUPPORTED, "vc_tokens_forward_tc: needs P*P + 1 <= 128");
+  VC_TRY(vc::tokens_tc_launch(f_sps, tparams, n_patches, P, K, logits, (const long long*)out_index, argmax_map, scratch,
+                              (cudaStream_t)stream));
   return VC_OK;
 }
 

@@ -1,0 +1,747 @@
+// Token stage of the ViT-CNN hybrid on the 5th-gen tensor cores (eval mode, P*P + 1 <= 128 tokens).
+//
+// Same function as transformer_fwd_kernel (transformer.cu; spec SURVEY.md App. A, following
+// model/compare_method/vit/timm/models/vision_transformer.py:57-105 Attention, :123-166 Block,
+// :598-629 cls/pos, :680-701 norm/head and timm/layers/mlp.py:13-47), re-laid for tcgen05:
+//
+//  * one patch = one M = 128 tile: token row r lives in TMEM lane r and in thread r of a
+//    128-thread group, so LayerNorm, the softmax row maximum and every bias / GELU / residual
+//    epilogue are thread-local (no shuffles); the residual stream stays in 32 registers;
+//  * every GEMM of the block (fusion 1x1 conv, qkv, QK^T per head, PV per head, proj, fc1, fc2)
+//    is a tcgen05.mma with the accumulator in TMEM; A operands are written by the row threads
+//    straight into the no-swizzle K-major canonical layout ([k/8][row][8] = 2 KB slabs), weights
+//    are re-laid into that layout once per persistent CTA;
+//  * head_dim = 8 is half of the K = 16 of one bf16 MMA: the K operand's second 8-element chunk
+//    is pointed (leading-byte-offset field) at a slab of zeros, so S_h = Q_h K_h^T needs no
+//    padded copies; V is consumed MN-major ([key][8 dims] slabs) and its second N chunk is a
+//    slab of (1,0,..,0) rows, so column 8 of the PV accumulator is the softmax denominator of
+//    the bf16-rounded probabilities;
+//  * a CTA runs two independent 128-thread groups ("slots", 256 TMEM columns each) so one
+//    slot's MMA round trips hide behind the other's softmax; the fusion-conv input of the next
+//    patch is prefetched by 1-D bulk copies (TMA unit) into its own buffer;
+//  * the last block only feeds the head through the cls token (x[:, 0]): K / V of every token
+//    come from one more MMA, the single-query attention is a thread-local dot product + a
+//    butterfly reduction per warp, and the cls row (proj, MLP, final LN, head) is finished by
+//    tokens_tail_kernel, one warp per patch, from a 704-byte record per patch.
+#include <math.h>
+#include "vc_common.cuh"
+#include "vc_kernels.h"
+#include "vc_tparams.h"
+#include "vc_tokens.cuh"
+
+namespace vc {
+
+namespace tc {
+constexpr int kThreads = 256;
+constexpr uint32_t SLAB = 2048;   // 128 rows x 16 B: one 8-element K chunk (or 8-dim V group) of a tile
+// ---- shared-memory map (bytes) ----
+constexpr uint32_t W_FUS = 0;                     // [64/8][32][8]
+constexpr uint32_t W_QKV1 = W_FUS + 4096;         // [32/8][96][8]
+constexpr uint32_t W_PROJ1 = W_QKV1 + 6144;       // [32/8][32][8]
+constexpr uint32_t W_FC1 = W_PROJ1 + 2048;        // [32/8][128][8]
+constexpr uint32_t W_FC2 = W_FC1 + 8192;          // [128/8][32][8]
+constexpr uint32_t W_QKV2 = W_FC2 + 8192;         // [32/8][96][8]
+constexpr uint32_t VEC = W_QKV2 + 6144;           // fp32 vectors, see V_* (floats)
+constexpr int V_FSC = 0, V_FBI = 32, V_LN1G = 64, V_LN1B = 96, V_BQKV = 128, V_BPROJ = 224, V_LN2G = 256, V_LN2B = 288,
+              V_BFC1 = 320, V_BFC2 = 448, V_L2G = 480, V_L2B = 512, V_BQKV2 = 544, V_TOTAL = 640;
+constexpr uint32_t POS = VEC + V_TOTAL * 4;       // [128][32] fp32, 16-byte granules XOR-swizzled by (row & 7)
+constexpr uint32_t SLOT0 = POS + 128 * 32 * 4;
+constexpr uint32_t S_FBUF = 0;                    // [8][128][8] fusion-conv input (stem outputs of the patch)
+constexpr uint32_t S_ABUF = S_FBUF + 8 * SLAB;    // [4][128][8] LN output / attention output
+constexpr uint32_t S_QBUF = S_ABUF + 4 * SLAB;    // [4 heads][128][8]; followed by K (finite) for head 3's second chunk
+constexpr uint32_t S_KBUF = S_QBUF + 4 * SLAB;
+constexpr uint32_t S_VBUF = S_KBUF + 4 * SLAB;    // [4 heads][128 keys][8 dims]
+constexpr uint32_t S_PBUF = S_VBUF + 4 * SLAB;    // [16][128][8] probabilities of one head / MLP hidden
+constexpr uint32_t SLOT_BYTES = S_PBUF + 16 * SLAB;
+constexpr uint32_t ONES = SLOT0 + 2 * SLOT_BYTES;  // [128][8] = (1,0,0,0,0,0,0,0)
+constexpr uint32_t ZERO = ONES + SLAB;
+constexpr uint32_t MISC = ZERO + SLAB;            // q0 [2][32] f32, wmax [2][4][4] f32, barriers, tmem slot
+constexpr uint32_t SMEM_BYTES = MISC + 512;
+// ---- TMEM columns inside a slot's 256 ----
+constexpr uint32_t C_S = 0, C_O = 128, C_SMALL = 192;
+constexpr int kTailFloats = 176;                  // per patch: [4 warps][32 o + 4 l], x0[32]
+}  // namespace tc
+
+struct TcArgs {
+  const __nv_bfloat16* f;   // [8][RT][8]: slices 0-3 HSI stem, 4-7 LiDAR stem
+  const uint8_t* blob;      // parameter blob (vc_tparams.h)
+  float* tail;              // [n][kTailFloats]
+  long long RT;
+  int n_patches, P, T;
+  TLayout L;
+};
+
+struct TailArgs {
+  const uint8_t* blob;
+  const float* tail;
+  float* logits;
+  const long long* out_index;
+  unsigned char* argmax_map;
+  int n_patches, K;
+  TLayout L;
+};
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// instruction descriptor: bf16 x bf16 -> fp32, A K-major, B K-major (b_mn = 0) or MN-major (1)
+__device__ __forceinline__ uint32_t idesc(int N, int b_mn) {
+  return umma_idesc_bf16(128, N) | ((uint32_t)b_mn << 16);
+}
+
+// LayerNorm (eps 1e-6) of the row held by this thread -> bf16 -> K-major A operand (4 slabs)
+__device__ __forceinline__ void ln_store(const float (&x)[32], uint32_t vec_g, uint32_t vec_b, uint32_t dst_row) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) s += x[c];
+  const float mean = s * (1.f / 32.f);
+  float v = 0.f;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) { const float d = x[c] - mean; v = fmaf(d, d, v); }
+  const float rs = rsqrtf(v * (1.f / 32.f) + 1e-6f);
+#pragma unroll
+  for (int sl = 0; sl < 4; ++sl) {
+    const float4 g0 = lds_f4(vec_g + sl * 32), g1 = lds_f4(vec_g + sl * 32 + 16);
+    const float4 b0 = lds_f4(vec_b + sl * 32), b1 = lds_f4(vec_b + sl * 32 + 16);
+    const float* xx = x + 8 * sl;
+    const uint32_t p0 = pack_bf16(fmaf((xx[0] - mean) * rs, g0.x, b0.x), fmaf((xx[1] - mean) * rs, g0.y, b0.y));
+    const uint32_t p1 = pack_bf16(fmaf((xx[2] - mean) * rs, g0.z, b0.z), fmaf((xx[3] - mean) * rs, g0.w, b0.w));
+    const uint32_t p2 = pack_bf16(fmaf((xx[4] - mean) * rs, g1.x, b1.x), fmaf((xx[5] - mean) * rs, g1.y, b1.y));
+    const uint32_t p3 = pack_bf16(fmaf((xx[6] - mean) * rs, g1.z, b1.z), fmaf((xx[7] - mean) * rs, g1.w, b1.w));
+    sts128(dst_row + sl * tc::SLAB, p0, p1, p2, p3);
+  }
+}
+
+__global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) {
+  using namespace tc;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, slot = tid >> 7, r = tid & 127, lane = tid & 31, wq = (tid >> 5) & 3;
+  const int T = a.T, P = a.P;
+  const TLayout& L = a.L;
+  const uint32_t sb = smem_u32(smem);
+  float* vecf = reinterpret_cast<float*>(smem + VEC);
+  float* q0_s = reinterpret_cast<float*>(smem + MISC) + slot * 32;          // [32]
+  float* wmax_s = reinterpret_cast<float*>(smem + MISC + 256) + slot * 16;  // [4 warps][4 heads]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MISC + 384) + slot * 4;
+  uint64_t* b_ffull = bars + 0;   // fusion input of the next patch has landed
+  uint64_t* b_mma = bars + 1;     // the GEMM just issued (fusion / qkv / proj / fc1 / fc2 / kv2) is done
+  uint64_t* b_s = bars + 2;       // S_h is in TMEM
+  uint64_t* b_pv = bars + 3;      // PV_h is done (P buffer free, O_h in TMEM)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + MISC + 448);
+  const float qscale = 0.35355339059327376220f * 1.44269504088896340736f;  // hd^-0.5 * log2(e)
+
+  // ---------------- one-time image of the parameters in the layouts the tensor core reads ----------------
+  {
+    auto copy_w = [&](uint32_t dst, int src, int N, int K, int ld) {
+      for (int i = tid; i < N * (K / 8); i += kThreads) {
+        const int n = i % N, kc = i / N;
+        const uint4 g = __ldg(reinterpret_cast<const uint4*>(a.blob + src + (size_t)(n * ld + kc * 8) * 2));
+        *reinterpret_cast<uint4*>(smem + dst + (size_t)kc * N * 16 + n * 16) = g;
+      }
+    };
+    copy_w(W_FUS, L.wfus, 32, 64, kLdFus);
+    copy_w(W_QKV1, L.layer[0].wqkv, 96, 32, kLdD);
+    copy_w(W_PROJ1, L.layer[0].wproj, 32, 32, kLdD);
+    copy_w(W_FC1, L.layer[0].wfc1, 128, 32, kLdD);
+    copy_w(W_FC2, L.layer[0].wfc2, 32, 128, kLdHid);
+    copy_w(W_QKV2, L.layer[1].wqkv, 96, 32, kLdD);
+    auto copy_v = [&](int dst, int src, int n, float scale_first32) {
+      for (int i = tid; i < n; i += kThreads) {
+        const float v = __ldg(reinterpret_cast<const float*>(a.blob + src) + i);
+        vecf[dst + i] = i < 32 ? v * scale_first32 : v;
+      }
+    };
+    copy_v(V_FSC, L.fus_scale, 32, 1.f);
+    copy_v(V_FBI, L.fus_bias, 32, 1.f);
+    copy_v(V_LN1G, L.layer[0].ln1_g, 32, 1.f);
+    copy_v(V_LN1B, L.layer[0].ln1_b, 32, 1.f);
+    copy_v(V_BQKV, L.layer[0].bqkv, 96, qscale);      // q bias pre-scaled: q = acc * qscale + b * qscale
+    copy_v(V_BPROJ, L.layer[0].bproj, 32, 1.f);
+    copy_v(V_LN2G, L.layer[0].ln2_g, 32, 1.f);
+    copy_v(V_LN2B, L.layer[0].ln2_b, 32, 1.f);
+    copy_v(V_BFC1, L.layer[0].bfc1, 128, 1.f);
+    copy_v(V_BFC2, L.layer[0].bfc2, 32, 1.f);
+    copy_v(V_L2G, L.layer[1].ln1_g, 32, 1.f);
+    copy_v(V_L2B, L.layer[1].ln1_b, 32, 1.f);
+    copy_v(V_BQKV2, L.layer[1].bqkv, 96, qscale);
+    // pos-embed rows (row 0 = cls + pos[0], rows >= T zero), 16-byte granules swizzled by row
+    const float* pos = reinterpret_cast<const float*>(a.blob + L.pos);
+    const float* cls = reinterpret_cast<const float*>(a.blob + L.cls);
+    for (int i = tid; i < 128 * 8; i += kThreads) {
+      const int row = i >> 3, g = i & 7;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < T) {
+        v = __ldg(reinterpret_cast<const float4*>(pos + row * 32 + 4 * g));
+        if (row == 0) {
+          const float4 c = __ldg(reinterpret_cast<const float4*>(cls + 4 * g));
+          v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+        }
+      }
+      *reinterpret_cast<float4*>(smem + POS + row * 128 + ((g ^ (row & 7)) << 4)) = v;
+    }
+    // slot buffers, ZERO slab: zeros (row 0 and rows >= T of FBUF are never written again); ONES slab
+    for (uint32_t i = tid; i < (2 * SLOT_BYTES + 2 * SLAB) / 16; i += kThreads)
+      *reinterpret_cast<uint4*>(smem + SLOT0 + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    for (int i = tid; i < 128; i += kThreads) *reinterpret_cast<uint32_t*>(smem + ONES + i * 16) = 0x00003F80u;
+    if (tid == 0) {
+      for (int i = 0; i < 8; ++i) mbar_init(reinterpret_cast<uint64_t*>(smem + MISC + 384) + i, 1);
+      fence_mbar_init();
+    }
+    if (tid < 32) {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tb = tmem_base + (uint32_t)slot * 256u;                  // columns of this slot (issuer view)
+  const uint32_t tl = tb + ((uint32_t)(wq * 32) << 16);                   // + the 32 lanes of this warp
+  const uint32_t slot_s = sb + SLOT0 + (uint32_t)slot * SLOT_BYTES;
+  const uint32_t fbuf = slot_s + S_FBUF, abuf = slot_s + S_ABUF, qbuf = slot_s + S_QBUF, kbuf = slot_s + S_KBUF,
+                 vbuf = slot_s + S_VBUF, pbuf = slot_s + S_PBUF;
+  const uint32_t row16 = (uint32_t)r * 16u;
+  const int NK16 = (T + 15) & ~15, NKS = NK16 >> 4;   // keys rounded to the MMA's N / K granularity
+  const int ct = (T - 1) >> 5;                         // last 32-key chunk holding a real key
+  const int PW = P + 1, PP = sps_pp(P), HALO = sps_halo(P);
+  const int bar_id = 1 + slot;
+  const bool w0 = wq == 0;
+  const int nslots = 2 * (int)gridDim.x;
+
+  auto fetch = [&](int b) {   // warp 0 of the slot: stem outputs of patch b -> FBUF rows 1..T-1 (one copy per image row and slice)
+    if (lane == 0) mbar_arrive_expect_tx(b_ffull, (uint32_t)(8 * P * P * 16));
+    __syncwarp();
+    for (int c = lane; c < 8 * P; c += 32) {
+      const int s = c / P, i = c - s * P;
+      bulk_g2s(smem + (fbuf - sb) + s * SLAB + (1 + i * P) * 16, a.f + ((long long)s * a.RT + HALO + (long long)b * PP + i * PW) * 8,
+               (uint32_t)(P * 16), b_ffull);
+    }
+  };
+  // operands written by the row threads -> visible to the tensor core; previous TMEM reads retired
+  auto publish = [&]() {
+    fence_proxy_async();
+    tc_fence_before();
+    bar_sync(bar_id, 128);
+  };
+
+  uint32_t ph_f = 0, ph_m = 0, ph_s = 0, ph_pv = 0;
+  int b = 2 * (int)blockIdx.x + slot;
+  if (w0 && b < a.n_patches) fetch(b);
+
+  for (; b < a.n_patches; b += nslots) {
+    float x[32];   // residual stream of token row r
+    // ================= fusion 1x1 conv (64 -> 32) + folded BN + ReLU, + cls / pos =================
+    if (w0) {
+      mbar_wait(b_ffull, ph_f);
+      ph_f ^= 1u;
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tb + C_SMALL, umma_desc(fbuf + 2 * k * SLAB, SLAB, 128), umma_desc(sb + W_FUS + 2 * k * 512, 512, 128),
+                    idesc(32, 0), k ? 1u : 0u);
+        umma_commit(b_mma);
+      }
+      __syncwarp();
+    }
+    mbar_wait(b_mma, ph_m);
+    ph_m ^= 1u;
+    tc_fence_after();
+    if (w0 && b + nslots < a.n_patches) fetch(b + nslots);   // FBUF is free again: prefetch the next patch
+    {
+      uint32_t v[32];
+      tmem_ld32(tl + C_SMALL, v);
+      tc_wait_ld();
+      const float rowmask = (r >= 1 && r < T) ? 1.f : 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 p = lds_f4(sb + POS + r * 128 + ((g ^ (r & 7)) << 4));
+        const float4 sc = lds_f4(sb + VEC + (V_FSC + 4 * g) * 4), bi = lds_f4(sb + VEC + (V_FBI + 4 * g) * 4);
+        x[4 * g + 0] = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * g + 0]), sc.x, bi.x), 0.f), rowmask, p.x);
+        x[4 * g + 1] = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * g + 1]), sc.y, bi.y), 0.f), rowmask, p.y);
+        x[4 * g + 2] = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * g + 2]), sc.z, bi.z), 0.f), rowmask, p.z);
+        x[4 * g + 3] = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * g + 3]), sc.w, bi.w), 0.f), rowmask, p.w);
+      }
+    }
+
+    // ================= block 1: LN1 -> qkv =================
+    ln_store(x, sb + VEC + V_LN1G * 4, sb + VEC + V_LN1B * 4, abuf + row16);
+    publish();
+    if (w0) {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          umma_bf16(tb + C_S, umma_desc(abuf + 2 * k * SLAB, SLAB, 128), umma_desc(sb + W_QKV1 + 2 * k * 1536, 1536, 128),
+                    idesc(96, 0), k ? 1u : 0u);
+        umma_commit(b_mma);
+      }
+      __syncwarp();
+    }
+    mbar_wait(b_mma, ph_m);
+    ph_m ^= 1u;
+    tc_fence_after();
+    {
+      uint32_t v[3][32];
+      tmem_ld32(tl + C_S, v[0]);
+      tmem_ld32(tl + C_S + 32, v[1]);
+      tmem_ld32(tl + C_S + 64, v[2]);
+      tc_wait_ld();
+#pragma unroll
+      for (int part = 0; part < 3; ++part) {
+        const uint32_t dst = (part == 0 ? qbuf : part == 1 ? kbuf : vbuf) + row16;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float4 b0 = lds_f4(sb + VEC + (V_BQKV + 32 * part + 8 * h) * 4), b1 = lds_f4(sb + VEC + (V_BQKV + 32 * part + 8 * h + 4) * 4);
+          const float sc = part == 0 ? qscale : 1.f;
+          const uint32_t* vv = v[part] + 8 * h;
+          sts128(dst + h * SLAB, pack_bf16(fmaf(__uint_as_float(vv[0]), sc, b0.x), fmaf(__uint_as_float(vv[1]), sc, b0.y)),
+                 pack_bf16(fmaf(__uint_as_float(vv[2]), sc, b0.z), fmaf(__uint_as_float(vv[3]), sc, b0.w)),
+                 pack_bf16(fmaf(__uint_as_float(vv[4]), sc, b1.x), fmaf(__uint_as_float(vv[5]), sc, b1.y)),
+                 pack_bf16(fmaf(__uint_as_float(vv[6]), sc, b1.z), fmaf(__uint_as_float(vv[7]), sc, b1.w)));
+        }
+      }
+    }
+    publish();
+    // S_h = Q_h K_h^T: A chunks (Q_h, Q_h+1), B chunks (K_h, zeros) -> the second half of K = 16 adds nothing
+    auto issue_s = [&](int h) {
+      umma_bf16(tb + C_S, umma_desc(qbuf + h * SLAB, SLAB, 128), umma_desc(kbuf + h * SLAB, (sb + ZERO) - (kbuf + h * SLAB), 128),
+                idesc(NK16, 0), 0u);
+      umma_commit(b_s);
+    };
+    if (w0) {
+      tc_fence_after();
+      if (elect_one()) issue_s(0);
+      __syncwarp();
+    }
+
+    // ================= attention, one head at a time =================
+#pragma unroll 1
+    for (int h = 0; h < 4; ++h) {
+      uint32_t s[4][32];
+      mbar_wait(b_s, ph_s);
+      ph_s ^= 1u;
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c <= ct) tmem_ld32(tl + C_S + 32 * c, s[c]);
+      tc_wait_ld();
+      tc_fence_before();
+      bar_sync(bar_id, 128);           // every row of S_h is in registers: the next head's S may overwrite it
+      if (w0 && h < 3) {
+        tc_fence_after();
+        if (elect_one()) issue_s(h + 1);
+        __syncwarp();
+      }
+      float m = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c <= ct) {
+          if (c == ct) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (32 * c + i >= T) s[c][i] = 0xFF800000u;   // -inf: padded keys
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 2)
+            m = fmaxf(m, fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
+        }
+      }
+      if (h > 0) {                      // PV of the previous head has consumed the P buffer
+        mbar_wait(b_pv, ph_pv);
+        ph_pv ^= 1u;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c <= ct) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              pk[e] = pack_bf16(ex2(__uint_as_float(s[c][8 * g + 2 * e]) - m), ex2(__uint_as_float(s[c][8 * g + 2 * e + 1]) - m));
+            sts128(pbuf + (4 * c + g) * SLAB + row16, pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+      publish();
+      if (w0) {
+        tc_fence_after();
+        if (elect_one()) {
+          // O_h[128 x 16] = P_h[128 x keys] . [V_h | ones]: B is MN-major, N chunk 0 = V_h slab, chunk 1 = ONES slab
+          const uint32_t vb = vbuf + h * SLAB;
+          for (int k = 0; k < NKS; ++k)
+            umma_bf16(tb + C_O + 16 * h, umma_desc(pbuf + 2 * k * SLAB, SLAB, 128), umma_desc(vb + k * 256, 128, (sb + ONES) - vb),
+                      idesc(16, 1), k ? 1u : 0u);
+          umma_commit(b_pv);
+        }
+        __syncwarp();
+      }
+    }
+    mbar_wait(b_pv, ph_pv);
+    ph_pv ^= 1u;
+    tc_fence_after();
+    // ---- attention output (normalised) -> A operand of proj ----
+    {
+      uint32_t o[4][16];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) tmem_ld16(tl + C_O + 16 * h, o[h]);
+      tc_wait_ld();
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const float il = 1.f / __uint_as_float(o[h][8]);
+        sts128(abuf + h * SLAB + row16, pack_bf16(__uint_as_float(o[h][0]) * il, __uint_as_float(o[h][1]) * il),
+               pack_bf16(__uint_as_float(o[h][2]) * il, __uint_as_float(o[h][3]) * il),
+               pack_bf16(__uint_as_float(o[h][4]) * il, __uint_as_float(o[h][5]) * il),
+               pack_bf16(__uint_as_float(o[h][6]) * il, __uint_as_float(o[h][7]) * il));
+      }
+    }
+    publish();
+    if (w0) {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          umma_bf16(tb + C_SMALL, umma_desc(abuf + 2 * k * SLAB, SLAB, 128), umma_desc(sb + W_PROJ1 + 2 * k * 512, 512, 128),
+                    idesc(32, 0), k ? 1u : 0u);
+        umma_commit(b_mma);
+      }
+      __syncwarp();
+    }
+    mbar_wait(b_mma, ph_m);
+    ph_m ^= 1u;
+    tc_fence_after();
+    {
+      uint32_t v[32];
+      tmem_ld32(tl + C_SMALL, v);
+      tc_wait_ld();
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 bb = lds_f4(sb + VEC + (V_BPROJ + 4 * g) * 4);
+        x[4 * g + 0] += __uint_as_float(v[4 * g + 0]) + bb.x;
+        x[4 * g + 1] += __uint_as_float(v[4 * g + 1]) + bb.y;
+        x[4 * g + 2] += __uint_as_float(v[4 * g + 2]) + bb.z;
+        x[4 * g + 3] += __uint_as_float(v[4 * g + 3]) + bb.w;
+      }
+    }
+
+    // ================= MLP: LN2 -> fc1 (+bias, GELU) -> fc2 (+bias, +residual) =================
+    ln_store(x, sb + VEC + V_LN2G * 4, sb + VEC + V_LN2B * 4, abuf + row16);
+    publish();
+    if (w0) {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          umma_bf16(tb + C_S, umma_desc(abuf + 2 * k * SLAB, SLAB, 128), umma_desc(sb + W_FC1 + 2 * k * 2048, 2048, 128),
+                    idesc(128, 0), k ? 1u : 0u);
+        umma_commit(b_mma);
+      }
+      __syncwarp();
+    }
+    mbar_wait(b_mma, ph_m);
+    ph_m ^= 1u;
+    tc_fence_after();
+#pragma unroll
+    for (int c2 = 0; c2 < 2; ++c2) {
+      uint32_t v[2][32];
+      tmem_ld32(tl + C_S + 64 * c2, v[0]);
+      tmem_ld32(tl + C_S + 64 * c2 + 32, v[1]);
+      tc_wait_ld();
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * c2 + cc;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float4 b0 = lds_f4(sb + VEC + (V_BFC1 + 32 * c + 8 * g) * 4), b1 = lds_f4(sb + VEC + (V_BFC1 + 32 * c + 8 * g + 4) * 4);
+          const uint32_t* vv = v[cc] + 8 * g;
+          sts128(pbuf + (4 * c + g) * SLAB + row16,
+                 pack_bf16(gelu_erf(__uint_as_float(vv[0]) + b0.x), gelu_erf(__uint_as_float(vv[1]) + b0.y)),
+                 pack_bf16(gelu_erf(__uint_as_float(vv[2]) + b0.z), gelu_erf(__uint_as_float(vv[3]) + b0.w)),
+                 pack_bf16(gelu_erf(__uint_as_float(vv[4]) + b1.x), gelu_erf(__uint_as_float(vv[5]) + b1.y)),
+                 pack_bf16(gelu_erf(__uint_as_float(vv[6]) + b1.z), gelu_erf(__uint_as_float(vv[7]) + b1.w)));
+        }
+      }
+    }
+    publish();
+    if (w0) {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tb + C_SMALL, umma_desc(pbuf + 2 * k * SLAB, SLAB, 128), umma_desc(sb + W_FC2 + 2 * k * 512, 512, 128),
+                    idesc(32, 0), k ? 1u : 0u);
+        umma_commit(b_mma);
+      }
+      __syncwarp();
+    }
+    mbar_wait(b_mma, ph_m);
+    ph_m ^= 1u;
+    tc_fence_after();
+    {
+      uint32_t v[32];
+      tmem_ld32(tl + C_SMALL, v);
+      tc_wait_ld();
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 bb = lds_f4(sb + VEC + (V_BFC2 + 4 * g) * 4);
+        x[4 * g + 0] += __uint_as_float(v[4 * g + 0]) + bb.x;
+        x[4 * g + 1] += __uint_as_float(v[4 * g + 1]) + bb.y;
+        x[4 * g + 2] += __uint_as_float(v[4 * g + 2]) + bb.z;
+        x[4 * g + 3] += __uint_as_float(v[4 * g + 3]) + bb.w;
+      }
+    }
+
+    // ================= last block: K / V of every token, attention of the cls query only =================
+    ln_store(x, sb + VEC + V_L2G * 4, sb + VEC + V_L2B * 4, abuf + row16);
+    publish();
+    if (w0) {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          umma_bf16(tb + C_S, umma_desc(abuf + 2 * k * SLAB, SLAB, 128), umma_desc(sb + W_QKV2 + 2 * k * 1536, 1536, 128),
+                    idesc(96, 0), k ? 1u : 0u);
+        umma_commit(b_mma);
+      }
+      __syncwarp();
+    }
+    mbar_wait(b_mma, ph_m);
+    ph_m ^= 1u;
+    tc_fence_after();
+    float* trec = a.tail + (long long)b * kTailFloats;
+    {
+      uint32_t kk[32], vv[32];
+      tmem_ld32(tl + C_S + 32, kk);
+      tmem_ld32(tl + C_S + 64, vv);
+      if (w0) {     // the cls token is row 0: its (scaled) query and its residual stream
+        uint32_t qq[32];
+        tmem_ld32(tl + C_S, qq);
+        tc_wait_ld();
+        if (lane == 0) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            q0_s[c] = fmaf(__uint_as_float(qq[c]), qscale, vecf[V_BQKV2 + c]);
+            trec[144 + c] = x[c];
+          }
+        }
+      }
+      tc_wait_ld();
+      tc_fence_before();
+      bar_sync(bar_id, 128);
+      float sc[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const float4 q0 = lds_f4(smem_u32(q0_s) + 32 * h), q1 = lds_f4(smem_u32(q0_s) + 32 * h + 16);
+        const float4 k0 = lds_f4(sb + VEC + (V_BQKV2 + 32 + 8 * h) * 4), k1 = lds_f4(sb + VEC + (V_BQKV2 + 36 + 8 * h) * 4);
+        float d = q0.x * (__uint_as_float(kk[8 * h + 0]) + k0.x);
+        d = fmaf(q0.y, __uint_as_float(kk[8 * h + 1]) + k0.y, d);
+        d = fmaf(q0.z, __uint_as_float(kk[8 * h + 2]) + k0.z, d);
+        d = fmaf(q0.w, __uint_as_float(kk[8 * h + 3]) + k0.w, d);
+        d = fmaf(q1.x, __uint_as_float(kk[8 * h + 4]) + k1.x, d);
+        d = fmaf(q1.y, __uint_as_float(kk[8 * h + 5]) + k1.y, d);
+        d = fmaf(q1.z, __uint_as_float(kk[8 * h + 6]) + k1.z, d);
+        d = fmaf(q1.w, __uint_as_float(kk[8 * h + 7]) + k1.w, d);
+        sc[h] = r < T ? d : -INFINITY;
+        float mw = sc[h];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+        if (lane == 0) wmax_s[wq * 4 + h] = mw;
+      }
+      bar_sync(bar_id, 128);
+      float val[32], pl[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const float m = fmaxf(fmaxf(wmax_s[h], wmax_s[4 + h]), fmaxf(wmax_s[8 + h], wmax_s[12 + h]));
+        const float p = ex2(sc[h] - m);
+        pl[h] = p;
+        const float4 v0 = lds_f4(sb + VEC + (V_BQKV2 + 64 + 8 * h) * 4), v1 = lds_f4(sb + VEC + (V_BQKV2 + 68 + 8 * h) * 4);
+        val[8 * h + 0] = p * (__uint_as_float(vv[8 * h + 0]) + v0.x);
+        val[8 * h + 1] = p * (__uint_as_float(vv[8 * h + 1]) + v0.y);
+        val[8 * h + 2] = p * (__uint_as_float(vv[8 * h + 2]) + v0.z);
+        val[8 * h + 3] = p * (__uint_as_float(vv[8 * h + 3]) + v0.w);
+        val[8 * h + 4] = p * (__uint_as_float(vv[8 * h + 4]) + v1.x);
+        val[8 * h + 5] = p * (__uint_as_float(vv[8 * h + 5]) + v1.y);
+        val[8 * h + 6] = p * (__uint_as_float(vv[8 * h + 6]) + v1.z);
+        val[8 * h + 7] = p * (__uint_as_float(vv[8 * h + 7]) + v1.w);
+      }
+      // butterfly reduction over the 32 rows of this warp: lane i ends with sum over rows of val[i]
+#pragma unroll
+      for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+          const float send = up ? val[i] : val[i + n / 2];
+          const float keep = up ? val[i + n / 2] : val[i];
+          val[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      {   // denominators: head = 2 * bit4 + bit3 of the lane after two halving steps, then a full reduce over bits 2..0
+        const bool up4 = (lane & 16) != 0, up3 = (lane & 8) != 0;
+        float a0 = (up4 ? pl[2] : pl[0]) + __shfl_xor_sync(0xffffffffu, up4 ? pl[0] : pl[2], 16);
+        float a1 = (up4 ? pl[3] : pl[1]) + __shfl_xor_sync(0xffffffffu, up4 ? pl[1] : pl[3], 16);
+        float l = (up3 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, up3 ? a0 : a1, 8);
+        l += __shfl_xor_sync(0xffffffffu, l, 4);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        trec[wq * 36 + lane] = val[0];
+        if ((lane & 7) == 0) trec[wq * 36 + 32 + (lane >> 3)] = l;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid < 32) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- cls row of the last block: attention normalisation, proj, MLP, final LayerNorm, head ----
+// One warp per patch, one channel per lane (the tail of transformer_fwd_kernel as its own launch).
+__global__ void __launch_bounds__(256) tokens_tail_kernel(TailArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const TLayout& L = a.L;
+  const TLayerOff& OL = L.layer[kLayers - 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int copy_bytes = L.pos;    // everything in front of the pos-embed table
+  for (int i = threadIdx.x; i < copy_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(a.blob) + i);
+  float* h_all = reinterpret_cast<float*>(smem + copy_bytes);
+  float* h_s = h_all + warp * (kHidden + 64);
+  float* logit_s = h_s + kHidden;
+  __syncthreads();
+  const __nv_bfloat16* wproj = reinterpret_cast<const __nv_bfloat16*>(smem + OL.wproj);
+  const __nv_bfloat16* wfc1 = reinterpret_cast<const __nv_bfloat16*>(smem + OL.wfc1);
+  const __nv_bfloat16* wfc2 = reinterpret_cast<const __nv_bfloat16*>(smem + OL.wfc2);
+  const float* f32 = reinterpret_cast<const float*>(smem);
+  for (int b = blockIdx.x * nwarps + warp; b < a.n_patches; b += gridDim.x * nwarps) {
+    const float* rec = a.tail + (long long)b * tc::kTailFloats;
+    float o = 0.f, l = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) { o += rec[w * 36 + lane]; l += rec[w * 36 + 32 + (lane >> 3)]; }
+    const float att = o / l;
+    float x0 = rec[144 + lane];
+    float y = f32[OL.bproj / 4 + lane];
+#pragma unroll
+    for (int k2 = 0; k2 < kD / 2; ++k2) {
+      const uint32_t wv = lds32(wproj + lane * kLdD + 2 * k2);
+      y = fmaf(bf_lo(wv), __shfl_sync(0xffffffffu, att, 2 * k2), y);
+      y = fmaf(bf_hi(wv), __shfl_sync(0xffffffffu, att, 2 * k2 + 1), y);
+    }
+    x0 += y;
+    float mean = warp_sum(x0) * (1.f / kD);
+    float d = x0 - mean;
+    float rstd = rsqrtf(warp_sum(d * d) * (1.f / kD) + 1e-6f);
+    const float y2 = d * rstd * f32[OL.ln2_g / 4 + lane] + f32[OL.ln2_b / 4 + lane];
+    float hacc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) hacc[i] = f32[OL.bfc1 / 4 + lane + 32 * i];
+#pragma unroll
+    for (int k2 = 0; k2 < kD / 2; ++k2) {
+      const float ya = __shfl_sync(0xffffffffu, y2, 2 * k2), yb = __shfl_sync(0xffffffffu, y2, 2 * k2 + 1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t wv = lds32(wfc1 + (lane + 32 * i) * kLdD + 2 * k2);
+        hacc[i] = fmaf(bf_lo(wv), ya, fmaf(bf_hi(wv), yb, hacc[i]));
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h_s[lane + 32 * i] = gelu_erf(hacc[i]);
+    __syncwarp();
+    float z = f32[OL.bfc2 / 4 + lane];
+#pragma unroll 8
+    for (int k2 = 0; k2 < kHidden / 2; ++k2) {
+      const uint32_t wv = lds32(wfc2 + lane * kLdHid + 2 * k2);
+      const float2 hh = *reinterpret_cast<const float2*>(h_s + 2 * k2);
+      z = fmaf(bf_lo(wv), hh.x, fmaf(bf_hi(wv), hh.y, z));
+    }
+    x0 += z;
+    mean = warp_sum(x0) * (1.f / kD);
+    d = x0 - mean;
+    rstd = rsqrtf(warp_sum(d * d) * (1.f / kD) + 1e-6f);
+    const float c = d * rstd * f32[L.lnf_g / 4 + lane] + f32[L.lnf_b / 4 + lane];
+    const long long orow = a.out_index ? a.out_index[b] : (long long)b;
+    for (int k0 = 0; k0 < a.K; k0 += 32) {
+      const int k = k0 + lane;
+      float acc = k < a.K ? f32[L.bhead / 4 + k] : 0.f;
+#pragma unroll
+      for (int dd = 0; dd < kD; ++dd) {
+        const float cd = __shfl_sync(0xffffffffu, c, dd);
+        if (k < a.K) acc = fmaf(f32[L.whead / 4 + k * kD + dd], cd, acc);
+      }
+      if (k < a.K) {
+        a.logits[orow * a.K + k] = acc;
+        logit_s[k] = acc;
+      }
+    }
+    if (a.argmax_map) {
+      __syncwarp();
+      if (lane == 0) {
+        int best = 0;
+        float bv = logit_s[0];
+        for (int k = 1; k < a.K; ++k)
+          if (logit_s[k] > bv) { bv = logit_s[k]; best = k; }   // first maximum, like np.argmax
+        a.argmax_map[orow] = (unsigned char)best;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+size_t tokens_tc_scratch_bytes(int n_patches) { return (size_t)n_patches * tc::kTailFloats * 4; }
+
+bool tokens_tc_supported(int P, int K) { return P >= 1 && P * P + 1 <= 128 && K >= 1 && K <= 64; }
+
+int tokens_tc_launch(const void* f_sps, const void* tparams, int n_patches, int P, int K, float* logits,
+                     const long long* out_index, unsigned char* argmax_map, void* scratch, cudaStream_t stream) {
+  if (n_patches <= 0 || !scratch || !tokens_tc_supported(P, K)) return VC_ERR_ARG;
+  int dev = 0, max_smem = 0, num_sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if ((int)tc::SMEM_BYTES > max_smem) return VC_ERR_UNSUPPORTED;
+  TcArgs a;
+  a.f = (const __nv_bfloat16*)f_sps;
+  a.blob = (const uint8_t*)tparams;
+  a.tail = (float*)scratch;
+  a.RT = sps_rows(n_patches, P);
+  a.n_patches = n_patches;
+  a.P = P;
+  a.T = P * P + 1;
+  a.L = tlayout(P, K);
+  if (cudaFuncSetAttribute(tokens_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES) != cudaSuccess)
+    return VC_ERR_CUDA;
+  int blocks = (n_patches + 1) / 2;
+  if (blocks > num_sms) blocks = num_sms;
+  tokens_tc_kernel<<<blocks, tc::kThreads, tc::SMEM_BYTES, stream>>>(a);
+  if (cudaGetLastError() != cudaSuccess) return VC_ERR_CUDA;
+
+  TailArgs t;
+  t.blob = a.blob;
+  t.tail = a.tail;
+  t.logits = logits;
+  t.out_index = out_index;
+  t.argmax_map = argmax_map;
+  t.n_patches = n_patches;
+  t.K = K;
+  t.L = a.L;
+  const int tail_threads = 256;
+  const size_t tail_smem = (size_t)a.L.pos + (size_t)(tail_threads / 32) * (kHidden + 64) * 4;
+  if (cudaFuncSetAttribute(tokens_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem) != cudaSuccess)
+    return VC_ERR_CUDA;
+  int tblocks = (n_patches + 7) / 8;
+  if (tblocks > 2 * num_sms) tblocks = 2 * num_sms;
+  tokens_tail_kernel<<<tblocks, tail_threads, tail_smem, stream>>>(t);
+  return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
+}
+
+}  // namespace vc

@@ -43,6 +43,13 @@ int transformer_fwd_launch(const void* f_sps, const void* tparams, int n_patches
                            const long long* out_index, unsigned char* argmax_map, int prefused, unsigned int drop_thr,
                            const unsigned int* drop_seed, cudaStream_t stream);
 
+// tokens_tc.cu -- the same token stage on tcgen05 (eval mode, P*P + 1 <= 128 tokens); scratch holds
+// tokens_tc_scratch_bytes(n) bytes (one 704-byte cls record per patch)
+size_t tokens_tc_scratch_bytes(int n_patches);
+bool tokens_tc_supported(int P, int K);
+int tokens_tc_launch(const void* f_sps, const void* tparams, int n_patches, int P, int K, float* logits,
+                     const long long* out_index, unsigned char* argmax_map, void* scratch, cudaStream_t stream);
+
 // wgrad_tc.cu -- weight gradients (rows are the reduction axis; both operands MN-major)
 size_t wgrad_workspace_bytes(int SB, int ntaps);
 int wgrad_sps_launch(const void* A, int SA, const void* B, int SB, int n_patches, int P, int ntaps, int shift_on_a,

@@ -250,6 +250,7 @@ class ViTCNN(nn.Module):
                 getattr(st, "nsplit_" + pre)[i] = ns
         blob = pack_tparams(self, _lib.tparams_layout(P, K))
         pk["keep"].append(blob)
+        pk["tparams"] = blob
         st.tparams = blob.data_ptr()
         if self.n_bands2 <= 8:
             lb = pack_lidar_blob(self)

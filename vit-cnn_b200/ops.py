@@ -109,6 +109,21 @@ def tokens_forward(f_sps, tparams, n, P, K, out_index=None, logits=None, argmax_
     return logits
 
 
+def tokens_forward_tc(f_sps, tparams, n, P, K, out_index=None, logits=None, argmax_map=None, scratch=None):
+    """Token stage on the tcgen05 kernel (P*P + 1 <= 128); same contract as tokens_forward."""
+    L = _lib.lib()
+    if logits is None:
+        logits = torch.empty(n, K, dtype=torch.float32, device=f_sps.device)
+    need = L.vc_tokens_tc_scratch_bytes(n)
+    if scratch is None or scratch.numel() * scratch.element_size() < need:
+        scratch = torch.empty(need, dtype=torch.uint8, device=f_sps.device)
+    with torch.cuda.device(f_sps.device):
+        _lib.check(L.vc_tokens_forward_tc(f_sps.data_ptr(), tparams.data_ptr(), n, P, K, logits.data_ptr(),
+                                          _ptr(out_index), _ptr(argmax_map), scratch.data_ptr(),
+                                          scratch.numel() * scratch.element_size(), _stream()), "vc_tokens_forward_tc")
+    return logits
+
+
 def wgrad_sps(a_sps, b_sps, n, P, taps, shift_on_a, out, M, N, sm, sn, st, bias_col=-1, out_bias=None,
               accumulate=False, workspace=None):
     """dW[tap][m][n] = sum_rows A[row+sa][m] * B[row+sb][n] over SPS buffers (tcgen05, MN-major
