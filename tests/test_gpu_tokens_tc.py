@@ -36,6 +36,24 @@ def test_tc_kernel_matches_mma_sync_kernel(cfg):
     assert err <= KERNEL_TOL, err
 
 
+def test_tc_kernel_exact_softmax_path_for_large_attention_weights():
+    """The kernel drops the softmax row maximum when a static bound on |q.k| (weight norms) rules out
+    overflow of 2^s; large q/k weights must select the two-pass path and still agree."""
+    from vitcnn_b200 import ops
+    P, K, n = 11, 16, 150
+    _, net = make_pair(16, 1, P, K, seed=9)
+    with torch.no_grad():
+        net.blocks[0].attn.qkv.weight[:64] *= 60.0      # q and k rows: scores of several hundred
+    blob = net.pack_for_inference()["tparams"]
+    f = _features(n, P, seed=7)
+    want = ops.tokens_forward(f, blob, n, P, K)
+    got = ops.tokens_forward_tc(f, blob, n, P, K)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got).all() and torch.isfinite(want).all()
+    err = (got - want).abs().max().item() / want.abs().max().item()
+    assert err <= 2e-2, err     # near one-hot attention: a bf16 rounding of a score moves a weight noticeably
+
+
 def test_tc_kernel_scatter_and_argmax():
     from vitcnn_b200 import ops
     P, K, n = 11, 16, 200

@@ -28,17 +28,37 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu for sm_100a into csrc/libvitcnn.so (nvcc cross-compiles without a GPU)."""
+    """Compile csrc/*.cu for sm_100a into csrc/libvitcnn.so (nvcc cross-compiles without a GPU).
+    One object per translation unit under csrc/build/ (compiled in parallel, reused while newer than
+    the source and every header), then one link step."""
     if not force and not _stale():
         return SO_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [s for s in SOURCES if os.path.isfile(os.path.join(CSRC, s))]
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + srcs
-    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    hdr_t = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS if os.path.isfile(os.path.join(CSRC, h)))
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src[:-3] + ".o")
+        if (not force and os.path.isfile(obj)
+                and os.path.getmtime(obj) > max(os.path.getmtime(os.path.join(CSRC, src)), hdr_t)):
+            return obj, ""
+        res = subprocess.run([nvcc] + cflags + ["-c", "-o", obj, src], cwd=CSRC, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 4)) as ex:
+        done = list(ex.map(compile_one, srcs))
     if verbose:
-        print(res.stderr)
+        print("".join(log for _, log in done))
+    res = subprocess.run([nvcc] + NVCC_FLAGS + ["-o", SO_PATH] + [o for o, _ in done], cwd=CSRC, capture_output=True,
+                         text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     return SO_PATH
 
 

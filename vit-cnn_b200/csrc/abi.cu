@@ -98,11 +98,12 @@ int zero_halos(const Workspace& w, int n, int P, cudaStream_t st) {
   return VC_OK;
 }
 
-// bring-up / A-B knob: VITCNN_TOKENS_IMPL=0 selects the mma.sync token kernel for every patch size
+// A-B knob: VITCNN_TOKENS_IMPL=1 selects the tcgen05 token kernel (tokens_tc.cu) where it applies; the default
+// is the mma.sync kernel, which is the faster one as measured (profiles/r01_SUMMARY.md)
 int tokens_impl() {
   static const int impl = [] {
     const char* e = getenv("VITCNN_TOKENS_IMPL");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : 0;
   }();
   return impl;
 }

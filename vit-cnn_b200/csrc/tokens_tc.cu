@@ -11,19 +11,26 @@
 //    is a tcgen05.mma with the accumulator in TMEM; A operands are written by the row threads
 //    straight into the no-swizzle K-major canonical layout ([k/8][row][8] = 2 KB slabs), weights
 //    are re-laid into that layout once per persistent CTA;
-//  * head_dim = 8 is half of the K = 16 of one bf16 MMA: the K operand's second 8-element chunk
-//    is pointed (leading-byte-offset field) at a slab of zeros, so S_h = Q_h K_h^T needs no
-//    padded copies; V is consumed MN-major ([key][8 dims] slabs) and its second N chunk is a
+//  * head_dim = 8 is half of the K = 16 of one bf16 MMA: the second 8-element chunk of Q is
+//    pointed (leading-byte-offset field) at a slab of (1,0,..,0) rows and that of K at a slab
+//    holding (-30000,0,..,0) for padded keys and zeros for real ones, so S_h = Q_h K_h^T needs no
+//    padded copies and padded keys arrive already masked; when a static bound on |q.k| (from the
+//    weight norms, LayerNorm output has norm sqrt(32)) shows 2^s cannot overflow, the softmax
+//    skips the row maximum altogether (softmax is shift invariant; bf16 keeps the fp32 exponent);
+//    V is consumed MN-major ([key][8 dims] slabs) and its second N chunk is a
 //    slab of (1,0,..,0) rows, so column 8 of the PV accumulator is the softmax denominator of
 //    the bf16-rounded probabilities;
 //  * a CTA runs two independent 128-thread groups ("slots", 256 TMEM columns each) so one
-//    slot's MMA round trips hide behind the other's softmax; the fusion-conv input of the next
-//    patch is prefetched by 1-D bulk copies (TMA unit) into its own buffer;
+//    slot's MMA round trips hide behind the other's softmax, plus one MMA-issuer warp per slot:
+//    row threads never wait for each other, they arrive on mbarriers the issuer waits on and
+//    wait only for tensor-core completions; the fusion-conv input of the next patch is
+//    prefetched with 16-byte cp.async (one token row per thread) into its own buffer;
 //  * the last block only feeds the head through the cls token (x[:, 0]): K / V of every token
 //    come from one more MMA, the single-query attention is a thread-local dot product + a
 //    butterfly reduction per warp, and the cls row (proj, MLP, final LN, head) is finished by
 //    tokens_tail_kernel, one warp per patch, from a 704-byte record per patch.
 #include <math.h>
+#include <type_traits>
 #include "vc_common.cuh"
 #include "vc_kernels.h"
 #include "vc_tparams.h"
@@ -32,7 +39,7 @@
 namespace vc {
 
 namespace tc {
-constexpr int kThreads = 256;
+constexpr int kThreads = 320;   // 8 warps of row threads (two slots) + 2 MMA-issuer warps
 constexpr uint32_t SLAB = 2048;   // 128 rows x 16 B: one 8-element K chunk (or 8-dim V group) of a tile
 // ---- shared-memory map (bytes) ----
 constexpr uint32_t W_FUS = 0;                     // [64/8][32][8]
@@ -54,8 +61,8 @@ constexpr uint32_t S_VBUF = S_KBUF + 4 * SLAB;    // [4 heads][128 keys][8 dims]
 constexpr uint32_t S_PBUF = S_VBUF + 4 * SLAB;    // [16][128][8] probabilities of one head / MLP hidden
 constexpr uint32_t SLOT_BYTES = S_PBUF + 16 * SLAB;
 constexpr uint32_t ONES = SLOT0 + 2 * SLOT_BYTES;  // [128][8] = (1,0,0,0,0,0,0,0)
-constexpr uint32_t ZERO = ONES + SLAB;
-constexpr uint32_t MISC = ZERO + SLAB;            // q0 [2][32] f32, wmax [2][4][4] f32, barriers, tmem slot
+constexpr uint32_t MASK = ONES + SLAB;             // [128 keys][8] = (0 | -30000 for padded keys, 0, ..): K's second K chunk
+constexpr uint32_t MISC = MASK + SLAB;            // q0 [2][32] f32, wmax [2][4][4] f32, barriers, tmem slot, bound flag
 constexpr uint32_t SMEM_BYTES = MISC + 512;
 // ---- TMEM columns inside a slot's 256 ----
 constexpr uint32_t C_S = 0, C_O = 128, C_SMALL = 192;
@@ -94,6 +101,12 @@ __device__ __forceinline__ uint32_t idesc(int N, int b_mn) {
   return umma_idesc_bf16(128, N) | ((uint32_t)b_mn << 16);
 }
 
+// 2 * GELU(v) in the tanh form of vc_tokens.cuh: v + v tanh(u); the factor 0.5 is folded into W_fc2
+__device__ __forceinline__ float gelu2(float v) {
+  const float u = v * fmaf(0.0356774081f, v * v, 0.7978845608f);
+  return fmaf(v, tanh_fast(u), v);
+}
+
 // LayerNorm (eps 1e-6) of the row held by this thread -> bf16 -> K-major A operand (4 slabs)
 __device__ __forceinline__ void ln_store(const float (&x)[32], uint32_t vec_g, uint32_t vec_b, uint32_t dst_row) {
   float s = 0.f;
@@ -117,30 +130,47 @@ __device__ __forceinline__ void ln_store(const float (&x)[32], uint32_t vec_g, u
   }
 }
 
-__global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) {
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Warp roles: warps 0-3 = row threads of slot 0, 4-7 = slot 1 (token row r = thread & 127, TMEM lane r),
+// warps 8 / 9 = MMA issuers of slot 0 / 1.  Row threads never wait for each other: they signal
+// "operands written" / "S consumed" on two mbarriers (128 arrivals) that only the issuer waits on, and
+// wait only for tensor-core completions (tcgen05.commit mbarriers).
+__global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) {   // 168 registers: the file is allocated per 4 warps
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int tid = threadIdx.x, slot = tid >> 7, r = tid & 127, lane = tid & 31, wq = (tid >> 5) & 3;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool issuer = warp >= 8;
+  const int slot = issuer ? warp - 8 : warp >> 2;
+  const int r = tid & 127, wq = warp & 3;
   const int T = a.T, P = a.P;
   const TLayout& L = a.L;
   const uint32_t sb = smem_u32(smem);
   float* vecf = reinterpret_cast<float*>(smem + VEC);
   float* q0_s = reinterpret_cast<float*>(smem + MISC) + slot * 32;          // [32]
   float* wmax_s = reinterpret_cast<float*>(smem + MISC + 256) + slot * 16;  // [4 warps][4 heads]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MISC + 384) + slot * 4;
-  uint64_t* b_ffull = bars + 0;   // fusion input of the next patch has landed
-  uint64_t* b_mma = bars + 1;     // the GEMM just issued (fusion / qkv / proj / fc1 / fc2 / kv2) is done
-  uint64_t* b_s = bars + 2;       // S_h is in TMEM
-  uint64_t* b_pv = bars + 3;      // PV_h is done (P buffer free, O_h in TMEM)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + MISC + 448);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MISC + 384) + slot * 5;
+  uint64_t* b_rp = bars + 0;      // row threads: operands of the next GEMM are written (128 arrivals)
+  uint64_t* b_rs = bars + 1;      // row threads: S_h has been read out of TMEM (128 arrivals)
+  uint64_t* b_mma = bars + 2;     // tensor core: the GEMM just issued (fusion / qkv / proj / fc1 / fc2 / kv2) is done
+  uint64_t* b_s = bars + 3;       // tensor core: S_h is in TMEM
+  uint64_t* b_pv = bars + 4;      // tensor core: PV_h is done (P buffer free, O_h in TMEM)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + MISC + 480);
   const float qscale = 0.35355339059327376220f * 1.44269504088896340736f;  // hd^-0.5 * log2(e)
 
   // ---------------- one-time image of the parameters in the layouts the tensor core reads ----------------
   {
-    auto copy_w = [&](uint32_t dst, int src, int N, int K, int ld) {
+    auto copy_w = [&](uint32_t dst, int src, int N, int K, int ld, bool halve = false) {
       for (int i = tid; i < N * (K / 8); i += kThreads) {
         const int n = i % N, kc = i / N;
-        const uint4 g = __ldg(reinterpret_cast<const uint4*>(a.blob + src + (size_t)(n * ld + kc * 8) * 2));
+        uint4 g = __ldg(reinterpret_cast<const uint4*>(a.blob + src + (size_t)(n * ld + kc * 8) * 2));
+        if (halve) {   // exact in bf16: one less in the exponent field (weights are far from subnormal)
+          __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&g);
+          for (int e = 0; e < 4; ++e) hp[e] = __hmul2(hp[e], __floats2bfloat162_rn(0.5f, 0.5f));
+        }
         *reinterpret_cast<uint4*>(smem + dst + (size_t)kc * N * 16 + n * 16) = g;
       }
     };
@@ -148,7 +178,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) {
     copy_w(W_QKV1, L.layer[0].wqkv, 96, 32, kLdD);
     copy_w(W_PROJ1, L.layer[0].wproj, 32, 32, kLdD);
     copy_w(W_FC1, L.layer[0].wfc1, 128, 32, kLdD);
-    copy_w(W_FC2, L.layer[0].wfc2, 32, 128, kLdHid);
+    copy_w(W_FC2, L.layer[0].wfc2, 32, 128, kLdHid, true);   // the 0.5 of GELU lives here: H = 2 gelu(.)
     copy_w(W_QKV2, L.layer[1].wqkv, 96, 32, kLdD);
     auto copy_v = [&](int dst, int src, int n, float scale_first32) {
       for (int i = tid; i < n; i += kThreads) {
@@ -188,9 +218,34 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) {
     for (uint32_t i = tid; i < (2 * SLOT_BYTES + 2 * SLAB) / 16; i += kThreads)
       *reinterpret_cast<uint4*>(smem + SLOT0 + i * 16) = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    for (int i = tid; i < 128; i += kThreads) *reinterpret_cast<uint32_t*>(smem + ONES + i * 16) = 0x00003F80u;
+    // static bound on |q.k| of block 1: row n of Wq / Wk contributes (||W_n diag(g)||^2, (W_n . beta + b_n)^2)
+    if (tid < 64) {
+      const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(a.blob + L.layer[0].wqkv) + tid * kLdD;
+      const float* g = reinterpret_cast<const float*>(a.blob + L.layer[0].ln1_g);
+      const float* be = reinterpret_cast<const float*>(a.blob + L.layer[0].ln1_b);
+      float f2 = 0.f, bs = __ldg(reinterpret_cast<const float*>(a.blob + L.layer[0].bqkv) + tid);
+      for (int c = 0; c < 32; ++c) {
+        const float wv = __bfloat162float(w[c]);
+        f2 = fmaf(wv * __ldg(g + c), wv * __ldg(g + c), f2);
+        bs = fmaf(wv, __ldg(be + c), bs);
+      }
+      float* scr = reinterpret_cast<float*>(smem + SLOT0 + S_PBUF);
+      scr[2 * tid] = f2;
+      scr[2 * tid + 1] = bs * bs;
+    }
+    for (int i = tid; i < 128; i += kThreads) {
+      *reinterpret_cast<uint32_t*>(smem + ONES + i * 16) = 0x00003F80u;                 // bf16 1.0
+      *reinterpret_cast<uint32_t*>(smem + MASK + i * 16) = i >= T ? 0x0000C6EAu : 0u;   // bf16 -29952 for padded keys
+    }
     if (tid == 0) {
-      for (int i = 0; i < 8; ++i) mbar_init(reinterpret_cast<uint64_t*>(smem + MISC + 384) + i, 1);
+      for (int s = 0; s < 2; ++s) {
+        uint64_t* bb = reinterpret_cast<uint64_t*>(smem + MISC + 384) + s * 5;
+        mbar_init(bb + 0, 128);
+        mbar_init(bb + 1, 128);
+        mbar_init(bb + 2, 1);
+        mbar_init(bb + 3, 1);
+        mbar_init(bb + 4, 1);
+      }
       fence_mbar_init();
     }
     if (tid < 32) {
@@ -202,179 +257,74 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) {
     __syncthreads();
     tc_fence_after();
   }
+  // |s| <= qscale * (sqrt(32) ||Wq_h diag(g)||_F + ||Wq_h beta + bq_h||) * (same for k): LayerNorm output is
+  // g * xhat + beta with ||xhat|| <= sqrt(32).  Below 2^100 neither 2^s nor its row sums leave fp32 / bf16
+  // range, so the row maximum is not needed (bf16 rounding of the operands is far inside the margin).
+  bool exact_softmax = false;
+  {
+    const float* scr = reinterpret_cast<const float*>(smem + SLOT0 + S_PBUF);
+    for (int h = 0; h < 4; ++h) {
+      float qf = 0.f, qb = 0.f, kf = 0.f, kb = 0.f;
+      for (int n = 0; n < 8; ++n) {
+        qf += scr[2 * (8 * h + n)]; qb += scr[2 * (8 * h + n) + 1];
+        kf += scr[2 * (32 + 8 * h + n)]; kb += scr[2 * (32 + 8 * h + n) + 1];
+      }
+      const float bound = qscale * (sqrtf(32.f * qf) + sqrtf(qb)) * (sqrtf(32.f * kf) + sqrtf(kb));
+      if (!(bound < 100.f)) exact_softmax = true;
+    }
+    __syncthreads();   // the scratch is part of a P buffer
+  }
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tb = tmem_base + (uint32_t)slot * 256u;                  // columns of this slot (issuer view)
   const uint32_t tl = tb + ((uint32_t)(wq * 32) << 16);                   // + the 32 lanes of this warp
   const uint32_t slot_s = sb + SLOT0 + (uint32_t)slot * SLOT_BYTES;
   const uint32_t fbuf = slot_s + S_FBUF, abuf = slot_s + S_ABUF, qbuf = slot_s + S_QBUF, kbuf = slot_s + S_KBUF,
                  vbuf = slot_s + S_VBUF, pbuf = slot_s + S_PBUF;
-  const uint32_t row16 = (uint32_t)r * 16u;
-  const int NK16 = (T + 15) & ~15, NKS = NK16 >> 4;   // keys rounded to the MMA's N / K granularity
-  const int ct = (T - 1) >> 5;                         // last 32-key chunk holding a real key
-  const int PW = P + 1, PP = sps_pp(P), HALO = sps_halo(P);
-  const int bar_id = 1 + slot;
-  const bool w0 = wq == 0;
+  const int NK = (T + 31) & ~31, NKS = NK >> 4;       // keys rounded to the 32-column chunks the row threads read
   const int nslots = 2 * (int)gridDim.x;
+  const int b0 = 2 * (int)blockIdx.x + slot;
 
-  auto fetch = [&](int b) {   // warp 0 of the slot: stem outputs of patch b -> FBUF rows 1..T-1 (one copy per image row and slice)
-    if (lane == 0) mbar_arrive_expect_tx(b_ffull, (uint32_t)(8 * P * P * 16));
-    __syncwarp();
-    for (int c = lane; c < 8 * P; c += 32) {
-      const int s = c / P, i = c - s * P;
-      bulk_g2s(smem + (fbuf - sb) + s * SLAB + (1 + i * P) * 16, a.f + ((long long)s * a.RT + HALO + (long long)b * PP + i * PW) * 8,
-               (uint32_t)(P * 16), b_ffull);
-    }
-  };
-  // operands written by the row threads -> visible to the tensor core; previous TMEM reads retired
-  auto publish = [&]() {
-    fence_proxy_async();
-    tc_fence_before();
-    bar_sync(bar_id, 128);
-  };
-
-  uint32_t ph_f = 0, ph_m = 0, ph_s = 0, ph_pv = 0;
-  int b = 2 * (int)blockIdx.x + slot;
-  if (w0 && b < a.n_patches) fetch(b);
-
-  for (; b < a.n_patches; b += nslots) {
-    float x[32];   // residual stream of token row r
-    // ================= fusion 1x1 conv (64 -> 32) + folded BN + ReLU, + cls / pos =================
-    if (w0) {
-      mbar_wait(b_ffull, ph_f);
-      ph_f ^= 1u;
+  if (issuer) {
+    // ============================ MMA issuer of this slot ============================
+    uint32_t ph_rp = 0, ph_rs = 0;
+    auto ready = [&]() {       // the row threads have written the operands of the next GEMM
+      mbar_wait(b_rp, ph_rp);
+      ph_rp ^= 1u;
       tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tb + C_SMALL, umma_desc(fbuf + 2 * k * SLAB, SLAB, 128), umma_desc(sb + W_FUS + 2 * k * 512, 512, 128),
-                    idesc(32, 0), k ? 1u : 0u);
-        umma_commit(b_mma);
-      }
-      __syncwarp();
-    }
-    mbar_wait(b_mma, ph_m);
-    ph_m ^= 1u;
-    tc_fence_after();
-    if (w0 && b + nslots < a.n_patches) fetch(b + nslots);   // FBUF is free again: prefetch the next patch
-    {
-      uint32_t v[32];
-      tmem_ld32(tl + C_SMALL, v);
-      tc_wait_ld();
-      const float rowmask = (r >= 1 && r < T) ? 1.f : 0.f;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const float4 p = lds_f4(sb + POS + r * 128 + ((g ^ (r & 7)) << 4));
-        const float4 sc = lds_f4(sb + VEC + (V_FSC + 4 * g) * 4), bi = lds_f4(sb + VEC + (V_FBI + 4 * g) * 4);
-        x[4 * g + 0] = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * g + 0]), sc.x, bi.x), 0.f), rowmask, p.x);
-        x[4 * g + 1] = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * g + 1]), sc.y, bi.y), 0.f), rowmask, p.y);
-        x[4 * g + 2] = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * g + 2]), sc.z, bi.z), 0.f), rowmask, p.z);
-        x[4 * g + 3] = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * g + 3]), sc.w, bi.w), 0.f), rowmask, p.w);
-      }
-    }
-
-    // ================= block 1: LN1 -> qkv =================
-    ln_store(x, sb + VEC + V_LN1G * 4, sb + VEC + V_LN1B * 4, abuf + row16);
-    publish();
-    if (w0) {
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-          umma_bf16(tb + C_S, umma_desc(abuf + 2 * k * SLAB, SLAB, 128), umma_desc(sb + W_QKV1 + 2 * k * 1536, 1536, 128),
-                    idesc(96, 0), k ? 1u : 0u);
-        umma_commit(b_mma);
-      }
-      __syncwarp();
-    }
-    mbar_wait(b_mma, ph_m);
-    ph_m ^= 1u;
-    tc_fence_after();
-    {
-      uint32_t v[3][32];
-      tmem_ld32(tl + C_S, v[0]);
-      tmem_ld32(tl + C_S + 32, v[1]);
-      tmem_ld32(tl + C_S + 64, v[2]);
-      tc_wait_ld();
-#pragma unroll
-      for (int part = 0; part < 3; ++part) {
-        const uint32_t dst = (part == 0 ? qbuf : part == 1 ? kbuf : vbuf) + row16;
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const float4 b0 = lds_f4(sb + VEC + (V_BQKV + 32 * part + 8 * h) * 4), b1 = lds_f4(sb + VEC + (V_BQKV + 32 * part + 8 * h + 4) * 4);
-          const float sc = part == 0 ? qscale : 1.f;
-          const uint32_t* vv = v[part] + 8 * h;
-          sts128(dst + h * SLAB, pack_bf16(fmaf(__uint_as_float(vv[0]), sc, b0.x), fmaf(__uint_as_float(vv[1]), sc, b0.y)),
-                 pack_bf16(fmaf(__uint_as_float(vv[2]), sc, b0.z), fmaf(__uint_as_float(vv[3]), sc, b0.w)),
-                 pack_bf16(fmaf(__uint_as_float(vv[4]), sc, b1.x), fmaf(__uint_as_float(vv[5]), sc, b1.y)),
-                 pack_bf16(fmaf(__uint_as_float(vv[6]), sc, b1.z), fmaf(__uint_as_float(vv[7]), sc, b1.w)));
-        }
-      }
-    }
-    publish();
-    // S_h = Q_h K_h^T: A chunks (Q_h, Q_h+1), B chunks (K_h, zeros) -> the second half of K = 16 adds nothing
-    auto issue_s = [&](int h) {
-      umma_bf16(tb + C_S, umma_desc(qbuf + h * SLAB, SLAB, 128), umma_desc(kbuf + h * SLAB, (sb + ZERO) - (kbuf + h * SLAB), 128),
-                idesc(NK16, 0), 0u);
-      umma_commit(b_s);
     };
-    if (w0) {
-      tc_fence_after();
-      if (elect_one()) issue_s(0);
+    // S_h = Q_h K_h^T + mask: A chunks (Q_h, ones), B chunks (K_h, mask) -> the second half of K = 16 adds
+    // 1 * (-30000) to the columns of padded keys and nothing to the others
+    auto issue_s = [&](int h) {
+      if (elect_one()) {
+        umma_bf16(tb + C_S, umma_desc(qbuf + h * SLAB, (sb + ONES) - (qbuf + h * SLAB), 128),
+                  umma_desc(kbuf + h * SLAB, (sb + MASK) - (kbuf + h * SLAB), 128), idesc(NK, 0), 0u);
+        umma_commit(b_s);
+      }
       __syncwarp();
-    }
-
-    // ================= attention, one head at a time =================
+    };
+    // D[128 x N] (TMEM column `col`) = A[128 x 16 ksteps] (K-major slabs at `abase`) . W^T (weights [k/8][N][8] at `wbase`)
+    auto issue_gemm = [&](uint32_t col, uint32_t abase, uint32_t wbase, int N, int ksteps) {
+      if (elect_one()) {
+        for (int k = 0; k < ksteps; ++k)
+          umma_bf16(tb + col, umma_desc(abase + 2 * k * SLAB, SLAB, 128), umma_desc(wbase + 2 * k * N * 16, (uint32_t)N * 16u, 128),
+                    idesc(N, 0), k ? 1u : 0u);
+        umma_commit(b_mma);
+      }
+      __syncwarp();
+    };
+    for (int b = b0; b < a.n_patches; b += nslots) {
+      ready(); issue_gemm(C_SMALL, fbuf, sb + W_FUS, 32, 4);       // fusion 1x1 conv
+      ready(); issue_gemm(C_S, abuf, sb + W_QKV1, 96, 2);          // qkv
+      ready(); issue_s(0);
 #pragma unroll 1
-    for (int h = 0; h < 4; ++h) {
-      uint32_t s[4][32];
-      mbar_wait(b_s, ph_s);
-      ph_s ^= 1u;
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c <= ct) tmem_ld32(tl + C_S + 32 * c, s[c]);
-      tc_wait_ld();
-      tc_fence_before();
-      bar_sync(bar_id, 128);           // every row of S_h is in registers: the next head's S may overwrite it
-      if (w0 && h < 3) {
-        tc_fence_after();
-        if (elect_one()) issue_s(h + 1);
-        __syncwarp();
-      }
-      float m = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c <= ct) {
-          if (c == ct) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (32 * c + i >= T) s[c][i] = 0xFF800000u;   // -inf: padded keys
-          }
-#pragma unroll
-          for (int i = 0; i < 32; i += 2)
-            m = fmaxf(m, fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
+      for (int h = 0; h < 4; ++h) {
+        if (h < 3) {
+          mbar_wait(b_rs, ph_rs);
+          ph_rs ^= 1u;
+          tc_fence_after();
+          issue_s(h + 1);
         }
-      }
-      if (h > 0) {                      // PV of the previous head has consumed the P buffer
-        mbar_wait(b_pv, ph_pv);
-        ph_pv ^= 1u;
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c <= ct) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              pk[e] = pack_bf16(ex2(__uint_as_float(s[c][8 * g + 2 * e]) - m), ex2(__uint_as_float(s[c][8 * g + 2 * e + 1]) - m));
-            sts128(pbuf + (4 * c + g) * SLAB + row16, pk[0], pk[1], pk[2], pk[3]);
-          }
-        }
-      }
-      publish();
-      if (w0) {
-        tc_fence_after();
+        ready();
         if (elect_one()) {
           // O_h[128 x 16] = P_h[128 x keys] . [V_h | ones]: B is MN-major, N chunk 0 = V_h slab, chunk 1 = ONES slab
           const uint32_t vb = vbuf + h * SLAB;
@@ -385,215 +335,305 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) {
         }
         __syncwarp();
       }
+      ready(); issue_gemm(C_SMALL, abuf, sb + W_PROJ1, 32, 2);     // proj
+      ready(); issue_gemm(C_S, abuf, sb + W_FC1, 128, 2);          // fc1
+      ready(); issue_gemm(C_SMALL, pbuf, sb + W_FC2, 32, 8);       // fc2
+      ready(); issue_gemm(C_S, abuf, sb + W_QKV2, 96, 2);          // last block: q (cls row), k, v
     }
-    mbar_wait(b_pv, ph_pv);
-    ph_pv ^= 1u;
-    tc_fence_after();
-    // ---- attention output (normalised) -> A operand of proj ----
-    {
-      uint32_t o[4][16];
+  } else {
+    // ============================ row threads ============================
+    const uint32_t row16 = (uint32_t)r * 16u;
+    const int ct = (T - 1) >> 5;                         // last 32-key chunk holding a real key
+    const int PW = P + 1, PP = sps_pp(P), HALO = sps_halo(P);
+    const int bar_id = 1 + slot;
+    const bool w0 = wq == 0;
+    uint32_t ph_m = 0, ph_s = 0, ph_pv = 0;
+    // stem outputs of token row r of patch b -> FBUF (8 slices x 16 B; cls row and padding rows stay zero)
+    auto fetch = [&](int b) {
+      if (r >= 1 && r < T) {
+        const int p = r - 1, i = p / P, j = p - i * P;
+        const __nv_bfloat16* src = a.f + (HALO + (long long)b * PP + i * PW + j) * 8;
 #pragma unroll
-      for (int h = 0; h < 4; ++h) tmem_ld16(tl + C_O + 16 * h, o[h]);
-      tc_wait_ld();
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const float il = 1.f / __uint_as_float(o[h][8]);
-        sts128(abuf + h * SLAB + row16, pack_bf16(__uint_as_float(o[h][0]) * il, __uint_as_float(o[h][1]) * il),
-               pack_bf16(__uint_as_float(o[h][2]) * il, __uint_as_float(o[h][3]) * il),
-               pack_bf16(__uint_as_float(o[h][4]) * il, __uint_as_float(o[h][5]) * il),
-               pack_bf16(__uint_as_float(o[h][6]) * il, __uint_as_float(o[h][7]) * il));
+        for (int s = 0; s < 8; ++s) cp_async16(fbuf + s * SLAB + row16, src + (long long)s * a.RT * 8);
       }
-    }
-    publish();
-    if (w0) {
+    };
+    // this thread's operand rows are written -> visible to the tensor core; its TMEM reads are retired
+    auto publish = [&]() {
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(b_rp);
+    };
+    auto wait_mma = [&]() {
+      mbar_wait(b_mma, ph_m);
+      ph_m ^= 1u;
       tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-          umma_bf16(tb + C_SMALL, umma_desc(abuf + 2 * k * SLAB, SLAB, 128), umma_desc(sb + W_PROJ1 + 2 * k * 512, 512, 128),
-                    idesc(32, 0), k ? 1u : 0u);
-        umma_commit(b_mma);
-      }
-      __syncwarp();
-    }
-    mbar_wait(b_mma, ph_m);
-    ph_m ^= 1u;
-    tc_fence_after();
-    {
-      uint32_t v[32];
-      tmem_ld32(tl + C_SMALL, v);
-      tc_wait_ld();
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const float4 bb = lds_f4(sb + VEC + (V_BPROJ + 4 * g) * 4);
-        x[4 * g + 0] += __uint_as_float(v[4 * g + 0]) + bb.x;
-        x[4 * g + 1] += __uint_as_float(v[4 * g + 1]) + bb.y;
-        x[4 * g + 2] += __uint_as_float(v[4 * g + 2]) + bb.z;
-        x[4 * g + 3] += __uint_as_float(v[4 * g + 3]) + bb.w;
-      }
-    }
+    };
+    if (b0 < a.n_patches) fetch(b0);
 
-    // ================= MLP: LN2 -> fc1 (+bias, GELU) -> fc2 (+bias, +residual) =================
-    ln_store(x, sb + VEC + V_LN2G * 4, sb + VEC + V_LN2B * 4, abuf + row16);
-    publish();
-    if (w0) {
-      tc_fence_after();
-      if (elect_one()) {
+    for (int b = b0; b < a.n_patches; b += nslots) {
+      float x[32];   // residual stream of token row r
+      // ================= fusion 1x1 conv (64 -> 32) + folded BN + ReLU, + cls / pos =================
+      cp_async_wait_all();
+      publish();
+      wait_mma();
+      if (b + nslots < a.n_patches) fetch(b + nslots);   // FBUF is free again: prefetch the next patch
+      {
+        uint32_t v[32];
+        tmem_ld32(tl + C_SMALL, v);
+        tc_wait_ld();
+        const float rowmask = (r >= 1 && r < T) ? 1.f : 0.f;
 #pragma unroll
-        for (int k = 0; k < 2; ++k)
-          umma_bf16(tb + C_S, umma_desc(abuf + 2 * k * SLAB, SLAB, 128), umma_desc(sb + W_FC1 + 2 * k * 2048, 2048, 128),
-                    idesc(128, 0), k ? 1u : 0u);
-        umma_commit(b_mma);
-      }
-      __syncwarp();
-    }
-    mbar_wait(b_mma, ph_m);
-    ph_m ^= 1u;
-    tc_fence_after();
-#pragma unroll
-    for (int c2 = 0; c2 < 2; ++c2) {
-      uint32_t v[2][32];
-      tmem_ld32(tl + C_S + 64 * c2, v[0]);
-      tmem_ld32(tl + C_S + 64 * c2 + 32, v[1]);
-      tc_wait_ld();
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = 2 * c2 + cc;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const float4 b0 = lds_f4(sb + VEC + (V_BFC1 + 32 * c + 8 * g) * 4), b1 = lds_f4(sb + VEC + (V_BFC1 + 32 * c + 8 * g + 4) * 4);
-          const uint32_t* vv = v[cc] + 8 * g;
-          sts128(pbuf + (4 * c + g) * SLAB + row16,
-                 pack_bf16(gelu_erf(__uint_as_float(vv[0]) + b0.x), gelu_erf(__uint_as_float(vv[1]) + b0.y)),
-                 pack_bf16(gelu_erf(__uint_as_float(vv[2]) + b0.z), gelu_erf(__uint_as_float(vv[3]) + b0.w)),
-                 pack_bf16(gelu_erf(__uint_as_float(vv[4]) + b1.x), gelu_erf(__uint_as_float(vv[5]) + b1.y)),
-                 pack_bf16(gelu_erf(__uint_as_float(vv[6]) + b1.z), gelu_erf(__uint_as_float(vv[7]) + b1.w)));
+        for (int g = 0; g < 8; ++g) {
+          const float4 p = lds_f4(sb + POS + r * 128 + ((g ^ (r & 7)) << 4));
+          const float4 sc = lds_f4(sb + VEC + (V_FSC + 4 * g) * 4), bi = lds_f4(sb + VEC + (V_FBI + 4 * g) * 4);
+          x[4 * g + 0] = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * g + 0]), sc.x, bi.x), 0.f), rowmask, p.x);
+          x[4 * g + 1] = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * g + 1]), sc.y, bi.y), 0.f), rowmask, p.y);
+          x[4 * g + 2] = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * g + 2]), sc.z, bi.z), 0.f), rowmask, p.z);
+          x[4 * g + 3] = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * g + 3]), sc.w, bi.w), 0.f), rowmask, p.w);
         }
       }
-    }
-    publish();
-    if (w0) {
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16(tb + C_SMALL, umma_desc(pbuf + 2 * k * SLAB, SLAB, 128), umma_desc(sb + W_FC2 + 2 * k * 512, 512, 128),
-                    idesc(32, 0), k ? 1u : 0u);
-        umma_commit(b_mma);
-      }
-      __syncwarp();
-    }
-    mbar_wait(b_mma, ph_m);
-    ph_m ^= 1u;
-    tc_fence_after();
-    {
-      uint32_t v[32];
-      tmem_ld32(tl + C_SMALL, v);
-      tc_wait_ld();
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const float4 bb = lds_f4(sb + VEC + (V_BFC2 + 4 * g) * 4);
-        x[4 * g + 0] += __uint_as_float(v[4 * g + 0]) + bb.x;
-        x[4 * g + 1] += __uint_as_float(v[4 * g + 1]) + bb.y;
-        x[4 * g + 2] += __uint_as_float(v[4 * g + 2]) + bb.z;
-        x[4 * g + 3] += __uint_as_float(v[4 * g + 3]) + bb.w;
-      }
-    }
 
-    // ================= last block: K / V of every token, attention of the cls query only =================
-    ln_store(x, sb + VEC + V_L2G * 4, sb + VEC + V_L2B * 4, abuf + row16);
-    publish();
-    if (w0) {
-      tc_fence_after();
-      if (elect_one()) {
+      // ================= block 1: LN1 -> qkv =================
+      ln_store(x, sb + VEC + V_LN1G * 4, sb + VEC + V_LN1B * 4, abuf + row16);
+      publish();
+      wait_mma();
+      {
+        uint32_t v[2][32];
+        tmem_ld32(tl + C_S, v[0]);
 #pragma unroll
-        for (int k = 0; k < 2; ++k)
-          umma_bf16(tb + C_S, umma_desc(abuf + 2 * k * SLAB, SLAB, 128), umma_desc(sb + W_QKV2 + 2 * k * 1536, 1536, 128),
-                    idesc(96, 0), k ? 1u : 0u);
-        umma_commit(b_mma);
-      }
-      __syncwarp();
-    }
-    mbar_wait(b_mma, ph_m);
-    ph_m ^= 1u;
-    tc_fence_after();
-    float* trec = a.tail + (long long)b * kTailFloats;
-    {
-      uint32_t kk[32], vv[32];
-      tmem_ld32(tl + C_S + 32, kk);
-      tmem_ld32(tl + C_S + 64, vv);
-      if (w0) {     // the cls token is row 0: its (scaled) query and its residual stream
-        uint32_t qq[32];
-        tmem_ld32(tl + C_S, qq);
-        tc_wait_ld();
-        if (lane == 0) {
+        for (int part = 0; part < 3; ++part) {
+          tc_wait_ld();
+          if (part < 2) tmem_ld32(tl + C_S + 32 * (part + 1), v[(part + 1) & 1]);
+          const uint32_t dst = (part == 0 ? qbuf : part == 1 ? kbuf : vbuf) + row16;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            q0_s[c] = fmaf(__uint_as_float(qq[c]), qscale, vecf[V_BQKV2 + c]);
-            trec[144 + c] = x[c];
+          for (int h = 0; h < 4; ++h) {
+            const float4 b0_ = lds_f4(sb + VEC + (V_BQKV + 32 * part + 8 * h) * 4), b1_ = lds_f4(sb + VEC + (V_BQKV + 32 * part + 8 * h + 4) * 4);
+            const float sc = part == 0 ? qscale : 1.f;
+            const uint32_t* vv = v[part & 1] + 8 * h;
+            sts128(dst + h * SLAB, pack_bf16(fmaf(__uint_as_float(vv[0]), sc, b0_.x), fmaf(__uint_as_float(vv[1]), sc, b0_.y)),
+                   pack_bf16(fmaf(__uint_as_float(vv[2]), sc, b0_.z), fmaf(__uint_as_float(vv[3]), sc, b0_.w)),
+                   pack_bf16(fmaf(__uint_as_float(vv[4]), sc, b1_.x), fmaf(__uint_as_float(vv[5]), sc, b1_.y)),
+                   pack_bf16(fmaf(__uint_as_float(vv[6]), sc, b1_.z), fmaf(__uint_as_float(vv[7]), sc, b1_.w)));
           }
         }
       }
-      tc_wait_ld();
-      tc_fence_before();
-      bar_sync(bar_id, 128);
-      float sc[4];
+      publish();
+
+      // ================= attention, one head at a time =================
+      // p = 2^(s - m) -> bf16 -> P buffer (A operand of PV); S_h is released to the issuer as soon as its last
+      // chunk is in registers.  `exact`: two passes over S_h in TMEM (row maximum first); otherwise m = 0.
+      auto softmax_head = [&](int h, auto exact_tag) {
+        constexpr bool kExact = decltype(exact_tag)::value;
+        uint32_t s[2][32];
+        mbar_wait(b_s, ph_s);
+        ph_s ^= 1u;
+        tc_fence_after();
+        float m = 0.f;
+        if constexpr (kExact) {
+          m = -INFINITY;
+          tmem_ld32(tl + C_S, s[0]);
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const float4 q0 = lds_f4(smem_u32(q0_s) + 32 * h), q1 = lds_f4(smem_u32(q0_s) + 32 * h + 16);
-        const float4 k0 = lds_f4(sb + VEC + (V_BQKV2 + 32 + 8 * h) * 4), k1 = lds_f4(sb + VEC + (V_BQKV2 + 36 + 8 * h) * 4);
-        float d = q0.x * (__uint_as_float(kk[8 * h + 0]) + k0.x);
-        d = fmaf(q0.y, __uint_as_float(kk[8 * h + 1]) + k0.y, d);
-        d = fmaf(q0.z, __uint_as_float(kk[8 * h + 2]) + k0.z, d);
-        d = fmaf(q0.w, __uint_as_float(kk[8 * h + 3]) + k0.w, d);
-        d = fmaf(q1.x, __uint_as_float(kk[8 * h + 4]) + k1.x, d);
-        d = fmaf(q1.y, __uint_as_float(kk[8 * h + 5]) + k1.y, d);
-        d = fmaf(q1.z, __uint_as_float(kk[8 * h + 6]) + k1.z, d);
-        d = fmaf(q1.w, __uint_as_float(kk[8 * h + 7]) + k1.w, d);
-        sc[h] = r < T ? d : -INFINITY;
-        float mw = sc[h];
+          for (int c = 0; c < 4; ++c) {
+            if (c <= ct) {
+              tc_wait_ld();
+              if (c + 1 <= ct) tmem_ld32(tl + C_S + 32 * (c + 1), s[(c + 1) & 1]);
+              const uint32_t(&sc)[32] = s[c & 1];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
-        if (lane == 0) wmax_s[wq * 4 + h] = mw;
+              for (int i = 0; i < 32; i += 2) m = fmaxf(m, fmaxf(__uint_as_float(sc[i]), __uint_as_float(sc[i + 1])));
+            }
+          }
+        }
+        tmem_ld32(tl + C_S, s[0]);
+        if (h > 0) {                      // PV of the previous head has consumed the P buffer
+          mbar_wait(b_pv, ph_pv);
+          ph_pv ^= 1u;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c <= ct) {
+            tc_wait_ld();
+            if (c + 1 <= ct) tmem_ld32(tl + C_S + 32 * (c + 1), s[(c + 1) & 1]);
+            else if (h < 3) {             // S_h is out of TMEM: the next head's S may overwrite it
+              tc_fence_before();
+              mbar_arrive(b_rs);
+            }
+            const uint32_t(&sc)[32] = s[c & 1];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float s0 = __uint_as_float(sc[8 * g + 2 * e]), s1 = __uint_as_float(sc[8 * g + 2 * e + 1]);
+                pk[e] = kExact ? pack_bf16(ex2(s0 - m), ex2(s1 - m)) : pack_bf16(ex2(s0), ex2(s1));
+              }
+              sts128(pbuf + (4 * c + g) * SLAB + row16, pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+        }
+        publish();
+      };
+      if (exact_softmax) {
+#pragma unroll 1
+        for (int h = 0; h < 4; ++h) softmax_head(h, std::true_type{});
+      } else {
+#pragma unroll 1
+        for (int h = 0; h < 4; ++h) softmax_head(h, std::false_type{});
       }
-      bar_sync(bar_id, 128);
-      float val[32], pl[4];
+      mbar_wait(b_pv, ph_pv);
+      ph_pv ^= 1u;
+      tc_fence_after();
+      // ---- attention output (normalised) -> A operand of proj ----
+      {
+        uint32_t o[4][16];
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const float m = fmaxf(fmaxf(wmax_s[h], wmax_s[4 + h]), fmaxf(wmax_s[8 + h], wmax_s[12 + h]));
-        const float p = ex2(sc[h] - m);
-        pl[h] = p;
-        const float4 v0 = lds_f4(sb + VEC + (V_BQKV2 + 64 + 8 * h) * 4), v1 = lds_f4(sb + VEC + (V_BQKV2 + 68 + 8 * h) * 4);
-        val[8 * h + 0] = p * (__uint_as_float(vv[8 * h + 0]) + v0.x);
-        val[8 * h + 1] = p * (__uint_as_float(vv[8 * h + 1]) + v0.y);
-        val[8 * h + 2] = p * (__uint_as_float(vv[8 * h + 2]) + v0.z);
-        val[8 * h + 3] = p * (__uint_as_float(vv[8 * h + 3]) + v0.w);
-        val[8 * h + 4] = p * (__uint_as_float(vv[8 * h + 4]) + v1.x);
-        val[8 * h + 5] = p * (__uint_as_float(vv[8 * h + 5]) + v1.y);
-        val[8 * h + 6] = p * (__uint_as_float(vv[8 * h + 6]) + v1.z);
-        val[8 * h + 7] = p * (__uint_as_float(vv[8 * h + 7]) + v1.w);
-      }
-      // butterfly reduction over the 32 rows of this warp: lane i ends with sum over rows of val[i]
+        for (int h = 0; h < 4; ++h) tmem_ld16(tl + C_O + 16 * h, o[h]);
+        tc_wait_ld();
 #pragma unroll
-      for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
-        const bool up = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < n / 2; ++i) {
-          const float send = up ? val[i] : val[i + n / 2];
-          const float keep = up ? val[i + n / 2] : val[i];
-          val[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        for (int h = 0; h < 4; ++h) {
+          const float il = 1.f / __uint_as_float(o[h][8]);
+          sts128(abuf + h * SLAB + row16, pack_bf16(__uint_as_float(o[h][0]) * il, __uint_as_float(o[h][1]) * il),
+                 pack_bf16(__uint_as_float(o[h][2]) * il, __uint_as_float(o[h][3]) * il),
+                 pack_bf16(__uint_as_float(o[h][4]) * il, __uint_as_float(o[h][5]) * il),
+                 pack_bf16(__uint_as_float(o[h][6]) * il, __uint_as_float(o[h][7]) * il));
         }
       }
-      {   // denominators: head = 2 * bit4 + bit3 of the lane after two halving steps, then a full reduce over bits 2..0
-        const bool up4 = (lane & 16) != 0, up3 = (lane & 8) != 0;
-        float a0 = (up4 ? pl[2] : pl[0]) + __shfl_xor_sync(0xffffffffu, up4 ? pl[0] : pl[2], 16);
-        float a1 = (up4 ? pl[3] : pl[1]) + __shfl_xor_sync(0xffffffffu, up4 ? pl[1] : pl[3], 16);
-        float l = (up3 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, up3 ? a0 : a1, 8);
-        l += __shfl_xor_sync(0xffffffffu, l, 4);
-        l += __shfl_xor_sync(0xffffffffu, l, 2);
-        l += __shfl_xor_sync(0xffffffffu, l, 1);
-        trec[wq * 36 + lane] = val[0];
-        if ((lane & 7) == 0) trec[wq * 36 + 32 + (lane >> 3)] = l;
+      publish();
+      wait_mma();
+      {
+        uint32_t v[32];
+        tmem_ld32(tl + C_SMALL, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 bb = lds_f4(sb + VEC + (V_BPROJ + 4 * g) * 4);
+          x[4 * g + 0] += __uint_as_float(v[4 * g + 0]) + bb.x;
+          x[4 * g + 1] += __uint_as_float(v[4 * g + 1]) + bb.y;
+          x[4 * g + 2] += __uint_as_float(v[4 * g + 2]) + bb.z;
+          x[4 * g + 3] += __uint_as_float(v[4 * g + 3]) + bb.w;
+        }
+      }
+
+      // ================= MLP: LN2 -> fc1 (+bias, GELU) -> fc2 (+bias, +residual) =================
+      ln_store(x, sb + VEC + V_LN2G * 4, sb + VEC + V_LN2B * 4, abuf + row16);
+      publish();
+      wait_mma();
+      {
+        uint32_t v[2][32];
+        tmem_ld32(tl + C_S, v[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tc_wait_ld();
+          if (c < 3) tmem_ld32(tl + C_S + 32 * (c + 1), v[(c + 1) & 1]);
+          const uint32_t(&vc_)[32] = v[c & 1];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float4 b0_ = lds_f4(sb + VEC + (V_BFC1 + 32 * c + 8 * g) * 4), b1_ = lds_f4(sb + VEC + (V_BFC1 + 32 * c + 8 * g + 4) * 4);
+            const uint32_t* vv = vc_ + 8 * g;
+            sts128(pbuf + (4 * c + g) * SLAB + row16,
+                   pack_bf16(gelu2(__uint_as_float(vv[0]) + b0_.x), gelu2(__uint_as_float(vv[1]) + b0_.y)),
+                   pack_bf16(gelu2(__uint_as_float(vv[2]) + b0_.z), gelu2(__uint_as_float(vv[3]) + b0_.w)),
+                   pack_bf16(gelu2(__uint_as_float(vv[4]) + b1_.x), gelu2(__uint_as_float(vv[5]) + b1_.y)),
+                   pack_bf16(gelu2(__uint_as_float(vv[6]) + b1_.z), gelu2(__uint_as_float(vv[7]) + b1_.w)));
+          }
+        }
+      }
+      publish();
+      wait_mma();
+      {
+        uint32_t v[32];
+        tmem_ld32(tl + C_SMALL, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 bb = lds_f4(sb + VEC + (V_BFC2 + 4 * g) * 4);
+          x[4 * g + 0] += __uint_as_float(v[4 * g + 0]) + bb.x;
+          x[4 * g + 1] += __uint_as_float(v[4 * g + 1]) + bb.y;
+          x[4 * g + 2] += __uint_as_float(v[4 * g + 2]) + bb.z;
+          x[4 * g + 3] += __uint_as_float(v[4 * g + 3]) + bb.w;
+        }
+      }
+
+      // ================= last block: K / V of every token, attention of the cls query only =================
+      ln_store(x, sb + VEC + V_L2G * 4, sb + VEC + V_L2B * 4, abuf + row16);
+      publish();
+      wait_mma();
+      float* trec = a.tail + (long long)b * kTailFloats;
+      {
+        uint32_t kk[32], vv[32];
+        tmem_ld32(tl + C_S + 32, kk);
+        tmem_ld32(tl + C_S + 64, vv);
+        if (w0) {     // the cls token is row 0: its (scaled) query and its residual stream
+          uint32_t qq[32];
+          tmem_ld32(tl + C_S, qq);
+          tc_wait_ld();
+          if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              q0_s[c] = fmaf(__uint_as_float(qq[c]), qscale, vecf[V_BQKV2 + c]);
+              trec[144 + c] = x[c];
+            }
+          }
+        }
+        tc_wait_ld();
+        bar_sync(bar_id, 128);
+        float sc[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float4 q0 = lds_f4(smem_u32(q0_s) + 32 * h), q1 = lds_f4(smem_u32(q0_s) + 32 * h + 16);
+          const float4 k0 = lds_f4(sb + VEC + (V_BQKV2 + 32 + 8 * h) * 4), k1 = lds_f4(sb + VEC + (V_BQKV2 + 36 + 8 * h) * 4);
+          float d = q0.x * (__uint_as_float(kk[8 * h + 0]) + k0.x);
+          d = fmaf(q0.y, __uint_as_float(kk[8 * h + 1]) + k0.y, d);
+          d = fmaf(q0.z, __uint_as_float(kk[8 * h + 2]) + k0.z, d);
+          d = fmaf(q0.w, __uint_as_float(kk[8 * h + 3]) + k0.w, d);
+          d = fmaf(q1.x, __uint_as_float(kk[8 * h + 4]) + k1.x, d);
+          d = fmaf(q1.y, __uint_as_float(kk[8 * h + 5]) + k1.y, d);
+          d = fmaf(q1.z, __uint_as_float(kk[8 * h + 6]) + k1.z, d);
+          d = fmaf(q1.w, __uint_as_float(kk[8 * h + 7]) + k1.w, d);
+          sc[h] = r < T ? d : -INFINITY;
+          float mw = sc[h];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+          if (lane == 0) wmax_s[wq * 4 + h] = mw;
+        }
+        bar_sync(bar_id, 128);
+        float val[32], pl[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float m = fmaxf(fmaxf(wmax_s[h], wmax_s[4 + h]), fmaxf(wmax_s[8 + h], wmax_s[12 + h]));
+          const float p = ex2(sc[h] - m);
+          pl[h] = p;
+          const float4 v0 = lds_f4(sb + VEC + (V_BQKV2 + 64 + 8 * h) * 4), v1 = lds_f4(sb + VEC + (V_BQKV2 + 68 + 8 * h) * 4);
+          val[8 * h + 0] = p * (__uint_as_float(vv[8 * h + 0]) + v0.x);
+          val[8 * h + 1] = p * (__uint_as_float(vv[8 * h + 1]) + v0.y);
+          val[8 * h + 2] = p * (__uint_as_float(vv[8 * h + 2]) + v0.z);
+          val[8 * h + 3] = p * (__uint_as_float(vv[8 * h + 3]) + v0.w);
+          val[8 * h + 4] = p * (__uint_as_float(vv[8 * h + 4]) + v1.x);
+          val[8 * h + 5] = p * (__uint_as_float(vv[8 * h + 5]) + v1.y);
+          val[8 * h + 6] = p * (__uint_as_float(vv[8 * h + 6]) + v1.z);
+          val[8 * h + 7] = p * (__uint_as_float(vv[8 * h + 7]) + v1.w);
+        }
+        // butterfly reduction over the 32 rows of this warp: lane i ends with sum over rows of val[i]
+#pragma unroll
+        for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < n / 2; ++i) {
+            const float send = up ? val[i] : val[i + n / 2];
+            const float keep = up ? val[i + n / 2] : val[i];
+            val[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        {   // denominators: head = 2 * bit4 + bit3 of the lane after two halving steps, then a full reduce over bits 2..0
+          const bool up4 = (lane & 16) != 0, up3 = (lane & 8) != 0;
+          float a0 = (up4 ? pl[2] : pl[0]) + __shfl_xor_sync(0xffffffffu, up4 ? pl[0] : pl[2], 16);
+          float a1 = (up4 ? pl[3] : pl[1]) + __shfl_xor_sync(0xffffffffu, up4 ? pl[1] : pl[3], 16);
+          float l = (up3 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, up3 ? a0 : a1, 8);
+          l += __shfl_xor_sync(0xffffffffu, l, 4);
+          l += __shfl_xor_sync(0xffffffffu, l, 2);
+          l += __shfl_xor_sync(0xffffffffu, l, 1);
+          trec[wq * 36 + lane] = val[0];
+          if ((lane & 7) == 0) trec[wq * 36 + 32 + (lane >> 3)] = l;
+        }
       }
     }
   }
