@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VC_ABI_VERSION 3
+#define VC_ABI_VERSION 4
 
 /* Parameters of one model instance in kernel-ready form (built by vc-side packing, see
  * vitcnn_b200/model.py::pack_for_inference).  Conv weights: bf16 [nsplit][taps][S_in][N/nsplit][8]
@@ -49,6 +49,10 @@ typedef struct vc_model {
                                   [5][16][same], [9 taps][32][16 ch] -- then fp32 scale/bias
                                   of the three layers (8+8, 16+16, 32+32); NULL = three
                                   tensor-core conv launches through w_l / scale_l / bias_l   */
+  const void* w_h1_border;     /* nullable: 9 packed copies of w_h[0], copy cy*3+cx with the taps that leave a
+                                  window dropped for a pixel in row class cy / column class cx of the window
+                                  (0: first row / column -> ky or kx == 0 zeroed, 1: interior, 2: last ->
+                                  ky or kx == 2 zeroed).  Enables the shared first conv of vc_scene_infer  */
 } vc_model;
 
 int vc_abi_version(void);
@@ -235,7 +239,15 @@ int vc_forward_patches(const vc_model* m, const float* hsi, const int64_t hsi_st
  * Windows are enumerated on the device from xs/ys (see vc_scene_index), processed in chunks of
  * `chunk` windows [first_window, first_window+n_windows); logits land in logits_map f32
  * [H][W][K] at the window centre (untouched pixels are left as they are: zero-fill first),
- * argmax_map (nullable) uint8 [H][W].  Row-band sharding = disjoint window ranges per GPU. */
+ * argmax_map (nullable) uint8 [H][W].  Row-band sharding = disjoint window ranges per GPU.
+ *
+ * Shared first conv: the first HSI conv's output at a window pixel depends on the window only through the
+ * zero padding at the window border (3 row classes x 3 column classes).  When m->w_h1_border is set, P >= 2,
+ * the raster is at least 15 x 15, the windows are dense enough for it to pay and the workspace holds
+ * vc_scene_workspace_bytes(), the 9 variants are computed once per call on overlapping 15 x 15 scene blocks and
+ * every window's conv-1 output is gathered from them (same bits as the per-window conv).  With only
+ * vc_workspace_bytes(chunk, ...) of workspace the per-window path runs. */
+int64_t vc_scene_workspace_bytes(const vc_model* m, int32_t H, int32_t W, int32_t chunk);
 int vc_scene_infer(const vc_model* m, const float* img1, const float* img2, int32_t H, int32_t W, const int32_t* xs,
                    const int32_t* ys, int32_t nx, int32_t ny, int64_t first_window, int64_t n_windows, int32_t chunk,
                    void* workspace, int64_t workspace_bytes, float* logits_map, uint8_t* argmax_map, void* stream);

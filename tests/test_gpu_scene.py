@@ -75,3 +75,27 @@ def test_device_metrics_match_reference_formulas():
             assert got[k] == want[k], k
         for k in ("F1 scores", "Precisions"):
             assert np.array_equal(got[k], want[k], equal_nan=True), k
+
+
+@pytest.mark.parametrize("cfg", [(61, 47, 144, 1, 11, 16), (40, 95, 64, 2, 8, 12), (15, 15, 20, 1, 2, 5), (44, 29, 180, 1, 15, 8),
+                                 (28, 41, 16, 1, 3, 4)])
+def test_shared_first_conv_is_bit_identical_to_the_per_window_path(cfg):
+    """Dense scenes compute the 9 border-class variants of the first HSI conv once per scene (15 x 15 blocks,
+    clamped at the far edges) and gather every window's conv-1 output from them; the logits map must equal the
+    per-window path bit for bit (the per-window path = the same library call without w_h1_border)."""
+    H, W, C1, C2, P, K = cfg
+    _, ours = make_pair(C1, C2, P, K, seed=H)
+    img1, img2, _ = R.synthetic_scene(H, W, C1, C2, K, seed=W)
+    t1, t2 = torch.from_numpy(img1).to(DEV), torch.from_numpy(img2).to(DEV)
+    shared, am_s = ours.predict_scene(t1, t2, chunk=500)
+    st = ours.pack_for_inference()["struct"]
+    keep = st.w_h1_border
+    assert keep, "the model must ship the border-class weight copies"
+    st.w_h1_border = None
+    try:
+        plain, am_p = ours.predict_scene(t1, t2, chunk=500)
+    finally:
+        st.w_h1_border = keep
+    torch.cuda.synchronize()
+    assert (shared != 0).any()
+    assert torch.equal(shared, plain) and torch.equal(am_s, am_p)

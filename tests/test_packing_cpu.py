@@ -61,7 +61,7 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(_lib.SO_PATH)
     for name in declared:
         assert hasattr(L, name), name
-    assert _lib.lib().vc_abi_version() == 3
+    assert _lib.lib().vc_abi_version() == 4
 
 
 def test_layout_helpers_match_c():

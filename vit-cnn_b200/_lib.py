@@ -72,6 +72,7 @@ class VcModel(ctypes.Structure):
         ("w_l", c_void_p * 3), ("scale_l", c_void_p * 3), ("bias_l", c_void_p * 3),
         ("tparams", c_void_p),
         ("lidar_blob", c_void_p),
+        ("w_h1_border", c_void_p),
     ]
 
 
@@ -141,6 +142,7 @@ _PROTOS = {
     "vc_train_backward": (c_int32, [POINTER(VcTrain), c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
     "vc_forward_patches": (c_int32, [POINTER(VcModel), c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64),
                                      c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
+    "vc_scene_workspace_bytes": (c_int64, [POINTER(VcModel), c_int32, c_int32, c_int32]),
     "vc_scene_infer": (c_int32, [POINTER(VcModel), c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32,
                                  c_int32, c_int64, c_int64, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
 }
@@ -163,7 +165,7 @@ def lib() -> ctypes.CDLL:
         for name, (res, args) in _PROTOS.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        if L.vc_abi_version() != 3:
+        if L.vc_abi_version() != 4:
             raise RuntimeError("libvitcnn.so ABI version mismatch")
         _lib = L
     return _lib

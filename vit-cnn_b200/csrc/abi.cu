@@ -87,6 +87,32 @@ Workspace carve(void* base, int n, int P, int S1, int S2) {
 
 inline int slices_for(int C) { return (C + 15) / 16 * 2; }
 
+// Scene-level buffers of the shared first conv, carved behind the chunk workspace: raster offsets of the
+// blocks, the blocks as SPS patches of kBlock x kBlock pixels, the 9 conv-1 variants over them.
+struct SceneWs {
+  long long* boff;
+  uint8_t *blocks, *variants;
+  long long RTb, wbytes, bytes;   // bytes == 0: the shared path does not apply to this model / raster
+  int nb;
+};
+
+SceneWs carve_scene(void* base, const vc_model* m, int H, int W, int chunk) {
+  SceneWs s;
+  memset(&s, 0, sizeof(s));
+  if (!m->w_h1_border || m->P < 2 || H < vc::kBlock || W < vc::kBlock) return s;
+  long long off = (carve(nullptr, chunk, m->P, m->S1, m->S2).bytes + 256 + 255) & ~255LL;
+  s.nb = vc::scene_blocks(H) * vc::scene_blocks(W);
+  s.RTb = vc::sps_rows(s.nb, vc::kBlock);
+  s.wbytes = 9LL * m->S1 * 128 * 16;    // one packed copy of the conv-1 weights
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  auto take = [&](long long bytes) { uint8_t* r = p + off; off += (bytes + 255) & ~255LL; return r; };
+  s.boff = reinterpret_cast<long long*>(take(8LL * s.nb));
+  s.blocks = take(s.RTb * 16 * m->S1);
+  s.variants = take(9LL * 16 * s.RTb * 16);
+  s.bytes = off;
+  return s;
+}
+
 // stems + token stage on packed inputs already in w.a0 / w.l0
 // lead / trailing halo rows of the intermediates are read by the next conv and written by no
 // kernel: zero them once per workspace geometry (they stay zero across chunks of equal size)
@@ -109,10 +135,11 @@ int tokens_impl() {
 }
 
 int forward_sps(const vc_model* m, const Workspace& w, int n, float* logits, const long long* out_index,
-                uint8_t* argmax_map, cudaStream_t st) {
+                uint8_t* argmax_map, cudaStream_t st, bool have_conv1 = false) {
   const int P = m->P;
-  VC_LAUNCH(KC_CONV_H1, st, vc::conv_sps_launch(w.a0, m->S1, m->w_h[0], m->scale_h[0], m->bias_h[0], w.a1, 0, 128, m->nsplit_h[0], n, P, 9,
-                             1, 0, 0, st));
+  if (!have_conv1)   // else w.a1 was gathered from the scene-level variants (shared first conv)
+    VC_LAUNCH(KC_CONV_H1, st, vc::conv_sps_launch(w.a0, m->S1, m->w_h[0], m->scale_h[0], m->bias_h[0], w.a1, 0, 128, m->nsplit_h[0], n, P, 9,
+                               1, 0, 0, st));
   VC_LAUNCH(KC_CONV_H2, st, vc::conv_sps_launch(w.a1, 16, m->w_h[1], m->scale_h[1], m->bias_h[1], w.a2, 0, 64, m->nsplit_h[1], n, P, 9, 1,
                              0, 0, st));
   VC_LAUNCH(KC_CONV_H3, st, vc::conv_sps_launch(w.a2, 8, m->w_h[2], m->scale_h[2], m->bias_h[2], w.f, 0, 32, m->nsplit_h[2], n, P, 9, 1, 0,
@@ -317,6 +344,18 @@ int vc_scene_infer(const vc_model* m, const float* img1, const float* img2, int3
     return fail(VC_ERR_ARG, "vc_scene_infer: bad arguments");
   if (workspace_bytes < vc_workspace_bytes(chunk, m->P, m->C1, m->C2)) return fail(VC_ERR_ARG, "workspace too small");
   const long long s1 = (long long)W * m->C1, s2 = (long long)W * m->C2;
+  // ---- shared first conv: 9 border-class variants of conv 1 over the scene blocks, once per call ----
+  const SceneWs sw = carve_scene(workspace, m, H, W, chunk);
+  const bool shared = sw.bytes > 0 && workspace_bytes >= sw.bytes &&
+                      n_windows * (int64_t)vc::sps_pp(m->P) > 12 * (int64_t)sw.nb * vc::sps_pp(vc::kBlock);
+  if (shared) {
+    VC_LAUNCH(KC_INDEX, st, vc::block_offsets_launch(H, W, m->C1, sw.boff, st));
+    VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(img1, 0, 1, s1, m->C1, sw.boff, nullptr, sw.nb, m->C1, vc::kBlock, sw.blocks, m->S1, st));
+    for (int v = 0; v < 9; ++v)
+      VC_LAUNCH(KC_CONV_H1, st, vc::conv_sps_launch(sw.blocks, m->S1, (const uint8_t*)m->w_h1_border + (size_t)v * sw.wbytes, m->scale_h[0],
+                                                    m->bias_h[0], sw.variants + (size_t)v * 16 * sw.RTb * 16, 0, 128, m->nsplit_h[0],
+                                                    sw.nb, vc::kBlock, 9, 1, 0, 0, st));
+  }
   for (int64_t done = 0; done < n_windows; done += chunk) {
     const int n = (int)((n_windows - done) < chunk ? (n_windows - done) : chunk);
     // the SPS geometry depends on n: carve per chunk (only the last chunk differs)
@@ -326,7 +365,9 @@ int vc_scene_infer(const vc_model* m, const float* img1, const float* img2, int3
                                                    m->K, w.off1, w.off2, w.oidx, nullptr, st));
     // strip-staged gather (stride-1 runs reuse the overlap of consecutive windows); the generic
     // per-row gather is the fallback for geometries the strip kernel does not take
-    {
+    if (shared) {
+      VC_LAUNCH(KC_PACK, st, vc::border_gather_launch(sw.variants, H, W, xs, ys, ny, (int)(first_window + done), n, m->P, 16, w.a1, st));
+    } else {
       Scope sc(KC_PACK, st);
       int rc = vc::pack_scene_launch(img1, W, m->C1, xs, ys, nx, ny, (int)(first_window + done), n, m->P, w.a0, m->S1, st);
       if (rc == VC_ERR_UNSUPPORTED) rc = vc::pack_sps_launch(img1, 0, 1, s1, m->C1, w.off1, nullptr, n, m->C1, m->P, w.a0, m->S1, st);
@@ -338,10 +379,15 @@ int vc_scene_infer(const vc_model* m, const float* img1, const float* img2, int3
       if (rc == VC_ERR_UNSUPPORTED) rc = vc::pack_sps_launch(img2, 0, 1, s2, m->C2, w.off2, nullptr, n, m->C2, m->P, w.l0, m->S2, st);
       if (rc != VC_OK) return fail(rc, "scene gather (lidar)");
     }
-    VC_TRY(forward_sps(m, w, n, logits_map, w.oidx, argmax_map, st));
+    VC_TRY(forward_sps(m, w, n, logits_map, w.oidx, argmax_map, st, shared));
   }
-  (void)H;
   return VC_OK;
+}
+
+int64_t vc_scene_workspace_bytes(const vc_model* m, int32_t H, int32_t W, int32_t chunk) {
+  if (check_model(m) != VC_OK || chunk <= 0) return -1;
+  const SceneWs sw = carve_scene(nullptr, m, H, W, chunk);
+  return sw.bytes > 0 ? sw.bytes : vc_workspace_bytes(chunk, m->P, m->C1, m->C2);
 }
 
 }  // extern "C"

@@ -26,6 +26,11 @@ __host__ __device__ inline long long sps_rows(int n, int P) {
   return (long long)sps_halo(P) * 2 + (long long)sps_tiles(n, P) * 128;
 }
 
+// Scene blocks of the shared first conv (pack.cu): kBlock x kBlock pixels = (kBlock+1)^2 = 256 SPS rows = two
+// full 128-row tiles, origins every kBlockStep pixels (clamped so the last block ends at the scene border).
+constexpr int kBlock = 15, kBlockStep = kBlock - 2;
+__host__ __device__ inline int scene_blocks(int extent) { return (extent - 2) / kBlockStep + 1; }
+
 // Source pixel of output pixel (i, j) of a P x P patch under the reference's spatial augmentations
 // (datasets.py:510-526): op 0 identity, 1 fliplr, 2 flipud, 3 both, 4/5/6 np.rot90 with k = 1/2/3.
 __host__ __device__ inline void dihedral_src(int op, int P, int i, int j, int& si, int& sj) {

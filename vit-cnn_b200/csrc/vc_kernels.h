@@ -23,6 +23,12 @@ int gather_labels_launch(const void* gt, int gt_elem_bytes, int H, int W, const 
 int scene_index_launch(const int* xs, const int* ys, int nx, int ny, int first, int count, int W, int C1, int C2, int P,
                        int K, long long* off1, long long* off2, long long* out_idx, int* xy, cudaStream_t stream);
 
+// shared first conv of dense sliding windows: raster offsets of the scene blocks, and the per-window gather of
+// the 9 border-class variants [9][S][sps_rows(blocks, kBlock)][8] into the chunk's conv-1 output [S][rows][8]
+int block_offsets_launch(int H, int W, int C, long long* off, cudaStream_t stream);
+int border_gather_launch(const void* variants, int H, int W, const int* xs, const int* ys, int ny, int first, int count, int P,
+                         int S, void* out, cudaStream_t stream);
+
 int center_offsets_launch(const int* xy, int n, int W, int C1, int C2, int P, long long* off1, long long* off2,
                           cudaStream_t stream);
 

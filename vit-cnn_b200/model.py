@@ -248,6 +248,26 @@ class ViTCNN(nn.Module):
                 getattr(st, "scale_" + pre)[i] = s.data_ptr()
                 getattr(st, "bias_" + pre)[i] = b.data_ptr()
                 getattr(st, "nsplit_" + pre)[i] = ns
+        # shared first conv of dense scene inference: conv-1 weights with the taps that leave a window dropped,
+        # one copy per (row class, column class) of a window pixel (include/vitcnn.h: w_h1_border)
+        w1 = self.hsi_stem[0].conv.weight.detach()
+        s_in, n_out, ns = stem_plan(self.n_bands, HSI_PLANES)[0]
+        border = []
+        for cy in range(3):
+            for cx in range(3):
+                wv = w1.clone()
+                if cy == 0:
+                    wv[:, :, 0, :] = 0
+                if cy == 2:
+                    wv[:, :, 2, :] = 0
+                if cx == 0:
+                    wv[:, :, :, 0] = 0
+                if cx == 2:
+                    wv[:, :, :, 2] = 0
+                border.append(pack_conv_weight(wv, s_in, n_out, ns).reshape(-1))
+        wb = torch.cat(border).contiguous()
+        pk["keep"].append(wb)
+        st.w_h1_border = wb.data_ptr()
         blob = pack_tparams(self, _lib.tparams_layout(P, K))
         pk["keep"].append(blob)
         pk["tparams"] = blob
@@ -344,7 +364,10 @@ class ViTCNN(nn.Module):
                 # equal-sized chunks (no short tail launch): ceil(count / ceil(count / chunk))
                 n_chunks = -(-count // int(chunk))
                 chunk = -(-count // n_chunks)
-                ws = self._workspace(chunk, dev)
+                need = L.vc_scene_workspace_bytes(ctypes.byref(pk["struct"]), H, W, chunk)
+                if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+                    self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+                ws = self._ws
                 stream = torch.cuda.current_stream().cuda_stream
                 _lib.check(L.vc_scene_infer(ctypes.byref(pk["struct"]), img1.data_ptr(), img2.data_ptr(), H, W,
                                             xs.data_ptr(), ys.data_ptr(), nx, ny, first, count, chunk, ws.data_ptr(),
