@@ -241,11 +241,12 @@ int vc_forward_patches(const vc_model* m, const float* hsi, const int64_t hsi_st
  * [H][W][K] at the window centre (untouched pixels are left as they are: zero-fill first),
  * argmax_map (nullable) uint8 [H][W].  Row-band sharding = disjoint window ranges per GPU.
  *
- * Shared first conv: the first HSI conv's output at a window pixel depends on the window only through the
- * zero padding at the window border (3 row classes x 3 column classes).  When m->w_h1_border is set, P >= 2,
- * the raster is at least 15 x 15, the windows are dense enough for it to pay and the workspace holds
- * vc_scene_workspace_bytes(), the 9 variants are computed once per call on overlapping 15 x 15 scene blocks and
- * every window's conv-1 output is gathered from them (same bits as the per-window conv).  With only
+ * Shared stem: the output of the first d HSI stem convs at a window pixel depends on the window only through
+ * the zero padding at the window border ((2d+1) row classes x (2d+1) column classes).  When m->w_h1_border is
+ * set, the raster is large enough, the windows are dense enough for it to pay and the workspace holds
+ * vc_scene_workspace_bytes(), the variants are computed once per call on overlapping scene blocks -- all three
+ * convs on 31 x 31 blocks when P >= 7, conv 1 only on 15 x 15 blocks otherwise (P >= 2) -- and every window's
+ * stem output is gathered from them (same bits as the per-window convs).  With only
  * vc_workspace_bytes(chunk, ...) of workspace the per-window path runs. */
 int64_t vc_scene_workspace_bytes(const vc_model* m, int32_t H, int32_t W, int32_t chunk);
 int vc_scene_infer(const vc_model* m, const float* img1, const float* img2, int32_t H, int32_t W, const int32_t* xs,

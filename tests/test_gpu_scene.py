@@ -78,11 +78,12 @@ def test_device_metrics_match_reference_formulas():
 
 
 @pytest.mark.parametrize("cfg", [(61, 47, 144, 1, 11, 16), (40, 95, 64, 2, 8, 12), (15, 15, 20, 1, 2, 5), (44, 29, 180, 1, 15, 8),
-                                 (28, 41, 16, 1, 3, 4)])
-def test_shared_first_conv_is_bit_identical_to_the_per_window_path(cfg):
-    """Dense scenes compute the 9 border-class variants of the first HSI conv once per scene (15 x 15 blocks,
-    clamped at the far edges) and gather every window's conv-1 output from them; the logits map must equal the
-    per-window path bit for bit (the per-window path = the same library call without w_h1_border)."""
+                                 (28, 41, 16, 1, 3, 4), (100, 100, 16, 1, 7, 4), (57, 120, 32, 1, 9, 6), (90, 40, 16, 2, 15, 3)])
+def test_shared_stem_is_bit_identical_to_the_per_window_path(cfg):
+    """Dense scenes compute the border-class variants of the HSI stem convs once per scene (all three convs on
+    31 x 31 blocks when P >= 7 and the raster allows, conv 1 only on 15 x 15 blocks otherwise; blocks clamped at
+    the far edges) and gather every window's stem output from them; the logits map must equal the per-window
+    path bit for bit (the per-window path = the same library call without w_h1_border)."""
     H, W, C1, C2, P, K = cfg
     _, ours = make_pair(C1, C2, P, K, seed=H)
     img1, img2, _ = R.synthetic_scene(H, W, C1, C2, K, seed=W)

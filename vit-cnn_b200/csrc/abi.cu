@@ -87,30 +87,113 @@ Workspace carve(void* base, int n, int P, int S1, int S2) {
 
 inline int slices_for(int C) { return (C + 15) / 16 * 2; }
 
-// Scene-level buffers of the shared first conv, carved behind the chunk workspace: raster offsets of the
-// blocks, the blocks as SPS patches of kBlock x kBlock pixels, the 9 conv-1 variants over them.
+// Scene-level buffers of the shared stem (pack.cu), carved behind the chunk workspace: raster offsets of the
+// blocks, the blocks as SPS patches of B x B pixels, the border-class variants of the first D stem convs.
+// mode = sharing depth D: 3 / 2: B = 31, the first three / two HSI convs shared (P >= 2D + 1); 1: B = 15, conv 1
+// only (P >= 2); 0: per-window path.
 struct SceneWs {
   long long* boff;
-  uint8_t *blocks, *variants;
-  long long RTb, wbytes, bytes;   // bytes == 0: the shared path does not apply to this model / raster
-  int nb;
+  uint8_t *blocks, *var[3];
+  long long RTb, wbytes, plane[3], bytes;   // bytes == 0: this mode does not apply to the model / raster
+  int nb, B, D;
 };
 
-SceneWs carve_scene(void* base, const vc_model* m, int H, int W, int chunk) {
+SceneWs carve_scene(void* base, const vc_model* m, int H, int W, int chunk, int mode) {
   SceneWs s;
   memset(&s, 0, sizeof(s));
-  if (!m->w_h1_border || m->P < 2 || H < vc::kBlock || W < vc::kBlock) return s;
+  const int B = mode >= 2 ? 31 : 15, D = mode;
+  if (mode < 1 || mode > 3 || !m->w_h1_border || H < B || W < B || m->P < (mode == 1 ? 2 : 2 * mode + 1)) return s;
+  s.B = B;
+  s.D = D;
   long long off = (carve(nullptr, chunk, m->P, m->S1, m->S2).bytes + 256 + 255) & ~255LL;
-  s.nb = vc::scene_blocks(H) * vc::scene_blocks(W);
-  s.RTb = vc::sps_rows(s.nb, vc::kBlock);
+  s.nb = vc::blk_count(H, B, D) * vc::blk_count(W, B, D);
+  s.RTb = vc::sps_rows(s.nb, B);
   s.wbytes = 9LL * m->S1 * 128 * 16;    // one packed copy of the conv-1 weights
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
   auto take = [&](long long bytes) { uint8_t* r = p + off; off += (bytes + 255) & ~255LL; return r; };
   s.boff = reinterpret_cast<long long*>(take(8LL * s.nb));
   s.blocks = take(s.RTb * 16 * m->S1);
-  s.variants = take(9LL * 16 * s.RTb * 16);
+  const int slices[3] = {16, 8, 4};
+  for (int l = 0; l < D; ++l) {
+    s.plane[l] = (long long)slices[l] * s.RTb * 16;
+    s.var[l] = take((long long)(2 * l + 3) * (2 * l + 3) * s.plane[l]);
+  }
   s.bytes = off;
   return s;
+}
+
+// Which sharing depth pays for n windows and fits the workspace the caller gave.  Costs in units of one per-window
+// conv-3 pass over a 128-row tile, measured on B200 at the Houston shape (profiles/r01_SUMMARY.md): per-window
+// conv 1 / 2 / 3 = 2.8 / 1.8 / 1 and patch gather 0.9; a shared conv 2 / 3 tile costs 1.6x / 1.8x its per-window
+// tile (it stages one input slab per input plane); the variant gather costs 1.65 / 0.82 / 0.66 (16 / 8 / 4 slices
+// per row).  VITCNN_SCENE_DEPTH forces a depth (0 = per-window path).
+int scene_mode(const vc_model* m, int H, int W, int chunk, long long n_windows, long long workspace_bytes) {
+  static const int forced = [] {
+    const char* e = getenv("VITCNN_SCENE_DEPTH");
+    return e ? atoi(e) : -1;
+  }();
+  const double win_tiles = (double)n_windows * vc::sps_pp(m->P) / 128.0;
+  const double conv[3] = {2.8, 1.8, 1.0}, shared[3] = {9 * 2.8, 25 * 1.8 * 1.6, 49 * 1.0 * 1.8}, gather[3] = {1.65, 0.82, 0.66};
+  int best = 0;
+  double best_cost = win_tiles * (conv[0] + conv[1] + conv[2] + 0.9);      // per-window path incl. its patch gather
+  for (int mode = 1; mode <= 3; ++mode) {
+    const SceneWs s = carve_scene(nullptr, m, H, W, chunk, mode);
+    if (s.bytes <= 0 || workspace_bytes < s.bytes) continue;
+    if (forced >= 0 && mode != forced) continue;
+    double cost = win_tiles * gather[mode - 1];
+    for (int l = 0; l < 3; ++l) cost += l < mode ? shared[l] * s.nb * vc::sps_pp(s.B) / 128.0 : win_tiles * conv[l];
+    if (cost < best_cost || forced == mode) { best = mode; best_cost = cost; }
+  }
+  return forced == 0 ? 0 : best;
+}
+
+// class (at depth L-1) of the neighbour d = -1 / 0 / +1 of a pixel whose class at depth L is c; -1: outside the window
+int neighbour_class(int L, int c, int d, int P) {
+  const int i = c < L ? c : (c == L ? L : P - 1 - (2 * L - c));
+  const int ip = i + d;
+  if (ip < 0 || ip > P - 1) return -1;
+  return vc::border_class(ip, P, L - 1);
+}
+
+// The shared stem over the scene blocks: conv 1 as 9 launches with the border-class weight copies, conv L >= 2 as
+// (2L+1)^2 launches that read, per tap, the conv L-1 variant of the neighbour's class (<= 9 planes per launch).
+int shared_stem(const vc_model* m, const SceneWs& sw, const float* img1, int H, int W, cudaStream_t st) {
+  VC_LAUNCH(KC_INDEX, st, vc::block_offsets_launch(H, W, m->C1, sw.B, sw.D, sw.boff, st));
+  VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(img1, 0, 1, (long long)W * m->C1, m->C1, sw.boff, nullptr, sw.nb, m->C1, sw.B, sw.blocks,
+                                             m->S1, st));
+  for (int v = 0; v < 9; ++v)
+    VC_LAUNCH(KC_CONV_H1, st, vc::conv_sps_launch(sw.blocks, m->S1, (const uint8_t*)m->w_h1_border + (size_t)v * sw.wbytes, m->scale_h[0],
+                                                  m->bias_h[0], sw.var[0] + (size_t)v * sw.plane[0], 0, 128, m->nsplit_h[0], sw.nb,
+                                                  sw.B, 9, 1, 0, 0, st));
+  const int s_in[3] = {0, 16, 8}, n_out[3] = {128, 64, 32};
+  for (int L = 2; L <= sw.D; ++L) {
+    const int NC = 2 * L + 1, NP = 2 * L - 1;     // classes per axis at depth L / L-1
+    for (int cy = 0; cy < NC; ++cy)
+      for (int cx = 0; cx < NC; ++cx) {
+        const void* planes[9];
+        unsigned int masks[9];
+        int ids[9], np = 0;
+        for (int dy = -1; dy <= 1; ++dy)
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int ry = neighbour_class(L, cy, dy, m->P), rx = neighbour_class(L, cx, dx, m->P);
+            if (ry < 0 || rx < 0) continue;           // the tap leaves the window: zero padding
+            const int id = ry * NP + rx;
+            int k = 0;
+            while (k < np && ids[k] != id) ++k;
+            if (k == np) {
+              ids[np] = id;
+              planes[np] = sw.var[L - 2] + (size_t)id * sw.plane[L - 2];
+              masks[np++] = 0u;
+            }
+            masks[k] |= 1u << ((dy + 1) * 3 + (dx + 1));
+          }
+        Scope sc(L == 2 ? KC_CONV_H2 : KC_CONV_H3, st);
+        VC_TRY(vc::conv_sps_planes_launch(planes, masks, np, s_in[L - 1], m->w_h[L - 1], m->scale_h[L - 1], m->bias_h[L - 1],
+                                          sw.var[L - 1] + (size_t)(cy * NC + cx) * sw.plane[L - 1], 0, n_out[L - 1],
+                                          m->nsplit_h[L - 1], sw.nb, sw.B, 9, 1, 0, 0, st));
+      }
+  }
+  return VC_OK;
 }
 
 // stems + token stage on packed inputs already in w.a0 / w.l0
@@ -135,15 +218,18 @@ int tokens_impl() {
 }
 
 int forward_sps(const vc_model* m, const Workspace& w, int n, float* logits, const long long* out_index,
-                uint8_t* argmax_map, cudaStream_t st, bool have_conv1 = false) {
+                uint8_t* argmax_map, cudaStream_t st, int stem_done = 0) {
   const int P = m->P;
-  if (!have_conv1)   // else w.a1 was gathered from the scene-level variants (shared first conv)
+  // stem_done: HSI stem convs already gathered from the scene-level variants (1: w.a1 holds conv 1, 2: w.a2 conv 2, 3: w.f conv 3)
+  if (stem_done < 1)
     VC_LAUNCH(KC_CONV_H1, st, vc::conv_sps_launch(w.a0, m->S1, m->w_h[0], m->scale_h[0], m->bias_h[0], w.a1, 0, 128, m->nsplit_h[0], n, P, 9,
                                1, 0, 0, st));
-  VC_LAUNCH(KC_CONV_H2, st, vc::conv_sps_launch(w.a1, 16, m->w_h[1], m->scale_h[1], m->bias_h[1], w.a2, 0, 64, m->nsplit_h[1], n, P, 9, 1,
-                             0, 0, st));
-  VC_LAUNCH(KC_CONV_H3, st, vc::conv_sps_launch(w.a2, 8, m->w_h[2], m->scale_h[2], m->bias_h[2], w.f, 0, 32, m->nsplit_h[2], n, P, 9, 1, 0,
-                             0, st));
+  if (stem_done < 2)
+    VC_LAUNCH(KC_CONV_H2, st, vc::conv_sps_launch(w.a1, 16, m->w_h[1], m->scale_h[1], m->bias_h[1], w.a2, 0, 64, m->nsplit_h[1], n, P, 9, 1,
+                               0, 0, st));
+  if (stem_done < 3)
+    VC_LAUNCH(KC_CONV_H3, st, vc::conv_sps_launch(w.a2, 8, m->w_h[2], m->scale_h[2], m->bias_h[2], w.f, 0, 32, m->nsplit_h[2], n, P, 9, 1, 0,
+                               0, st));
   bool lidar_done = false;
   if (m->lidar_blob && m->C2 <= 8) {   // one fused launch instead of three latency-bound ones
     Scope sc(KC_CONV_L, st);
@@ -344,18 +430,10 @@ int vc_scene_infer(const vc_model* m, const float* img1, const float* img2, int3
     return fail(VC_ERR_ARG, "vc_scene_infer: bad arguments");
   if (workspace_bytes < vc_workspace_bytes(chunk, m->P, m->C1, m->C2)) return fail(VC_ERR_ARG, "workspace too small");
   const long long s1 = (long long)W * m->C1, s2 = (long long)W * m->C2;
-  // ---- shared first conv: 9 border-class variants of conv 1 over the scene blocks, once per call ----
-  const SceneWs sw = carve_scene(workspace, m, H, W, chunk);
-  const bool shared = sw.bytes > 0 && workspace_bytes >= sw.bytes &&
-                      n_windows * (int64_t)vc::sps_pp(m->P) > 12 * (int64_t)sw.nb * vc::sps_pp(vc::kBlock);
-  if (shared) {
-    VC_LAUNCH(KC_INDEX, st, vc::block_offsets_launch(H, W, m->C1, sw.boff, st));
-    VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(img1, 0, 1, s1, m->C1, sw.boff, nullptr, sw.nb, m->C1, vc::kBlock, sw.blocks, m->S1, st));
-    for (int v = 0; v < 9; ++v)
-      VC_LAUNCH(KC_CONV_H1, st, vc::conv_sps_launch(sw.blocks, m->S1, (const uint8_t*)m->w_h1_border + (size_t)v * sw.wbytes, m->scale_h[0],
-                                                    m->bias_h[0], sw.variants + (size_t)v * 16 * sw.RTb * 16, 0, 128, m->nsplit_h[0],
-                                                    sw.nb, vc::kBlock, 9, 1, 0, 0, st));
-  }
+  // ---- shared stem: border-class variants of the HSI stem convs over the scene blocks, once per call ----
+  const int mode = scene_mode(m, H, W, chunk, n_windows, workspace_bytes);
+  const SceneWs sw = carve_scene(workspace, m, H, W, chunk, mode);
+  if (mode) VC_TRY(shared_stem(m, sw, img1, H, W, st));
   for (int64_t done = 0; done < n_windows; done += chunk) {
     const int n = (int)((n_windows - done) < chunk ? (n_windows - done) : chunk);
     // the SPS geometry depends on n: carve per chunk (only the last chunk differs)
@@ -365,8 +443,9 @@ int vc_scene_infer(const vc_model* m, const float* img1, const float* img2, int3
                                                    m->K, w.off1, w.off2, w.oidx, nullptr, st));
     // strip-staged gather (stride-1 runs reuse the overlap of consecutive windows); the generic
     // per-row gather is the fallback for geometries the strip kernel does not take
-    if (shared) {
-      VC_LAUNCH(KC_PACK, st, vc::border_gather_launch(sw.variants, H, W, xs, ys, ny, (int)(first_window + done), n, m->P, 16, w.a1, st));
+    if (mode) {
+      VC_LAUNCH(KC_PACK, st, vc::border_gather_launch(sw.var[sw.D - 1], mode == 3 ? 4 : mode == 2 ? 8 : 16, sw.B, sw.D, H, W, xs, ys, ny,
+                                                      (int)(first_window + done), n, m->P, mode == 3 ? w.f : mode == 2 ? w.a2 : w.a1, st));
     } else {
       Scope sc(KC_PACK, st);
       int rc = vc::pack_scene_launch(img1, W, m->C1, xs, ys, nx, ny, (int)(first_window + done), n, m->P, w.a0, m->S1, st);
@@ -379,15 +458,19 @@ int vc_scene_infer(const vc_model* m, const float* img1, const float* img2, int3
       if (rc == VC_ERR_UNSUPPORTED) rc = vc::pack_sps_launch(img2, 0, 1, s2, m->C2, w.off2, nullptr, n, m->C2, m->P, w.l0, m->S2, st);
       if (rc != VC_OK) return fail(rc, "scene gather (lidar)");
     }
-    VC_TRY(forward_sps(m, w, n, logits_map, w.oidx, argmax_map, st, shared));
+    VC_TRY(forward_sps(m, w, n, logits_map, w.oidx, argmax_map, st, mode));
   }
   return VC_OK;
 }
 
 int64_t vc_scene_workspace_bytes(const vc_model* m, int32_t H, int32_t W, int32_t chunk) {
   if (check_model(m) != VC_OK || chunk <= 0) return -1;
-  const SceneWs sw = carve_scene(nullptr, m, H, W, chunk);
-  return sw.bytes > 0 ? sw.bytes : vc_workspace_bytes(chunk, m->P, m->C1, m->C2);
+  long long need = vc_workspace_bytes(chunk, m->P, m->C1, m->C2);
+  for (int mode = 1; mode <= 3; ++mode) {
+    const SceneWs sw = carve_scene(nullptr, m, H, W, chunk, mode);
+    if (sw.bytes > need) need = sw.bytes;
+  }
+  return need;
 }
 
 }  // extern "C"

@@ -24,6 +24,11 @@ struct ConvArgs {
   __nv_bfloat16* out;        // [S_out_total][RT][8]
   long long RT;
   int S_in, ncta, ntaps, P, n_patches, ntiles, out_slice_off, relu, nstages, kpb, debug_flags;
+  // multi-plane input (shared stem of dense scene inference, abi.cu): tap t reads plane p iff bit t of
+  // tapmask[p]; taps in no mask are dropped (they would leave the window).  Plain conv: one plane, all taps.
+  const __nv_bfloat16* planes[9];
+  unsigned int tapmask[9];
+  int nplanes;
 };
 
 constexpr int kConvThreads = 192;  // warp0 producer, warp1 MMA issuer, warps 2..5 epilogue
@@ -33,7 +38,8 @@ __global__ void __launch_bounds__(kConvThreads) conv_sps_tc_kernel(ConvArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int HALO = sps_halo(a.P), ROWS = 128 + 2 * HALO, PP = sps_pp(a.P), PW = a.P + 1;
   const int KPB = a.kpb;  // K=16 steps per pipeline stage
-  const uint32_t slice_bytes = (uint32_t)ROWS * 16u, kstep_bytes = 2u * slice_bytes, stage_bytes = (uint32_t)KPB * kstep_bytes;
+  const int NPL = a.nplanes;  // input planes resident per K step (1 for a plain conv)
+  const uint32_t slice_bytes = (uint32_t)ROWS * 16u, kstep_bytes = 2u * slice_bytes, stage_bytes = (uint32_t)(KPB * NPL) * kstep_bytes;
   const uint32_t wbytes = (uint32_t)a.ntaps * a.S_in * a.ncta * 16u;
   const int KS = a.S_in / 2;  // K=16 steps per tap
   const int half = blockIdx.y;
@@ -102,11 +108,13 @@ __global__ void __launch_bounds__(kConvThreads) conv_sps_tc_kernel(ConvArgs a) {
           if (a.debug_flags & 2) {   // timing probe: no operand traffic
             mbar_arrive(&full[st]);
           } else {
-            mbar_arrive_expect_tx(&full[st], (uint32_t)nk * kstep_bytes);
+            mbar_arrive_expect_tx(&full[st], (uint32_t)(nk * NPL) * kstep_bytes);
             uint8_t* dst = stage_s + (size_t)st * stage_bytes;
-            for (int sl = 0; sl < 2 * nk; ++sl)
-              bulk_g2s(dst + (size_t)sl * slice_bytes, a.in + ((long long)(2 * ks0 + sl) * a.RT + row0) * 8, slice_bytes,
-                       &full[st]);
+            for (int kl = 0; kl < nk; ++kl)       // stage layout: [K step][plane][2 slices][ROWS][16 B]
+              for (int pl = 0; pl < NPL; ++pl)
+                for (int h2 = 0; h2 < 2; ++h2)
+                  bulk_g2s(dst + (size_t)((kl * NPL + pl) * 2 + h2) * slice_bytes,
+                           a.planes[pl] + ((long long)(2 * (ks0 + kl) + h2) * a.RT + row0) * 8, slice_bytes, &full[st]);
           }
           if (++st == a.nstages) { st = 0; ph ^= 1u; }
         }
@@ -127,6 +135,13 @@ __global__ void __launch_bounds__(kConvThreads) conv_sps_tc_kernel(ConvArgs a) {
     const uint32_t b_tap = (uint32_t)(a.S_in * a.ncta);     // ... between taps
     const uint32_t b_ks = (uint32_t)(2 * a.ncta);           // ... between K=16 steps
     const bool nine = a.ntaps == 9;
+    unsigned long long tap_plane = 0;      // 4 bits per tap: the plane it reads, 15 = dropped
+    for (int tap = 0; tap < 9; ++tap) {
+      unsigned long long pl = 15;
+      for (int q = 0; q < NPL; ++q)
+        if (a.tapmask[q] & (1u << tap)) pl = (unsigned long long)q;
+      tap_plane |= pl << (4 * tap);
+    }
     mbar_wait(wfull, 0);
     int st = 0;
     uint32_t ph = 0;
@@ -136,24 +151,32 @@ __global__ void __launch_bounds__(kConvThreads) conv_sps_tc_kernel(ConvArgs a) {
       if (!(a.debug_flags & 32)) mbar_wait(&tempty[acc], accph ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.ncta);
+      // taps are issued in the plain conv's order (K step, then tap 0..8) whatever plane they read, so a
+      // multi-plane conv accumulates in exactly the order of the per-window conv it replaces
       for (int ks0 = 0; ks0 < KS; ks0 += KPB) {
         const int nk = KS - ks0 < KPB ? KS - ks0 : KPB;
         if (!(a.debug_flags & 8)) mbar_wait(&full[st], ph);
         tc_fence_after();
         if (elect_one()) {
+          uint32_t go = ks0 != 0 ? 1u : 0u;   // the first MMA of a tile overwrites the accumulator
           for (int kl = 0; kl < nk; ++kl) {
             const int ks = ks0 + kl;
-            const uint32_t a_lo = a_lo0 + (uint32_t)st * a_stage + (uint32_t)kl * (kstep_bytes >> 4);
+            const uint32_t a_lo = a_lo0 + (uint32_t)st * a_stage + (uint32_t)(kl * NPL) * (kstep_bytes >> 4);
             const uint32_t b_lo = w_lo + (uint32_t)ks * b_ks;
             if (nine) {
 #pragma unroll
               for (int tap = 0; tap < 9; ++tap) {
-                const int shift = (tap / 3 - 1) * PW + (tap % 3 - 1);
-                umma_bf16(d_tmem, a_hi | (uint64_t)(a_lo + (uint32_t)shift), b_hi | (uint64_t)(b_lo + (uint32_t)tap * b_tap),
-                          idesc, (ks | tap) != 0 ? 1u : 0u);
+                const int pl = (int)((tap_plane >> (4 * tap)) & 15ull);
+                if (pl != 15) {
+                  const int shift = (tap / 3 - 1) * PW + (tap % 3 - 1);
+                  umma_bf16(d_tmem, a_hi | (uint64_t)(a_lo + (uint32_t)pl * (kstep_bytes >> 4) + (uint32_t)shift),
+                            b_hi | (uint64_t)(b_lo + (uint32_t)tap * b_tap), idesc, go);
+                  go = 1u;
+                }
               }
             } else {
-              umma_bf16(d_tmem, a_hi | (uint64_t)a_lo, b_hi | (uint64_t)b_lo, idesc, ks != 0 ? 1u : 0u);
+              umma_bf16(d_tmem, a_hi | (uint64_t)a_lo, b_hi | (uint64_t)b_lo, idesc, go);
+              go = 1u;
             }
           }
           umma_commit(&empty[st]);
@@ -466,19 +489,37 @@ __global__ void conv_sps_simt_kernel(ConvArgs a, int nsplit) {
   }
 }
 
-static size_t conv_smem_bytes(int S_in, int ncta, int ntaps, int P, int nstages, int kpb) {
+static size_t conv_smem_bytes(int S_in, int ncta, int ntaps, int P, int nstages, int kpb, int nplanes = 1) {
   const int ROWS = 128 + 2 * sps_halo(P);
   size_t wbytes = ((size_t)ntaps * S_in * ncta * 16 + 127) & ~size_t(127);
-  return wbytes + (size_t)nstages * kpb * 2 * ROWS * 16 + (size_t)ncta * 8 + 8 + (2 * nstages + 5) * 8 + 16;
+  return wbytes + (size_t)nstages * kpb * nplanes * 2 * ROWS * 16 + (size_t)ncta * 8 + 8 + (2 * nstages + 5) * 8 + 16;
 }
 
 int conv_sps_launch(const void* in, int S_in, const void* w, const float* scale, const float* bias, void* out,
                     int out_slice_off, int n_out, int nsplit, int n_patches, int P, int ntaps, int relu, int impl,
                     int debug_flags, cudaStream_t stream) {
-  if (S_in <= 0 || (S_in & 1) || nsplit <= 0 || n_out % nsplit) return VC_ERR_ARG;
+  const unsigned int mask = ntaps == 9 ? 0x1FFu : 1u;
+  return conv_sps_planes_launch(&in, &mask, 1, S_in, w, scale, bias, out, out_slice_off, n_out, nsplit, n_patches, P, ntaps,
+                                relu, impl, debug_flags, stream);
+}
+
+int conv_sps_planes_launch(const void* const* planes, const unsigned int* tapmasks, int nplanes, int S_in, const void* w,
+                           const float* scale, const float* bias, void* out, int out_slice_off, int n_out, int nsplit,
+                           int n_patches, int P, int ntaps, int relu, int impl, int debug_flags, cudaStream_t stream) {
+  if (S_in <= 0 || (S_in & 1) || nsplit <= 0 || n_out % nsplit || nplanes < 1 || nplanes > 9) return VC_ERR_ARG;
   const int ncta = n_out / nsplit;
   if (ncta % 16 || ncta < 16 || ncta > 128 || (ntaps != 9 && ntaps != 1) || P < 1 || n_patches <= 0) return VC_ERR_ARG;
+  const unsigned int all_taps = ntaps == 9 ? 0x1FFu : 1u;
+  const bool plain = nplanes == 1 && tapmasks[0] == all_taps;
+  if (!plain && impl != 0) return VC_ERR_UNSUPPORTED;
   ConvArgs a;
+  a.nplanes = nplanes;
+  for (int i = 0; i < 9; ++i) {
+    a.planes[i] = (const __nv_bfloat16*)planes[i < nplanes ? i : 0];
+    a.tapmask[i] = i < nplanes ? (tapmasks[i] & all_taps) : 0u;
+    if (i < nplanes && !a.tapmask[i]) return VC_ERR_ARG;
+  }
+  const void* in = planes[0];
   a.in = (const __nv_bfloat16*)in;
   a.w = (const __nv_bfloat16*)w;
   a.scale = scale;
@@ -520,8 +561,8 @@ int conv_sps_launch(const void* in, int S_in, const void* w, const float* scale,
     for (int cand = 1; cand <= 4; ++cand) {
       if (cand > KS || (force_kpb && cand != force_kpb)) continue;
       int n = force_nst ? force_nst : 6;
-      while (n > 2 && conv_smem_bytes(S_in, ncta, ntaps, P, n, cand) > (size_t)max_smem) --n;
-      if (conv_smem_bytes(S_in, ncta, ntaps, P, n, cand) > (size_t)max_smem) continue;
+      while (n > 2 && conv_smem_bytes(S_in, ncta, ntaps, P, n, cand, nplanes) > (size_t)max_smem) --n;
+      if (conv_smem_bytes(S_in, ncta, ntaps, P, n, cand, nplanes) > (size_t)max_smem) continue;
       if (n < 3 && cand > 1) continue;
       const int iters = (KS + cand - 1) / cand;
       if (iters < best_iters) { best_iters = iters; kpb = cand; nst = n; }
@@ -534,7 +575,7 @@ int conv_sps_launch(const void* in, int S_in, const void* w, const float* scale,
     const char* e = getenv("VC_CONV_PAIR");
     pair_ok = (e && e[0] == '0') ? 0 : 1;
   }
-  if (impl == 0 && pair_ok && nsplit == 2 && ncta == 64 && a.ntiles >= 2) {
+  if (impl == 0 && plain && pair_ok && nsplit == 2 && ncta == 64 && a.ntiles >= 2) {
     const size_t smem2 = conv_smem_bytes(S_in, ncta, ntaps, P, nst, kpb) + (size_t)nst * 8 + 64 + 2 * 128 * 4;
     if (smem2 <= (size_t)max_smem) {
       a.nstages = nst;
@@ -548,7 +589,7 @@ int conv_sps_launch(const void* in, int S_in, const void* w, const float* scale,
       return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
     }
   }
-  const size_t smem = conv_smem_bytes(S_in, ncta, ntaps, P, nst, kpb);
+  const size_t smem = conv_smem_bytes(S_in, ncta, ntaps, P, nst, kpb, nplanes);
   a.nstages = nst;
   a.kpb = kpb;
   if (cudaFuncSetAttribute(conv_sps_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)

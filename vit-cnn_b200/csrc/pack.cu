@@ -250,59 +250,55 @@ int zero_halo_launch(void* sps, int S, int n_patches, int P, cudaStream_t stream
 }
 
 // ------------------------------------------------------------------------------------------
-// Shared first conv for dense sliding windows.  The output of a 3x3 pad-1 conv at pixel (i, j) of a
-// window depends on the window only through the zero padding at the window's border: the value at
-// scene pixel (y, x) is one of 9 variants, chosen by (i == 0 | interior | i == P-1) x (same for j),
-// each a conv with the taps that leave the window dropped.  So the 9 variants are computed ONCE per
-// scene on overlapping kBlock x kBlock blocks (stride kBlock - 2: the ring of a block sees the
-// block's own padding and is only used where it coincides with the scene border), and every
-// window's conv-1 output is a gather from them -- 121 / 9 times fewer conv-1 FLOPs at P = 11 and the
-// same bits as the per-window conv (same accumulation order, dropped taps add exact zeros).
-__global__ void block_offsets_kernel(int H, int W, int C, int nby, int nbx, long long* __restrict__ off) {
+// Shared stem for dense sliding windows.  The output of a stack of d 3x3 pad-1 convs at pixel (i, j) of a
+// window depends on the window only through the zero padding at the window's border: the value at scene
+// pixel (y, x) is one of (2d+1)^2 variants, chosen by border_class(i) x border_class(j).  The variants are
+// computed ONCE per scene on overlapping B x B blocks (abi.cu: conv 1 with the taps that leave the window
+// dropped; deeper convs read, per tap, the variant plane of the neighbour's own class) and every window's
+// stem output is a gather from them -- e.g. 121 / 9 times fewer conv-1 FLOPs at P = 11 -- with the same
+// bits as the per-window convs (same accumulation order, dropped taps contribute exact zeros).
+__global__ void block_offsets_kernel(int H, int W, int C, int B, int D, int nby, int nbx, long long* __restrict__ off) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nby * nbx) return;
   const int by = idx / nbx, bx = idx - by * nbx;
-  const int y0 = min(by * kBlockStep, H - kBlock), x0 = min(bx * kBlockStep, W - kBlock);
-  off[idx] = ((long long)y0 * W + x0) * C;
+  off[idx] = ((long long)blk_origin(by, H, B, D) * W + blk_origin(bx, W, B, D)) * C;
 }
 
-int block_offsets_launch(int H, int W, int C, long long* off, cudaStream_t stream) {
-  if (H < kBlock || W < kBlock) return VC_ERR_ARG;
-  const int nby = scene_blocks(H), nbx = scene_blocks(W);
-  block_offsets_kernel<<<(nby * nbx + 255) / 256, 256, 0, stream>>>(H, W, C, nby, nbx, off);
+int block_offsets_launch(int H, int W, int C, int B, int D, long long* off, cudaStream_t stream) {
+  if (H < B || W < B || B <= 2 * D) return VC_ERR_ARG;
+  const int nby = blk_count(H, B, D), nbx = blk_count(W, B, D);
+  block_offsets_kernel<<<(nby * nbx + 255) / 256, 256, 0, stream>>>(H, W, C, B, D, nby, nbx, off);
   return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
 }
 
 struct BorderGatherArgs {
-  const __nv_bfloat16* v;     // [9 variants][S][RTb][8]: conv-1 variants over the scene blocks
-  __nv_bfloat16* out;         // [S][RTo][8]: conv-1 output of the chunk's windows
+  const __nv_bfloat16* v;     // [(2D+1)^2 variants][S][RTb][8]: depth-D stem variants over the scene blocks
+  __nv_bfloat16* out;         // [>= S][RTo][8]: stem output of the chunk's windows (slices 0..S-1 are written)
   const int* xs;              // window-row starts [nx]
   const int* ys;              // window-column starts [ny]
   long long RTb, RTo;
-  int S, ny, first, count, P, H, W, nbx, ntiles;
+  int S, ny, first, count, P, H, W, B, D, nbx, rows;
 };
 
 __global__ void __launch_bounds__(256) border_gather_kernel(BorderGatherArgs a) {
-  const int P = a.P, PW = P + 1, PP = sps_pp(P), HALO = sps_halo(P), HB = sps_halo(kBlock), PPB = sps_pp(kBlock);
-  const long long rows = (long long)a.ntiles * 128;
-  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
-    const long long b = r / PP;
-    const int q = (int)(r - b * PP);
+  const int P = a.P, PW = P + 1, PP = sps_pp(P), HALO = sps_halo(P), B = a.B, D = a.D;
+  const int HB = sps_halo(B), PPB = sps_pp(B), NC = 2 * D + 1;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < a.rows; r += gridDim.x * blockDim.x) {
+    const int b = r / PP, q = r - b * PP;
     const int i = q / PW, j = q - i * PW;
     const uint4* src = nullptr;
     if (b < a.count && i < P && j < P) {
-      const long long widx = a.first + b;
-      const int ix = (int)(widx / a.ny), iy = (int)(widx - (long long)ix * a.ny);
+      const int widx = a.first + b;
+      const int ix = widx / a.ny, iy = widx - ix * a.ny;
       const int y = __ldg(a.xs + ix) + i, x = __ldg(a.ys + iy) + j;
-      const int cy = i == 0 ? 0 : (i == P - 1 ? 2 : 1), cx = j == 0 ? 0 : (j == P - 1 ? 2 : 1);
-      const int ky = max(y - 1, 0) / kBlockStep, kx = max(x - 1, 0) / kBlockStep;
-      const int y0 = min(ky * kBlockStep, a.H - kBlock), x0 = min(kx * kBlockStep, a.W - kBlock);
-      const long long srow = HB + (long long)(ky * a.nbx + kx) * PPB + (y - y0) * (kBlock + 1) + (x - x0);
-      src = reinterpret_cast<const uint4*>(a.v) + (long long)(cy * 3 + cx) * a.S * a.RTb + srow;
+      const int ky = blk_index(y, B, D), kx = blk_index(x, B, D);
+      const long long srow = HB + (long long)(ky * a.nbx + kx) * PPB + (y - blk_origin(ky, a.H, B, D)) * (B + 1) +
+                             (x - blk_origin(kx, a.W, B, D));
+      src = reinterpret_cast<const uint4*>(a.v) + (long long)(border_class(i, P, D) * NC + border_class(j, P, D)) * a.S * a.RTb + srow;
     }
     uint4* dst = reinterpret_cast<uint4*>(a.out) + HALO + r;
     if (src) {
-#pragma unroll 8
+#pragma unroll 4
       for (int s = 0; s < a.S; ++s) dst[(long long)s * a.RTo] = __ldg(src + (long long)s * a.RTb);
     } else {
       for (int s = 0; s < a.S; ++s) dst[(long long)s * a.RTo] = make_uint4(0u, 0u, 0u, 0u);
@@ -310,19 +306,21 @@ __global__ void __launch_bounds__(256) border_gather_kernel(BorderGatherArgs a) 
   }
 }
 
-int border_gather_launch(const void* variants, int H, int W, const int* xs, const int* ys, int ny, int first, int count, int P,
-                         int S, void* out, cudaStream_t stream) {
-  if (count <= 0 || P < 2 || H < kBlock || W < kBlock) return VC_ERR_ARG;
+int border_gather_launch(const void* variants, int S, int B, int D, int H, int W, const int* xs, const int* ys, int ny, int first,
+                         int count, int P, void* out, cudaStream_t stream) {
+  if (count <= 0 || H < B || W < B || B <= 2 * D || (D == 1 ? P < 2 : P < 2 * D + 1)) return VC_ERR_ARG;
+  const long long rows = (long long)sps_tiles(count, P) * 128;
+  if (rows >= (1LL << 31) || (long long)first + count >= (1LL << 31)) return VC_ERR_ARG;
   BorderGatherArgs a;
   a.v = (const __nv_bfloat16*)variants;
   a.out = (__nv_bfloat16*)out;
   a.xs = xs; a.ys = ys;
-  a.RTb = sps_rows(scene_blocks(H) * scene_blocks(W), kBlock);
+  a.RTb = sps_rows(blk_count(H, B, D) * blk_count(W, B, D), B);
   a.RTo = sps_rows(count, P);
-  a.S = S; a.ny = ny; a.first = first; a.count = count; a.P = P; a.H = H; a.W = W;
-  a.nbx = scene_blocks(W);
-  a.ntiles = sps_tiles(count, P);
-  long long blocks = ((long long)a.ntiles * 128 + 255) / 256;
+  a.S = S; a.ny = ny; a.first = first; a.count = count; a.P = P; a.H = H; a.W = W; a.B = B; a.D = D;
+  a.nbx = blk_count(W, B, D);
+  a.rows = (int)rows;
+  long long blocks = (rows + 255) / 256;
   if (blocks > 148LL * 64) blocks = 148LL * 64;
   border_gather_kernel<<<(int)blocks, 256, 0, stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;

@@ -26,10 +26,20 @@ __host__ __device__ inline long long sps_rows(int n, int P) {
   return (long long)sps_halo(P) * 2 + (long long)sps_tiles(n, P) * 128;
 }
 
-// Scene blocks of the shared first conv (pack.cu): kBlock x kBlock pixels = (kBlock+1)^2 = 256 SPS rows = two
-// full 128-row tiles, origins every kBlockStep pixels (clamped so the last block ends at the scene border).
-constexpr int kBlock = 15, kBlockStep = kBlock - 2;
-__host__ __device__ inline int scene_blocks(int extent) { return (extent - 2) / kBlockStep + 1; }
+// Scene blocks of the shared stem (pack.cu, abi.cu): B x B pixel blocks packed as SPS "patches" ((B+1)^2 rows =
+// whole 128-row tiles for B = 15 / 31), sharing depth D = number of stem convs computed on them.  A depth-D output
+// is exact D pixels inside the block (closer to the block border only where that border is the scene border), so
+// origins advance by B - 2D and the last block is clamped to end at the scene border.
+__host__ __device__ inline int blk_step(int B, int D) { return B - 2 * D; }
+__host__ __device__ inline int blk_count(int extent, int B, int D) { return (extent - 1 - D > 0 ? extent - 1 - D : 0) / blk_step(B, D) + 1; }
+__host__ __device__ inline int blk_index(int y, int B, int D) { return (y - D > 0 ? y - D : 0) / blk_step(B, D); }
+__host__ __device__ inline int blk_origin(int k, int extent, int B, int D) {
+  const int o = k * blk_step(B, D);
+  return o < extent - B ? o : extent - B;
+}
+// Border class of index i of a P-wide window for a depth-d output: 0..d-1 = i (near the first row / column),
+// d = interior, d+1..2d near the last one (2d = last).  Needs P >= 2d + 1 (P >= 2 for d = 1).
+__host__ __device__ inline int border_class(int i, int P, int d) { return i < d ? i : (i > P - 1 - d ? 2 * d - (P - 1 - i) : d); }
 
 // Source pixel of output pixel (i, j) of a P x P patch under the reference's spatial augmentations
 // (datasets.py:510-526): op 0 identity, 1 fliplr, 2 flipud, 3 both, 4/5/6 np.rot90 with k = 1/2/3.

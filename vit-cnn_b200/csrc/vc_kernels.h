@@ -10,6 +10,12 @@ int conv_sps_launch(const void* in, int S_in, const void* w, const float* scale,
                     int out_slice_off, int n_out, int nsplit, int n_patches, int P, int ntaps, int relu, int impl,
                     int debug_flags, cudaStream_t stream);
 
+// the same conv reading up to 9 input planes (same geometry): tap t takes its rows from plane p iff bit t of
+// tapmasks[p]; taps in no mask are dropped.  tcgen05 single-CTA kernel only (impl 0)
+int conv_sps_planes_launch(const void* const* planes, const unsigned int* tapmasks, int nplanes, int S_in, const void* w,
+                           const float* scale, const float* bias, void* out, int out_slice_off, int n_out, int nsplit,
+                           int n_patches, int P, int ntaps, int relu, int impl, int debug_flags, cudaStream_t stream);
+
 // pack.cu
 int pack_sps_launch(const float* src, long long sb, long long sc, long long si, long long sj, const long long* patch_off,
                     const unsigned char* ops, int n_patches, int C, int P, void* sps, int S, cudaStream_t stream);
@@ -23,11 +29,12 @@ int gather_labels_launch(const void* gt, int gt_elem_bytes, int H, int W, const 
 int scene_index_launch(const int* xs, const int* ys, int nx, int ny, int first, int count, int W, int C1, int C2, int P,
                        int K, long long* off1, long long* off2, long long* out_idx, int* xy, cudaStream_t stream);
 
-// shared first conv of dense sliding windows: raster offsets of the scene blocks, and the per-window gather of
-// the 9 border-class variants [9][S][sps_rows(blocks, kBlock)][8] into the chunk's conv-1 output [S][rows][8]
-int block_offsets_launch(int H, int W, int C, long long* off, cudaStream_t stream);
-int border_gather_launch(const void* variants, int H, int W, const int* xs, const int* ys, int ny, int first, int count, int P,
-                         int S, void* out, cudaStream_t stream);
+// shared stem of dense sliding windows (B x B scene blocks, sharing depth D): raster offsets of the blocks, and
+// the per-window gather of the (2D+1)^2 border-class variants [v][S][sps_rows(blocks, B)][8] into slices 0..S-1
+// of the chunk's stem output [.][sps_rows(count, P)][8]
+int block_offsets_launch(int H, int W, int C, int B, int D, long long* off, cudaStream_t stream);
+int border_gather_launch(const void* variants, int S, int B, int D, int H, int W, const int* xs, const int* ys, int ny, int first,
+                         int count, int P, void* out, cudaStream_t stream);
 
 int center_offsets_launch(const int* xy, int n, int W, int C1, int C2, int P, long long* off1, long long* off2,
                           cudaStream_t stream);

@@ -349,15 +349,25 @@ class ViTCNN(nn.Module):
         ys = window_starts(W, P, stride) if ys is None else np.ascontiguousarray(ys, dtype=np.int32)
         if len(xs) and (xs.min() < 0 or xs.max() + P > H) or len(ys) and (ys.min() < 0 or ys.max() + P > W):
             raise ValueError("window starts fall outside the raster")
-        xs = torch.from_numpy(xs).to(device=dev, dtype=torch.int32)
-        ys = torch.from_numpy(ys).to(device=dev, dtype=torch.int32)
-        nx, ny = xs.numel(), ys.numel()
+        nx, ny = len(xs), len(ys)
         first, count = (0, nx * ny) if window_range is None else window_range
         if logits_map is None:
             logits_map = torch.zeros(H, W, K, dtype=torch.float32, device=dev)
         if argmax_map is None:
             argmax_map = torch.zeros(H, W, dtype=torch.uint8, device=dev)
         if count > 0:
+            # hand the library only the raster rows this window range touches (a row band of a sharded scene):
+            # its scene-level work (the shared first conv) then covers the band, not the whole raster
+            r_first, r_last = first // ny, (first + count - 1) // ny
+            y_lo, y_hi = int(xs[r_first:r_last + 1].min()), int(xs[r_first:r_last + 1].max()) + P
+            xs = xs[r_first:r_last + 1] - y_lo
+            first -= r_first * ny
+            nx = len(xs)
+            img1, img2 = img1[y_lo:y_hi], img2[y_lo:y_hi]
+            lg_view, am_view = logits_map[y_lo:y_hi], argmax_map[y_lo:y_hi]
+            H = y_hi - y_lo
+            xs = torch.from_numpy(np.ascontiguousarray(xs, dtype=np.int32)).to(dev)
+            ys = torch.from_numpy(ys).to(dev)
             L = _lib.lib()
             with torch.cuda.device(dev):
                 pk = self.pack_for_inference()
@@ -371,6 +381,6 @@ class ViTCNN(nn.Module):
                 stream = torch.cuda.current_stream().cuda_stream
                 _lib.check(L.vc_scene_infer(ctypes.byref(pk["struct"]), img1.data_ptr(), img2.data_ptr(), H, W,
                                             xs.data_ptr(), ys.data_ptr(), nx, ny, first, count, chunk, ws.data_ptr(),
-                                            ws.numel(), logits_map.data_ptr(), argmax_map.data_ptr(), stream),
+                                            ws.numel(), lg_view.data_ptr(), am_view.data_ptr(), stream),
                            "vc_scene_infer")
         return logits_map, argmax_map
