@@ -16,6 +16,7 @@ of its own and ships no ViT-CNN source: the oracle port is its stand-in).
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -397,29 +398,53 @@ def main():
     token_flops = (2 * P * P * 64 * 32 + 2 * (2 * T_ * 32 * 96 + 2 * T_ * 32 * 32 + 2 * 4 * 2 * T_ * T_ * 8 + 2 * 2 * T_ * 32 * 128)
                    + 2 * 32 * K)                                      # fusion + 2 blocks + head
     S1 = (C1 + 15) // 16 * 2
-    kernels = {   # class -> (name, bound, algorithmic work per window, unit scale, peak)
-        "conv_h1": ("conv_sps_tc_kernel (HSI stem conv1, tcgen05)", "tensor", 2.0 * P * P * 128 * C1 * 9, 1e12, tf_sust, "TFLOP/s"),
-        "conv_h2": ("conv_sps_tc_kernel (HSI stem conv2, tcgen05)", "tensor", 2.0 * P * P * 64 * 128 * 9, 1e12, tf_sust, "TFLOP/s"),
-        "tokens": ("transformer_fwd_kernel (token stage, mma.sync)", "tensor", float(token_flops), 1e12, tf_sust, "TFLOP/s"),
-        # HBM bytes that must move: the bf16 SPS rows written (HSI + LiDAR slices) plus the raster read once
-        # per scene; the P*P-fold re-reads of raster pixels are L2 hits by construction (strip staging)
-        "pack": ("pack_strip_kernel (TMA-staged patch gather -> bf16 SPS)", "hbm",
-                 float((S1 + 2) * (P + 1) * (P + 1) * 16 + (C1 + C2) * 4 * H * W / (nx * ny)), 1e9, hbm, "GB/s"),
+    # Shared stem (vc_scene_infer): the first `depth` HSI convs run once per scene on 31 x 31 (depth 1: 15 x 15)
+    # blocks as (2L+1)^2 border-class variants and the windows gather their stem output from them.  The work of
+    # those kernels is the work they execute on the blocks (taps that leave a window are not issued), NOT the
+    # per-window figure of SURVEY App. D -- the sharing is an algorithmic saving, not tensor throughput.
+    pk = net.pack_for_inference()
+    band_rows_dev = (first + count - 1) // ny - first // ny + P      # raster rows predict_scene hands to the library
+    n_chunks = -(-count // args.chunk)
+    chunk_eff = -(-count // n_chunks)
+    ws_bytes = _lib.lib().vc_scene_workspace_bytes(ctypes.byref(pk["struct"]), band_rows_dev, W, chunk_eff)
+    depth = _lib.lib().vc_scene_shared_depth(ctypes.byref(pk["struct"]), band_rows_dev, W, chunk_eff, count, ws_bytes)
+    Bb = 31 if depth >= 2 else 15
+    step_b = Bb - 2 * max(depth, 1)
+    nb = ((band_rows_dev - Bb + step_b - 1) // step_b + 1) * ((W - Bb + step_b - 1) // step_b + 1) if depth else 0
+    taps1, taps2 = 49, 169                                            # issued (variant, tap) pairs: (2+3+2)^2, (2+3+3+3+2)^2
+    blk_px = Bb * Bb
+    w_c1 = 2.0 * 128 * C1 * taps1 * blk_px * nb * scenes if depth >= 1 else 2.0 * P * P * 128 * C1 * 9 * nwin
+    w_c2 = 2.0 * 64 * 128 * taps2 * blk_px * nb * scenes if depth >= 2 else 2.0 * P * P * 64 * 128 * 9 * nwin
+    g_slices = {0: S1, 1: 16, 2: 8, 3: 4}[depth]
+    kernels = {   # class -> (name, bound, work of this rank in one step, unit scale, peak)
+        "conv_h1": (("conv_sps_tc2_kernel x 9 border-class variants on %d x %d scene blocks (HSI conv 1, tcgen05)" % (Bb, Bb))
+                    if depth >= 1 else "conv_sps_tc2_kernel (HSI stem conv1, tcgen05)", "tensor", w_c1, 1e12, tf_sust, "TFLOP/s"),
+        "conv_h2": ("conv_sps_tc_kernel x 25 variants, multi-plane input (HSI conv 2, tcgen05)" if depth >= 2
+                    else "conv_sps_tc_kernel (HSI stem conv2, tcgen05)", "tensor", w_c2, 1e12, tf_sust, "TFLOP/s"),
+        "tokens": ("transformer_fwd_kernel (token stage, mma.sync)", "tensor", float(token_flops) * nwin, 1e12, tf_sust, "TFLOP/s"),
+        # HBM bytes that must move: the bf16 SPS rows written per window (gathered stem slices + LiDAR slices) and
+        # the same bytes read (variant planes / raster; re-reads across overlapping windows are L2 hits)
+        "pack": ("border_gather_kernel (stem variants -> window SPS) + pack_strip_kernel (LiDAR)" if depth
+                 else "pack_strip_kernel (TMA-staged patch gather -> bf16 SPS)", "hbm",
+                 float((g_slices + 2) * (P + 1) * (P + 1) * 16) * nwin
+                 + (float((2 * depth + 1) ** 2 * g_slices * 16 * nb * (Bb + 1) ** 2) * scenes if depth
+                    else float((C1 + C2) * 4 * H * W) * scenes * count / (nx * ny)), 1e9, hbm, "GB/s"),
     }
 
     def entry(cls):
-        name, bound, per_win, scale, peak, unit = kernels[cls]
+        name, bound, work, scale, peak, unit = kernels[cls]
         t_ms, n_l = prof[cls]
-        ach = per_win * nwin / (t_ms / 1e3) / scale if t_ms > 0 else 0.0
+        ach = work / (t_ms / 1e3) / scale if t_ms > 0 else 0.0
         return {"kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                 "peak_source": which + (" bf16 sustained" if bound == "tensor" else " HBM copy"),
                 "launches": n_l, "avg_launch_ms": t_ms / max(n_l, 1), "share_of_step": t_ms / total_ms if total_ms else None}
 
     dominant = max(("conv_h1", "tokens"), key=lambda c: prof[c][0])   # the single kernel with the largest share
     roofline = entry(dominant)
-    roofline["traffic"] = traffic if dominant == "conv_h1" else None
+    roofline["traffic"] = traffic if (dominant == "conv_h1" and depth == 0) else None
+    roofline["shared_stem_depth"] = int(depth)
     roofline["breakdown_ms"] = {k: round(v[0], 3) for k, v in prof.items() if v[1]}
-    roofline["other_kernels"] = [dict(entry(c), traffic=(traffic if c == "conv_h1" else None)) for c in kernels if c != dominant]
+    roofline["other_kernels"] = [dict(entry(c), traffic=(traffic if (c == "conv_h1" and depth == 0) else None)) for c in kernels if c != dominant]
 
     if rank == 0:
         cpu_v, cpu_n, cpu_dt = (float("nan"), 0, 0.0) if args.no_cpu else cpu_oracle_rate(args.cpu_seconds,

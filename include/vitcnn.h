@@ -249,6 +249,8 @@ int vc_forward_patches(const vc_model* m, const float* hsi, const int64_t hsi_st
  * stem output is gathered from them (same bits as the per-window convs).  With only
  * vc_workspace_bytes(chunk, ...) of workspace the per-window path runs. */
 int64_t vc_scene_workspace_bytes(const vc_model* m, int32_t H, int32_t W, int32_t chunk);
+/* how many HSI stem convs vc_scene_infer would share for this call (0 = per-window path); instrumentation */
+int32_t vc_scene_shared_depth(const vc_model* m, int32_t H, int32_t W, int32_t chunk, int64_t n_windows, int64_t workspace_bytes);
 int vc_scene_infer(const vc_model* m, const float* img1, const float* img2, int32_t H, int32_t W, const int32_t* xs,
                    const int32_t* ys, int32_t nx, int32_t ny, int64_t first_window, int64_t n_windows, int32_t chunk,
                    void* workspace, int64_t workspace_bytes, float* logits_map, uint8_t* argmax_map, void* stream);

@@ -1,6 +1,6 @@
 #!/bin/bash
-# Round evidence: all gpu tests, smoke, bench (both arms), ncu launch lists and full captures of the
-# dominant kernels of the inference scene and of the training step (B200_PROFILING.md recipe).
+# Round evidence: all gpu tests, smoke, bench (both arms), ncu launch list and full captures of every kernel of
+# one inference step (B200_PROFILING.md recipe).  TRAIN=1 adds the training-step launch list and captures.
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" | tail -1
 timeout 900 python -m pytest tests -m gpu -x -q -p no:cacheprovider 2>&1 | tail -3
@@ -9,16 +9,20 @@ python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; cat gpurun_out/bench_ref.json
 PROF="python bench.py --steps 1 --warmup 3 --windows 65536 --no-cpu --no-e2e --no-train"
 $PROF > gpurun_out/prof_plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $PROF > gpurun_out/ncu_list.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $PROF > gpurun_out/ncu_list.log 2>&1
 echo "ncu list rc=$?"
+# one whole step of the shared-stem scene path: 9 conv-1 variants, 25 conv-2 variants, then per chunk the LiDAR
+# gather, the variant gather, conv 3, the LiDAR stem and the token stage (second step: skip the first one's launches)
 $PROF > gpurun_out/prof_plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"conv_sps_tc|transformer_fwd|pack_strip_kernel|lidar_stem" -s 6 -c 7 -o gpurun_out/prof_infer $PROF > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"conv_sps_tc|transformer_fwd|pack_strip_kernel|lidar_stem|border_gather" -s 44 -c 44 -o gpurun_out/prof_infer -f $PROF > gpurun_out/ncu_full.log 2>&1
 echo "ncu infer rc=$?"; tail -1 gpurun_out/ncu_full.log
+if [ -n "$TRAIN" ]; then
 TPROF="python bench.py --no-infer --no-graph --steps 1 --warmup 3"
 $TPROF > gpurun_out/train_plain1.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 400 --csv --log-file gpurun_out/train_launches.csv $TPROF > gpurun_out/ncu_train_list.log 2>&1
 echo "ncu train list rc=$?"
 $TPROF > gpurun_out/train_plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"wgrad_sps_tc|transformer_bwd|bn_bwd_apply" -s 18 -c 19 -o gpurun_out/prof_train $TPROF > gpurun_out/ncu_train_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"wgrad_sps_tc|transformer_bwd|bn_bwd_apply" -s 18 -c 19 -o gpurun_out/prof_train -f $TPROF > gpurun_out/ncu_train_full.log 2>&1
 echo "ncu train rc=$?"; tail -1 gpurun_out/ncu_train_full.log
+fi
 ls -la gpurun_out | head -40

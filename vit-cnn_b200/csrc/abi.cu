@@ -463,6 +463,11 @@ int vc_scene_infer(const vc_model* m, const float* img1, const float* img2, int3
   return VC_OK;
 }
 
+int32_t vc_scene_shared_depth(const vc_model* m, int32_t H, int32_t W, int32_t chunk, int64_t n_windows, int64_t workspace_bytes) {
+  if (check_model(m) != VC_OK || chunk <= 0) return -1;
+  return scene_mode(m, H, W, chunk, n_windows, workspace_bytes);
+}
+
 int64_t vc_scene_workspace_bytes(const vc_model* m, int32_t H, int32_t W, int32_t chunk) {
   if (check_model(m) != VC_OK || chunk <= 0) return -1;
   long long need = vc_workspace_bytes(chunk, m->P, m->C1, m->C2);

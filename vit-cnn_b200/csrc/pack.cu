@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(256) border_gather_kernel(BorderGatherArgs a) 
       const int widx = a.first + b;
       const int ix = widx / a.ny, iy = widx - ix * a.ny;
       const int y = __ldg(a.xs + ix) + i, x = __ldg(a.ys + iy) + j;
-      const int ky = blk_index(y, B, D), kx = blk_index(x, B, D);
+      const int ky = blk_index(y, a.H, B, D), kx = blk_index(x, a.W, B, D);
       const long long srow = HB + (long long)(ky * a.nbx + kx) * PPB + (y - blk_origin(ky, a.H, B, D)) * (B + 1) +
                              (x - blk_origin(kx, a.W, B, D));
       src = reinterpret_cast<const uint4*>(a.v) + (long long)(border_class(i, P, D) * NC + border_class(j, P, D)) * a.S * a.RTb + srow;

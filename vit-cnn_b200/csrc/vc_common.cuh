@@ -31,8 +31,11 @@ __host__ __device__ inline long long sps_rows(int n, int P) {
 // is exact D pixels inside the block (closer to the block border only where that border is the scene border), so
 // origins advance by B - 2D and the last block is clamped to end at the scene border.
 __host__ __device__ inline int blk_step(int B, int D) { return B - 2 * D; }
-__host__ __device__ inline int blk_count(int extent, int B, int D) { return (extent - 1 - D > 0 ? extent - 1 - D : 0) / blk_step(B, D) + 1; }
-__host__ __device__ inline int blk_index(int y, int B, int D) { return (y - D > 0 ? y - D : 0) / blk_step(B, D); }
+__host__ __device__ inline int blk_count(int extent, int B, int D) { return (extent - B + blk_step(B, D) - 1) / blk_step(B, D) + 1; }
+__host__ __device__ inline int blk_index(int y, int extent, int B, int D) {   // block whose exact region holds pixel y
+  const int k = (y - D > 0 ? y - D : 0) / blk_step(B, D), last = blk_count(extent, B, D) - 1;
+  return k < last ? k : last;
+}
 __host__ __device__ inline int blk_origin(int k, int extent, int B, int D) {
   const int o = k * blk_step(B, D);
   return o < extent - B ? o : extent - B;

@@ -33,7 +33,9 @@ def predict_scene_host(net, img1: torch.Tensor, img2: torch.Tensor, stride: int 
     # so the PCIe traffic (386 MB up, 42 MB down for a Houston scene) hides behind the kernels.
     xs_rel, P2 = geo["xs"], P // 2
     nrows = len(xs_rel)
-    nsub = max(1, min(int(pipeline), nrows))
+    # sub-bands of at least 21 window rows (31 raster rows at P = 11): the shared stem of vc_scene_infer needs
+    # 31-row rasters, and shorter sub-bands would spend their time on launch tails
+    nsub = max(1, min(int(pipeline), nrows // 21))
     bounds = [(nrows * k) // nsub for k in range(nsub + 1)]
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream()
