@@ -1,0 +1,68 @@
+"""CPU tests of the host-side mirrors around the hot path: sample_gt against splits the
+reference's own sample_gt produced (tests/golden/split_golden.npz, made by make_split_golden.py) and the checkpoint
+writer's naming / round trip."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(HERE, "golden", "split_golden.npz"))
+
+
+@pytest.mark.parametrize("tag,mode,ts", [("random_frac", "random", 0.2), ("random_count", "random", 50),
+                                         ("disjoint_50", "disjoint", 0.5), ("disjoint_30", "disjoint", 0.3)])
+def test_sample_gt_matches_reference_splits(golden, tag, mode, ts):
+    from vitcnn_b200.utils import sample_gt
+    np.random.seed(7)
+    tr, te = sample_gt(golden["gt"], ts, mode=mode)
+    assert tr.dtype == golden[tag + "_train"].dtype
+    assert np.array_equal(tr, golden[tag + "_train"]) and np.array_equal(te, golden[tag + "_test"])
+
+
+def test_fixed_number_split_matches_reference_draw(golden):
+    from vitcnn_b200.utils import _fixed_number_split, sample_gt
+    gt = golden["gt"]
+    tr, te = _fixed_number_split(5, gt.reshape(-1).astype(np.int64), 11)
+    assert np.array_equal(tr, golden["fixednum_train_idx"]) and np.array_equal(te, golden["fixednum_test_idx"])
+    a, b = sample_gt(gt, 5, mode="random_fixednumber", seed=11)       # upstream dies on np.int here (utils.py:836)
+    assert a.shape == gt.shape and a.dtype == np.float64
+    assert all(int((a == c).sum()) == 5 for c in range(1, int(gt.max()) + 1))
+    assert not ((a > 0) & (b > 0)).any() and np.array_equal(a + b, gt.astype(np.float64))
+
+
+def test_sample_gt_fixed_mode_and_errors(golden):
+    from vitcnn_b200.utils import sample_gt
+    gt = golden["gt"]
+    np.random.seed(2)
+    tr, te = sample_gt(gt, 0.25, mode="fixed")
+    assert np.array_equal(tr + te, gt) and not ((tr > 0) & (te > 0)).any()
+    for c in range(1, int(gt.max()) + 1):
+        n = int((gt == c).sum())
+        assert int((tr == c).sum()) == int(0.25 * n)           # sklearn floors the train share
+    with pytest.raises(ValueError):
+        sample_gt(gt, 0.5, mode="nope")
+    with pytest.raises(ValueError):
+        sample_gt(gt.reshape(-1), 0.5)
+
+
+def test_save_model_naming_and_round_trip(tmp_path, monkeypatch):
+    import vitcnn_b200
+    from vitcnn_b200.model_utils import save_model
+    from oracle.model_ref import ViTCNNRef
+    monkeypatch.chdir(tmp_path)
+    torch.manual_seed(0)
+    net = vitcnn_b200.ViTCNN(12, 1, patch_size=5, num_classes=4)
+    path = save_model("ViTCNN", net, "ViTCNN", "Houston2013", "train", "best", run=2, epoch=7, metric=91.256)
+    assert path.startswith("./checkpoints/ViTCNN/Houston2013/train/best/") and path.endswith("ViTCNN_run2_epoch7_91.26.pth")
+    ref = ViTCNNRef(12, 1, patch_size=5, num_classes=4)
+    ref.load_state_dict(torch.load(path))                        # the reference-style module takes our checkpoint as it is
+    sd = net.state_dict()
+    assert all(torch.equal(v, sd[k]) for k, v in ref.state_dict().items())
+    other = save_model("x", {"a": 1}, "SVM", "d", "train", "last")
+    assert other.endswith(".pkl") and os.path.isfile(other)

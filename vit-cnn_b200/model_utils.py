@@ -104,3 +104,25 @@ def val(net, data_loader, device="cpu", supervision="full"):
             accuracy += ((pred == target.view(-1)) & keep).sum()
             total += keep.sum()
     return float(accuracy.item()) / float(total.item())
+
+
+def save_model(savename, model, model_name, dataset_name, train_state, type, **kwargs):
+    """Checkpoint writer with the reference's path and file-name scheme (model_utils.py:1047-1064):
+    ``./checkpoints/<model_name>/<dataset_name>/<train_state>/<type>/<time><savename>_run{run}_epoch{epoch}_{metric:.2f}.pth``
+    holding ``model.state_dict()`` (the keys of ViTCNN are those of the oracle / reference-style module, so
+    ``main.py --restore`` -> ``model.load_state_dict(torch.load(path))`` works in both directions).  Anything that
+    is not an ``nn.Module`` is pickled with joblib like upstream.  Returns the path written."""
+    import datetime
+    import os
+    model_dir = "./checkpoints/" + model_name + "/" + dataset_name + "/" + train_state + "/" + type + "/"
+    time_str = datetime.datetime.now().strftime("%Y_%m_%d_%H_%M_%S")
+    os.makedirs(model_dir, exist_ok=True)
+    if isinstance(model, torch.nn.Module):
+        filename = time_str + savename + "_run{run}_epoch{epoch}_{metric:.2f}".format(**kwargs)
+        path = model_dir + filename + ".pth"
+        torch.save(model.state_dict(), path)
+    else:
+        import joblib
+        path = model_dir + time_str + ".pkl"
+        joblib.dump(model, path)
+    return path

@@ -156,3 +156,85 @@ def minmax_normalise_(img, per_band: bool = True):
                                                   scratch.data_ptr(), torch.cuda.current_stream().cuda_stream),
                    "vc_minmax_normalise")
     return img
+
+
+def _fixed_number_split(sample_num: int, labels: np.ndarray, seed: int):
+    """Flat train / test index lists with ``sample_num`` training pixels per class, drawn exactly like
+    the reference's samplingFixedNum (utils.py:754-773): ``np.random.seed(seed)``, one shuffle of every
+    class's pixel list in class order, then one shuffle of each concatenated list."""
+    np.random.seed(seed)
+    flat = labels.ravel()
+    train, test = [], []
+    for c in range(1, int(flat.max()) + 1 if flat.size else 1):
+        idx = np.flatnonzero(flat == c).tolist()
+        np.random.shuffle(idx)
+        train += idx[:sample_num]
+        test += idx[sample_num:]
+    np.random.shuffle(train)
+    np.random.shuffle(test)
+    return train, test
+
+
+def sample_gt(gt, train_size, mode="random", seed=0):
+    """Split a 2-D label map into (train_gt, test_gt) -- the reference's sample_gt (utils.py:775-846):
+
+    * ``random``: stratified ``sklearn.model_selection.train_test_split`` over the labelled pixels (the same
+      third-party call, so the same draw under the same numpy RNG state); ``train_size`` > 1 is a count;
+    * ``fixed``: per class an unstratified ``train_test_split`` of that class's pixels;
+    * ``disjoint``: per class the rows above the first row where 90 % of ``train_size`` of the class's pixels
+      lie above go to the test side;
+    * ``random_fixednumber``: ``train_size`` pixels per class (`_fixed_number_split`).
+
+    Upstream bugs not reproduced: ``fixed`` indexes with a list of lists (an error on numpy >= 1.23; the intent
+    -- a (rows, cols) pair -- is used here) and ``random_fixednumber`` uses the removed ``np.int`` (utils.py:836)."""
+    gt = np.asarray(gt)
+    if gt.ndim != 2:
+        raise ValueError("gt must be a 2-D label map")
+    rows, cols = np.nonzero(gt)
+    train_gt, test_gt = np.zeros_like(gt), np.zeros_like(gt)
+    if train_size > 1:
+        train_size = int(train_size)
+    if mode in ("random", "fixed"):
+        try:
+            from sklearn.model_selection import train_test_split
+        except ImportError as e:     # the reference has the same dependency
+            raise RuntimeError("sample_gt modes 'random' / 'fixed' need scikit-learn") from e
+    if mode == "random":
+        X = list(zip(rows, cols))
+        tr, te = train_test_split(X, train_size=train_size, stratify=gt[rows, cols].ravel())
+        tr, te = np.asarray(tr).reshape(-1, 2), np.asarray(te).reshape(-1, 2)
+        train_gt[tr[:, 0], tr[:, 1]] = gt[tr[:, 0], tr[:, 1]]
+        test_gt[te[:, 0], te[:, 1]] = gt[te[:, 0], te[:, 1]]
+    elif mode == "fixed":
+        for c in np.unique(gt):
+            if c == 0:
+                continue
+            X = list(zip(*np.nonzero(gt == c)))
+            tr, te = train_test_split(X, train_size=train_size)
+            tr, te = np.asarray(tr).reshape(-1, 2), np.asarray(te).reshape(-1, 2)
+            train_gt[tr[:, 0], tr[:, 1]] = c
+            test_gt[te[:, 0], te[:, 1]] = c
+    elif mode == "disjoint":
+        train_gt, test_gt = np.copy(gt), np.copy(gt)
+        for c in np.unique(gt):
+            mask = gt == c
+            total = int(mask.sum())
+            above = np.concatenate([[0], np.cumsum(mask.sum(axis=1))])       # pixels of the class in rows [0, x)
+            x = gt.shape[0] - 1
+            for r in range(gt.shape[0]):
+                if total and above[r] / total > 0.9 * train_size:
+                    x = r
+                    break
+            mask[:x, :] = False
+            train_gt[mask] = 0
+        test_gt[train_gt > 0] = 0
+    elif mode == "random_fixednumber":
+        flat = gt.reshape(-1).astype(np.int64)
+        tr, te = _fixed_number_split(int(train_size), flat, seed)
+        train_flat, test_flat = np.zeros(flat.shape), np.zeros(flat.shape)      # float64, like the reference
+        train_flat[tr] = flat[tr]
+        test_flat[te] = flat[te]
+        train_gt, test_gt = train_flat.reshape(gt.shape), test_flat.reshape(gt.shape)
+    else:
+        raise ValueError("{} sampling is not implemented yet.".format(mode))
+    return train_gt, test_gt
