@@ -207,14 +207,17 @@ int zero_halos(const Workspace& w, int n, int P, cudaStream_t st) {
   return VC_OK;
 }
 
-// A-B knob: VITCNN_TOKENS_IMPL=1 selects the tcgen05 token kernel (tokens_tc.cu) where it applies; the default
-// is the mma.sync kernel, which is the faster one as measured (profiles/r01_SUMMARY.md)
-int tokens_impl() {
-  static const int impl = [] {
+// Which token-stage kernel: the tcgen05 kernel (tokens_tc.cu) treats one patch as one M = 128 tile, so it wins where
+// the token set nearly fills the tile (measured per 32 768 patches: P = 11 1.52 vs 1.75 ms, P = 9 1.40 vs 1.42 ms,
+// P = 7 1.27 vs 0.95 ms): default = tcgen05 for 100 <= P*P + 1 <= 128, mma.sync otherwise.
+// VITCNN_TOKENS_IMPL=0 / 1 forces mma.sync / tcgen05 (where it applies).
+bool use_tokens_tc(int P, int K) {
+  static const int forced = [] {
     const char* e = getenv("VITCNN_TOKENS_IMPL");
-    return e ? atoi(e) : 0;
+    return e ? atoi(e) : -1;
   }();
-  return impl;
+  if (!vc::tokens_tc_supported(P, K) || forced == 0) return false;
+  return forced == 1 || P * P + 1 >= 100;
 }
 
 int forward_sps(const vc_model* m, const Workspace& w, int n, float* logits, const long long* out_index,
@@ -245,9 +248,9 @@ int forward_sps(const vc_model* m, const Workspace& w, int n, float* logits, con
     VC_LAUNCH(KC_CONV_L, st, vc::conv_sps_launch(w.l2, 2, m->w_l[2], m->scale_l[2], m->bias_l[2], w.f, 4, 32, m->nsplit_l[2], n, P, 9, 1,
                                                  0, 0, st));
   }
-  // token stage: tcgen05 kernel when the token set fits one M = 128 tile (P <= 11), the mma.sync kernel
-  // otherwise.  conv 1's output (w.a1) is dead by now and serves as the cls-record scratch.
-  if (tokens_impl() == 1 && vc::tokens_tc_supported(P, m->K))
+  // token stage (see use_tokens_tc).  conv 1's output buffer (w.a1) is dead or unused by now and serves as the
+  // cls-record scratch of the tcgen05 kernel.
+  if (use_tokens_tc(P, m->K))
     VC_LAUNCH(KC_TOKENS, st, vc::tokens_tc_launch(w.f, m->tparams, n, P, m->K, logits, out_index, argmax_map, w.a1, st));
   else
     VC_LAUNCH(KC_TOKENS, st, vc::transformer_fwd_launch(w.f, m->tparams, n, P, m->K, logits, out_index, argmax_map, 0, 0, nullptr, st));

@@ -20,16 +20,19 @@
 //    V is consumed MN-major ([key][8 dims] slabs) and its second N chunk is a
 //    slab of (1,0,..,0) rows, so column 8 of the PV accumulator is the softmax denominator of
 //    the bf16-rounded probabilities;
-//  * a CTA runs two independent 128-thread groups ("slots", 256 TMEM columns each) so one
-//    slot's MMA round trips hide behind the other's softmax, plus one MMA-issuer warp per slot:
+//  * a CTA runs three independent 128-thread groups ("slots": 56 KB of operand buffers with
+//    non-overlapping lifetimes aliased, 160 TMEM columns each) so one slot's MMA round trips hide
+//    behind the others' softmax, plus one MMA-issuer warp per slot:
 //    row threads never wait for each other, they arrive on mbarriers the issuer waits on and
 //    wait only for tensor-core completions; the fusion-conv input of the next patch is
-//    prefetched with 16-byte cp.async (one token row per thread) into its own buffer;
+//    prefetched with 16-byte cp.async (one token row per thread) over the K / V buffers once
+//    the last PV of the current patch is done;
 //  * the last block only feeds the head through the cls token (x[:, 0]): K / V of every token
 //    come from one more MMA, the single-query attention is a thread-local dot product + a
 //    butterfly reduction per warp, and the cls row (proj, MLP, final LN, head) is finished by
 //    tokens_tail_kernel, one warp per patch, from a 704-byte record per patch.
 #include <math.h>
+#include <stdlib.h>
 #include <type_traits>
 #include "vc_common.cuh"
 #include "vc_kernels.h"
@@ -39,7 +42,8 @@
 namespace vc {
 
 namespace tc {
-constexpr int kThreads = 320;   // 8 warps of row threads (two slots) + 2 MMA-issuer warps
+constexpr int kSlots = 3;       // patches in flight per CTA
+constexpr int kThreads = (4 * kSlots + kSlots) * 32;   // 4 warps of row threads per slot + one MMA-issuer warp per slot
 constexpr uint32_t SLAB = 2048;   // 128 rows x 16 B: one 8-element K chunk (or 8-dim V group) of a tile
 // ---- shared-memory map (bytes) ----
 constexpr uint32_t W_FUS = 0;                     // [64/8][32][8]
@@ -53,19 +57,22 @@ constexpr int V_FSC = 0, V_FBI = 32, V_LN1G = 64, V_LN1B = 96, V_BQKV = 128, V_B
               V_BFC1 = 320, V_BFC2 = 448, V_L2G = 480, V_L2B = 512, V_BQKV2 = 544, V_TOTAL = 640;
 constexpr uint32_t POS = VEC + V_TOTAL * 4;       // [128][32] fp32, 16-byte granules XOR-swizzled by (row & 7)
 constexpr uint32_t SLOT0 = POS + 128 * 32 * 4;
-constexpr uint32_t S_FBUF = 0;                    // [8][128][8] fusion-conv input (stem outputs of the patch)
-constexpr uint32_t S_ABUF = S_FBUF + 8 * SLAB;    // [4][128][8] LN output / attention output
-constexpr uint32_t S_QBUF = S_ABUF + 4 * SLAB;    // [4 heads][128][8]; followed by K (finite) for head 3's second chunk
+// 56 KB per slot so that three fit: buffers whose lifetimes do not overlap share storage
+constexpr uint32_t S_QBUF = 0;                    // [4 heads][128][8] scaled queries
+constexpr uint32_t S_ABUF = S_QBUF;               // [4][128][8] LN output (dead once qkv is done) / attention output (after the last S)
 constexpr uint32_t S_KBUF = S_QBUF + 4 * SLAB;
 constexpr uint32_t S_VBUF = S_KBUF + 4 * SLAB;    // [4 heads][128 keys][8 dims]
 constexpr uint32_t S_PBUF = S_VBUF + 4 * SLAB;    // [16][128][8] probabilities of one head / MLP hidden
+constexpr uint32_t S_FBUF = S_KBUF;               // [8][128][8] fusion-conv input of the NEXT patch: over K and V once the last PV is done
 constexpr uint32_t SLOT_BYTES = S_PBUF + 16 * SLAB;
-constexpr uint32_t ONES = SLOT0 + 2 * SLOT_BYTES;  // [128][8] = (1,0,0,0,0,0,0,0)
+constexpr uint32_t ONES = SLOT0 + kSlots * SLOT_BYTES;  // [128][8] = (1,0,0,0,0,0,0,0)
 constexpr uint32_t MASK = ONES + SLAB;             // [128 keys][8] = (0 | -30000 for padded keys, 0, ..): K's second K chunk
-constexpr uint32_t MISC = MASK + SLAB;            // q0 [2][32] f32, wmax [2][4][4] f32, barriers, tmem slot, bound flag
-constexpr uint32_t SMEM_BYTES = MISC + 512;
-// ---- TMEM columns inside a slot's 256 ----
-constexpr uint32_t C_S = 0, C_O = 128, C_SMALL = 192;
+constexpr uint32_t MISC = MASK + SLAB;            // q0 [slots][32] f32, wmax [slots][4][4] f32, barriers [slots][5], tmem slot
+constexpr uint32_t M_Q0 = 0, M_WMAX = M_Q0 + kSlots * 128, M_BARS = M_WMAX + kSlots * 64, M_TMEM = M_BARS + kSlots * 40;
+constexpr uint32_t SMEM_BYTES = MISC + ((M_TMEM + 4 + 127) & ~127u);
+// ---- TMEM columns inside a slot's 160: S / qkv / fc1 accumulators at 0, two 16-column O_h buffers at 128 (the
+// 32-column fusion / proj / fc2 accumulators reuse them) ----
+constexpr uint32_t C_SLOT = 160, C_S = 0, C_O = 128, C_SMALL = 128;
 constexpr int kTailFloats = 176;                  // per patch: [4 warps][32 o + 4 l], x0[32]
 }  // namespace tc
 
@@ -74,7 +81,7 @@ struct TcArgs {
   const uint8_t* blob;      // parameter blob (vc_tparams.h)
   float* tail;              // [n][kTailFloats]
   long long RT;
-  int n_patches, P, T;
+  int n_patches, P, T, stagger_ns;
   TLayout L;
 };
 
@@ -139,26 +146,26 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // warps 8 / 9 = MMA issuers of slot 0 / 1.  Row threads never wait for each other: they signal
 // "operands written" / "S consumed" on two mbarriers (128 arrivals) that only the issuer waits on, and
 // wait only for tensor-core completions (tcgen05.commit mbarriers).
-__global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) {   // 168 registers: the file is allocated per 4 warps
+__global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) {   // 15 warps -> 128 registers (the file is allocated per 4 warps)
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool issuer = warp >= 8;
-  const int slot = issuer ? warp - 8 : warp >> 2;
+  const bool issuer = warp >= 4 * kSlots;
+  const int slot = issuer ? warp - 4 * kSlots : warp >> 2;
   const int r = tid & 127, wq = warp & 3;
   const int T = a.T, P = a.P;
   const TLayout& L = a.L;
   const uint32_t sb = smem_u32(smem);
   float* vecf = reinterpret_cast<float*>(smem + VEC);
-  float* q0_s = reinterpret_cast<float*>(smem + MISC) + slot * 32;          // [32]
-  float* wmax_s = reinterpret_cast<float*>(smem + MISC + 256) + slot * 16;  // [4 warps][4 heads]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MISC + 384) + slot * 5;
+  float* q0_s = reinterpret_cast<float*>(smem + MISC + M_Q0) + slot * 32;          // [32]
+  float* wmax_s = reinterpret_cast<float*>(smem + MISC + M_WMAX) + slot * 16;      // [4 warps][4 heads]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MISC + M_BARS) + slot * 5;
   uint64_t* b_rp = bars + 0;      // row threads: operands of the next GEMM are written (128 arrivals)
   uint64_t* b_rs = bars + 1;      // row threads: S_h has been read out of TMEM (128 arrivals)
   uint64_t* b_mma = bars + 2;     // tensor core: the GEMM just issued (fusion / qkv / proj / fc1 / fc2 / kv2) is done
   uint64_t* b_s = bars + 3;       // tensor core: S_h is in TMEM
   uint64_t* b_pv = bars + 4;      // tensor core: PV_h is done (P buffer free, O_h in TMEM)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + MISC + 480);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + MISC + M_TMEM);
   const float qscale = 0.35355339059327376220f * 1.44269504088896340736f;  // hd^-0.5 * log2(e)
 
   // ---------------- one-time image of the parameters in the layouts the tensor core reads ----------------
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) { 
       *reinterpret_cast<float4*>(smem + POS + row * 128 + ((g ^ (row & 7)) << 4)) = v;
     }
     // slot buffers, ZERO slab: zeros (row 0 and rows >= T of FBUF are never written again); ONES slab
-    for (uint32_t i = tid; i < (2 * SLOT_BYTES + 2 * SLAB) / 16; i += kThreads)
+    for (uint32_t i = tid; i < (kSlots * SLOT_BYTES + 2 * SLAB) / 16; i += kThreads)
       *reinterpret_cast<uint4*>(smem + SLOT0 + i * 16) = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     // static bound on |q.k| of block 1: row n of Wq / Wk contributes (||W_n diag(g)||^2, (W_n . beta + b_n)^2)
@@ -238,8 +245,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) { 
       *reinterpret_cast<uint32_t*>(smem + MASK + i * 16) = i >= T ? 0x0000C6EAu : 0u;   // bf16 -29952 for padded keys
     }
     if (tid == 0) {
-      for (int s = 0; s < 2; ++s) {
-        uint64_t* bb = reinterpret_cast<uint64_t*>(smem + MISC + 384) + s * 5;
+      for (int s = 0; s < kSlots; ++s) {
+        uint64_t* bb = reinterpret_cast<uint64_t*>(smem + MISC + M_BARS) + s * 5;
         mbar_init(bb + 0, 128);
         mbar_init(bb + 1, 128);
         mbar_init(bb + 2, 1);
@@ -275,14 +282,14 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) { 
     __syncthreads();   // the scratch is part of a P buffer
   }
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tb = tmem_base + (uint32_t)slot * 256u;                  // columns of this slot (issuer view)
+  const uint32_t tb = tmem_base + (uint32_t)slot * C_SLOT;                // columns of this slot (issuer view)
   const uint32_t tl = tb + ((uint32_t)(wq * 32) << 16);                   // + the 32 lanes of this warp
   const uint32_t slot_s = sb + SLOT0 + (uint32_t)slot * SLOT_BYTES;
   const uint32_t fbuf = slot_s + S_FBUF, abuf = slot_s + S_ABUF, qbuf = slot_s + S_QBUF, kbuf = slot_s + S_KBUF,
                  vbuf = slot_s + S_VBUF, pbuf = slot_s + S_PBUF;
   const int NK = (T + 31) & ~31, NKS = NK >> 4;       // keys rounded to the 32-column chunks the row threads read
-  const int nslots = 2 * (int)gridDim.x;
-  const int b0 = 2 * (int)blockIdx.x + slot;
+  const int nslots = kSlots * (int)gridDim.x;
+  const int b0 = kSlots * (int)blockIdx.x + slot;
 
   if (issuer) {
     // ============================ MMA issuer of this slot ============================
@@ -329,7 +336,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) { 
           // O_h[128 x 16] = P_h[128 x keys] . [V_h | ones]: B is MN-major, N chunk 0 = V_h slab, chunk 1 = ONES slab
           const uint32_t vb = vbuf + h * SLAB;
           for (int k = 0; k < NKS; ++k)
-            umma_bf16(tb + C_O + 16 * h, umma_desc(pbuf + 2 * k * SLAB, SLAB, 128), umma_desc(vb + k * 256, 128, (sb + ONES) - vb),
+            umma_bf16(tb + C_O + 16 * (h & 1), umma_desc(pbuf + 2 * k * SLAB, SLAB, 128), umma_desc(vb + k * 256, 128, (sb + ONES) - vb),
                       idesc(16, 1), k ? 1u : 0u);
           umma_commit(b_pv);
         }
@@ -355,6 +362,9 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) { 
         const __nv_bfloat16* src = a.f + (HALO + (long long)b * PP + i * PW + j) * 8;
 #pragma unroll
         for (int s = 0; s < 8; ++s) cp_async16(fbuf + s * SLAB + row16, src + (long long)s * a.RT * 8);
+      } else {          // the buffer doubles as P / hidden: the cls row and the padding rows are zeroed every time
+#pragma unroll
+        for (int s = 0; s < 8; ++s) sts128(fbuf + s * SLAB + row16, 0u, 0u, 0u, 0u);
       }
     };
     // this thread's operand rows are written -> visible to the tensor core; its TMEM reads are retired
@@ -369,6 +379,16 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) { 
       tc_fence_after();
     };
     if (b0 < a.n_patches) fetch(b0);
+    // the slots run the same program: started together they would hit the SFU-bound softmax phases together and
+    // idle together in the latency-bound ones, so slot k starts k thirds of a patch time later
+    if (slot > 0 && a.stagger_ns > 0) {
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      do {
+        __nanosleep(500);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      } while (t1 - t0 < (unsigned long long)a.stagger_ns * slot);
+    }
 
     for (int b = b0; b < a.n_patches; b += nslots) {
       float x[32];   // residual stream of token row r
@@ -376,7 +396,6 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) { 
       cp_async_wait_all();
       publish();
       wait_mma();
-      if (b + nslots < a.n_patches) fetch(b + nslots);   // FBUF is free again: prefetch the next patch
       {
         uint32_t v[32];
         tmem_ld32(tl + C_SMALL, v);
@@ -422,42 +441,54 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) { 
       // ================= attention, one head at a time =================
       // p = 2^(s - m) -> bf16 -> P buffer (A operand of PV); S_h is released to the issuer as soon as its last
       // chunk is in registers.  `exact`: two passes over S_h in TMEM (row maximum first); otherwise m = 0.
+      // O_h lands in one of two 16-column buffers and is read (normalised by column 8, the softmax denominator
+      // of the bf16 probabilities) while the next head's probabilities are produced.
+      // The normalised O_h goes straight into slab h of the Q buffer (= the A operand of proj): S_h is done, so
+      // Q_h is dead, and later heads read their own slabs only.
+      auto read_o = [&](int h) {
+        uint32_t o[16];
+        tmem_ld16(tl + C_O + 16 * (h & 1), o);
+        tc_wait_ld();
+        const float il = 1.f / __uint_as_float(o[8]);
+        sts128(abuf + h * SLAB + row16, pack_bf16(__uint_as_float(o[0]) * il, __uint_as_float(o[1]) * il),
+               pack_bf16(__uint_as_float(o[2]) * il, __uint_as_float(o[3]) * il),
+               pack_bf16(__uint_as_float(o[4]) * il, __uint_as_float(o[5]) * il),
+               pack_bf16(__uint_as_float(o[6]) * il, __uint_as_float(o[7]) * il));
+      };
       auto softmax_head = [&](int h, auto exact_tag) {
         constexpr bool kExact = decltype(exact_tag)::value;
-        uint32_t s[2][32];
+        uint32_t sc[32];
         mbar_wait(b_s, ph_s);
         ph_s ^= 1u;
         tc_fence_after();
         float m = 0.f;
         if constexpr (kExact) {
           m = -INFINITY;
-          tmem_ld32(tl + C_S, s[0]);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             if (c <= ct) {
+              tmem_ld32(tl + C_S + 32 * c, sc);
               tc_wait_ld();
-              if (c + 1 <= ct) tmem_ld32(tl + C_S + 32 * (c + 1), s[(c + 1) & 1]);
-              const uint32_t(&sc)[32] = s[c & 1];
 #pragma unroll
               for (int i = 0; i < 32; i += 2) m = fmaxf(m, fmaxf(__uint_as_float(sc[i]), __uint_as_float(sc[i + 1])));
             }
           }
         }
-        tmem_ld32(tl + C_S, s[0]);
-        if (h > 0) {                      // PV of the previous head has consumed the P buffer
+        if (h > 0) {                      // PV of the previous head is done: the P buffer is free, O_{h-1} is in TMEM
           mbar_wait(b_pv, ph_pv);
           ph_pv ^= 1u;
+          tc_fence_after();
+          read_o(h - 1);
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (c <= ct) {
+            tmem_ld32(tl + C_S + 32 * c, sc);
             tc_wait_ld();
-            if (c + 1 <= ct) tmem_ld32(tl + C_S + 32 * (c + 1), s[(c + 1) & 1]);
-            else if (h < 3) {             // S_h is out of TMEM: the next head's S may overwrite it
+            if (c == ct && h < 3) {       // S_h is out of TMEM: the next head's S may overwrite it
               tc_fence_before();
               mbar_arrive(b_rs);
             }
-            const uint32_t(&sc)[32] = s[c & 1];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               uint32_t pk[4];
@@ -482,21 +513,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) { 
       mbar_wait(b_pv, ph_pv);
       ph_pv ^= 1u;
       tc_fence_after();
-      // ---- attention output (normalised) -> A operand of proj ----
-      {
-        uint32_t o[4][16];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) tmem_ld16(tl + C_O + 16 * h, o[h]);
-        tc_wait_ld();
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const float il = 1.f / __uint_as_float(o[h][8]);
-          sts128(abuf + h * SLAB + row16, pack_bf16(__uint_as_float(o[h][0]) * il, __uint_as_float(o[h][1]) * il),
-                 pack_bf16(__uint_as_float(o[h][2]) * il, __uint_as_float(o[h][3]) * il),
-                 pack_bf16(__uint_as_float(o[h][4]) * il, __uint_as_float(o[h][5]) * il),
-                 pack_bf16(__uint_as_float(o[h][6]) * il, __uint_as_float(o[h][7]) * il));
-        }
-      }
+      if (b + nslots < a.n_patches) fetch(b + nslots);   // K and V are dead: the next patch's fusion input lands over them
+      read_o(3);
       publish();
       wait_mma();
       {
@@ -758,9 +776,16 @@ int tokens_tc_launch(const void* f_sps, const void* tparams, int n_patches, int 
   a.P = P;
   a.T = P * P + 1;
   a.L = tlayout(P, K);
+  {
+    static const int stagger = [] {
+      const char* e = getenv("VITCNN_TC_STAGGER_NS");
+      return e ? atoi(e) : 7000;
+    }();
+    a.stagger_ns = stagger;
+  }
   if (cudaFuncSetAttribute(tokens_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES) != cudaSuccess)
     return VC_ERR_CUDA;
-  int blocks = (n_patches + 1) / 2;
+  int blocks = (n_patches + tc::kSlots - 1) / tc::kSlots;
   if (blocks > num_sms) blocks = num_sms;
   tokens_tc_kernel<<<blocks, tc::kThreads, tc::SMEM_BYTES, stream>>>(a);
   if (cudaGetLastError() != cudaSuccess) return VC_ERR_CUDA;
