@@ -421,7 +421,8 @@ def main():
                     if depth >= 1 else "conv_sps_tc2_kernel (HSI stem conv1, tcgen05)", "tensor", w_c1, 1e12, tf_sust, "TFLOP/s"),
         "conv_h2": ("conv_sps_tc_kernel x 25 variants, multi-plane input (HSI conv 2, tcgen05)" if depth >= 2
                     else "conv_sps_tc_kernel (HSI stem conv2, tcgen05)", "tensor", w_c2, 1e12, tf_sust, "TFLOP/s"),
-        "tokens": ("transformer_fwd_kernel (token stage, mma.sync)", "tensor", float(token_flops) * nwin, 1e12, tf_sust, "TFLOP/s"),
+        "tokens": ("tokens_tc_kernel + tokens_tail_kernel (token stage, tcgen05)" if (100 <= P * P + 1 <= 128 and os.environ.get("VITCNN_TOKENS_IMPL") != "0")
+                   else "transformer_fwd_kernel (token stage, mma.sync)", "tensor", float(token_flops) * nwin, 1e12, tf_sust, "TFLOP/s"),
         # HBM bytes that must move: the bf16 SPS rows written per window (gathered stem slices + LiDAR slices) and
         # the same bytes read (variant planes / raster; re-reads across overlapping windows are L2 hits)
         "pack": ("border_gather_kernel (stem variants -> window SPS) + pack_strip_kernel (LiDAR)" if depth
@@ -443,6 +444,10 @@ def main():
     roofline = entry(dominant)
     roofline["traffic"] = traffic if (dominant == "conv_h1" and depth == 0) else None
     roofline["shared_stem_depth"] = int(depth)
+    if dominant == "tokens":   # what actually bounds this kernel: transcendentals, not the tensor pipe
+        sfu_ms = (4 * T_ * 128 + T_ * 128) * nwin / (16.0 * 148 * clocks.get("sm_mhz", 1965.0) * 1e6) * 1e3 if clocks.get("sm_mhz") else None
+        roofline["limiter"] = {"unit": "SFU (MUFU ex2 / tanh), 16 results per clock and SM (tools/probe/mufu_probe.cu)",
+                               "floor_ms_per_step": sfu_ms, "frac_of_floor": (sfu_ms / prof["tokens"][0]) if sfu_ms else None}
     roofline["breakdown_ms"] = {k: round(v[0], 3) for k, v in prof.items() if v[1]}
     roofline["other_kernels"] = [dict(entry(c), traffic=(traffic if (c == "conv_h1" and depth == 0) else None)) for c in kernels if c != dominant]
 

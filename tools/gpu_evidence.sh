@@ -11,11 +11,16 @@ PROF="python bench.py --steps 1 --warmup 3 --windows 65536 --no-cpu --no-e2e --n
 $PROF > gpurun_out/prof_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $PROF > gpurun_out/ncu_list.log 2>&1
 echo "ncu list rc=$?"
-# one whole step of the shared-stem scene path: 9 conv-1 variants, 25 conv-2 variants, then per chunk the LiDAR
-# gather, the variant gather, conv 3, the LiDAR stem and the token stage (second step: skip the first one's launches)
-$PROF > gpurun_out/prof_plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"conv_sps_tc|transformer_fwd|pack_strip_kernel|lidar_stem|border_gather" -s 44 -c 44 -o gpurun_out/prof_infer -f $PROF > gpurun_out/ncu_full.log 2>&1
-echo "ncu infer rc=$?"; tail -1 gpurun_out/ncu_full.log
+# full captures (no source import: gpurun brings back at most 64 MiB) of one launch of every kernel of the second
+# step of the shared-stem scene path.  Per step: 9 conv-1 variants (pair kernel), 25 conv-2 variants + 2 per-window
+# conv 3 (single-CTA kernel), then per chunk LiDAR strip gather, variant gather, LiDAR stem, token stage + cls tail.
+NCU="ncu --set full --clock-control none"
+$PROF > gpurun_out/prof_plain2.log 2>&1 || echo "plain run failed"
+$NCU -k regex:conv_sps_tc2_kernel -s 13 -c 1 -o gpurun_out/prof_conv1_interior -f $PROF > gpurun_out/ncu_full_a.log 2>&1; echo "ncu conv1 rc=$?"
+$NCU -k regex:conv_sps_tc_kernel -s 27 -c 1 -o gpurun_out/prof_conv2_corner -f $PROF > gpurun_out/ncu_full_b.log 2>&1; echo "ncu conv2 corner rc=$?"
+$NCU -k regex:conv_sps_tc_kernel -s 39 -c 1 -o gpurun_out/prof_conv2_interior -f $PROF > gpurun_out/ncu_full_c.log 2>&1; echo "ncu conv2 interior rc=$?"
+$NCU -k regex:conv_sps_tc_kernel -s 52 -c 1 -o gpurun_out/prof_conv3 -f $PROF > gpurun_out/ncu_full_d.log 2>&1; echo "ncu conv3 rc=$?"
+$NCU -k regex:"border_gather|tokens_tc|tokens_tail|transformer_fwd|lidar_stem|pack_strip_kernel" -s 10 -c 5 -o gpurun_out/prof_chunk -f $PROF > gpurun_out/ncu_full_e.log 2>&1; echo "ncu chunk rc=$?"
 if [ -n "$TRAIN" ]; then
 TPROF="python bench.py --no-infer --no-graph --steps 1 --warmup 3"
 $TPROF > gpurun_out/train_plain1.log 2>&1 && \
@@ -25,4 +30,4 @@ $TPROF > gpurun_out/train_plain2.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:"wgrad_sps_tc|transformer_bwd|bn_bwd_apply" -s 18 -c 19 -o gpurun_out/prof_train -f $TPROF > gpurun_out/ncu_train_full.log 2>&1
 echo "ncu train rc=$?"; tail -1 gpurun_out/ncu_train_full.log
 fi
-ls -la gpurun_out | head -40
+du -sh gpurun_out; ls -la gpurun_out | head -40

@@ -60,7 +60,7 @@ struct Scope {  // brackets one kernel launch with events when profiling is on
   } while (0)
 
 struct Workspace {
-  uint8_t *a0, *l0, *a1, *a2, *f, *l1, *l2;
+  uint8_t *a0, *l0, *a1, *a2, *f, *l1, *l2, *tscr;
   long long *off1, *off2, *oidx;
   long long bytes;
 };
@@ -81,6 +81,7 @@ Workspace carve(void* base, int n, int P, int S1, int S2) {
   w.off1 = reinterpret_cast<long long*>(take(8LL * n));
   w.off2 = reinterpret_cast<long long*>(take(8LL * n));
   w.oidx = reinterpret_cast<long long*>(take(8LL * n));
+  w.tscr = take((long long)vc::tokens_tc_scratch_bytes(n));     // cls records of the tcgen05 token kernel
   w.bytes = p - reinterpret_cast<uint8_t*>(base);
   return w;
 }
@@ -248,10 +249,9 @@ int forward_sps(const vc_model* m, const Workspace& w, int n, float* logits, con
     VC_LAUNCH(KC_CONV_L, st, vc::conv_sps_launch(w.l2, 2, m->w_l[2], m->scale_l[2], m->bias_l[2], w.f, 4, 32, m->nsplit_l[2], n, P, 9, 1,
                                                  0, 0, st));
   }
-  // token stage (see use_tokens_tc).  conv 1's output buffer (w.a1) is dead or unused by now and serves as the
-  // cls-record scratch of the tcgen05 kernel.
+  // token stage (see use_tokens_tc)
   if (use_tokens_tc(P, m->K))
-    VC_LAUNCH(KC_TOKENS, st, vc::tokens_tc_launch(w.f, m->tparams, n, P, m->K, logits, out_index, argmax_map, w.a1, st));
+    VC_LAUNCH(KC_TOKENS, st, vc::tokens_tc_launch(w.f, m->tparams, n, P, m->K, logits, out_index, argmax_map, w.tscr, st));
   else
     VC_LAUNCH(KC_TOKENS, st, vc::transformer_fwd_launch(w.f, m->tparams, n, P, m->K, logits, out_index, argmax_map, 0, 0, nullptr, st));
   return VC_OK;
