@@ -280,6 +280,7 @@ struct BorderGatherArgs {
   int S, ny, first, count, P, H, W, B, D, nbx, rows;
 };
 
+template <int S>    // slices per row: 16 / 8 / 4 for sharing depth 1 / 2 / 3 -- all S loads of a row are in flight together
 __global__ void __launch_bounds__(256) border_gather_kernel(BorderGatherArgs a) {
   const int P = a.P, PW = P + 1, PP = sps_pp(P), HALO = sps_halo(P), B = a.B, D = a.D;
   const int HB = sps_halo(B), PPB = sps_pp(B), NC = 2 * D + 1;
@@ -294,15 +295,14 @@ __global__ void __launch_bounds__(256) border_gather_kernel(BorderGatherArgs a) 
       const int ky = blk_index(y, a.H, B, D), kx = blk_index(x, a.W, B, D);
       const long long srow = HB + (long long)(ky * a.nbx + kx) * PPB + (y - blk_origin(ky, a.H, B, D)) * (B + 1) +
                              (x - blk_origin(kx, a.W, B, D));
-      src = reinterpret_cast<const uint4*>(a.v) + (long long)(border_class(i, P, D) * NC + border_class(j, P, D)) * a.S * a.RTb + srow;
+      src = reinterpret_cast<const uint4*>(a.v) + (long long)(border_class(i, P, D) * NC + border_class(j, P, D)) * S * a.RTb + srow;
     }
     uint4* dst = reinterpret_cast<uint4*>(a.out) + HALO + r;
-    if (src) {
-#pragma unroll 4
-      for (int s = 0; s < a.S; ++s) dst[(long long)s * a.RTo] = __ldg(src + (long long)s * a.RTb);
-    } else {
-      for (int s = 0; s < a.S; ++s) dst[(long long)s * a.RTo] = make_uint4(0u, 0u, 0u, 0u);
-    }
+    uint4 v[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) v[s] = src ? __ldg(src + (long long)s * a.RTb) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int s = 0; s < S; ++s) dst[(long long)s * a.RTo] = v[s];
   }
 }
 
@@ -322,7 +322,10 @@ int border_gather_launch(const void* variants, int S, int B, int D, int H, int W
   a.rows = (int)rows;
   long long blocks = (rows + 255) / 256;
   if (blocks > 148LL * 64) blocks = 148LL * 64;
-  border_gather_kernel<<<(int)blocks, 256, 0, stream>>>(a);
+  if (S == 16) border_gather_kernel<16><<<(int)blocks, 256, 0, stream>>>(a);
+  else if (S == 8) border_gather_kernel<8><<<(int)blocks, 256, 0, stream>>>(a);
+  else if (S == 4) border_gather_kernel<4><<<(int)blocks, 256, 0, stream>>>(a);
+  else return VC_ERR_ARG;
   return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
 }
 

@@ -669,17 +669,20 @@ __global__ void __launch_bounds__(256) tokens_tail_kernel(TailArgs a) {
   const TLayout& L = a.L;
   const TLayerOff& OL = L.layer[kLayers - 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int copy_bytes = L.pos;    // everything in front of the pos-embed table
+  // only the blob range this kernel reads: the last block's proj / fc1 / fc2 weights and every fp32 vector
+  // (contiguous: [layer[last].wproj, pos)); ~27 KB per CTA, so six CTAs share an SM
+  const int base = OL.wproj, copy_bytes = L.pos - OL.wproj;
   for (int i = threadIdx.x; i < copy_bytes / 16; i += blockDim.x)
-    reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(a.blob) + i);
+    reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(a.blob + base) + i);
   float* h_all = reinterpret_cast<float*>(smem + copy_bytes);
   float* h_s = h_all + warp * (kHidden + 64);
   float* logit_s = h_s + kHidden;
   __syncthreads();
-  const __nv_bfloat16* wproj = reinterpret_cast<const __nv_bfloat16*>(smem + OL.wproj);
-  const __nv_bfloat16* wfc1 = reinterpret_cast<const __nv_bfloat16*>(smem + OL.wfc1);
-  const __nv_bfloat16* wfc2 = reinterpret_cast<const __nv_bfloat16*>(smem + OL.wfc2);
-  const float* f32 = reinterpret_cast<const float*>(smem);
+  const uint8_t* sm0 = smem - base;      // blob offsets index this
+  const __nv_bfloat16* wproj = reinterpret_cast<const __nv_bfloat16*>(sm0 + OL.wproj);
+  const __nv_bfloat16* wfc1 = reinterpret_cast<const __nv_bfloat16*>(sm0 + OL.wfc1);
+  const __nv_bfloat16* wfc2 = reinterpret_cast<const __nv_bfloat16*>(sm0 + OL.wfc2);
+  const float* f32 = reinterpret_cast<const float*>(sm0);
   for (int b = blockIdx.x * nwarps + warp; b < a.n_patches; b += gridDim.x * nwarps) {
     const float* rec = a.tail + (long long)b * tc::kTailFloats;
     float o = 0.f, l = 0.f;
@@ -800,11 +803,11 @@ int tokens_tc_launch(const void* f_sps, const void* tparams, int n_patches, int 
   t.K = K;
   t.L = a.L;
   const int tail_threads = 256;
-  const size_t tail_smem = (size_t)a.L.pos + (size_t)(tail_threads / 32) * (kHidden + 64) * 4;
+  const size_t tail_smem = (size_t)(a.L.pos - a.L.layer[kLayers - 1].wproj) + (size_t)(tail_threads / 32) * (kHidden + 64) * 4;
   if (cudaFuncSetAttribute(tokens_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem) != cudaSuccess)
     return VC_ERR_CUDA;
   int tblocks = (n_patches + 7) / 8;
-  if (tblocks > 2 * num_sms) tblocks = 2 * num_sms;
+  if (tblocks > 6 * num_sms) tblocks = 6 * num_sms;
   tokens_tail_kernel<<<tblocks, tail_threads, tail_smem, stream>>>(t);
   return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
 }
