@@ -443,6 +443,11 @@ def main():
     dominant = max(("conv_h1", "tokens"), key=lambda c: prof[c][0])   # the single kernel with the largest share
     roofline = entry(dominant)
     roofline["traffic"] = traffic if (dominant == "conv_h1" and depth == 0) else None
+    ttpath = os.path.join(ROOT, "profiles", "r01_tokens_traffic.json")
+    if dominant == "tokens" and "tokens_tc" in roofline["kernel"] and os.path.isfile(ttpath):
+        tj = json.load(open(ttpath))      # dram bytes per launch from the committed ncu capture (same chunk size only)
+        if tj.get("chunk_windows") == min(args.chunk, count):
+            roofline["traffic"] = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     roofline["shared_stem_depth"] = int(depth)
     if dominant == "tokens":   # what actually bounds this kernel: transcendentals, not the tensor pipe
         sfu_ms = (4 * T_ * 128 + T_ * 128) * nwin / (16.0 * 148 * clocks.get("sm_mhz", 1965.0) * 1e6) * 1e3 if clocks.get("sm_mhz") else None
