@@ -44,6 +44,7 @@ def test_tc_kernel_exact_softmax_path_for_large_attention_weights():
     _, net = make_pair(16, 1, P, K, seed=9)
     with torch.no_grad():
         net.blocks[0].attn.qkv.weight[:64] *= 60.0      # q and k rows: scores of several hundred
+        net.blocks[1].attn.qkv.weight[:64] *= 60.0      # ... and for the cls query of the last block
     blob = net.pack_for_inference()["tparams"]
     f = _features(n, P, seed=7)
     want = ops.tokens_forward(f, blob, n, P, K)

@@ -243,19 +243,20 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) { 
     for (uint32_t i = tid; i < (kSlots * SLOT_BYTES + 2 * SLAB) / 16; i += kThreads)
       *reinterpret_cast<uint4*>(smem + SLOT0 + i * 16) = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    // static bound on |q.k| of block 1: row n of Wq / Wk contributes (||W_n diag(g)||^2, (W_n . beta + b_n)^2)
-    if (tid < 64) {
-      const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(a.blob + L.layer[0].wqkv) + tid * kLdD;
-      const float* g = reinterpret_cast<const float*>(a.blob + L.layer[0].ln1_g);
-      const float* be = reinterpret_cast<const float*>(a.blob + L.layer[0].ln1_b);
-      float f2 = 0.f, bs = __ldg(reinterpret_cast<const float*>(a.blob + L.layer[0].bqkv) + tid);
+    // static bound on |q.k| of both blocks: row n of Wq / Wk contributes (||W_n diag(g)||^2, (W_n . beta + b_n)^2)
+    if (tid < 128) {
+      const int l = tid >> 6, n = tid & 63;
+      const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(a.blob + L.layer[l].wqkv) + n * kLdD;
+      const float* g = reinterpret_cast<const float*>(a.blob + L.layer[l].ln1_g);
+      const float* be = reinterpret_cast<const float*>(a.blob + L.layer[l].ln1_b);
+      float f2 = 0.f, bs = __ldg(reinterpret_cast<const float*>(a.blob + L.layer[l].bqkv) + n);
       for (int c = 0; c < 32; ++c) {
         const float wv = __bfloat162float(w[c]);
         f2 = fmaf(wv * __ldg(g + c), wv * __ldg(g + c), f2);
         bs = fmaf(wv, __ldg(be + c), bs);
       }
       float* scr = reinterpret_cast<float*>(smem + SLOT0 + S_PBUF);
-      scr[2 * tid] = f2;
+      scr[2 * tid] = f2;           // [layer][64 rows][2]
       scr[2 * tid + 1] = bs * bs;
     }
     for (int i = tid; i < 128; i += kThreads) {
@@ -285,17 +286,20 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) { 
   // |s| <= qscale * (sqrt(32) ||Wq_h diag(g)||_F + ||Wq_h beta + bq_h||) * (same for k): LayerNorm output is
   // g * xhat + beta with ||xhat|| <= sqrt(32).  Below 2^100 neither 2^s nor its row sums leave fp32 / bf16
   // range, so the row maximum is not needed (bf16 rounding of the operands is far inside the margin).
-  bool exact_softmax = false;
+  bool exact_softmax = false, exact_cls = false;   // block 1 (all queries) / last block (cls query only)
   {
-    const float* scr = reinterpret_cast<const float*>(smem + SLOT0 + S_PBUF);
-    for (int h = 0; h < 4; ++h) {
-      float qf = 0.f, qb = 0.f, kf = 0.f, kb = 0.f;
-      for (int n = 0; n < 8; ++n) {
-        qf += scr[2 * (8 * h + n)]; qb += scr[2 * (8 * h + n) + 1];
-        kf += scr[2 * (32 + 8 * h + n)]; kb += scr[2 * (32 + 8 * h + n) + 1];
+    const float* scr0 = reinterpret_cast<const float*>(smem + SLOT0 + S_PBUF);
+    for (int l = 0; l < 2; ++l) {
+      const float* scr = scr0 + 128 * l;
+      for (int h = 0; h < 4; ++h) {
+        float qf = 0.f, qb = 0.f, kf = 0.f, kb = 0.f;
+        for (int n = 0; n < 8; ++n) {
+          qf += scr[2 * (8 * h + n)]; qb += scr[2 * (8 * h + n) + 1];
+          kf += scr[2 * (32 + 8 * h + n)]; kb += scr[2 * (32 + 8 * h + n) + 1];
+        }
+        const float bound = qscale * (sqrtf(32.f * qf) + sqrtf(qb)) * (sqrtf(32.f * kf) + sqrtf(kb));
+        if (!(bound < 100.f)) (l == 0 ? exact_softmax : exact_cls) = true;
       }
-      const float bound = qscale * (sqrtf(32.f * qf) + sqrtf(qb)) * (sqrtf(32.f * kf) + sqrtf(kb));
-      if (!(bound < 100.f)) exact_softmax = true;
     }
     __syncthreads();   // the scratch is part of a P buffer
   }
@@ -632,16 +636,18 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) { 
           d = fmaf(q1.z, __uint_as_float(kk[8 * h + 6]) + k1.z, d);
           d = fmaf(q1.w, __uint_as_float(kk[8 * h + 7]) + k1.w, d);
           sc[h] = r < T ? d : -INFINITY;
-          float mw = sc[h];
+          if (exact_cls) {           // the maximum over all keys is only needed when 2^s could overflow
+            float mw = sc[h];
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
-          if (lane == 0) wmax_s[wq * 4 + h] = mw;
+            for (int o = 16; o > 0; o >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+            if (lane == 0) wmax_s[wq * 4 + h] = mw;
+          }
         }
-        bar_sync(bar_id, 128);
+        if (exact_cls) bar_sync(bar_id, 128);
         float val[32], pl[4];
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
-          const float m = fmaxf(fmaxf(wmax_s[h], wmax_s[4 + h]), fmaxf(wmax_s[8 + h], wmax_s[12 + h]));
+          const float m = exact_cls ? fmaxf(fmaxf(wmax_s[h], wmax_s[4 + h]), fmaxf(wmax_s[8 + h], wmax_s[12 + h])) : 0.f;
           const float p = ex2(sc[h] - m);
           pl[h] = p;
           const float4 v0 = lds_f4(sb + VEC + (V_BQKV2 + 64 + 8 * h) * 4), v1 = lds_f4(sb + VEC + (V_BQKV2 + 68 + 8 * h) * 4);
