@@ -30,7 +30,7 @@
 //  * the last block only feeds the head through the cls token (x[:, 0]): K / V of every token
 //    come from one more MMA, the single-query attention is a thread-local dot product + a
 //    butterfly reduction per warp, and the cls row (proj, MLP, final LN, head) is finished by
-//    tokens_tail_kernel, one warp per patch, from a 704-byte record per patch.
+//    tokens_tail_kernel, one thread per patch, from a 704-byte record per patch.
 #include <math.h>
 #include <stdlib.h>
 #include <type_traits>
@@ -693,99 +693,125 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) { 
 }
 
 // ---- cls row of the last block: attention normalisation, proj, MLP, final LayerNorm, head ----
-// One warp per patch, one channel per lane (the tail of transformer_fwd_kernel as its own launch).
-__global__ void __launch_bounds__(256) tokens_tail_kernel(TailArgs a) {
+// One THREAD per patch (the tail of transformer_fwd_kernel as its own launch): the cls row is 32 channels, so
+// the whole tail is ~9.5 k FMAs with 32 independent accumulators per thread and no shuffles; the weights are
+// converted to fp32 once per CTA and read as warp-uniform (broadcast) 16-byte loads.
+constexpr int kTailThreads = 64;
+constexpr int T_WPROJ = 0, T_WFC1 = T_WPROJ + kD * kD, T_WFC2T = T_WFC1 + kHidden * kD, T_END = T_WFC2T + kHidden * kD;   // floats
+
+__global__ void __launch_bounds__(kTailThreads) tokens_tail_kernel(TailArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const TLayout& L = a.L;
   const TLayerOff& OL = L.layer[kLayers - 1];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  // only the blob range this kernel reads: the last block's proj / fc1 / fc2 weights and every fp32 vector
-  // (contiguous: [layer[last].wproj, pos)); ~27 KB per CTA, so six CTAs share an SM
-  const int base = OL.wproj, copy_bytes = L.pos - OL.wproj;
-  for (int i = threadIdx.x; i < copy_bytes / 16; i += blockDim.x)
-    reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(a.blob + base) + i);
-  float* h_all = reinterpret_cast<float*>(smem + copy_bytes);
-  float* h_s = h_all + warp * (kHidden + 64);
-  float* logit_s = h_s + kHidden;
-  __syncthreads();
-  const uint8_t* sm0 = smem - base;      // blob offsets index this
-  const __nv_bfloat16* wproj = reinterpret_cast<const __nv_bfloat16*>(sm0 + OL.wproj);
-  const __nv_bfloat16* wfc1 = reinterpret_cast<const __nv_bfloat16*>(sm0 + OL.wfc1);
-  const __nv_bfloat16* wfc2 = reinterpret_cast<const __nv_bfloat16*>(sm0 + OL.wfc2);
-  const float* f32 = reinterpret_cast<const float*>(sm0);
-  for (int b = blockIdx.x * nwarps + warp; b < a.n_patches; b += gridDim.x * nwarps) {
-    const float* rec = a.tail + (long long)b * tc::kTailFloats;
-    float o = 0.f, l = 0.f;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) { o += rec[w * 36 + lane]; l += rec[w * 36 + 32 + (lane >> 3)]; }
-    const float att = o / l;
-    float x0 = rec[144 + lane];
-    float y = f32[OL.bproj / 4 + lane];
-#pragma unroll
-    for (int k2 = 0; k2 < kD / 2; ++k2) {
-      const uint32_t wv = lds32(wproj + lane * kLdD + 2 * k2);
-      y = fmaf(bf_lo(wv), __shfl_sync(0xffffffffu, att, 2 * k2), y);
-      y = fmaf(bf_hi(wv), __shfl_sync(0xffffffffu, att, 2 * k2 + 1), y);
-    }
-    x0 += y;
-    float mean = warp_sum(x0) * (1.f / kD);
-    float d = x0 - mean;
-    float rstd = rsqrtf(warp_sum(d * d) * (1.f / kD) + 1e-6f);
-    const float y2 = d * rstd * f32[OL.ln2_g / 4 + lane] + f32[OL.ln2_b / 4 + lane];
-    float hacc[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) hacc[i] = f32[OL.bfc1 / 4 + lane + 32 * i];
-#pragma unroll
-    for (int k2 = 0; k2 < kD / 2; ++k2) {
-      const float ya = __shfl_sync(0xffffffffu, y2, 2 * k2), yb = __shfl_sync(0xffffffffu, y2, 2 * k2 + 1);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t wv = lds32(wfc1 + (lane + 32 * i) * kLdD + 2 * k2);
-        hacc[i] = fmaf(bf_lo(wv), ya, fmaf(bf_hi(wv), yb, hacc[i]));
-      }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h_s[lane + 32 * i] = gelu_erf(hacc[i]);
-    __syncwarp();
-    float z = f32[OL.bfc2 / 4 + lane];
-#pragma unroll 8
-    for (int k2 = 0; k2 < kHidden / 2; ++k2) {
-      const uint32_t wv = lds32(wfc2 + lane * kLdHid + 2 * k2);
-      const float2 hh = *reinterpret_cast<const float2*>(h_s + 2 * k2);
-      z = fmaf(bf_lo(wv), hh.x, fmaf(bf_hi(wv), hh.y, z));
-    }
-    x0 += z;
-    mean = warp_sum(x0) * (1.f / kD);
-    d = x0 - mean;
-    rstd = rsqrtf(warp_sum(d * d) * (1.f / kD) + 1e-6f);
-    const float c = d * rstd * f32[L.lnf_g / 4 + lane] + f32[L.lnf_b / 4 + lane];
-    const long long orow = a.out_index ? a.out_index[b] : (long long)b;
-    for (int k0 = 0; k0 < a.K; k0 += 32) {
-      const int k = k0 + lane;
-      float acc = k < a.K ? f32[L.bhead / 4 + k] : 0.f;
-#pragma unroll
-      for (int dd = 0; dd < kD; ++dd) {
-        const float cd = __shfl_sync(0xffffffffu, c, dd);
-        if (k < a.K) acc = fmaf(f32[L.whead / 4 + k * kD + dd], cd, acc);
-      }
-      if (k < a.K) {
-        a.logits[orow * a.K + k] = acc;
-        logit_s[k] = acc;
-      }
-    }
-    if (a.argmax_map) {
-      __syncwarp();
-      if (lane == 0) {
-        int best = 0;
-        float bv = logit_s[0];
-        for (int k = 1; k < a.K; ++k)
-          if (logit_s[k] > bv) { bv = logit_s[k]; best = k; }   // first maximum, like np.argmax
-        a.argmax_map[orow] = (unsigned char)best;
-      }
-    }
-    __syncwarp();
+  float* w = reinterpret_cast<float*>(smem);
+  {
+    const __nv_bfloat16* wproj = reinterpret_cast<const __nv_bfloat16*>(a.blob + OL.wproj);
+    const __nv_bfloat16* wfc1 = reinterpret_cast<const __nv_bfloat16*>(a.blob + OL.wfc1);
+    const __nv_bfloat16* wfc2 = reinterpret_cast<const __nv_bfloat16*>(a.blob + OL.wfc2);
+    for (int i = threadIdx.x; i < kD * kD; i += blockDim.x) w[T_WPROJ + i] = __bfloat162float(wproj[(i >> 5) * kLdD + (i & 31)]);
+    for (int i = threadIdx.x; i < kHidden * kD; i += blockDim.x) w[T_WFC1 + i] = __bfloat162float(wfc1[(i >> 5) * kLdD + (i & 31)]);
+    for (int i = threadIdx.x; i < kHidden * kD; i += blockDim.x)     // transposed: [hidden j][out n]
+      w[T_WFC2T + i] = __bfloat162float(wfc2[(i & 31) * kLdHid + (i >> 5)]);
   }
+  __syncthreads();
+  const float* fb = reinterpret_cast<const float*>(a.blob);      // fp32 vectors: warp-uniform read-only loads
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.n_patches) return;
+  const float4* rec = reinterpret_cast<const float4*>(a.tail + (long long)b * tc::kTailFloats);
+  float x0[kD], y[kD];
+  {
+    float o[kD], l[kHeads];
+#pragma unroll
+    for (int q4 = 0; q4 < 9; ++q4) {          // warp 0's partial: 32 o + 4 l
+      const float4 v = __ldg(rec + q4);
+      if (q4 < 8) { o[4 * q4] = v.x; o[4 * q4 + 1] = v.y; o[4 * q4 + 2] = v.z; o[4 * q4 + 3] = v.w; }
+      else { l[0] = v.x; l[1] = v.y; l[2] = v.z; l[3] = v.w; }
+    }
+#pragma unroll
+    for (int wq = 1; wq < 4; ++wq)
+#pragma unroll
+      for (int q4 = 0; q4 < 9; ++q4) {
+        const float4 v = __ldg(rec + wq * 9 + q4);
+        if (q4 < 8) { o[4 * q4] += v.x; o[4 * q4 + 1] += v.y; o[4 * q4 + 2] += v.z; o[4 * q4 + 3] += v.w; }
+        else { l[0] += v.x; l[1] += v.y; l[2] += v.z; l[3] += v.w; }
+      }
+#pragma unroll
+    for (int q4 = 0; q4 < 8; ++q4) {
+      const float4 v = __ldg(rec + 36 + q4);
+      x0[4 * q4] = v.x; x0[4 * q4 + 1] = v.y; x0[4 * q4 + 2] = v.z; x0[4 * q4 + 3] = v.w;
+    }
+#pragma unroll
+    for (int d = 0; d < kD; ++d) y[d] = o[d] / l[d >> 3];       // attention output of the cls query
+  }
+  // proj (+bias, +residual)
+#pragma unroll 4
+  for (int n = 0; n < kD; ++n) {
+    float acc = __ldg(fb + OL.bproj / 4 + n);
+    const float4* wr = reinterpret_cast<const float4*>(w + T_WPROJ + n * kD);
+#pragma unroll
+    for (int k4 = 0; k4 < kD / 4; ++k4) {
+      const float4 wv = wr[k4];
+      acc = fmaf(wv.x, y[4 * k4], fmaf(wv.y, y[4 * k4 + 1], fmaf(wv.z, y[4 * k4 + 2], fmaf(wv.w, y[4 * k4 + 3], acc))));
+    }
+    x0[n] += acc;
+  }
+  auto layer_norm = [&](const float (&x)[kD], float (&out)[kD], int g_off, int b_off) {
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < kD; ++d) s += x[d];
+    const float mean = s * (1.f / kD);
+    float v = 0.f;
+#pragma unroll
+    for (int d = 0; d < kD; ++d) { const float dd = x[d] - mean; v = fmaf(dd, dd, v); }
+    const float rs = rsqrtf(v * (1.f / kD) + 1e-6f);
+#pragma unroll
+    for (int d = 0; d < kD; ++d) out[d] = (x[d] - mean) * rs * __ldg(fb + g_off / 4 + d) + __ldg(fb + b_off / 4 + d);
+  };
+  layer_norm(x0, y, OL.ln2_g, OL.ln2_b);
+  // fc1 + GELU + fc2 (+bias, +residual), one hidden unit at a time: 32 FMAs in, 32 FMAs out
+  float z[kD];
+#pragma unroll
+  for (int n = 0; n < kD; ++n) z[n] = __ldg(fb + OL.bfc2 / 4 + n);
+#pragma unroll 2
+  for (int j = 0; j < kHidden; ++j) {
+    float h0 = __ldg(fb + OL.bfc1 / 4 + j), h1 = 0.f;
+    const float4* w1 = reinterpret_cast<const float4*>(w + T_WFC1 + j * kD);
+#pragma unroll
+    for (int k4 = 0; k4 < kD / 4; k4 += 2) {
+      const float4 wa = w1[k4], wb = w1[k4 + 1];
+      h0 = fmaf(wa.x, y[4 * k4], fmaf(wa.y, y[4 * k4 + 1], fmaf(wa.z, y[4 * k4 + 2], fmaf(wa.w, y[4 * k4 + 3], h0))));
+      h1 = fmaf(wb.x, y[4 * k4 + 4], fmaf(wb.y, y[4 * k4 + 5], fmaf(wb.z, y[4 * k4 + 6], fmaf(wb.w, y[4 * k4 + 7], h1))));
+    }
+    const float hv = gelu_erf(h0 + h1);
+    const float4* w2 = reinterpret_cast<const float4*>(w + T_WFC2T + j * kD);
+#pragma unroll
+    for (int n4 = 0; n4 < kD / 4; ++n4) {
+      const float4 wv = w2[n4];
+      z[4 * n4] = fmaf(wv.x, hv, z[4 * n4]);
+      z[4 * n4 + 1] = fmaf(wv.y, hv, z[4 * n4 + 1]);
+      z[4 * n4 + 2] = fmaf(wv.z, hv, z[4 * n4 + 2]);
+      z[4 * n4 + 3] = fmaf(wv.w, hv, z[4 * n4 + 3]);
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < kD; ++n) x0[n] += z[n];
+  layer_norm(x0, y, L.lnf_g, L.lnf_b);
+  // head + first-maximum argmax (like np.argmax)
+  const long long orow = a.out_index ? a.out_index[b] : (long long)b;
+  int best = 0;
+  float bv = -INFINITY;
+  for (int k = 0; k < a.K; ++k) {
+    float acc = __ldg(fb + L.bhead / 4 + k);
+    const float4* wh = reinterpret_cast<const float4*>(fb + L.whead / 4 + k * kD);
+#pragma unroll
+    for (int d4 = 0; d4 < kD / 4; ++d4) {
+      const float4 wv = __ldg(wh + d4);
+      acc = fmaf(wv.x, y[4 * d4], fmaf(wv.y, y[4 * d4 + 1], fmaf(wv.z, y[4 * d4 + 2], fmaf(wv.w, y[4 * d4 + 3], acc))));
+    }
+    a.logits[orow * a.K + k] = acc;
+    if (acc > bv) { bv = acc; best = k; }
+  }
+  if (a.argmax_map) a.argmax_map[orow] = (unsigned char)best;
 }
 
 size_t tokens_tc_scratch_bytes(int n_patches) { return (size_t)n_patches * tc::kTailFloats * 4; }
@@ -832,13 +858,10 @@ int tokens_tc_launch(const void* f_sps, const void* tparams, int n_patches, int 
   t.n_patches = n_patches;
   t.K = K;
   t.L = a.L;
-  const int tail_threads = 256;
-  const size_t tail_smem = (size_t)(a.L.pos - a.L.layer[kLayers - 1].wproj) + (size_t)(tail_threads / 32) * (kHidden + 64) * 4;
+  const size_t tail_smem = (size_t)T_END * 4;
   if (cudaFuncSetAttribute(tokens_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem) != cudaSuccess)
     return VC_ERR_CUDA;
-  int tblocks = (n_patches + 7) / 8;
-  if (tblocks > 6 * num_sms) tblocks = 6 * num_sms;
-  tokens_tail_kernel<<<tblocks, tail_threads, tail_smem, stream>>>(t);
+  tokens_tail_kernel<<<(n_patches + kTailThreads - 1) / kTailThreads, kTailThreads, tail_smem, stream>>>(t);
   return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
 }
 
