@@ -421,7 +421,7 @@ def main():
                     if depth >= 1 else "conv_sps_tc2_kernel (HSI stem conv1, tcgen05)", "tensor", w_c1, 1e12, tf_sust, "TFLOP/s"),
         "conv_h2": ("conv_sps_tc_kernel x 25 variants, multi-plane input (HSI conv 2, tcgen05)" if depth >= 2
                     else "conv_sps_tc_kernel (HSI stem conv2, tcgen05)", "tensor", w_c2, 1e12, tf_sust, "TFLOP/s"),
-        "tokens": ("tokens_tc_kernel + tokens_tail_kernel (token stage, tcgen05)" if (100 <= P * P + 1 <= 128 and os.environ.get("VITCNN_TOKENS_IMPL") != "0")
+        "tokens": ("tokens_tc_kernel + tokens_tail_kernel (token stage, tcgen05)" if (82 <= P * P + 1 <= 128 and os.environ.get("VITCNN_TOKENS_IMPL") != "0")
                    else "transformer_fwd_kernel (token stage, mma.sync)", "tensor", float(token_flops) * nwin, 1e12, tf_sust, "TFLOP/s"),
         # HBM bytes that must move: the bf16 SPS rows written per window (gathered stem slices + LiDAR slices) and
         # the same bytes read (variant planes / raster; re-reads across overlapping windows are L2 hits)

@@ -209,16 +209,17 @@ int zero_halos(const Workspace& w, int n, int P, cudaStream_t st) {
 }
 
 // Which token-stage kernel: the tcgen05 kernel (tokens_tc.cu) treats one patch as one M = 128 tile, so it wins where
-// the token set nearly fills the tile (measured per 32 768 patches: P = 11 1.52 vs 1.75 ms, P = 9 1.40 vs 1.42 ms,
-// P = 7 1.27 vs 0.95 ms): default = tcgen05 for 100 <= P*P + 1 <= 128, mma.sync otherwise.
-// VITCNN_TOKENS_IMPL=0 / 1 forces mma.sync / tcgen05 (where it applies).
+// the token set fills most of the tile (measured per 32 768 patches, tcgen05 vs mma.sync: P = 11 1.41 vs 1.75 ms,
+// P = 10 1.41 vs 1.51, P = 9 1.29 vs 1.42, P = 8 1.28 vs 1.17, P = 7 1.27 vs 0.95): default = tcgen05 for
+// 82 <= P*P + 1 <= 128 (P = 9, 10, 11), mma.sync otherwise.  VITCNN_TOKENS_IMPL=0 / 1 forces mma.sync / tcgen05
+// (where it applies).
 bool use_tokens_tc(int P, int K) {
   static const int forced = [] {
     const char* e = getenv("VITCNN_TOKENS_IMPL");
     return e ? atoi(e) : -1;
   }();
   if (!vc::tokens_tc_supported(P, K) || forced == 0) return false;
-  return forced == 1 || P * P + 1 >= 100;
+  return forced == 1 || P * P + 1 >= 82;
 }
 
 int forward_sps(const vc_model* m, const Workspace& w, int n, float* logits, const long long* out_index,
