@@ -13,6 +13,7 @@ from __future__ import annotations
 import ctypes
 import math
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -322,6 +323,19 @@ class ViTCNN(nn.Module):
                        "vc_forward_patches")
         return logits
 
+    def _starts_on_device(self, starts, dev) -> torch.Tensor:
+        """Window-start list as an int32 device tensor.  Cached by content: a pageable-host upload blocks the
+        host until the stream has drained, which would serialise the sub-bands of predict_scene_host."""
+        arr = np.ascontiguousarray(starts, dtype=np.int32)
+        key = (str(dev), arr.tobytes())
+        cache = self.__dict__.setdefault("_starts_cache", {})
+        t = cache.get(key)
+        if t is None:
+            if len(cache) >= 256:
+                cache.clear()
+            t = cache[key] = torch.from_numpy(arr).to(dev)
+        return t
+
     # ---- full-scene inference ---------------------------------------------------------------------
     @torch.no_grad()
     def predict_scene(self, img1: torch.Tensor, img2: torch.Tensor, stride: int = 1, chunk: int = 2048,
@@ -366,8 +380,7 @@ class ViTCNN(nn.Module):
             img1, img2 = img1[y_lo:y_hi], img2[y_lo:y_hi]
             lg_view, am_view = logits_map[y_lo:y_hi], argmax_map[y_lo:y_hi]
             H = y_hi - y_lo
-            xs = torch.from_numpy(np.ascontiguousarray(xs, dtype=np.int32)).to(dev)
-            ys = torch.from_numpy(ys).to(dev)
+            xs, ys = self._starts_on_device(xs, dev), self._starts_on_device(ys, dev)
             L = _lib.lib()
             with torch.cuda.device(dev):
                 pk = self.pack_for_inference()
