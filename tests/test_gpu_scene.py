@@ -100,3 +100,23 @@ def test_shared_stem_is_bit_identical_to_the_per_window_path(cfg):
     torch.cuda.synchronize()
     assert (shared != 0).any()
     assert torch.equal(shared, plain) and torch.equal(am_s, am_p)
+
+
+@pytest.mark.parametrize("split", ["blocks", "equal"])
+def test_host_pipeline_sub_bands_reproduce_the_single_pass_map(split, monkeypatch):
+    """predict_scene_host cuts the band into sub-bands (whole block rows of the shared stem, or equal parts) and
+    pipelines upload / compute / download; whatever the cut, the maps must equal predict_scene's bit for bit."""
+    import vitcnn_b200
+    monkeypatch.setenv("VITCNN_SUBBAND_SPLIT", split)
+    H, W, C1, C2, P, K = 131, 52, 32, 1, 11, 6
+    _, ours = make_pair(C1, C2, P, K, seed=7)
+    img1, img2, _ = R.synthetic_scene(H, W, C1, C2, K, seed=9)
+    t1, t2 = torch.from_numpy(img1), torch.from_numpy(img2)
+    full, amax = ours.predict_scene(t1.to(DEV), t2.to(DEV), chunk=700)
+    for world in (1, 2):
+        lg = torch.zeros(H, W, K).pin_memory()
+        am = torch.zeros(H, W, dtype=torch.uint8).pin_memory()
+        for rank in range(world):
+            vitcnn_b200.predict_scene_host(ours, t1.pin_memory(), t2.pin_memory(), rank=rank, world=world, chunk=700,
+                                           logits_out=lg, argmax_out=am, device=DEV)
+        assert torch.equal(lg, full.cpu()) and torch.equal(am, amax.cpu())

@@ -66,3 +66,30 @@ def test_save_model_naming_and_round_trip(tmp_path, monkeypatch):
     assert all(torch.equal(v, sd[k]) for k, v in ref.state_dict().items())
     other = save_model("x", {"a": 1}, "SVM", "d", "train", "last")
     assert other.endswith(".pkl") and os.path.isfile(other)
+
+
+@pytest.mark.parametrize("P", [7, 9, 11, 15])
+@pytest.mark.parametrize("block,depth", [(31, 2), (31, 3), (15, 1), (0, 0)])
+def test_subband_bounds_cover_the_band_in_whole_block_rows(P, block, depth):
+    """Sub-bands of the host pipeline (scene.py): contiguous, cover every window row once, at most `pipeline`
+    of them, and cut so that the shared stem's block rows (csrc/vc_common.cuh blk_count) never exceed what
+    equal parts would need."""
+    from vitcnn_b200.utils import subband_bounds
+
+    def block_rows(wr):          # blk_count of a sub-band of wr window rows (raster rows = wr + P - 1)
+        ext = wr + P - 1
+        return 1 if ext <= block else (ext - block + block - 2 * depth - 1) // (block - 2 * depth) + 1
+
+    for nrows in list(range(1, 130)) + [339, 340, 1000]:
+        for pipeline in (1, 2, 6, 8):
+            b = subband_bounds(nrows, P, pipeline, block, depth)
+            assert b[0] == 0 and b[-1] == nrows and len(b) - 1 <= pipeline
+            sizes = np.diff(b)
+            assert (sizes > 0).all()
+            if block and block - (P - 1) > 0:
+                nsub = max(1, min(pipeline, nrows // 21))
+                equal = [(nrows * k) // nsub for k in range(nsub + 1)]
+                assert sum(block_rows(s) for s in sizes) <= sum(block_rows(s) for s in np.diff(equal)) + (len(sizes) > nsub)
+    assert subband_bounds(339, 11, 8, 31, 2) == [0, 21, 69, 117, 165, 213, 261, 309, 339]      # Houston: 15 block rows
+    assert subband_bounds(339, 11, 6, 31, 2) == [0, 48, 96, 144, 192, 267, 339]                # 14 block rows
+    assert subband_bounds(339, 11, 6, 31, 2, lead_small=True) == [0, 21, 69, 117, 192, 267, 339]

@@ -4,15 +4,19 @@ This is the `e2e` path of bench.py and what test() uses; row bands need no colle
 (SURVEY.md section 8(e))."""
 from __future__ import annotations
 
+import ctypes
+import os
+
 import torch
 
-from .utils import band_geometry
+from . import _lib
+from .utils import band_geometry, subband_bounds
 
 
 @torch.no_grad()
 def predict_scene_host(net, img1: torch.Tensor, img2: torch.Tensor, stride: int = 1, rank: int = 0, world: int = 1,
                        chunk: int = 2048, logits_out: torch.Tensor = None, argmax_out: torch.Tensor = None,
-                       device=None, pipeline: int = 8):
+                       device=None, pipeline: int = None):
     """img1 f32 [H,W,C1], img2 f32 [H,W,C2] CPU tensors (pinned for async copies).  Writes the
     rows owned by ``rank`` into ``logits_out`` f32 [H,W,K] / ``argmax_out`` uint8 [H,W] (CPU,
     allocated zero-filled when None) and returns them.  Rows no window is centred on are not
@@ -28,15 +32,27 @@ def predict_scene_host(net, img1: torch.Tensor, img2: torch.Tensor, stride: int 
     if geo["count"] == 0:
         return logits_out, argmax_out
     x0, x1 = geo["x0"], geo["x1"]
+    if pipeline is None:
+        pipeline = int(os.environ.get("VITCNN_PIPELINE", "6"))
     # Software pipeline over `pipeline` sub-bands of the band: the pinned-host -> HBM upload of sub-band
     # k+1 and the HBM -> host download of sub-band k-1 run on copy streams while sub-band k computes,
     # so the PCIe traffic (386 MB up, 42 MB down for a Houston scene) hides behind the kernels.
     xs_rel, P2 = geo["xs"], P // 2
     nrows = len(xs_rel)
     # sub-bands of at least 21 window rows (31 raster rows at P = 11): the shared stem of vc_scene_infer needs
-    # 31-row rasters, and shorter sub-bands would spend their time on launch tails
+    # 31-row rasters, and shorter sub-bands would spend their time on launch tails.  Dense scenes (stride 1)
+    # are cut at whole block rows of that stem (utils.subband_bounds).  Measured on B200, Houston scene
+    # (tools/gpu_subbands.sh): 8 equal parts (16 block rows) 60.0 ms; whole block rows at 8 / 7 / 6 / 5 sub-bands
+    # 59.4 / 59.4 / 58.2 / 58.2 ms (15 / 15 / 14 / 14 block rows; one uncut band needs 13); a 21-row lead
+    # sub-band (shorter first upload) gains nothing (58.4 / 58.5 ms at 5 / 6), so the default is 6 even ones
     nsub = max(1, min(int(pipeline), nrows // 21))
     bounds = [(nrows * k) // nsub for k in range(nsub + 1)]
+    if stride == 1 and nsub > 1 and os.environ.get("VITCNN_SUBBAND_SPLIT", "blocks") != "equal":
+        depth = _shared_depth(net, nrows // nsub + P - 1, W, (nrows // nsub) * len(geo["ys"]), chunk, dev)
+        if depth > 0:
+            bounds = subband_bounds(nrows, P, pipeline, 31 if depth >= 2 else 15, depth,
+                                    lead_small=os.environ.get("VITCNN_SUBBAND_LEAD", "even") == "small")
+            nsub = len(bounds) - 1
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream()
         up, down = _copy_streams(dev)
@@ -76,6 +92,20 @@ def predict_scene_host(net, img1: torch.Tensor, img2: torch.Tensor, stride: int 
         main.wait_stream(down)
         main.synchronize()
     return logits_out, argmax_out
+
+
+def _shared_depth(net, rows: int, W: int, count: int, chunk: int, dev) -> int:
+    """Sharing depth vc_scene_infer picks for a sub-band of ``rows`` raster rows holding ``count`` windows
+    (0: per-window stem), asked of the library with the chunking predict_scene will use."""
+    if count <= 0:
+        return 0
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        pk = net.pack_for_inference()
+    n_chunks = -(-count // int(chunk))
+    chunk_eff = -(-count // n_chunks)
+    ws = L.vc_scene_workspace_bytes(ctypes.byref(pk["struct"]), rows, W, chunk_eff)
+    return max(0, int(L.vc_scene_shared_depth(ctypes.byref(pk["struct"]), rows, W, chunk_eff, count, ws)))
 
 
 _STREAMS = {}

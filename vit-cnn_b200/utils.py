@@ -75,6 +75,42 @@ def band_geometry(H: int, W: int, P: int, stride: int, rank: int, world: int) ->
                 xs=xs[r0:r1 + 1] - x0, ys=ys)
 
 
+def subband_bounds(nrows: int, P: int, pipeline: int, block: int = 0, depth: int = 0, min_rows: int = 21,
+                   lead_small: bool = False) -> list:
+    """Cut the ``nrows`` contiguous (stride 1) window rows of a band into at most ``pipeline`` sub-bands for
+    the upload / compute / download pipeline of predict_scene_host; returns the bounds [0, ..., nrows].
+    ``block`` / ``depth`` = the scene-block edge B and sharing depth D of the library's shared stem
+    (csrc/vc_common.cuh blk_step / blk_count): n block rows are exact for B + (B - 2D)(n - 1) raster rows =
+    that many - (P - 1) window rows, so sub-bands are sized to whole block rows (a cut elsewhere makes both
+    neighbours recompute a block row) and handed out in ascending size; ``lead_small`` makes the first one
+    the smallest allowed (a shorter first upload, the one nothing hides; measured: no gain).  ``block == 0``
+    (no shared stem): equal sub-bands of >= ``min_rows`` rows."""
+    if nrows <= 0:
+        return [0, 0]
+    step = block - 2 * depth
+    cap1 = block - (P - 1)                       # window rows one block row serves
+    if block <= 0 or depth <= 0 or step <= 0 or cap1 <= 0:
+        nsub = max(1, min(int(pipeline), nrows // min_rows))
+        return [(nrows * k) // nsub for k in range(nsub + 1)]
+    n_min = 1 + max(0, -(-(min_rows - cap1) // step))          # block rows of the smallest sub-band allowed
+    total_1 = 1 + max(0, -(-(nrows - cap1) // step))           # block rows of the band cut nowhere
+    nsub = max(1, min(int(pipeline), total_1 // n_min))
+    total = max(nsub * n_min, -(-(nrows - nsub * (cap1 - step)) // step))
+    if lead_small and nsub > 1 and total - n_min >= (nsub - 1) * n_min:
+        rest, m = total - n_min, nsub - 1        # the first sub-band is the smallest allowed, the others share the rest
+        per = [n_min] + [rest // m + (1 if k >= m - rest % m else 0) for k in range(m)]
+    else:
+        per = [total // nsub + (1 if k >= nsub - total % nsub else 0) for k in range(nsub)]      # ascending
+    bounds, left = [0], nrows
+    for k, n in enumerate(per):
+        later = sum(cap1 + step * (m - 1) for m in per[k + 1:])
+        take = min(cap1 + step * (n - 1), left)
+        take = max(take if k < nsub - 1 else left, left - later)
+        bounds.append(bounds[-1] + take)
+        left -= take
+    return bounds
+
+
 def seed_torch(seed: int = 1029) -> None:
     """utils.py:887-895: seed Python, numpy and torch RNGs (the determinism contract of the
     sample shuffle, datasets.py:506, and of weight initialisation)."""
