@@ -272,7 +272,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--chunk", type=int, default=int(os.environ.get("VITCNN_CHUNK", "32768")))
+    ap.add_argument("--chunk", type=int, default=int(os.environ.get("VITCNN_CHUNK", "131072")))
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--windows", type=int, default=0, help="profiling aid: only the first N windows of the band")
     ap.add_argument("--no-cpu", action="store_true", help="profiling aid: skip the cpu_baseline leg")

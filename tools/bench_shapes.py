@@ -45,7 +45,7 @@ for name, H, W, C1, C2, K, P in CASES:
     net = vitcnn_b200.ViTCNN(C1, C2, patch_size=P, num_classes=K).to(dev).eval()
     lm = torch.zeros(H, W, K, device=dev)
     am = torch.zeros(H, W, dtype=torch.uint8, device=dev)
-    ms_inf = timed(lambda: net.predict_scene(img1, img2, chunk=32768, logits_map=lm, argmax_map=am))
+    ms_inf = timed(lambda: net.predict_scene(img1, img2, logits_map=lm, argmax_map=am))
     pk = net.pack_for_inference()
     import ctypes
     nwin = (H - P + 1) * (W - P + 1)

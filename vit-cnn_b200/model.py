@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -22,6 +23,10 @@ from . import _lib
 HSI_PLANES = (128, 64, 32)
 LIDAR_PLANES = (8, 16, 32)
 _W_BUDGET = 180_000   # bytes of shared memory one CTA may spend on resident conv weights
+# Windows per launch group of scene inference.  Measured on B200, Houston scene (tools/chunk_sweep.py,
+# profiles/r01_chunk_sweep.jsonl): 32768 -> 54.8 ms, 65536 -> 54.0, 131072 -> 53.5, 196608 / 262144 -> 52.8 (all maps
+# bit-identical); the workspace is sized to min(chunk, windows of the call): 26 GB of the 180 GB at 131072.
+SCENE_CHUNK = int(os.environ.get("VITCNN_CHUNK", "131072"))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -338,7 +343,7 @@ class ViTCNN(nn.Module):
 
     # ---- full-scene inference ---------------------------------------------------------------------
     @torch.no_grad()
-    def predict_scene(self, img1: torch.Tensor, img2: torch.Tensor, stride: int = 1, chunk: int = 2048,
+    def predict_scene(self, img1: torch.Tensor, img2: torch.Tensor, stride: int = 1, chunk: int = SCENE_CHUNK,
                       window_range=None, logits_map=None, argmax_map=None, xs=None, ys=None):
         """Sliding-window inference over device-resident rasters img1 f32 [H,W,C1], img2 f32
         [H,W,C2] (the loop of test(), model_utils.py:1086-1129).  Returns (logits_map f32

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 import torch.optim as optim
 
-from .model import ViTCNN
+from .model import SCENE_CHUNK, ViTCNN
 
 MODEL_NAMES = ("ViT-CNN",)
 
@@ -80,7 +80,7 @@ def test(run, net, img1, img2, hyperparams):
     from .scene import predict_scene_host
     t1 = torch.as_tensor(np.ascontiguousarray(img1, dtype=np.float32))
     t2 = torch.as_tensor(np.ascontiguousarray(img2, dtype=np.float32))
-    chunk = int(hyperparams.get("scene_chunk", 2048))
+    chunk = int(hyperparams.get("scene_chunk", SCENE_CHUNK))
     logits_map, _ = predict_scene_host(net, t1, t2, stride=hyperparams["test_stride"], chunk=chunk, device=device)
     return logits_map.numpy().astype(np.float64)
 

@@ -10,12 +10,13 @@ import os
 import torch
 
 from . import _lib
+from .model import SCENE_CHUNK
 from .utils import band_geometry, subband_bounds
 
 
 @torch.no_grad()
 def predict_scene_host(net, img1: torch.Tensor, img2: torch.Tensor, stride: int = 1, rank: int = 0, world: int = 1,
-                       chunk: int = 2048, logits_out: torch.Tensor = None, argmax_out: torch.Tensor = None,
+                       chunk: int = SCENE_CHUNK, logits_out: torch.Tensor = None, argmax_out: torch.Tensor = None,
                        device=None, pipeline: int = None):
     """img1 f32 [H,W,C1], img2 f32 [H,W,C2] CPU tensors (pinned for async copies).  Writes the
     rows owned by ``rank`` into ``logits_out`` f32 [H,W,K] / ``argmax_out`` uint8 [H,W] (CPU,
