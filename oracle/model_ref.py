@@ -2,9 +2,15 @@
 
 TEST INFRASTRUCTURE ONLY - see ``oracle/data_ref.py`` for the import rule.
 
-PARITY UNPINNED: the reference ships no ``ViT-CNN`` / ``FICNN_VIT`` source, no
-checkpoint, no test and no golden vector for the model, so
-this file is a reconstruction from the surviving evidence, not a transcription:
+PARITY: the TOKEN STAGE (cls / pos-embed, the two pre-norm blocks with MHSA and the GELU MLP, final
+LayerNorm, cls pooling, head: everything after the fusion conv) is PINNED to the reference's own source:
+``tests/golden/make_block_golden.py`` extracts ``Attention`` / ``Block`` / ``Mlp`` and
+``VisionTransformer._pos_embed / forward_features / forward_head`` by AST from the vendored timm files
+and runs them unchanged; ``tests/test_oracle_blocks_cpu.py`` checks this file against their outputs
+(committed fixture ``tests/golden/block_golden.npz``; bit for bit against the live source when
+``/root/reference`` is mounted).  The CNN STEM IS PARITY UNPINNED: the reference ships no ``ViT-CNN`` /
+``FICNN_VIT`` source, no checkpoint, no test and no golden vector for it, so that
+half is a reconstruction from the surviving evidence, not a transcription:
 
 * constructor contract and training recipe  - model_utils.py:206-218
 * conv_bn_relu idiom (Conv2d 3x3 pad 1 bias -> BatchNorm2d -> ReLU), planes
@@ -135,20 +141,26 @@ class ViTCNNRef(nn.Module):
                 nn.init.ones_(m.weight)
                 nn.init.zeros_(m.bias)
 
+    def embed_tokens(self, x):
+        """vision_transformer.py:598-629 (_pos_embed, class token, no_embed_class False): x [B, P*P, D]."""
+        x = torch.cat([self.cls_token.expand(x.shape[0], -1, -1), x], dim=1)
+        return self.pos_drop(x + self.pos_embed)
+
     def tokens(self, hsi, lidar):
         h = self.hsi_stem(hsi)
         l = self.lidar_stem(lidar)
         f = self.fusion(torch.cat([h, l], dim=1))           # [B, D, P, P]
-        x = f.flatten(2).transpose(1, 2)                    # [B, P*P, D], row-major pixels
-        x = torch.cat([self.cls_token.expand(x.shape[0], -1, -1), x], dim=1)
-        return self.pos_drop(x + self.pos_embed)
+        return self.embed_tokens(f.flatten(2).transpose(1, 2))     # [B, P*P, D], row-major pixels (patch_embed.py:65,89)
 
-    def forward(self, hsi, lidar):
-        x = self.tokens(hsi, lidar)
+    def forward_tokens(self, x):
+        """vision_transformer.py:682-702 (forward_features after the embedding, forward_head with cls pooling)."""
         for blk in self.blocks:
             x = blk(x)
         x = self.norm(x)
         return self.head(x[:, 0])
+
+    def forward(self, hsi, lidar):
+        return self.forward_tokens(self.tokens(hsi, lidar))
 
 
 def randomize_bn_stats(model: nn.Module, seed: int = 1) -> None:

@@ -1,12 +1,15 @@
-"""Import the reference toolkit's own data / loop modules (dev container only).
+"""Import the reference toolkit's own data / loop modules, unmodified.
 
-TEST INFRASTRUCTURE ONLY.  ``/root/reference`` exists in the dev container and not
-on the GPU box, so this is used by ``tests/golden/make_golden.py`` (fixture
-generation) and by not-gpu tests that skip when the tree is absent.
+TEST INFRASTRUCTURE ONLY.  ``/root/reference`` exists in the dev container and not on the GPU
+box; ``tools/install_ref.sh`` (run by ``__graft_entry__.build()``) puts the four files the loops
+live in (``utils.py``, ``datasets.py``, ``model_utils.py``, ``losses.py``) into the git-ignored
+``baseline/_ref/``, which travels to the box.  Used by ``tests/golden/make_golden.py`` (fixture
+generation), by the tests that drive the reference's own ``train()`` / ``val()`` / ``test()`` over
+the CUDA module, and by ``bench.py``'s reference arm.
 
-Recipe: SURVEY.md Appendix B - stub the absent third-party modules and the 13
-first-party model files the reference imports but does not ship, then import
-``utils``, ``datasets`` and ``model_utils`` unmodified.
+Recipe: SURVEY.md Appendix B - stub the absent third-party modules and every first-party model
+file ``model_utils.py`` imports that is not there (13 are never shipped; under ``baseline/_ref``
+none is), then import ``utils``, ``datasets`` and ``model_utils`` as they are.
 """
 from __future__ import annotations
 
@@ -14,7 +17,18 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("VITCNN_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root() -> str:
+    cands = [os.environ.get("VITCNN_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "model_utils.py")):
+            return c
+    return cands[1]
+
+
+REFERENCE_ROOT = _find_root()
 
 _THIRD_PARTY = ["seaborn", "spectral", "visdom", "matplotlib", "matplotlib.pyplot"]
 _MISSING_FIRST_PARTY = {
@@ -28,6 +42,14 @@ _MISSING_FIRST_PARTY = {
     "model.S2ENet_ResNet18": ["S2ENet_ResNet18"], "model.multiScaleCNN": ["multiScaleCNN"],
     "model.FI_CNN3D": ["FI_CNN3D"], "model.VIT": ["VIT"], "model.proposed": ["proposed"],
     "model.nncnet": ["moco_based_NNCNet"],
+}
+# model files the reference does ship (importable from /root/reference): stubbed too when the root is
+# baseline/_ref, which holds the loop modules only
+_SHIPPED_FIRST_PARTY = {
+    "model.compare_method.MFT": ["MFT"], "model.compare_method.GLT_Net.GLT_Net": ["GLT"],
+    "model.compare_method.spectralformer": ["SpectralFormer"], "model.compare_method.FusAtNet": ["FusAtNet"],
+    "model.compare_method.EndNet": ["EndNet"], "model.compare_method.S2EFT": ["ViT"],
+    "model.compare_method.DML_Hong": ["Early_fusion_CNN", "Middle_fusion_CNN", "Late_fusion_CNN", "Cross_fusion_CNN"],
 }
 
 
@@ -49,9 +71,19 @@ def import_reference(with_model_utils: bool = True):
     import datasets as ref_datasets    # noqa
     ref_model_utils = None
     if with_model_utils:
-        for mod, names in _MISSING_FIRST_PARTY.items():
+        stubs = dict(_MISSING_FIRST_PARTY)
+        for mod, names in _SHIPPED_FIRST_PARTY.items():
+            if not os.path.isfile(os.path.join(REFERENCE_ROOT, *mod.split(".")) + ".py"):
+                stubs[mod] = names
+        if not os.path.isdir(os.path.join(REFERENCE_ROOT, "model")):          # parent packages of the stubs
+            for mod in list(stubs):
+                parts = mod.split(".")
+                for k in range(1, len(parts)):
+                    stubs.setdefault(".".join(parts[:k]), [])
+        for mod, names in stubs.items():
             if mod not in sys.modules:
                 m = types.ModuleType(mod)
+                m.__path__ = []
                 for k in names:
                     setattr(m, k, type(k, (), {}))
                 sys.modules[mod] = m

@@ -819,7 +819,7 @@ int vc_train_forward_gather(const vc_train* t, const float* img1, const float* i
     return fail(VC_ERR_ARG, "vc_train_forward_gather: bad arguments");
   if (workspace_bytes < vc_train_workspace_bytes(t, n)) return fail(VC_ERR_ARG, "workspace too small");
   const TrainWs w = carve_train(workspace, t, pl, n);
-  VC_LAUNCH(KC_INDEX, st, vc::center_offsets_launch(xy, n, W, t->C1, t->C2, t->P, w.off1, w.off2, st));
+  VC_LAUNCH(KC_INDEX, st, vc::center_offsets_launch(xy, n, H, W, t->C1, t->C2, t->P, w.off1, w.off2, st));
   VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(img1, 0, 1, (long long)W * t->C1, t->C1, w.off1, ops, n, t->C1, t->P, w.a0, pl[0].S_in, st));
   VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(img2, 0, 1, (long long)W * t->C2, t->C2, w.off2, ops, n, t->C2, t->P, w.l0, pl[3].S_in, st));
   if (gt && labels)

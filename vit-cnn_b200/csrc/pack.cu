@@ -340,6 +340,10 @@ __global__ void gather_f32_kernel(const float* __restrict__ img, int H, int W, i
   for (int b = blockIdx.x; b < n; b += gridDim.x) {
     int x0 = xy[2 * b], y0 = xy[2 * b + 1];
     if (center_mode) { x0 -= P / 2; y0 -= P / 2; }
+    // memory safety only: callers validate the coordinates (ops.validate_xy); a window that leaves the raster
+    // is moved inside instead of reading out of bounds
+    x0 = min(max(x0, 0), H - P);
+    y0 = min(max(y0, 0), W - P);
     __syncthreads();
     if (vec_in) {
       const int rl4 = rowlen / 4;
@@ -420,6 +424,8 @@ __global__ void gather_labels_kernel(const void* gt, int eb, int H, int W, const
       x += si_ - P / 2;
       y += sj_ - P / 2;
     }
+    x = min(max(x, 0), H - 1);      // memory safety (see gather_f32_kernel)
+    y = min(max(y, 0), W - 1);
     const long long e = (long long)x * W + y;
     long long v;
     if (eb == 1) v = reinterpret_cast<const unsigned char*>(gt)[e];
@@ -461,18 +467,19 @@ int scene_index_launch(const int* xs, const int* ys, int nx, int ny, int first, 
 
 // Element offsets of the top-left corner of the P x P patch centred on (x, y) in the two rasters
 // (MultiModalX.__getitem__: x1 = x - P//2, y1 = y - P//2, datasets.py:551-556).
-__global__ void center_offsets_kernel(const int* xy, int n, int W, int C1, int C2, int P, long long* off1, long long* off2) {
+__global__ void center_offsets_kernel(const int* xy, int n, int H, int W, int C1, int C2, int P, long long* off1, long long* off2) {
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-    const long long pix = (long long)(xy[2 * t] - P / 2) * W + (xy[2 * t + 1] - P / 2);
+    const int x0 = min(max(xy[2 * t] - P / 2, 0), H - P), y0 = min(max(xy[2 * t + 1] - P / 2, 0), W - P);   // memory safety
+    const long long pix = (long long)x0 * W + y0;
     off1[t] = pix * C1;
     off2[t] = pix * C2;
   }
 }
 
-int center_offsets_launch(const int* xy, int n, int W, int C1, int C2, int P, long long* off1, long long* off2,
+int center_offsets_launch(const int* xy, int n, int H, int W, int C1, int C2, int P, long long* off1, long long* off2,
                           cudaStream_t stream) {
-  if (n <= 0) return VC_ERR_ARG;
-  center_offsets_kernel<<<(n + 255) / 256, 256, 0, stream>>>(xy, n, W, C1, C2, P, off1, off2);
+  if (n <= 0 || P > H || P > W) return VC_ERR_ARG;
+  center_offsets_kernel<<<(n + 255) / 256, 256, 0, stream>>>(xy, n, H, W, C1, C2, P, off1, off2);
   return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
 }
 

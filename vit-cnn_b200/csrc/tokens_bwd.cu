@@ -369,8 +369,8 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
         }
         const float2 b0 = *reinterpret_cast<const float2*>(f32 + O0.bfc1 / 4 + 16 * hk + 2 * q);
         const float2 b1 = *reinterpret_cast<const float2*>(f32 + O0.bfc1 / 4 + 16 * hk + 8 + 2 * q);
-        h0[0] = gelu_erf(h0[0] + b0.x); h0[1] = gelu_erf(h0[1] + b0.y); h0[2] = gelu_erf(h0[2] + b0.x); h0[3] = gelu_erf(h0[3] + b0.y);
-        h1[0] = gelu_erf(h1[0] + b1.x); h1[1] = gelu_erf(h1[1] + b1.y); h1[2] = gelu_erf(h1[2] + b1.x); h1[3] = gelu_erf(h1[3] + b1.y);
+        h0[0] = gelu_tanh_approx(h0[0] + b0.x); h0[1] = gelu_tanh_approx(h0[1] + b0.y); h0[2] = gelu_tanh_approx(h0[2] + b0.x); h0[3] = gelu_tanh_approx(h0[3] + b0.y);
+        h1[0] = gelu_tanh_approx(h1[0] + b1.x); h1[1] = gelu_tanh_approx(h1[1] + b1.y); h1[2] = gelu_tanh_approx(h1[2] + b1.x); h1[3] = gelu_tanh_approx(h1[3] + b1.y);
         if (DROP) {
           drop2(h0[0], h0[1], drop_key(b, 2, r0, 8 * hk + q), dcfg);
           drop2(h0[2], h0[3], drop_key(b, 2, r1, 8 * hk + q), dcfg);
@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          gelu_erf_grad(u[i], hv[i], hder[i]);
+          gelu_tanh_approx_grad(u[i], hv[i], hder[i]);
           if (DROP) {   // post-dropout activation; the mask (0 or 1/keep) also multiplies the derivative
             hv[i] = drop1(hv[i], drop_key(b, 5, 0, (lane + 32 * i) >> 1), lane & 1, dcfg);
             hder[i] = drop1(hder[i], drop_key(b, 5, 0, (lane + 32 * i) >> 1), lane & 1, dcfg);
@@ -777,9 +777,9 @@ __global__ void __launch_bounds__(NW * 32, 1) transformer_bwd_kernel(TBArgs a) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           float der;
-          gelu_erf_grad(h0[e] + ((e & 1) ? b0.y : b0.x), hv0[e], der);
+          gelu_tanh_approx_grad(h0[e] + ((e & 1) ? b0.y : b0.x), hv0[e], der);
           du0[e] = e0[e] * der;
-          gelu_erf_grad(h1[e] + ((e & 1) ? b1.y : b1.x), hv1[e], der);
+          gelu_tanh_approx_grad(h1[e] + ((e & 1) ? b1.y : b1.x), hv1[e], der);
           du1[e] = e1[e] * der;
         }
         if (DROP) {

@@ -782,7 +782,7 @@ __global__ void __launch_bounds__(kTailThreads) tokens_tail_kernel(TailArgs a) {
       h0 = fmaf(wa.x, y[4 * k4], fmaf(wa.y, y[4 * k4 + 1], fmaf(wa.z, y[4 * k4 + 2], fmaf(wa.w, y[4 * k4 + 3], h0))));
       h1 = fmaf(wb.x, y[4 * k4 + 4], fmaf(wb.y, y[4 * k4 + 5], fmaf(wb.z, y[4 * k4 + 6], fmaf(wb.w, y[4 * k4 + 7], h1))));
     }
-    const float hv = gelu_erf(h0 + h1);
+    const float hv = gelu_tanh_approx(h0 + h1);
     const float4* w2 = reinterpret_cast<const float4*>(w + T_WFC2T + j * kD);
 #pragma unroll
     for (int n4 = 0; n4 < kD / 4; ++n4) {

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float hv = gelu_erf(hacc[i]);
+        float hv = gelu_tanh_approx(hacc[i]);
         if (DROP) hv = drop1(hv, drop_key(b, 5, 0, (lane + 32 * i) >> 1), lane & 1, dc);
         h_s[lane + 32 * i] = hv;
       }
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 ? 2 : 1)) transformer_
           mma16816(h1, A2[1], B1[2], B1[3]);
         }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { h0[e] = gelu_erf(h0[e]); h1[e] = gelu_erf(h1[e]); }
+        for (int e = 0; e < 4; ++e) { h0[e] = gelu_tanh_approx(h0[e]); h1[e] = gelu_tanh_approx(h1[e]); }
         if (DROP) {
           drop2(h0[0], h0[1], drop_key(b, 2 + 3 * l, r0, 8 * hk + q), dc);
           drop2(h0[2], h0[3], drop_key(b, 2 + 3 * l, r1, 8 * hk + q), dc);

@@ -36,7 +36,7 @@ int block_offsets_launch(int H, int W, int C, int B, int D, long long* off, cuda
 int border_gather_launch(const void* variants, int S, int B, int D, int H, int W, const int* xs, const int* ys, int ny, int first,
                          int count, int P, void* out, cudaStream_t stream);
 
-int center_offsets_launch(const int* xy, int n, int W, int C1, int C2, int P, long long* off1, long long* off2,
+int center_offsets_launch(const int* xy, int n, int H, int W, int C1, int C2, int P, long long* off1, long long* off2,
                           cudaStream_t stream);
 
 // lidar_stem.cu -- fused eval-mode LiDAR stem (C2 <= 8)

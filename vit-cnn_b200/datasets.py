@@ -90,7 +90,7 @@ class MultiModalX(torch.utils.data.Dataset):
             c, rad = self.draw_augmentation(idx.numel())
             codes = torch.from_numpy(c).to(self.device) if c.any() else None
         data, data2, target = ops.gather_patches(self.data, self.data2, xy, self.patch_size, center_mode=True,
-                                                 gt=self.label, ops=codes)
+                                                 gt=self.label, ops=codes, validate=False)
         for i, alpha, noise in rad:                                   # datasets.py:528-532
             nz = torch.from_numpy(noise).to(self.device).permute(2, 0, 1)
             # numpy: python-float alpha times a float32 array stays float32; the float64 noise term promotes the sum
@@ -109,8 +109,20 @@ class MultiModalX(torch.utils.data.Dataset):
         return _Loader(self, batch_size, shuffle, generator)
 
 
+def batch_indices(n: int, batch_size: int, shuffle: bool, generator=None):
+    """Index batches in exactly the order ``torch.utils.data.DataLoader(dataset_of_n, batch_size, shuffle)``
+    visits them under the current torch RNG state (main.py:434-447: no drop_last, num_workers=0): the order is
+    produced by torch's own DataLoader over the index range, so the draws from the global generator (the
+    iterator's base seed, then the RandomSampler's seed) are the same calls in the same order."""
+    index_loader = torch.utils.data.DataLoader(range(n), batch_size=int(batch_size), shuffle=bool(shuffle),
+                                               generator=generator, num_workers=0,
+                                               collate_fn=lambda items: torch.as_tensor(items, dtype=torch.int64))
+    return iter(index_loader)
+
+
 class _Loader:
-    """Minimal DataLoader stand-in (what train() / val() touch: iteration, len(), .dataset)."""
+    """DataLoader stand-in (what train() / val() touch: iteration, len(), .dataset) that cuts one batch per
+    launch of the gather kernel; same batches in the same order as the stock DataLoader over this dataset."""
 
     def __init__(self, dataset, batch_size, shuffle, generator):
         self.dataset, self.batch_size, self.shuffle, self.generator = dataset, int(batch_size), shuffle, generator
@@ -119,7 +131,5 @@ class _Loader:
         return (len(self.dataset) + self.batch_size - 1) // self.batch_size      # no drop_last (main.py:434-447)
 
     def __iter__(self):
-        n = len(self.dataset)
-        order = torch.randperm(n, generator=self.generator) if self.shuffle else torch.arange(n)
-        for s in range(0, n, self.batch_size):
-            yield self.dataset.batch(order[s:s + self.batch_size])
+        for idx in batch_indices(len(self.dataset), self.batch_size, self.shuffle, self.generator):
+            yield self.dataset.batch(idx)

@@ -20,7 +20,22 @@ def sps_rows(n: int, P: int) -> int:
     return int(_lib.lib().vc_sps_rows(n, P))
 
 
-def gather_patches(img1, img2, xy, P, center_mode=True, gt=None, ops=None):
+def validate_xy(xy, H: int, W: int, P: int, center_mode: bool = True) -> None:
+    """Raise ``ValueError`` unless every P x P window of ``xy`` (int [n,2], centres or top-left corners) lies
+    inside the H x W raster -- what the reference's strict-border rule (datasets.py:497-504) and
+    ``sliding_window`` (utils.py:374-397) guarantee for their own coordinates.  One device->host read."""
+    if xy.numel() == 0:
+        return
+    if P > H or P > W:
+        raise ValueError(f"patch {P} does not fit a {H} x {W} raster")
+    lo, hi = xy.amin(0).tolist(), xy.amax(0).tolist()
+    off = P // 2 if center_mode else 0
+    if lo[0] - off < 0 or lo[1] - off < 0 or hi[0] - off + P > H or hi[1] - off + P > W:
+        raise ValueError(f"patch coordinates leave the {H} x {W} raster for P = {P} "
+                         f"(rows {lo[0]}..{hi[0]}, columns {lo[1]}..{hi[1]}, center_mode={bool(center_mode)})")
+
+
+def gather_patches(img1, img2, xy, P, center_mode=True, gt=None, ops=None, validate=True):
     """Exact fp32 patch extraction.  img1 [H,W,C1] f32, img2 [H,W,C2] f32 (CUDA, contiguous),
     xy int32 [n,2] centres (center_mode) or top-left corners.  Returns (hsi [n,C1,P,P],
     lidar [n,C2,P,P], labels int64 [n] or None).  ``ops`` (uint8 [n], optional): flip / rot90 code of each
@@ -33,6 +48,8 @@ def gather_patches(img1, img2, xy, P, center_mode=True, gt=None, ops=None):
     C2 = img2.shape[2]
     xy = xy.to(device=img1.device, dtype=torch.int32).contiguous()
     n = xy.shape[0]
+    if validate:          # callers whose coordinates are valid by construction (MultiModalX) skip the read-back
+        validate_xy(xy, H, W, P, center_mode)
     hsi = torch.empty(n, C1, P, P, dtype=torch.float32, device=img1.device)
     lid = torch.empty(n, C2, P, P, dtype=torch.float32, device=img1.device)
     labels, eb = None, 0

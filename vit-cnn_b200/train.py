@@ -9,7 +9,7 @@ libvitcnn.so.
 * ``Trainer``        - the fast path: patches gathered on the device from the rasters, loss,
   backward, (NCCL all-reduce of one flat fp32 gradient bucket), Adam - no torch operator on
   the step except the collective.
-* ``train``          - the reference's ``train()`` signature on top of either.
+* ``train``          - the reference's ``train()``: same signature, same results (model_utils.py:854-1045).
 
 Parameters are kept in ONE flat fp32 buffer (the nn.Parameters are views into it, in the
 canonical order of include/vitcnn.h) so that packing, all-reduce and Adam are single launches.
@@ -129,7 +129,9 @@ class TrainState:
         self.struct = st
         self._bn_ptrs = [b.running_mean.data_ptr() for b in _bn_layers(model)]
         self.ws = {}
+        self.on_evict = []      # callbacks(batch size) run when a per-batch-size workspace is dropped
         self.pending = None     # batch size of a forward whose backward has not run yet
+        self.generation = 0     # stamp of the last training forward: its activations are the ones in the workspace
 
     def __deepcopy__(self, memo):   # copies / pickles of the module rebuild their own state lazily
         return None
@@ -173,7 +175,10 @@ class TrainState:
                 raise RuntimeError("this configuration is not supported by the training kernels "
                                    "(patch_size <= 11 or 13 / 15, n_classes <= 64)")
             if len(self.ws) >= 4:
-                self.ws.pop(next(iter(self.ws)))
+                evicted = next(iter(self.ws))
+                self.ws.pop(evicted)
+                for cb in self.on_evict:          # CUDA graphs hold raw pointers into the workspace they captured
+                    cb(evicted)
             ws = torch.empty(need, dtype=torch.uint8, device=self.device)
             _lib.check(L.vc_train_workspace_init(ctypes.byref(self.struct), n, ws.data_ptr(), ws.numel(),
                                                  torch.cuda.current_stream().cuda_stream), "vc_train_workspace_init")
@@ -192,6 +197,7 @@ class TrainState:
                                                    ws.data_ptr(), ws.numel(), logits.data_ptr(),
                                                    torch.cuda.current_stream().cuda_stream), "vc_train_forward")
         self.pending = n
+        self.generation += 1
         self.model._pack = None      # running statistics changed: eval-mode packing is stale
         return logits
 
@@ -209,13 +215,17 @@ class TrainState:
                 logits.data_ptr(), 0 if labels is None else labels.data_ptr(),
                 torch.cuda.current_stream().cuda_stream), "vc_train_forward_gather")
         self.pending = n
+        self.generation += 1
         self.model._pack = None
         return logits, labels
 
-    def backward(self, dlogits):
+    def backward(self, dlogits, generation=None):
         n = dlogits.shape[0]
         if self.pending != n:
             raise RuntimeError("backward() without a matching training forward on this model")
+        if generation is not None and generation != self.generation:
+            raise RuntimeError("backward() of a forward whose activations were overwritten by a later training-mode "
+                               "forward of this model (one forward per backward: the workspace holds one batch)")
         with torch.cuda.device(self.device):
             ws = self.workspace(n)
             _lib.check(_lib.lib().vc_train_backward(ctypes.byref(self.struct), dlogits.data_ptr(), n, ws.data_ptr(),
@@ -241,12 +251,14 @@ class _TrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, state, hsi, lidar, *params):
         ctx.state = state
-        return state.forward_patches(hsi, lidar)
+        out = state.forward_patches(hsi, lidar)
+        ctx.generation = state.generation
+        return out
 
     @staticmethod
     def backward(ctx, dlogits):
         st = ctx.state
-        st.backward(dlogits.contiguous().float())
+        st.backward(dlogits.contiguous().float(), ctx.generation)
         return (None, None, None) + st.grad_views(st.grads.clone())
 
 
@@ -313,6 +325,7 @@ class Trainer:
         self.world = self.dist.get_world_size(process_group) if self.dist else 1
         self.use_graph, self.graph_warmup = use_graph, graph_warmup
         self._graphs = {}       # batch size -> (graph, static xy, static loss)
+        self.state.on_evict.append(lambda n: self._graphs.pop(n, None))
         self.launches_per_step = 0
         self._eager_steps = 0
 
@@ -347,10 +360,15 @@ class Trainer:
                        "vc_adam_step_dev")
         return loss
 
-    def step(self, img1, img2, gt, xy, ops=None):
+    def step(self, img1, img2, gt, xy, ops=None, validate=False):
         """One optimisation step on patches centred at xy (int32 [n,2], device); ``ops`` (uint8 [n],
         device, optional) = flip / rot90 augmentation code per sample, drawn by the host.  Returns the
-        loss tensor [2] (mean loss of this rank, weight sum) without synchronising."""
+        loss tensor [2] (mean loss of this rank, weight sum) without synchronising.  The centres must keep
+        their P x P windows inside the raster (MultiModalX.indices do); ``validate=True`` checks that with one
+        device->host read and raises ``ValueError`` (the kernels themselves only guarantee memory safety)."""
+        if validate:
+            from .ops import validate_xy
+            validate_xy(xy, img1.shape[0], img1.shape[1], self.model.patch_size, True)
         st = self.state
         if not st.valid():
             raise RuntimeError("model parameters were moved after the Trainer was built")
@@ -369,6 +387,7 @@ class Trainer:
             self._eager_steps += 1
             return self._step_impl(img1, img2, gt, xy)
         xy_s = xy.clone()
+        st.workspace(n)                                   # allocated and initialised outside the capture
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         l0 = _lib.lib().vc_launch_count()
@@ -380,45 +399,82 @@ class Trainer:
         return loss_s
 
 
-def train(net, optimizer, criterion, data_loader, epoch, scheduler=None, display_iter=100, device=torch.device("cpu"),
-          display=None, val_loader=None, supervision="full"):
-    """The reference's training loop (model_utils.py:854-1045) without its visdom plotting and
-    checkpoint writing: same iteration order, loss, optimiser and scheduler stepping, validation
-    after every epoch, returns the best ``state_dict`` by validation accuracy."""
+def train(savename, run, bands, net, optimizer, criterion, data_loader, epoch, scheduler=None, display_iter=100,
+          device=torch.device("cpu"), display=None, val_loader=None, supervision="full"):
+    """The reference's training loop (model_utils.py:854-1045) with its signature (main.py:478 calls it
+    positionally) and its results: iteration order, loss, optimiser and scheduler stepping, validation after
+    every epoch **in training mode** (the reference never switches the mode before ``val()``, :908 / :991),
+    the running-mean loss plotted to ``display`` every ``display_iter`` iterations (:940-974), the best
+    weights kept with the reference's rule ``abs(metric) >= best`` where ``metric = -val_acc``, or the
+    epoch's mean loss without a validation loader (:1015-1017; ties go to the LATER epoch, and without
+    validation the rule keeps the HIGHEST mean loss, as upstream), checkpoints through ``save_model``
+    every ``save_epoch`` epochs among the best ones and at the last epoch (:1018-1043).  ``bands`` is
+    unused upstream too.  Returns the best ``state_dict`` (a deep copy)."""
     import copy
-    from .model_utils import val
+
+    from .model_utils import save_model, val
+    from .utils import camel_to_snake
+    best_val_acc = 0.0
     if criterion is None:
         raise Exception("Missing criterion. You must specify a loss function.")
     net.to(device)
-    best_acc, best_state = -1.0, None
-    losses = []
+    save_epoch = 16 if epoch == 128 else (epoch // 20 if epoch > 20 else 1)
+    recent = []                       # losses[max(0, iter_-100) : iter_+1] of the reference: slot 0 is never written
+    mean_losses = {}
+    iter_ = 1
+    loss_win, val_win = None, None
+    val_accuracies = []
+    model_name = camel_to_snake(str(net.__class__.__name__))
     for e in range(1, epoch + 1):
         net.train()
-        for data, data2, target in data_loader:
+        avg_loss = 0.0
+        for batch_idx, (data, data2, target) in enumerate(data_loader):
             data, data2, target = data.to(device), data2.to(device), target.to(device)
             optimizer.zero_grad()
             if supervision == "full":
                 output = net(data, data2)
-                if isinstance(output, tuple):
-                    output = output[0]
                 loss = criterion(output, target)
             else:
                 raise ValueError('supervision mode "{}" is unknown.'.format(supervision))
             loss.backward()
             optimizer.step()
-            losses.append(loss.detach())
+            value = loss.item()
+            avg_loss += value
+            recent.append(value)
+            if len(recent) > 101:
+                recent.pop(0)
+            window = recent if iter_ > 100 else [0.0] + recent      # the zero-initialised slot 0 (:900, :938)
+            mean_losses[iter_] = float(np.mean(np.asarray(window, dtype=np.float64)))
+            if display_iter and iter_ % display_iter == 0:
+                update = None if loss_win is None else "append"
+                loss_win = display.line(
+                    X=np.arange(iter_ - display_iter, iter_),
+                    Y=np.array([mean_losses.get(k, 0.0) for k in range(iter_ - display_iter, iter_)]),
+                    win=loss_win, update=update,
+                    opts={"title": "Training loss run:{}".format(run), "xlabel": "Iterations", "ylabel": "Loss"})
+                if len(val_accuracies) > 0:
+                    val_win = display.line(
+                        Y=np.array(val_accuracies), X=np.arange(len(val_accuracies)), win=val_win,
+                        opts={"title": "Validation accuracy run:{}".format(run), "xlabel": "Epochs", "ylabel": "Accuracy"})
+            iter_ += 1
+        avg_loss /= len(data_loader)
         if val_loader is not None:
-            net.eval()
-            acc = val(net, val_loader, device=device, supervision=supervision)
-            metric = acc
+            val_acc = val(net, val_loader, device=device, supervision=supervision)
+            val_accuracies.append(val_acc)
+            metric = -val_acc
         else:
-            metric = -float(torch.stack(losses[-len(data_loader):]).mean().item())
-            acc = metric
-        if scheduler is not None:
-            if isinstance(scheduler, torch.optim.lr_scheduler.ReduceLROnPlateau):
-                scheduler.step(metric)
-            else:
-                scheduler.step()
-        if acc > best_acc:
-            best_acc, best_state = acc, copy.deepcopy(net.state_dict())
-    return best_state
+            metric = avg_loss
+        if isinstance(scheduler, torch.optim.lr_scheduler.ReduceLROnPlateau):
+            scheduler.step(metric)
+        elif scheduler is not None:
+            scheduler.step()
+        if abs(metric) >= best_val_acc:
+            best_val_acc = abs(metric)
+            best_model_wts = copy.deepcopy(net.state_dict())
+            if e % save_epoch == 0:
+                save_model(savename, net, model_name, data_loader.dataset.name, train_state="train", type="best_epoch",
+                           run=run, epoch=e, metric=abs(metric))
+        if e == epoch:
+            save_model(savename, net, model_name, data_loader.dataset.name, train_state="train", type="final_epoch",
+                       run=run, epoch=e, metric=abs(metric))
+    return best_model_wts

@@ -111,6 +111,15 @@ def subband_bounds(nrows: int, P: int, pipeline: int, block: int = 0, depth: int
     return bounds
 
 
+def camel_to_snake(name: str) -> str:
+    """utils.py:883-885: ``ViTCNN`` -> ``vi_tcnn``-style folder name of the checkpoint path (the two regular
+    expressions are the identifier-splitting idiom the reference uses; the result must match for
+    ``main.py --restore`` paths to line up)."""
+    import re
+    head = re.sub("(.)([A-Z][a-z]+)", r"\1_\2", name)
+    return re.sub("([a-z0-9])([A-Z])", r"\1_\2", head).lower()
+
+
 def seed_torch(seed: int = 1029) -> None:
     """utils.py:887-895: seed Python, numpy and torch RNGs (the determinism contract of the
     sample shuffle, datasets.py:506, and of weight initialisation)."""
