@@ -282,7 +282,7 @@ def minmax_normalise(img: np.ndarray) -> np.ndarray:
 # --------------------------------------------------------------------------
 # Synthetic inputs
 # --------------------------------------------------------------------------
-def synthetic_scene(H, W, C1, C2, K, seed=0, structured=True):
+def synthetic_scene(H, W, C1, C2, K, seed=0, structured=True, block=8):
     """Synthetic co-registered rasters.
 
     structured=False: U[0,1) noise (throughput rasters).
@@ -296,7 +296,7 @@ def synthetic_scene(H, W, C1, C2, K, seed=0, structured=True):
         img2 = rng.random((H, W, C2), dtype=np.float32)
         gt = rng.integers(0, K, size=(H, W)).astype(np.uint8)
         return img1, img2, gt
-    bs = 8
+    bs = int(block)      # edge of the label blocks (8 by default: every P >= 9 window straddles several classes)
     gh, gw = (H + bs - 1) // bs, (W + bs - 1) // bs
     blocks = rng.integers(1, K, size=(gh, gw))
     blocks[rng.random((gh, gw)) < 1 / 3] = 0

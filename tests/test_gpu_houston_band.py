@@ -15,16 +15,19 @@ from oracle.model_ref import ViTCNNRef
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 REL_TOL = 2e-2
+LR = 1e-3        # the reference trains ViT-style models with Adam(lr=0.001) (model_utils.py:214-215)
 
 
 def _briefly_trained(C1, C2, P, K, img1, img2, gt, steps, seed=0):
+    """A short oracle training run on a crop of the scene.  Every label (0 included) is a class here: the
+    synthetic scene leaves a third of its blocks "unlabelled", and a network that never saw those pixels has
+    arbitrary, near-tied logits there -- argmax agreement would then measure coin flips, not arithmetic."""
     torch.manual_seed(seed)
     ref = ViTCNNRef(C1, C2, patch_size=P, num_classes=K, dropout=0.0)
-    idx = R.train_indices(gt, [0], P)
+    idx = R.train_indices(gt, [], P)
     rng = np.random.default_rng(seed)
-    opt = torch.optim.Adam(ref.parameters(), lr=2e-3)
+    opt = torch.optim.Adam(ref.parameters(), lr=LR)
     w = torch.ones(K)
-    w[0] = 0
     ref.train()
     for _ in range(steps):
         sel = idx[rng.choice(len(idx), 48)]
@@ -39,8 +42,8 @@ def _briefly_trained(C1, C2, P, K, img1, img2, gt, steps, seed=0):
 def test_houston_width_band_vs_fp32_oracle():
     import vitcnn_b200
     H, W, C1, C2, P, K = 41, 1905, 144, 1, 11, 16
-    img1, img2, gt = R.synthetic_scene(H, W, C1, C2, K, seed=12)
-    ref = _briefly_trained(C1, C2, P, K, img1[:, :160], img2[:, :160], gt[:, :160], steps=40)
+    img1, img2, gt = R.synthetic_scene(H, W, C1, C2, K, seed=12, block=24)
+    ref = _briefly_trained(C1, C2, P, K, img1[:, :400], img2[:, :400], gt[:, :400], steps=150)
     net = vitcnn_b200.ViTCNN(C1, C2, patch_size=P, num_classes=K)
     net.load_state_dict(ref.state_dict())
     net = net.to(DEV).eval()
@@ -69,7 +72,8 @@ def test_houston_width_band_vs_fp32_oracle():
     err = np.abs(got - want).max() / np.abs(want).max()
     agree = (got.argmax(1) == want.argmax(1)).mean()
     assert len(corners) > 19000
-    assert err <= REL_TOL, err
+    per_window = np.abs(got - want).max(1) / np.abs(want).max()
+    assert err <= REL_TOL, (err, np.percentile(per_window, [50, 99, 99.9]).tolist())
     assert agree >= 0.999, (agree, len(corners))
     assert np.array_equal(amax[corners[:, 0] + P // 2, corners[:, 1] + P // 2], got.argmax(1).astype(np.uint8))
     assert (logits[:P // 2] == 0).all() and (logits[:, :P // 2] == 0).all() and (logits[:, W - P // 2:] == 0).all()

@@ -154,6 +154,7 @@ def test_reference_train_loop_and_mirror_agree(ref_mods, tmp_path, with_val):
     args = (ref_ds, sd, img1, img2, gt, train_gt, val_gt, C1, C2, P, K, epochs, with_val)
     best_r, lines_r, files_r, lr_r, last_r = _train_run(ref_mu.train, *args, str(tmp_path / "ref"))
     best_o, lines_o, files_o, lr_o, last_o = _train_run(vitcnn_b200.train, *args, str(tmp_path / "ours"))
+    best_2, lines_2, _, _, last_2 = _train_run(vitcnn_b200.train, *args, str(tmp_path / "ours2"))
     assert files_r == files_o and len(files_r) >= 2 and lr_r == lr_o
     assert len(lines_r) == len(lines_o) > 0
     for a, b in zip(lines_r, lines_o):
@@ -161,13 +162,26 @@ def test_reference_train_loop_and_mirror_agree(ref_mods, tmp_path, with_val):
         for k in a:
             assert a[k].shape == b[k].shape and np.allclose(a[k], b[k], rtol=2e-3, atol=2e-4), k
     assert best_r.keys() == best_o.keys() == last_r.keys()
-    for k in best_r:
-        assert torch.allclose(best_r[k].float(), best_o[k].float(), rtol=5e-3, atol=5e-4), k
-        assert torch.allclose(last_r[k].float(), last_o[k].float(), rtol=5e-3, atol=5e-4), k
-    # the best epoch differs from the last one in at least one of the two settings: without validation the rule
-    # keeps the epoch with the HIGHEST mean loss (model_utils.py:1015), i.e. the first
+
+    # Yardstick: the backward kernels sum the LayerNorm / pos-embed gradients with fp32 atomics, so two runs of the
+    # SAME loop differ in the last bits, and Adam's normalised update amplifies that over the steps.  The mirror must
+    # be as close to the reference's loop as it is to its own repeat (the two loops execute the same launches).
+    def dist(a, b):
+        num = sum(float((a[k].float() - b[k].float()).pow(2).sum()) for k in a if a[k].is_floating_point())
+        den = sum(float(a[k].float().pow(2).sum()) for k in a if a[k].is_floating_point())
+        return (num / den) ** 0.5
+
+    self_best, self_last = dist(best_o, best_2), dist(last_o, last_2)
+    assert dist(best_r, best_o) <= max(4.0 * self_best, 2e-4), (dist(best_r, best_o), self_best)
+    assert dist(last_r, last_o) <= max(4.0 * self_last, 2e-4), (dist(last_r, last_o), self_last)
+    assert dist(best_r, best_o) <= 2e-2                      # ... and small in absolute terms
+    for k in best_r:                                         # integer state (num_batches_tracked) is exact
+        if not best_r[k].is_floating_point():
+            assert torch.equal(best_r[k], best_o[k]) and torch.equal(last_r[k], last_o[k]), k
+    # the best epoch is the same one: without validation the rule keeps the epoch with the HIGHEST mean loss
+    # (model_utils.py:1015), i.e. the first, so the returned weights are far from the final ones in both loops
     if not with_val:
-        assert any(not torch.equal(best_r[k], last_r[k]) for k in best_r)
+        assert dist(best_r, last_r) > 20 * dist(best_r, best_o) and dist(best_o, last_o) > 20 * dist(best_r, best_o)
 
 
 def test_train_mirror_signature_and_errors():

@@ -88,64 +88,120 @@ Workspace carve(void* base, int n, int P, int S1, int S2) {
 
 inline int slices_for(int C) { return (C + 15) / 16 * 2; }
 
+// One 3-conv stem as the shared-stem code sees it (HSI: 128 / 64 / 32 channels, LiDAR: 8 / 16 / 32 padded to 16 / 16 / 32).
+struct StemDesc {
+  int C, S0;                   // raster channels, slices of the packed blocks
+  const void* w[3];
+  const float *scale[3], *bias[3];
+  int nsplit[3], n_out[3];
+  const void* w1_border;       // conv 1: nine weight copies with the taps that leave the window zeroed (the CTA-pair
+  long long w1_bytes;          //   kernel takes no tap masks), or null: one copy + tap masks
+  int kc[3];                   // profiling class of each layer
+};
+
+StemDesc hsi_stem(const vc_model* m) {
+  StemDesc d;
+  d.C = m->C1; d.S0 = m->S1;
+  const int n_out[3] = {128, 64, 32};
+  for (int i = 0; i < 3; ++i) {
+    d.w[i] = m->w_h[i]; d.scale[i] = m->scale_h[i]; d.bias[i] = m->bias_h[i]; d.nsplit[i] = m->nsplit_h[i]; d.n_out[i] = n_out[i];
+  }
+  d.w1_border = m->w_h1_border;
+  d.w1_bytes = 9LL * m->S1 * 128 * 16;
+  d.kc[0] = KC_CONV_H1; d.kc[1] = KC_CONV_H2; d.kc[2] = KC_CONV_H3;
+  return d;
+}
+
+StemDesc lidar_stem(const vc_model* m) {
+  StemDesc d;
+  d.C = m->C2; d.S0 = m->S2;
+  const int n_out[3] = {16, 16, 32};
+  for (int i = 0; i < 3; ++i) {
+    d.w[i] = m->w_l[i]; d.scale[i] = m->scale_l[i]; d.bias[i] = m->bias_l[i]; d.nsplit[i] = m->nsplit_l[i]; d.n_out[i] = n_out[i];
+  }
+  d.w1_border = nullptr;
+  d.w1_bytes = 0;
+  d.kc[0] = d.kc[1] = d.kc[2] = KC_CONV_L;
+  return d;
+}
+
 // Scene-level buffers of the shared stem (pack.cu), carved behind the chunk workspace: raster offsets of the
 // blocks, the blocks as SPS patches of B x B pixels, the border-class variants of the first D stem convs.
-// mode = sharing depth D: 3 / 2: B = 31, the first three / two HSI convs shared (P >= 2D + 1); 1: B = 15, conv 1
-// only (P >= 2); 0: per-window path.
+// depth D: 3 / 2: B = 31, the first three / two convs shared (P >= 2D + 1); 1: B = 15, conv 1 only (P >= 2).
 struct SceneWs {
   long long* boff;
   uint8_t *blocks, *var[3];
-  long long RTb, wbytes, plane[3], bytes;   // bytes == 0: this mode does not apply to the model / raster
+  long long RTb, plane[3], bytes;   // bytes == 0: this depth does not apply to the model / raster; else the END offset
   int nb, B, D;
 };
 
-SceneWs carve_scene(void* base, const vc_model* m, int H, int W, int chunk, int mode) {
+SceneWs carve_scene(void* base, long long off, const StemDesc& sd, int H, int W, int P, int depth) {
   SceneWs s;
   memset(&s, 0, sizeof(s));
-  const int B = mode >= 2 ? 31 : 15, D = mode;
-  if (mode < 1 || mode > 3 || !m->w_h1_border || H < B || W < B || m->P < (mode == 1 ? 2 : 2 * mode + 1)) return s;
+  const int B = depth >= 2 ? 31 : 15, D = depth;
+  if (depth < 1 || depth > 3 || H < B || W < B || P < (depth == 1 ? 2 : 2 * depth + 1)) return s;
   s.B = B;
   s.D = D;
-  long long off = (carve(nullptr, chunk, m->P, m->S1, m->S2).bytes + 256 + 255) & ~255LL;
   s.nb = vc::blk_count(H, B, D) * vc::blk_count(W, B, D);
   s.RTb = vc::sps_rows(s.nb, B);
-  s.wbytes = 9LL * m->S1 * 128 * 16;    // one packed copy of the conv-1 weights
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
   auto take = [&](long long bytes) { uint8_t* r = p + off; off += (bytes + 255) & ~255LL; return r; };
   s.boff = reinterpret_cast<long long*>(take(8LL * s.nb));
-  s.blocks = take(s.RTb * 16 * m->S1);
-  const int slices[3] = {16, 8, 4};
+  s.blocks = take(s.RTb * 16 * sd.S0);
   for (int l = 0; l < D; ++l) {
-    s.plane[l] = (long long)slices[l] * s.RTb * 16;
+    s.plane[l] = (long long)(sd.n_out[l] / 8) * s.RTb * 16;
     s.var[l] = take((long long)(2 * l + 3) * (2 * l + 3) * s.plane[l]);
   }
   s.bytes = off;
   return s;
 }
 
-// Which sharing depth pays for n windows and fits the workspace the caller gave.  Costs in units of one per-window
-// conv-3 pass over a 128-row tile, measured on B200 at the Houston shape (profiles/r01_SUMMARY.md): per-window
-// conv 1 / 2 / 3 = 2.8 / 1.8 / 1 and patch gather 0.9; a shared conv 2 / 3 tile costs 1.6x / 1.8x its per-window
-// tile (it stages one input slab per input plane); the variant gather costs 1.65 / 0.82 / 0.66 (16 / 8 / 4 slices
-// per row).  VITCNN_SCENE_DEPTH forces a depth (0 = per-window path).
+long long chunk_ws_end(const vc_model* m, int chunk) {
+  return (carve(nullptr, chunk, m->P, m->S1, m->S2).bytes + 256 + 255) & ~255LL;
+}
+
+// The token kernel that reads its stem inputs straight from the depth-3 variant planes (tokens_tc.cu): see use_tokens_tc
+bool use_tokens_tc(int P, int K);
+
+// The LiDAR stem is shared at depth 3 whenever the geometry allows: its planes are small (C2 -> 8 -> 16 -> 32
+// channels) and the per-window alternative recomputes every LiDAR pixel up to P^2 times.
+bool lidar_shared_ok(const vc_model* m, int H, int W) {
+  static const int off = [] {
+    const char* e = getenv("VITCNN_LIDAR_SHARED");
+    return e && e[0] == '0';
+  }();
+  return !off && m->w_h1_border && m->P >= 7 && H >= 31 && W >= 31;
+}
+
+// Which sharing depth of the HSI stem pays for n windows and fits the workspace the caller gave.  Costs in units of
+// one per-window conv-3 pass over a 128-row tile, measured on B200 at the Houston shape (profiles/r02_SUMMARY.md):
+// per-window conv 1 / 2 / 3 = 2.8 / 1.8 / 1 and patch gather 0.9; a block tile of the shared conv 1 (9 variants) /
+// conv 2 (25) / conv 3 (49) costs 27 / 53 / 38 (conv 2 / 3: conv_var.cu, all variants of a row class per work unit);
+// the variant gather costs 1.65 / 0.6 / 0.5 (16 / 8 / 4 slices per row) and nothing at depth 3 when the tcgen05 token
+// kernel runs (it reads the planes itself).  VITCNN_SCENE_DEPTH forces a depth (0 = per-window path).
 int scene_mode(const vc_model* m, int H, int W, int chunk, long long n_windows, long long workspace_bytes) {
   static const int forced = [] {
     const char* e = getenv("VITCNN_SCENE_DEPTH");
     return e ? atoi(e) : -1;
   }();
+  if (!m->w_h1_border || forced == 0) return 0;
+  const StemDesc sd = hsi_stem(m);
   const double win_tiles = (double)n_windows * vc::sps_pp(m->P) / 128.0;
-  const double conv[3] = {2.8, 1.8, 1.0}, shared[3] = {9 * 2.8, 25 * 1.8 * 1.6, 49 * 1.0 * 1.8}, gather[3] = {1.65, 0.82, 0.66};
+  const double conv[3] = {2.8, 1.8, 1.0}, shared[3] = {27.0, 53.0, 38.0};
+  double gather[3] = {1.65, 0.6, 0.5};
+  if (use_tokens_tc(m->P, m->K)) gather[2] = 0.0;
+  const long long lid = lidar_shared_ok(m, H, W) ? carve_scene(nullptr, 0, lidar_stem(m), H, W, m->P, 3).bytes : 0;
   int best = 0;
   double best_cost = win_tiles * (conv[0] + conv[1] + conv[2] + 0.9);      // per-window path incl. its patch gather
   for (int mode = 1; mode <= 3; ++mode) {
-    const SceneWs s = carve_scene(nullptr, m, H, W, chunk, mode);
-    if (s.bytes <= 0 || workspace_bytes < s.bytes) continue;
+    const SceneWs s = carve_scene(nullptr, chunk_ws_end(m, chunk), sd, H, W, m->P, mode);
+    if (s.bytes <= 0 || workspace_bytes < s.bytes + lid) continue;
     if (forced >= 0 && mode != forced) continue;
     double cost = win_tiles * gather[mode - 1];
     for (int l = 0; l < 3; ++l) cost += l < mode ? shared[l] * s.nb * vc::sps_pp(s.B) / 128.0 : win_tiles * conv[l];
     if (cost < best_cost || forced == mode) { best = mode; best_cost = cost; }
   }
-  return forced == 0 ? 0 : best;
+  return best;
 }
 
 // class (at depth L-1) of the neighbour d = -1 / 0 / +1 of a pixel whose class at depth L is c; -1: outside the window
@@ -156,19 +212,48 @@ int neighbour_class(int L, int c, int d, int P) {
   return vc::border_class(ip, P, L - 1);
 }
 
-// The shared stem over the scene blocks: conv 1 as 9 launches with the border-class weight copies, conv L >= 2 as
-// (2L+1)^2 launches that read, per tap, the conv L-1 variant of the neighbour's class (<= 9 planes per launch).
-int shared_stem(const vc_model* m, const SceneWs& sw, const float* img1, int H, int W, cudaStream_t st) {
-  VC_LAUNCH(KC_INDEX, st, vc::block_offsets_launch(H, W, m->C1, sw.B, sw.D, sw.boff, st));
-  VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(img1, 0, 1, (long long)W * m->C1, m->C1, sw.boff, nullptr, sw.nb, m->C1, sw.B, sw.blocks,
-                                             m->S1, st));
-  for (int v = 0; v < 9; ++v)
-    VC_LAUNCH(KC_CONV_H1, st, vc::conv_sps_launch(sw.blocks, m->S1, (const uint8_t*)m->w_h1_border + (size_t)v * sw.wbytes, m->scale_h[0],
-                                                  m->bias_h[0], sw.var[0] + (size_t)v * sw.plane[0], 0, 128, m->nsplit_h[0], sw.nb,
-                                                  sw.B, 9, 1, 0, 0, st));
-  const int s_in[3] = {0, 16, 8}, n_out[3] = {128, 64, 32};
+// The shared stem over the scene blocks: conv 1 as 9 launches (border-class weight copies, or one copy with the taps
+// that leave the window masked out), conv L >= 2 as (2L+1)^2 launches that read, per tap, the conv L-1 variant of
+// the neighbour's class (<= 9 planes per launch).
+int shared_stem(const StemDesc& sd, const SceneWs& sw, const float* img, int H, int W, int P, cudaStream_t st) {
+  VC_LAUNCH(KC_INDEX, st, vc::block_offsets_launch(H, W, sd.C, sw.B, sw.D, sw.boff, st));
+  VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(img, 0, 1, (long long)W * sd.C, sd.C, sw.boff, nullptr, sw.nb, sd.C, sw.B, sw.blocks,
+                                             sd.S0, st));
+  for (int v = 0; v < 9; ++v) {
+    Scope sc(sd.kc[0], st);
+    uint8_t* out = sw.var[0] + (size_t)v * sw.plane[0];
+    if (sd.w1_border) {
+      VC_TRY(vc::conv_sps_launch(sw.blocks, sd.S0, (const uint8_t*)sd.w1_border + (size_t)v * sd.w1_bytes, sd.scale[0], sd.bias[0], out, 0,
+                                 sd.n_out[0], sd.nsplit[0], sw.nb, sw.B, 9, 1, 0, 0, st));
+    } else {
+      const int cy = v / 3, cx = v % 3;
+      unsigned int mask = 0;
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx)
+          if (!((cy == 0 && dy < 0) || (cy == 2 && dy > 0) || (cx == 0 && dx < 0) || (cx == 2 && dx > 0)))
+            mask |= 1u << ((dy + 1) * 3 + (dx + 1));
+      const void* plane = sw.blocks;
+      VC_TRY(vc::conv_sps_planes_launch(&plane, &mask, 1, sd.S0, sd.w[0], sd.scale[0], sd.bias[0], out, 0, sd.n_out[0], sd.nsplit[0], sw.nb,
+                                        sw.B, 9, 1, 0, 0, st));
+    }
+  }
+  static const bool per_variant = [] {       // VITCNN_STEM_IMPL=planes: one launch per output variant (the round-1 path)
+    const char* e = getenv("VITCNN_STEM_IMPL");
+    return e && e[0] == 'p';
+  }();
   for (int L = 2; L <= sw.D; ++L) {
     const int NC = 2 * L + 1, NP = 2 * L - 1;     // classes per axis at depth L / L-1
+    if (!per_variant && sd.nsplit[L - 1] == 1) {
+      // all variants of a row class per work unit: input slabs staged once for 2L+1 accumulators (conv_var.cu)
+      signed char cls[7 * 3];
+      for (int c = 0; c < NC; ++c)
+        for (int d = 0; d < 3; ++d) cls[c * 3 + d] = (signed char)neighbour_class(L, c, d - 1, P);
+      Scope sc(sd.kc[L - 1], st);
+      const int rc = vc::conv_var_launch(sw.var[L - 2], sd.n_out[L - 2] / 8, sd.w[L - 1], sd.scale[L - 1], sd.bias[L - 1], sw.var[L - 1],
+                                         sd.n_out[L - 1], L, cls, cls, sw.nb, sw.B, 1, st);
+      if (rc == VC_OK) continue;
+      if (rc != VC_ERR_UNSUPPORTED) return fail(rc, "conv_var_launch");
+    }
     for (int cy = 0; cy < NC; ++cy)
       for (int cx = 0; cx < NC; ++cx) {
         const void* planes[9];
@@ -176,7 +261,7 @@ int shared_stem(const vc_model* m, const SceneWs& sw, const float* img1, int H, 
         int ids[9], np = 0;
         for (int dy = -1; dy <= 1; ++dy)
           for (int dx = -1; dx <= 1; ++dx) {
-            const int ry = neighbour_class(L, cy, dy, m->P), rx = neighbour_class(L, cx, dx, m->P);
+            const int ry = neighbour_class(L, cy, dy, P), rx = neighbour_class(L, cx, dx, P);
             if (ry < 0 || rx < 0) continue;           // the tap leaves the window: zero padding
             const int id = ry * NP + rx;
             int k = 0;
@@ -188,16 +273,15 @@ int shared_stem(const vc_model* m, const SceneWs& sw, const float* img1, int H, 
             }
             masks[k] |= 1u << ((dy + 1) * 3 + (dx + 1));
           }
-        Scope sc(L == 2 ? KC_CONV_H2 : KC_CONV_H3, st);
-        VC_TRY(vc::conv_sps_planes_launch(planes, masks, np, s_in[L - 1], m->w_h[L - 1], m->scale_h[L - 1], m->bias_h[L - 1],
-                                          sw.var[L - 1] + (size_t)(cy * NC + cx) * sw.plane[L - 1], 0, n_out[L - 1],
-                                          m->nsplit_h[L - 1], sw.nb, sw.B, 9, 1, 0, 0, st));
+        Scope sc(sd.kc[L - 1], st);
+        VC_TRY(vc::conv_sps_planes_launch(planes, masks, np, sd.n_out[L - 2] / 8, sd.w[L - 1], sd.scale[L - 1], sd.bias[L - 1],
+                                          sw.var[L - 1] + (size_t)(cy * NC + cx) * sw.plane[L - 1], 0, sd.n_out[L - 1],
+                                          sd.nsplit[L - 1], sw.nb, sw.B, 9, 1, 0, 0, st));
       }
   }
   return VC_OK;
 }
 
-// stems + token stage on packed inputs already in w.a0 / w.l0
 // lead / trailing halo rows of the intermediates are read by the next conv and written by no
 // kernel: zero them once per workspace geometry (they stay zero across chunks of equal size)
 int zero_halos(const Workspace& w, int n, int P, cudaStream_t st) {
@@ -222,10 +306,14 @@ bool use_tokens_tc(int P, int K) {
   return forced == 1 || P * P + 1 >= 82;
 }
 
+// stems + token stage on packed inputs already in w.a0 / w.l0.
+// stem_done: HSI stem convs already taken from the scene-level variants (1: w.a1 holds conv 1, 2: w.a2 conv 2, 3: w.f
+//            slices 0-3 hold conv 3 -- or nothing does and `planes->h` is set: the token kernel reads the planes);
+// lidar_done: w.f slices 4-7 already hold the LiDAR stem, or `planes->l` is set.
 int forward_sps(const vc_model* m, const Workspace& w, int n, float* logits, const long long* out_index,
-                uint8_t* argmax_map, cudaStream_t st, int stem_done = 0) {
+                uint8_t* argmax_map, cudaStream_t st, int stem_done = 0, bool lidar_done = false,
+                const vc::TcPlanes* planes = nullptr) {
   const int P = m->P;
-  // stem_done: HSI stem convs already gathered from the scene-level variants (1: w.a1 holds conv 1, 2: w.a2 conv 2, 3: w.f conv 3)
   if (stem_done < 1)
     VC_LAUNCH(KC_CONV_H1, st, vc::conv_sps_launch(w.a0, m->S1, m->w_h[0], m->scale_h[0], m->bias_h[0], w.a1, 0, 128, m->nsplit_h[0], n, P, 9,
                                1, 0, 0, st));
@@ -235,8 +323,14 @@ int forward_sps(const vc_model* m, const Workspace& w, int n, float* logits, con
   if (stem_done < 3)
     VC_LAUNCH(KC_CONV_H3, st, vc::conv_sps_launch(w.a2, 8, m->w_h[2], m->scale_h[2], m->bias_h[2], w.f, 0, 32, m->nsplit_h[2], n, P, 9, 1, 0,
                                0, st));
-  bool lidar_done = false;
-  if (m->lidar_blob && m->C2 <= 8) {   // one fused launch instead of three latency-bound ones
+  // Per-window LiDAR stem: three tcgen05 convs -- the same kernel and accumulation order as the shared LiDAR stem of
+  // dense scenes, so forward() and the scene path agree bit for bit.  VITCNN_LIDAR_IMPL=fused selects the single-launch
+  // mma.sync kernel (lidar_stem.cu: 7.3 instead of 9.6 ms per 642 k windows, results differ in the last bf16 bit).
+  static const bool fused_lidar = [] {
+    const char* e = getenv("VITCNN_LIDAR_IMPL");
+    return e && e[0] == 'f';
+  }();
+  if (!lidar_done && fused_lidar && m->lidar_blob && m->C2 <= 8) {
     Scope sc(KC_CONV_L, st);
     const int rc = vc::lidar_stem_launch(w.l0, m->lidar_blob, w.f, 4, n, P, st);
     if (rc == VC_OK) lidar_done = true;
@@ -252,7 +346,7 @@ int forward_sps(const vc_model* m, const Workspace& w, int n, float* logits, con
   }
   // token stage (see use_tokens_tc)
   if (use_tokens_tc(P, m->K))
-    VC_LAUNCH(KC_TOKENS, st, vc::tokens_tc_launch(w.f, m->tparams, n, P, m->K, logits, out_index, argmax_map, w.tscr, st));
+    VC_LAUNCH(KC_TOKENS, st, vc::tokens_tc_launch(w.f, m->tparams, n, P, m->K, logits, out_index, argmax_map, w.tscr, planes, st));
   else
     VC_LAUNCH(KC_TOKENS, st, vc::transformer_fwd_launch(w.f, m->tparams, n, P, m->K, logits, out_index, argmax_map, 0, 0, nullptr, st));
   return VC_OK;
@@ -393,7 +487,7 @@ int vc_tokens_forward_tc(const void* f_sps, const void* tparams, int32_t n_patch
     return fail(VC_ERR_ARG, "vc_tokens_forward_tc: bad argument / scratch too small");
   if (!vc::tokens_tc_supported(P, K)) return fail(VC_ERR_UNSUPPORTED, "vc_tokens_forward_tc: needs P*P + 1 <= 128");
   VC_TRY(vc::tokens_tc_launch(f_sps, tparams, n_patches, P, K, logits, (const long long*)out_index, argmax_map, scratch,
-                              (cudaStream_t)stream));
+                              nullptr, (cudaStream_t)stream));
   return VC_OK;
 }
 
@@ -434,35 +528,60 @@ int vc_scene_infer(const vc_model* m, const float* img1, const float* img2, int3
     return fail(VC_ERR_ARG, "vc_scene_infer: bad arguments");
   if (workspace_bytes < vc_workspace_bytes(chunk, m->P, m->C1, m->C2)) return fail(VC_ERR_ARG, "workspace too small");
   const long long s1 = (long long)W * m->C1, s2 = (long long)W * m->C2;
-  // ---- shared stem: border-class variants of the HSI stem convs over the scene blocks, once per call ----
+  // ---- shared stem: border-class variants of the stem convs over the scene blocks, once per call ----
   const int mode = scene_mode(m, H, W, chunk, n_windows, workspace_bytes);
-  const SceneWs sw = carve_scene(workspace, m, H, W, chunk, mode);
-  if (mode) VC_TRY(shared_stem(m, sw, img1, H, W, st));
+  const StemDesc hd = hsi_stem(m), ld = lidar_stem(m);
+  const SceneWs sw = carve_scene(workspace, chunk_ws_end(m, chunk), hd, H, W, m->P, mode);
+  const long long hsi_end = mode ? sw.bytes : chunk_ws_end(m, chunk);
+  SceneWs lw;
+  memset(&lw, 0, sizeof(lw));
+  if (lidar_shared_ok(m, H, W)) {
+    lw = carve_scene(workspace, hsi_end, ld, H, W, m->P, 3);
+    if (lw.bytes <= 0 || lw.bytes > workspace_bytes) memset(&lw, 0, sizeof(lw));     // the caller's workspace is the smaller kind
+  }
+  const bool lid_shared = lw.bytes > 0;
+  if (mode) VC_TRY(shared_stem(hd, sw, img1, H, W, m->P, st));
+  if (lid_shared) VC_TRY(shared_stem(ld, lw, img2, H, W, m->P, st));
+  // the tcgen05 token kernel takes depth-3 stem outputs straight from the variant planes: no per-window copy of them
+  const bool direct = use_tokens_tc(m->P, m->K);
   for (int64_t done = 0; done < n_windows; done += chunk) {
     const int n = (int)((n_windows - done) < chunk ? (n_windows - done) : chunk);
+    const int first = (int)(first_window + done);
     // the SPS geometry depends on n: carve per chunk (only the last chunk differs)
     const Workspace w = carve(workspace, n, m->P, m->S1, m->S2);
-    if (done == 0 || n != chunk) VC_TRY(zero_halos(w, n, m->P, st));
-    VC_LAUNCH(KC_INDEX, st, vc::scene_index_launch(xs, ys, nx, ny, (int)(first_window + done), n, W, m->C1, m->C2, m->P,
-                                                   m->K, w.off1, w.off2, w.oidx, nullptr, st));
-    // strip-staged gather (stride-1 runs reuse the overlap of consecutive windows); the generic
-    // per-row gather is the fallback for geometries the strip kernel does not take
-    if (mode) {
+    const long long sl = vc::sps_rows(n, m->P) * 16;
+    if ((done == 0 || n != chunk) && (mode < 3 || !lid_shared)) VC_TRY(zero_halos(w, n, m->P, st));
+    VC_LAUNCH(KC_INDEX, st, vc::scene_index_launch(xs, ys, nx, ny, first, n, W, m->C1, m->C2, m->P, m->K, w.off1, w.off2, w.oidx, nullptr,
+                                                   st));
+    vc::TcPlanes tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.xs = xs; tp.ys = ys; tp.ny = ny; tp.first = first; tp.H = H; tp.W = W;
+    if (mode == 3 && direct) {
+      tp.h = (const __nv_bfloat16*)sw.var[2];
+      tp.RTb = sw.RTb; tp.B = sw.B; tp.D = sw.D; tp.nbx = vc::blk_count(W, sw.B, sw.D);
+    } else if (mode) {
       VC_LAUNCH(KC_PACK, st, vc::border_gather_launch(sw.var[sw.D - 1], mode == 3 ? 4 : mode == 2 ? 8 : 16, sw.B, sw.D, H, W, xs, ys, ny,
-                                                      (int)(first_window + done), n, m->P, mode == 3 ? w.f : mode == 2 ? w.a2 : w.a1, st));
+                                                      first, n, m->P, mode == 3 ? w.f : mode == 2 ? w.a2 : w.a1, st));
     } else {
+      // strip-staged gather (stride-1 runs reuse the overlap of consecutive windows); the generic
+      // per-row gather is the fallback for geometries the strip kernel does not take
       Scope sc(KC_PACK, st);
-      int rc = vc::pack_scene_launch(img1, W, m->C1, xs, ys, nx, ny, (int)(first_window + done), n, m->P, w.a0, m->S1, st);
+      int rc = vc::pack_scene_launch(img1, W, m->C1, xs, ys, nx, ny, first, n, m->P, w.a0, m->S1, st);
       if (rc == VC_ERR_UNSUPPORTED) rc = vc::pack_sps_launch(img1, 0, 1, s1, m->C1, w.off1, nullptr, n, m->C1, m->P, w.a0, m->S1, st);
       if (rc != VC_OK) return fail(rc, "scene gather (hsi)");
     }
-    {
+    if (lid_shared && direct) {
+      tp.l = (const __nv_bfloat16*)lw.var[2];      // same block geometry as the depth-3 HSI planes (B = 31, D = 3)
+      tp.RTb = lw.RTb; tp.B = lw.B; tp.D = lw.D; tp.nbx = vc::blk_count(W, lw.B, lw.D);
+    } else if (lid_shared) {
+      VC_LAUNCH(KC_PACK, st, vc::border_gather_launch(lw.var[2], 4, lw.B, lw.D, H, W, xs, ys, ny, first, n, m->P, w.f + 4 * sl, st));
+    } else {
       Scope sc(KC_PACK, st);
-      int rc = vc::pack_scene_launch(img2, W, m->C2, xs, ys, nx, ny, (int)(first_window + done), n, m->P, w.l0, m->S2, st);
+      int rc = vc::pack_scene_launch(img2, W, m->C2, xs, ys, nx, ny, first, n, m->P, w.l0, m->S2, st);
       if (rc == VC_ERR_UNSUPPORTED) rc = vc::pack_sps_launch(img2, 0, 1, s2, m->C2, w.off2, nullptr, n, m->C2, m->P, w.l0, m->S2, st);
       if (rc != VC_OK) return fail(rc, "scene gather (lidar)");
     }
-    VC_TRY(forward_sps(m, w, n, logits_map, w.oidx, argmax_map, st, mode));
+    VC_TRY(forward_sps(m, w, n, logits_map, w.oidx, argmax_map, st, mode, lid_shared, (tp.h || tp.l) ? &tp : nullptr));
   }
   return VC_OK;
 }
@@ -475,9 +594,21 @@ int32_t vc_scene_shared_depth(const vc_model* m, int32_t H, int32_t W, int32_t c
 int64_t vc_scene_workspace_bytes(const vc_model* m, int32_t H, int32_t W, int32_t chunk) {
   if (check_model(m) != VC_OK || chunk <= 0) return -1;
   long long need = vc_workspace_bytes(chunk, m->P, m->C1, m->C2);
-  for (int mode = 1; mode <= 3; ++mode) {
-    const SceneWs sw = carve_scene(nullptr, m, H, W, chunk, mode);
-    if (sw.bytes > need) need = sw.bytes;
+  if (!m->w_h1_border) return need;
+  const StemDesc hd = hsi_stem(m), ld = lidar_stem(m);
+  const bool lid = lidar_shared_ok(m, H, W);
+  for (int mode = 0; mode <= 3; ++mode) {
+    long long end = chunk_ws_end(m, chunk);
+    if (mode) {
+      const SceneWs sw = carve_scene(nullptr, end, hd, H, W, m->P, mode);
+      if (sw.bytes <= 0) continue;
+      end = sw.bytes;
+    }
+    if (lid) {
+      const SceneWs lw = carve_scene(nullptr, end, ld, H, W, m->P, 3);
+      if (lw.bytes > 0) end = lw.bytes;
+    }
+    if (end > need) need = end;
   }
   return need;
 }

@@ -98,6 +98,24 @@ __global__ void __launch_bounds__(kConvThreads) conv_sps_tc_kernel(ConvArgs a) {
         uint32_t n = wbytes - off < 32768u ? wbytes - off : 32768u;
         bulk_g2s(w_s + off, wsrc + off, n, wfull);
       }
+      // rows of a plane's slab that its taps read: [HALO + lo, HALO + hi + 128) with lo / hi the smallest / largest
+      // tap shift -- a plane read by one tap only (corner variants of the shared stem: up to nine such planes per
+      // tile) is staged as 128 rows instead of 128 + 2 HALO, which is what bounds those launches (L2 -> smem)
+      uint32_t pl_off[9], pl_bytes[9], stage_tx = 0;
+      for (int pl = 0; pl < NPL; ++pl) {
+        int lo = 1 << 20, hi = -(1 << 20);
+        for (int tap = 0; tap < a.ntaps; ++tap)
+          if (a.tapmask[pl] & (1u << tap)) {
+            const int shift = a.ntaps == 9 ? (tap / 3 - 1) * PW + (tap % 3 - 1) : 0;
+            lo = shift < lo ? shift : lo;
+            hi = shift > hi ? shift : hi;
+          }
+        // whole 128-byte lines (8 rows): HALO is a multiple of 8, so a plane read by every tap is staged as before
+        const int r0 = (HALO + lo) & ~7, r1 = (HALO + hi + 128 + 7) & ~7;
+        pl_off[pl] = (uint32_t)r0;
+        pl_bytes[pl] = (uint32_t)(r1 - r0) * 16u;
+        stage_tx += 2u * pl_bytes[pl];
+      }
       int st = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < ((a.debug_flags & 8) ? 0 : a.ntiles); tile += gridDim.x) {
@@ -108,13 +126,13 @@ __global__ void __launch_bounds__(kConvThreads) conv_sps_tc_kernel(ConvArgs a) {
           if (a.debug_flags & 2) {   // timing probe: no operand traffic
             mbar_arrive(&full[st]);
           } else {
-            mbar_arrive_expect_tx(&full[st], (uint32_t)(nk * NPL) * kstep_bytes);
+            mbar_arrive_expect_tx(&full[st], (uint32_t)nk * stage_tx);
             uint8_t* dst = stage_s + (size_t)st * stage_bytes;
             for (int kl = 0; kl < nk; ++kl)       // stage layout: [K step][plane][2 slices][ROWS][16 B]
               for (int pl = 0; pl < NPL; ++pl)
                 for (int h2 = 0; h2 < 2; ++h2)
-                  bulk_g2s(dst + (size_t)((kl * NPL + pl) * 2 + h2) * slice_bytes,
-                           a.planes[pl] + ((long long)(2 * (ks0 + kl) + h2) * a.RT + row0) * 8, slice_bytes, &full[st]);
+                  bulk_g2s(dst + (size_t)((kl * NPL + pl) * 2 + h2) * slice_bytes + pl_off[pl] * 16u,
+                           a.planes[pl] + ((long long)(2 * (ks0 + kl) + h2) * a.RT + row0 + pl_off[pl]) * 8, pl_bytes[pl], &full[st]);
           }
           if (++st == a.nstages) { st = 0; ph ^= 1u; }
         }

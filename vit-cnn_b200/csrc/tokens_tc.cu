@@ -33,6 +33,7 @@
 //    tokens_tail_kernel, one thread per patch, from a 704-byte record per patch.
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include <type_traits>
 #include "vc_common.cuh"
 #include "vc_kernels.h"
@@ -78,6 +79,7 @@ constexpr int kTailFloats = 176;                  // per patch: [4 warps][32 o +
 
 struct TcArgs {
   const __nv_bfloat16* f;   // [8][RT][8]: slices 0-3 HSI stem, 4-7 LiDAR stem
+  TcPlanes pl;              // stem outputs taken straight from the scene-level variant planes instead (h / l non-null)
   const uint8_t* blob;      // parameter blob (vc_tparams.h)
   float* tail;              // [n][kTailFloats]
   long long RT;
@@ -382,8 +384,25 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) { 
       if (r >= 1 && r < T) {
         const int p = r - 1, i = p / P, j = p - i * P;
         const __nv_bfloat16* src = a.f + (HALO + (long long)b * PP + i * PW + j) * 8;
+        const __nv_bfloat16 *sh = src, *sl = src + 4 * a.RT * 8;
+        long long ph = a.RT * 8, pls = a.RT * 8;          // slice pitch (elements) of the HSI / LiDAR source
+        if (a.pl.h || a.pl.l) {
+          // shared stem, depth D: the stem output of window pixel (i, j) is the variant plane of
+          // border_class(i) x border_class(j) at the scene pixel's row in its scene block (pack.cu)
+          const TcPlanes& q = a.pl;
+          const int widx = q.first + b, ix = widx / q.ny, iy = widx - ix * q.ny;
+          const int y = __ldg(q.xs + ix) + i, x = __ldg(q.ys + iy) + j;
+          const int ky = blk_index(y, q.H, q.B, q.D), kx = blk_index(x, q.W, q.B, q.D);
+          const long long srow = sps_halo(q.B) + (long long)(ky * q.nbx + kx) * sps_pp(q.B) +
+                                 (y - blk_origin(ky, q.H, q.B, q.D)) * (q.B + 1) + (x - blk_origin(kx, q.W, q.B, q.D));
+          const long long voff = ((long long)(border_class(i, P, q.D) * (2 * q.D + 1) + border_class(j, P, q.D)) * 4 * q.RTb + srow) * 8;
+          if (q.h) { sh = q.h + voff; ph = q.RTb * 8; }
+          if (q.l) { sl = q.l + voff; pls = q.RTb * 8; }
+        }
 #pragma unroll
-        for (int s = 0; s < 8; ++s) cp_async16(fbuf + s * SLAB + row16, src + (long long)s * a.RT * 8);
+        for (int s = 0; s < 4; ++s) cp_async16(fbuf + s * SLAB + row16, sh + s * ph);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) cp_async16(fbuf + (4 + s) * SLAB + row16, sl + s * pls);
       } else {          // the buffer doubles as P / hidden: the cls row and the padding rows are zeroed every time
 #pragma unroll
         for (int s = 0; s < 8; ++s) sts128(fbuf + s * SLAB + row16, 0u, 0u, 0u, 0u);
@@ -819,8 +838,10 @@ size_t tokens_tc_scratch_bytes(int n_patches) { return (size_t)n_patches * tc::k
 bool tokens_tc_supported(int P, int K) { return P >= 1 && P * P + 1 <= 128 && K >= 1 && K <= 64; }
 
 int tokens_tc_launch(const void* f_sps, const void* tparams, int n_patches, int P, int K, float* logits,
-                     const long long* out_index, unsigned char* argmax_map, void* scratch, cudaStream_t stream) {
+                     const long long* out_index, unsigned char* argmax_map, void* scratch, const TcPlanes* planes,
+                     cudaStream_t stream) {
   if (n_patches <= 0 || !scratch || !tokens_tc_supported(P, K)) return VC_ERR_ARG;
+  if (planes && (planes->h || planes->l) && (P < 2 * planes->D + 1 || !planes->xs || !planes->ys)) return VC_ERR_ARG;
   int dev = 0, max_smem = 0, num_sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -835,6 +856,8 @@ int tokens_tc_launch(const void* f_sps, const void* tparams, int n_patches, int 
   a.P = P;
   a.T = P * P + 1;
   a.L = tlayout(P, K);
+  if (planes) a.pl = *planes;
+  else memset(&a.pl, 0, sizeof(a.pl));
   {
     static const int stagger = [] {
       const char* e = getenv("VITCNN_TC_STAGGER_NS");

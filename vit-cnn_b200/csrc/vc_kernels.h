@@ -1,6 +1,7 @@
 // Internal launch prototypes shared by the translation units of libvitcnn.so.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 
 namespace vc {
@@ -15,6 +16,13 @@ int conv_sps_launch(const void* in, int S_in, const void* w, const float* scale,
 int conv_sps_planes_launch(const void* const* planes, const unsigned int* tapmasks, int nplanes, int S_in, const void* w,
                            const float* scale, const float* bias, void* out, int out_slice_off, int n_out, int nsplit,
                            int n_patches, int P, int ntaps, int relu, int impl, int debug_flags, cudaStream_t stream);
+
+// conv_var.cu -- shared stem, conv L >= 2: all (2L+1)^2 border-class variants from the (2L-1)^2 variant planes of
+// conv L-1 in ONE launch (work unit = tile x output row class; input slabs staged once per unit and K step).
+// ry / rx: [2L+1][3] input class of tap row / column d - 1 for each output class (-1: the tap leaves the window).
+// VC_ERR_UNSUPPORTED: not the B = 31 block geometry / does not fit -- fall back to conv_sps_planes_launch.
+int conv_var_launch(const void* in, int S_in, const void* w, const float* scale, const float* bias, void* out, int n_out, int L,
+                    const signed char* ry, const signed char* rx, int n_blocks, int B, int relu, cudaStream_t stream);
 
 // pack.cu
 int pack_sps_launch(const float* src, long long sb, long long sc, long long si, long long sj, const long long* patch_off,
@@ -60,8 +68,20 @@ int transformer_fwd_launch(const void* f_sps, const void* tparams, int n_patches
 // tokens_tc_scratch_bytes(n) bytes (one 704-byte cls record per patch)
 size_t tokens_tc_scratch_bytes(int n_patches);
 bool tokens_tc_supported(int P, int K);
+// Stem outputs read straight from the variant planes of the shared stem (dense scenes, sharing depth D on B x B
+// scene blocks): h / l = [(2D+1)^2 variants][4 slices][RTb][8] conv-3 planes of the HSI / LiDAR stem (null: that
+// half comes from slices 0-3 / 4-7 of f_sps); patch b of the launch is window first + b of the (xs, ys) grid.
+struct TcPlanes {
+  const __nv_bfloat16* h;
+  const __nv_bfloat16* l;
+  const int* xs;
+  const int* ys;
+  long long RTb;
+  int ny, first, H, W, B, D, nbx;
+};
 int tokens_tc_launch(const void* f_sps, const void* tparams, int n_patches, int P, int K, float* logits,
-                     const long long* out_index, unsigned char* argmax_map, void* scratch, cudaStream_t stream);
+                     const long long* out_index, unsigned char* argmax_map, void* scratch, const TcPlanes* planes,
+                     cudaStream_t stream);
 
 // wgrad_tc.cu -- weight gradients (rows are the reduction axis; both operands MN-major)
 size_t wgrad_workspace_bytes(int SB, int ntaps);
