@@ -13,8 +13,8 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_uint8, c_void
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libvitcnn.so")
-SOURCES = ["abi.cu", "conv_tc.cu", "conv_var.cu", "pack.cu", "transformer.cu", "tokens_tc.cu", "lidar_stem.cu", "metrics.cu", "wgrad_tc.cu", "wgrad_small.cu", "train.cu", "tokens_bwd.cu"]
-HEADERS = ["vc_common.cuh", "vc_kernels.h", "vc_tparams.h", "vc_tokens.cuh", os.path.join("..", "..", "include", "vitcnn.h")]
+SOURCES = ["abi.cu", "conv_tc.cu", "conv_var.cu", "pack.cu", "transformer.cu", "tokens_tc.cu", "tokens_tc2.cu", "lidar_stem.cu", "metrics.cu", "wgrad_tc.cu", "wgrad_small.cu", "train.cu", "tokens_bwd.cu"]
+HEADERS = ["tokens_tc_common.cuh", "vc_common.cuh", "vc_kernels.h", "vc_tparams.h", "vc_tokens.cuh", os.path.join("..", "..", "include", "vitcnn.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -158,11 +158,12 @@ def lib() -> ctypes.CDLL:
     """The loaded library.  Fails loudly when it has not been built."""
     global _lib
     if _lib is None:
-        if not os.path.isfile(SO_PATH):
+        so_path = os.environ.get("VITCNN_LIB", SO_PATH)       # development: a variant built by tools/build_variants.py
+        if not os.path.isfile(so_path):
             raise RuntimeError(
-                f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"{so_path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU / PyTorch fallback for the ViT-CNN hot path)")
-        L = ctypes.CDLL(SO_PATH)
+        L = ctypes.CDLL(so_path)
         for name, (res, args) in _PROTOS.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
