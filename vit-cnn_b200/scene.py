@@ -17,11 +17,18 @@ from .utils import band_geometry, subband_bounds
 @torch.no_grad()
 def predict_scene_host(net, img1: torch.Tensor, img2: torch.Tensor, stride: int = 1, rank: int = 0, world: int = 1,
                        chunk: int = SCENE_CHUNK, logits_out: torch.Tensor = None, argmax_out: torch.Tensor = None,
-                       device=None, pipeline: int = None):
+                       device=None, pipeline: int = None, sync: bool = True):
     """img1 f32 [H,W,C1], img2 f32 [H,W,C2] CPU tensors (pinned for async copies).  Writes the
     rows owned by ``rank`` into ``logits_out`` f32 [H,W,K] / ``argmax_out`` uint8 [H,W] (CPU,
     allocated zero-filled when None) and returns them.  Rows no window is centred on are not
-    touched."""
+    touched.
+
+    ``sync=False`` (streaming: scene after scene, e.g. the N scenes of a bench step) returns as soon as the
+    work is queued: the uploads of the NEXT call then overlap the tail of this one instead of waiting for its
+    last download.  The outputs are complete once the device is synchronised (``torch.cuda.synchronize``) or
+    the returned tensors' ``ready`` event (``predict_scene_host.last_event(device)``) has passed; at most two
+    calls are in flight per device (the third waits for the first), pinned outputs must not be reused before
+    their call has completed."""
     H, W, _ = img1.shape
     P, K = net.patch_size, net.num_classes
     dev = torch.device(device) if device is not None else net.cls_token.device
@@ -57,7 +64,11 @@ def predict_scene_host(net, img1: torch.Tensor, img2: torch.Tensor, stride: int 
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream()
         up, down = _copy_streams(dev)
-        up.wait_stream(main)
+        inflight = _INFLIGHT.setdefault(dev, [])
+        if sync:
+            up.wait_stream(main)
+        elif len(inflight) >= 2:              # bounded look-ahead: staging memory of at most two calls
+            up.wait_event(inflight.pop(0))
         staged, done = [], []
         for k in range(nsub):
             a, b = bounds[k], bounds[k + 1]
@@ -90,9 +101,25 @@ def predict_scene_host(net, img1: torch.Tensor, img2: torch.Tensor, stride: int 
             lg.record_stream(down)
             am.record_stream(down)
             done.append((lg, am))
-        main.wait_stream(down)
-        main.synchronize()
+        if sync:
+            main.wait_stream(down)
+            main.synchronize()
+            inflight.clear()
+        else:                                 # the downloads are ordered on `down` after the kernels they read from
+            ev = torch.cuda.Event()
+            ev.record(down)
+            inflight.append(ev)
     return logits_out, argmax_out
+
+
+def last_event(device):
+    """Event recorded after the most recent ``sync=False`` call on ``device`` (None when nothing is in flight)."""
+    q = _INFLIGHT.get(torch.device(device), [])
+    return q[-1] if q else None
+
+
+predict_scene_host.last_event = last_event
+_INFLIGHT = {}
 
 
 def _shared_depth(net, rows: int, W: int, count: int, chunk: int, dev) -> int:

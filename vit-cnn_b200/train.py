@@ -346,6 +346,23 @@ class Trainer:
         self.set_lr(base_lr * gamma ** (epoch // step_size))
         return self.lr
 
+    def allreduce_ms(self, iters: int = 20) -> float:
+        """Device time of the gradient all-reduce alone (one flat fp32 bucket, NCCL), CUDA events, mean of `iters`
+        back-to-back calls after two warm-ups; 0 for a single rank.  The bucket is scratch here (call between steps)."""
+        if self.world <= 1:
+            return 0.0
+        g = self.state.grads
+        for _ in range(2):
+            self.dist.all_reduce(g, op=self.dist.ReduceOp.SUM, group=self.group)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            self.dist.all_reduce(g, op=self.dist.ReduceOp.SUM, group=self.group)
+        e1.record()
+        torch.cuda.synchronize()
+        g.zero_()
+        return e0.elapsed_time(e1) / iters
+
     def _step_impl(self, img1, img2, gt, xy, ops=None):
         st = self.state
         logits, labels = st.forward_gather(img1, img2, gt, xy, ops)
