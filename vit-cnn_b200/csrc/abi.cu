@@ -429,7 +429,11 @@ int vc_gather_patches_f32(const float* img1, const float* img2, const void* gt, 
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) return VC_OK;
   if (!xy || n < 0) return fail(VC_ERR_ARG, "vc_gather_patches_f32: bad arguments");
-  if (img1 && hsi) VC_TRY(vc::gather_f32_launch(img1, H, W, C1, xy, ops, n, P, center_mode, hsi, st));
+  if (img1 && hsi) {      // tensor-map TMA form where the raster allows it (C1 % 4 == 0, aligned), else the generic kernel
+    int rc = vc::gather_tma_launch(img1, H, W, C1, xy, ops, n, P, center_mode, hsi, st);
+    if (rc == VC_ERR_UNSUPPORTED) rc = vc::gather_f32_launch(img1, H, W, C1, xy, ops, n, P, center_mode, hsi, st);
+    if (rc != VC_OK) return fail(rc, "patch gather (hsi)");
+  }
   if (img2 && lidar) VC_TRY(vc::gather_f32_launch(img2, H, W, C2, xy, ops, n, P, center_mode, lidar, st));
   if (gt && labels)
     VC_TRY(vc::gather_labels_launch(gt, gt_elem_bytes, H, W, xy, ops, n, P, center_mode, (long long*)labels, st));
@@ -658,6 +662,7 @@ bool make_plans(const vc_train* t, ConvPlan pl[7]) {
 
 const int kTokSlices[10] = {6, 12, 6, 4, 6, 16, 18, 4, 6, 12};   // xln1_0 dqkv_0 xo0 dxa0 xln2_0 dh0 xh0 dxb0 xln1_1 dqkv_1
 const int kClsSlices[8] = {6, 4, 6, 16, 18, 4, 6, 8};            // c_xo c_dxa c_xln2 c_dh c_xh c_dxb c_xc c_dlog
+const int kLinSB[9] = {6, 6, 6, 18, 6, 6, 6, 18, 6};   // slices of the N-side operand of the nine linear weight-gradient GEMMs
 const int kTokOnes[10] = {4, -1, 4, -1, 4, -1, 16, -1, 4, -1};    // slice holding the constant-one channel
 const int kClsOnes[8] = {4, -1, 4, -1, 16, -1, 4, -1};
 
@@ -669,9 +674,8 @@ struct TrainWs {
   uint8_t *wf[7], *wd[7], *blob;
   float *bias_pad[7], *ones, *zeros;
   float *bn_scale[7], *bn_shift[7], *bn_mean[7], *bn_rstd[7];
-  double* sums;
-  uint8_t* wg;
-  long long wg_bytes;
+  double* sums;                 // [14][256]: batch sums of layer i forward at 256 i, backward at 256 (7 + i)
+  uint8_t *wgl[9], *wgc[7];     // split-K partials of the nine linear / seven conv weight-gradient GEMMs (reduced in one launch)
   long long *off1, *off2;
   long long RT, RTt, RTc;
   long long bytes;
@@ -711,18 +715,14 @@ TrainWs carve_train(void* base, const vc_train* t, const ConvPlan pl[7], int n) 
     w.bn_mean[i] = reinterpret_cast<float*>(take(128 * 4));
     w.bn_rstd[i] = reinterpret_cast<float*>(take(128 * 4));
   }
-  w.sums = reinterpret_cast<double*>(take(256 * 8));
-  long long wg = 0;
+  w.sums = reinterpret_cast<double*>(take(14 * 256 * 8));
+  for (int j = 0; j < 9; ++j) w.wgl[j] = take((long long)vc::wgrad_workspace_bytes(kLinSB[j], 1));
   for (int i = 0; i < 7; ++i) {
     const int SB = pl[i].shift_on_a ? pl[i].n_out / 8 : pl[i].S_in;
-    const long long b = (long long)vc::wgrad_workspace_bytes(SB, pl[i].taps);
-    if (b > wg) wg = b;
+    long long b = (long long)vc::wgrad_workspace_bytes(SB, pl[i].taps);
+    if ((long long)vc::wgrad_small_workspace_bytes() > b) b = (long long)vc::wgrad_small_workspace_bytes();
+    w.wgc[i] = take(b);
   }
-  const long long bt = (long long)vc::wgrad_workspace_bytes(18, 1);
-  if (bt > wg) wg = bt;
-  if ((long long)vc::wgrad_small_workspace_bytes() > wg) wg = (long long)vc::wgrad_small_workspace_bytes();
-  w.wg_bytes = wg;
-  w.wg = take(wg);
   w.off1 = reinterpret_cast<long long*>(take(8LL * n));
   w.off2 = reinterpret_cast<long long*>(take(8LL * n));
   w.bytes = p - reinterpret_cast<uint8_t*>(base);
@@ -754,18 +754,27 @@ int check_train(const vc_train* t, ConvPlan pl[7]) {
 
 int train_forward_core(const vc_train* t, const ConvPlan pl[7], const TrainWs& w, int n, float* logits, cudaStream_t st) {
   const int P = t->P;
-  // bf16 operand forms of the current fp32 master weights
+  // bf16 operand forms of the current fp32 master weights, conv biases, cleared BatchNorm sums: ONE launch
+  vc::PrepTable pt;
+  pt.n = 0;
+  auto add = [&](int type, const float* src, void* dst, long long n_) -> vc::PrepJob& {
+    vc::PrepJob& j = pt.job[pt.n++];
+    memset(&j, 0, sizeof(j));
+    j.type = type; j.src = src; j.dst = dst; j.n = n_;
+    return j;
+  };
   for (int i = 0; i < 7; ++i) {
     const ConvPlan& c = pl[i];
-    VC_LAUNCH(KC_MISC, st, vc::pack_conv_w_launch(t->params + t->off[4 * i], c.cout, c.cin, c.taps, 0, c.S_in, c.n_out, c.nsplit,
-                                                 w.wf[i], st));
-    if (c.has_dgrad)
-      VC_LAUNCH(KC_MISC, st, vc::pack_conv_w_launch(t->params + t->off[4 * i], c.cout, c.cin, c.taps, 1, c.d_S_in, c.d_n_out,
-                                                   c.d_nsplit, w.wd[i], st));
-    if (cudaMemcpyAsync(w.bias_pad[i], t->params + t->off[4 * i + 1], sizeof(float) * c.cout, cudaMemcpyDeviceToDevice, st) !=
-        cudaSuccess)
-      return fail(VC_ERR_CUDA, "bias copy");
+    vc::PrepJob& f = add(0, t->params + t->off[4 * i], w.wf[i], (long long)c.taps * c.S_in * c.n_out * 8);
+    f.cout = c.cout; f.cin = c.cin; f.taps = c.taps; f.transpose = 0; f.S_in = c.S_in; f.n_out = c.n_out; f.nsplit = c.nsplit;
+    if (c.has_dgrad) {
+      vc::PrepJob& d = add(0, t->params + t->off[4 * i], w.wd[i], (long long)c.taps * c.d_S_in * c.d_n_out * 8);
+      d.cout = c.cout; d.cin = c.cin; d.taps = c.taps; d.transpose = 1; d.S_in = c.d_S_in; d.n_out = c.d_n_out; d.nsplit = c.d_nsplit;
+    }
+    add(1, t->params + t->off[4 * i + 1], w.bias_pad[i], c.cout);
   }
+  add(3, nullptr, w.sums, 14 * 256);
+  VC_LAUNCH(KC_MISC, st, vc::train_prep_launch(&pt, st));
   VC_LAUNCH(KC_MISC, st, vc::pack_segments_launch(t->params, w.blob, (const long long*)t->blob_segments, t->n_blob_segments, st));
   // stems: conv (+bias) -> raw y -> BatchNorm with batch statistics -> ReLU -> z
   for (int i = 0; i < 7; ++i) {
@@ -774,10 +783,10 @@ int train_forward_core(const vc_train* t, const ConvPlan pl[7], const TrainWs& w
     const int cls = i == 0 ? KC_CONV_H1 : i == 1 ? KC_CONV_H2 : i == 2 ? KC_CONV_H3 : i < 6 ? KC_CONV_L : KC_TOKENS;
     VC_LAUNCH(cls, st, vc::conv_sps_launch(in, c.S_in, w.wf[i], w.ones, w.bias_pad[i], w.y[i], 0, c.n_out, c.nsplit, n, P, c.taps,
                                            0, 0, 0, st));
-    VC_LAUNCH(KC_BN, st, vc::bn_forward_launch(w.y[i], w.z[i], c.n_out / 8, c.cout, n, P, t->params + t->off[4 * i + 2],
-                                               t->params + t->off[4 * i + 3], t->bn_eps, t->bn_momentum, t->bn_running_mean[i],
-                                               t->bn_running_var[i], (long long*)t->bn_num_batches[i], w.sums, w.bn_scale[i],
-                                               w.bn_shift[i], w.bn_mean[i], w.bn_rstd[i], 1, st));
+    VC_LAUNCH(KC_BN, st, vc::bn_forward_fused_launch(w.y[i], w.z[i], c.n_out / 8, c.cout, n, P, t->params + t->off[4 * i + 2],
+                                                     t->params + t->off[4 * i + 3], t->bn_eps, t->bn_momentum, t->bn_running_mean[i],
+                                                     t->bn_running_var[i], (long long*)t->bn_num_batches[i], w.sums + 256 * i,
+                                                     w.bn_scale[i], w.bn_shift[i], w.bn_mean[i], w.bn_rstd[i], 1, st));
   }
   const unsigned int thr = drop_threshold(t);
   if (thr) bump_seed_kernel<<<1, 1, 0, st>>>(t->drop_seed);     // a fresh mask set for this step
@@ -785,25 +794,66 @@ int train_forward_core(const vc_train* t, const ConvPlan pl[7], const TrainWs& w
   return VC_OK;
 }
 
+// Side streams of the training step: the weight-gradient GEMMs of a layer depend only on that layer's dz and on forward
+// activations, never on each other or on the data-gradient chain, so they run on a second stream beside the
+// BatchNorm-backward -> data-gradient chain (fork / join with events; under CUDA-graph capture they become parallel
+// branches of the graph).  At 512 samples per GPU the chain and the GEMMs are ~0.3 ms each: the step is bound by
+// launch latencies, not by SM time.  VITCNN_TRAIN_STREAMS=0 keeps everything on the caller's stream.
+struct SideStreams {
+  cudaStream_t s[2];
+  cudaEvent_t ev[32];
+  int next;
+  bool ok;
+};
+SideStreams* side_streams() {
+  static SideStreams pool[16];
+  static bool tried[16] = {false};
+  static const bool off = [] {
+    const char* e = getenv("VITCNN_TRAIN_STREAMS");
+    return e && e[0] == '0';
+  }();
+  if (off) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideStreams& p = pool[dev];
+  if (!tried[dev]) {
+    tried[dev] = true;
+    p.ok = true;
+    for (int i = 0; i < 2; ++i) p.ok = p.ok && cudaStreamCreateWithFlags(&p.s[i], cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 32; ++i) p.ok = p.ok && cudaEventCreateWithFlags(&p.ev[i], cudaEventDisableTiming) == cudaSuccess;
+    p.next = 0;
+  }
+  return p.ok ? &p : nullptr;
+}
+// `to` waits for everything queued on `from` so far
+int stream_dep(SideStreams* ss, cudaStream_t from, cudaStream_t to) {
+  cudaEvent_t e = ss->ev[ss->next];
+  ss->next = (ss->next + 1) & 31;
+  if (cudaEventRecord(e, from) != cudaSuccess || cudaStreamWaitEvent(to, e, 0) != cudaSuccess) return VC_ERR_CUDA;
+  return VC_OK;
+}
+
 int conv_wgrad(const vc_train* t, const ConvPlan& c, int i, const void* x, const void* dy, const TrainWs& w, int n,
-               cudaStream_t st) {
+               cudaStream_t st, vc::WgradReduceTable* defer) {
   float* out = t->grads + t->off[4 * i];
   const int P = t->P;
   if (c.taps == 9 && c.n_out <= 32 && c.S_in == 2) {   // thin LiDAR layers: mma.sync kernel
-    const int rc = vc::wgrad_small_launch(dy, c.n_out / 8, x, c.S_in, n, P, w.wg, out, c.cout, c.cin, st);
+    const int rc = vc::wgrad_small_launch(dy, c.n_out / 8, x, c.S_in, n, P, w.wgc[i], out, c.cout, c.cin, st);
     if (rc != VC_ERR_UNSUPPORTED) return rc;
   }
   if (c.shift_on_a)
-    return vc::wgrad_sps_launch(x, c.S_in, dy, c.n_out / 8, n, P, c.taps, 1, w.wg, out, c.cin, c.cout, c.taps,
-                                (long long)c.cin * c.taps, 1, -1, nullptr, 0, st);
-  return vc::wgrad_sps_launch(dy, c.n_out / 8, x, c.S_in, n, P, c.taps, 0, w.wg, out, c.cout, c.cin, (long long)c.cin * c.taps,
-                              c.taps, 1, -1, nullptr, 0, st);
+    return vc::wgrad_sps_launch(x, c.S_in, dy, c.n_out / 8, n, P, c.taps, 1, w.wgc[i], out, c.cin, c.cout, c.taps,
+                                (long long)c.cin * c.taps, 1, -1, nullptr, 0, st, defer);
+  return vc::wgrad_sps_launch(dy, c.n_out / 8, x, c.S_in, n, P, c.taps, 0, w.wgc[i], out, c.cout, c.cin, (long long)c.cin * c.taps,
+                              c.taps, 1, -1, nullptr, 0, st, defer);
 }
 
-int linear_wgrad(const vc_train* t, const void* dy, int SA, const void* x, int SB, long long rows, int M, int N, int iw,
-                 const TrainWs& w, cudaStream_t st) {
-  return vc::wgrad_sps_launch(dy, SA, x, SB, (int)(rows / 128), 0, 1, 0, w.wg, t->grads + t->off[iw], M, N, N, 1, 0, N,
-                              t->grads + t->off[iw + 1], 0, st);
+// j: which of the nine linear GEMMs (its own split-K workspace: the reductions run in one launch at the end of the pass)
+int linear_wgrad(const vc_train* t, int j, const void* dy, int SA, const void* x, int SB, long long rows, int M, int N, int iw,
+                 const TrainWs& w, cudaStream_t st, vc::WgradReduceTable* defer) {
+  if (SB != kLinSB[j]) return VC_ERR_ARG;
+  return vc::wgrad_sps_launch(dy, SA, x, SB, (int)(rows / 128), 0, 1, 0, w.wgl[j], t->grads + t->off[iw], M, N, N, 1, 0, N,
+                              t->grads + t->off[iw + 1], 0, st, defer);
 }
 
 int train_backward_core(const vc_train* t, const ConvPlan pl[7], const TrainWs& w, int n, const float* dlogits,
@@ -813,23 +863,37 @@ int train_backward_core(const vc_train* t, const ConvPlan pl[7], const TrainWs& 
   // ---- token stage ----
   const int small_idx[12] = {30, 31, 36, 37, 42, 43, 48, 49, 54, 55, 28, 29};
   float* small[12];
+  vc::PrepTable pt;             // the small gradients the backward kernel accumulates with atomics start from zero: one launch
+  pt.n = 0;
   for (int i = 0; i < 12; ++i) {
     small[i] = G + t->off[small_idx[i]];
-    const size_t cnt = small_idx[i] == 29 ? (size_t)T * 32 : 32;
-    if (cudaMemsetAsync(small[i], 0, cnt * sizeof(float), st) != cudaSuccess) return fail(VC_ERR_CUDA, "memset");
+    vc::PrepJob& j = pt.job[pt.n++];
+    memset(&j, 0, sizeof(j));
+    j.type = 2; j.dst = small[i]; j.n = small_idx[i] == 29 ? (long long)T * 32 : 32;
   }
+  VC_LAUNCH(KC_MISC, st, vc::train_prep_launch(&pt, st));
+  vc::WgradReduceTable rt;      // split-K reductions of every weight-gradient GEMM of the pass: one launch at the end
+  rt.n = 0;
   VC_LAUNCH(KC_TOKENS_BWD, st, vc::transformer_bwd_launch(w.z[6], w.blob, dlogits, w.dzf, (void* const*)w.tok, (void* const*)w.cls,
                                                          small, n, P, K, drop_threshold(t), t->drop_seed, st));
+  SideStreams* ss = side_streams();
+  cudaStream_t main_st = st;
+  if (ss) {                     // the weight-gradient GEMMs run beside the BatchNorm-backward / data-gradient chain
+    VC_TRY(stream_dep(ss, main_st, ss->s[0]));
+    st = ss->s[0];
+  }
   // linear-layer weight / bias gradients: contraction over all token rows on the tensor cores
-  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, w.tok[1], 12, w.tok[0], 6, w.RTt, 96, 32, 32, w, st));    // block 0 qkv
-  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, w.tok[3], 4, w.tok[2], 6, w.RTt, 32, 32, 34, w, st));     //         proj
-  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, w.tok[5], 16, w.tok[4], 6, w.RTt, 128, 32, 38, w, st));   //         fc1
-  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, w.tok[7], 4, w.tok[6], 18, w.RTt, 32, 128, 40, w, st));   //         fc2
-  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, w.tok[9], 12, w.tok[8], 6, w.RTt, 96, 32, 44, w, st));    // block 1 qkv
-  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, w.cls[1], 4, w.cls[0], 6, w.RTc, 32, 32, 46, w, st));     //         proj (cls row)
-  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, w.cls[3], 16, w.cls[2], 6, w.RTc, 128, 32, 50, w, st));   //         fc1
-  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, w.cls[5], 4, w.cls[4], 18, w.RTc, 32, 128, 52, w, st));   //         fc2
-  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, w.cls[7], (K + 15) / 16 * 2, w.cls[6], 6, w.RTc, K, 32, 56, w, st));   // head
+  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, 0, w.tok[1], 12, w.tok[0], 6, w.RTt, 96, 32, 32, w, st, &rt));    // block 0 qkv
+  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, 1, w.tok[3], 4, w.tok[2], 6, w.RTt, 32, 32, 34, w, st, &rt));     //         proj
+  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, 2, w.tok[5], 16, w.tok[4], 6, w.RTt, 128, 32, 38, w, st, &rt));   //         fc1
+  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, 3, w.tok[7], 4, w.tok[6], 18, w.RTt, 32, 128, 40, w, st, &rt));   //         fc2
+  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, 4, w.tok[9], 12, w.tok[8], 6, w.RTt, 96, 32, 44, w, st, &rt));    // block 1 qkv
+  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, 5, w.cls[1], 4, w.cls[0], 6, w.RTc, 32, 32, 46, w, st, &rt));     //         proj (cls row)
+  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, 6, w.cls[3], 16, w.cls[2], 6, w.RTc, 128, 32, 50, w, st, &rt));   //         fc1
+  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, 7, w.cls[5], 4, w.cls[4], 18, w.RTc, 32, 128, 52, w, st, &rt));   //         fc2
+  VC_LAUNCH(KC_WGRAD, st, linear_wgrad(t, 8, w.cls[7], (K + 15) / 16 * 2, w.cls[6], 6, w.RTc, K, 32, 56, w, st, &rt));   // head
+  cudaStream_t wst = st;        // stream of the weight-gradient GEMMs
+  st = main_st;
   // ---- convolutions, last to first ----
   const int order[7] = {6, 2, 1, 0, 5, 4, 3};
   const long long sl = w.RT * 16;
@@ -838,16 +902,19 @@ int train_backward_core(const vc_train* t, const ConvPlan pl[7], const TrainWs& 
     const ConvPlan& c = pl[i];
     uint8_t* dz = i == 6 ? w.dzf : i == 2 ? w.df : i == 1 ? w.dzh2 : i == 0 ? w.dzh1 : i == 5 ? w.df + 4 * sl : i == 4 ? w.dzl2 : w.dzl1;
     const uint8_t* x = (i == 0) ? w.a0 : (i == 3) ? w.l0 : (i == 6) ? w.f : w.z[i - 1];
-    VC_LAUNCH(KC_BN, st, vc::bn_backward_launch(dz, w.y[i], dz, c.n_out / 8, c.cout, n, P, w.bn_scale[i], w.bn_shift[i], w.bn_mean[i],
-                                                w.bn_rstd[i], 1, w.sums, G + t->off[4 * i + 2], G + t->off[4 * i + 3],
-                                                G + t->off[4 * i + 1], 0, st));
-    VC_LAUNCH(KC_WGRAD, st, conv_wgrad(t, c, i, x, dz, w, n, st));
+    VC_LAUNCH(KC_BN, st, vc::bn_backward_fused_launch(dz, w.y[i], dz, c.n_out / 8, c.cout, n, P, w.bn_scale[i], w.bn_shift[i],
+                                                      w.bn_mean[i], w.bn_rstd[i], 1, w.sums + 256 * (7 + i), G + t->off[4 * i + 2],
+                                                      G + t->off[4 * i + 3], G + t->off[4 * i + 1], st));
+    if (ss) VC_TRY(stream_dep(ss, st, wst));       // dz of this layer is final
+    VC_LAUNCH(KC_WGRAD, wst, conv_wgrad(t, c, i, x, dz, w, n, wst, &rt));
     if (c.has_dgrad) {
       uint8_t* dprev = i == 6 ? w.df : i == 2 ? w.dzh2 : i == 1 ? w.dzh1 : i == 5 ? w.dzl2 : w.dzl1;
       VC_LAUNCH(KC_DGRAD, st, vc::conv_sps_launch(dz, c.d_S_in, w.wd[i], w.ones, w.zeros, dprev, 0, c.d_n_out, c.d_nsplit, n, P,
                                                   c.taps, 0, 0, 0, st));
     }
   }
+  VC_LAUNCH(KC_WGRAD, wst, vc::wgrad_reduce_batched_launch(&rt, wst));
+  if (ss) VC_TRY(stream_dep(ss, wst, st));         // join: every gradient is in place when the caller's stream continues
   return VC_OK;
 }
 

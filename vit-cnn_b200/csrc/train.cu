@@ -264,6 +264,138 @@ int bn_backward_launch(const void* dz, const void* y, void* dy, int S, int C, in
   return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
 }
 
+// ---- two-launch forms for the training step ----------------------------------------------------------
+// bn_apply_kernel with the finalisation folded in: every block derives scale / shift from the batch sums itself,
+// block 0 also records them (+ mean, rstd for the backward pass) and updates the running statistics.
+__global__ void __launch_bounds__(256) bn_apply_finalize_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ z,
+                                                                int S, long long RT, const double* __restrict__ sums, double count,
+                                                                int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                float eps, float momentum, float* running_mean, float* running_var,
+                                                                long long* num_batches_tracked, float* scale, float* shift, float* mean,
+                                                                float* rstd, int relu, int P, int n) {
+  __shared__ float sc_s[256], sh_s[256];
+  const int Cp = S * 8;
+  for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
+    float sc = 0.f, sh = 0.f, mf = 0.f, rs = 0.f;
+    if (c < C) {
+      const double m = sums[c] / count;
+      double var = sums[Cp + c] / count - m * m;
+      if (var < 0.0) var = 0.0;
+      rs = (float)(1.0 / sqrt(var + (double)eps));
+      sc = gamma[c] * rs;
+      sh = beta[c] - (float)m * sc;
+      mf = (float)m;
+      if (blockIdx.x == 0 && running_mean) {
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mf;
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+      }
+    }
+    sc_s[c] = sc;
+    sh_s[c] = sh;
+    if (blockIdx.x == 0) { scale[c] = sc; shift[c] = sh; mean[c] = mf; rstd[c] = rs; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked) *num_batches_tracked += 1;
+  __syncthreads();
+  const int HALO = sps_halo(P), PP = sps_pp(P), PW = P + 1;
+  for (long long R = (long long)blockIdx.x * blockDim.x + threadIdx.x; R < RT; R += (long long)gridDim.x * blockDim.x) {
+    const bool valid = sps_row_valid((int)R, HALO, PP, PW, P, n);
+    const uint4* src = reinterpret_cast<const uint4*>(y) + R;
+    uint4* dst = reinterpret_cast<uint4*>(z) + R;
+    if (!valid) {
+      for (int s = 0; s < S; ++s) dst[(long long)s * RT] = make_uint4(0u, 0u, 0u, 0u);
+      continue;
+    }
+#pragma unroll 4
+    for (int s = 0; s < S; ++s) {
+      float v[8];
+      unpack8(__ldg(src + (long long)s * RT), v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        v[k] = fmaf(v[k], sc_s[s * 8 + k], sh_s[s * 8 + k]);
+        if (relu) v[k] = fmaxf(v[k], 0.f);
+      }
+      dst[(long long)s * RT] = pack8(v);
+    }
+  }
+}
+
+int bn_forward_fused_launch(const void* y, void* z, int S, int C, int n_patches, int P, const float* gamma, const float* beta,
+                            float eps, float momentum, float* running_mean, float* running_var, long long* nbt, double* sums,
+                            float* scale, float* shift, float* mean, float* rstd, int relu, cudaStream_t st) {
+  if (S < 1 || S > 32 || C > S * 8 || n_patches <= 0) return VC_ERR_ARG;
+  const long long RT = sps_rows(n_patches, P);
+  const int Cp = S * 8;
+  bn_stats_kernel<<<dim3(rows_grid(RT, S), S), 256, 0, st>>>((const __nv_bfloat16*)y, RT, Cp, sums);
+  bn_apply_finalize_kernel<<<flat_grid(RT), 256, 0, st>>>((const __nv_bfloat16*)y, (__nv_bfloat16*)z, S, RT, sums,
+                                                          (double)n_patches * P * P, C, gamma, beta, eps, momentum, running_mean,
+                                                          running_var, nbt, scale, shift, mean, rstd, relu, P, n_patches);
+  return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
+}
+
+// bn_bwd_apply_kernel + bn_bwd_params_kernel: block 0 also writes dgamma / dbeta (and zeroes the conv bias gradient)
+__global__ void __launch_bounds__(256) bn_bwd_apply_params_kernel(const __nv_bfloat16* dz, const __nv_bfloat16* __restrict__ y,
+                                                                  __nv_bfloat16* dy, int S, long long RT, int C,
+                                                                  const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                  int relu, const double* __restrict__ sums, double inv_count,
+                                                                  float* dgamma, float* dbeta, float* dbias, int P, int n) {
+  __shared__ float sc_s[256], sh_s[256], k1_s[256], k2_s[256];
+  const int Cp = S * 8;
+  for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
+    const float sc = scale[c];
+    const float k2 = sc * rstd[c] * (float)(sums[Cp + c] * inv_count);
+    sc_s[c] = sc;
+    sh_s[c] = shift[c];
+    k2_s[c] = k2;
+    k1_s[c] = sc * (float)(sums[c] * inv_count) - k2 * mean[c];
+    if (blockIdx.x == 0 && c < C) {
+      dgamma[c] = (float)sums[Cp + c];
+      dbeta[c] = (float)sums[c];
+      if (dbias) dbias[c] = 0.f;
+    }
+  }
+  __syncthreads();
+  const int HALO = sps_halo(P), PP = sps_pp(P), PW = P + 1;
+  for (long long R = (long long)blockIdx.x * blockDim.x + threadIdx.x; R < RT; R += (long long)gridDim.x * blockDim.x) {
+    const bool valid = sps_row_valid((int)R, HALO, PP, PW, P, n);
+    const uint4* pdz = reinterpret_cast<const uint4*>(dz) + R;
+    const uint4* py = reinterpret_cast<const uint4*>(y) + R;
+    uint4* pdy = reinterpret_cast<uint4*>(dy) + R;
+    if (!valid) {
+      for (int s = 0; s < S; ++s) pdy[(long long)s * RT] = make_uint4(0u, 0u, 0u, 0u);
+      continue;
+    }
+#pragma unroll 4
+    for (int s = 0; s < S; ++s) {
+      float g[8], v[8];
+      unpack8(pdz[(long long)s * RT], g);
+      unpack8(__ldg(py + (long long)s * RT), v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = s * 8 + k;
+        const float gg = (!relu || fmaf(v[k], sc_s[c], sh_s[c]) > 0.f) ? g[k] : 0.f;
+        g[k] = fmaf(sc_s[c], gg, -fmaf(k2_s[c], v[k], k1_s[c]));
+      }
+      pdy[(long long)s * RT] = pack8(g);
+    }
+  }
+}
+
+int bn_backward_fused_launch(const void* dz, const void* y, void* dy, int S, int C, int n_patches, int P, const float* scale,
+                             const float* shift, const float* mean, const float* rstd, int relu, double* sums, float* dgamma,
+                             float* dbeta, float* dbias, cudaStream_t st) {
+  if (S < 1 || S > 32 || C > S * 8 || n_patches <= 0) return VC_ERR_ARG;
+  const long long RT = sps_rows(n_patches, P);
+  const int Cp = S * 8;
+  bn_bwd_reduce_kernel<<<dim3(rows_grid(RT, S), S), 256, 0, st>>>((const __nv_bfloat16*)dz, (const __nv_bfloat16*)y, RT, Cp,
+                                                                   scale, shift, mean, rstd, relu, sums);
+  bn_bwd_apply_params_kernel<<<flat_grid(RT), 256, 0, st>>>((const __nv_bfloat16*)dz, (const __nv_bfloat16*)y, (__nv_bfloat16*)dy, S,
+                                                            RT, C, scale, shift, mean, rstd, relu, sums,
+                                                            1.0 / ((double)n_patches * P * P), dgamma, dbeta, dbias, P, n_patches);
+  return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
+}
+
 // ---- weighted cross entropy ----------------------------------------------------------------------
 // loss = sum_i w[y_i] * nll_i / sum_i w[y_i]   (nn.CrossEntropyLoss(weight=w), reduction 'mean',
 // ignore_index -100); dlogits = grad_scale * w[y_i] * (softmax - onehot) / sum w.
@@ -413,6 +545,49 @@ int pack_conv_w_launch(const float* w, int cout, int cin, int taps, int transpos
   const int total = taps * S_in * n_out * 8;
   pack_conv_w_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, cout, cin, taps, transpose, S_in, n_out, nsplit,
                                                           (__nv_bfloat16*)dst);
+  return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
+}
+
+// The per-step chores in one launch (blockIdx.y = job): weight packing of every conv (forward and data-gradient
+// operands), bias copies, zeroing of the atomically accumulated small gradients and of the BatchNorm sums.
+__global__ void __launch_bounds__(256) train_prep_kernel(PrepTable t) {
+  const PrepJob& j = t.job[blockIdx.y];
+  const long long stride = (long long)gridDim.x * blockDim.x, i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j.type == 0) {
+    const int ncta = j.n_out / j.nsplit, taps = j.taps, S_in = j.S_in, cin = j.cin, cout = j.cout;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(j.dst);
+    for (long long idx = i0; idx < j.n; idx += stride) {
+      const int k = (int)(idx & 7);
+      int q = (int)(idx >> 3);
+      const int nn = q % ncta; q /= ncta;
+      const int s = q % S_in; q /= S_in;
+      const int tap = q % taps;
+      const int sp = q / taps;
+      const int o = sp * ncta + nn, i = s * 8 + k;
+      float v = 0.f;
+      if (!j.transpose) {
+        if (o < cout && i < cin) v = j.src[((long long)o * cin + i) * taps + tap];
+      } else {
+        if (o < cin && i < cout) v = j.src[((long long)i * cin + o) * taps + (taps - 1 - tap)];
+      }
+      dst[idx] = __float2bfloat16_rn(v);
+    }
+  } else if (j.type == 1) {
+    float* dst = reinterpret_cast<float*>(j.dst);
+    for (long long idx = i0; idx < j.n; idx += stride) dst[idx] = j.src[idx];
+  } else if (j.type == 2) {
+    float* dst = reinterpret_cast<float*>(j.dst);
+    for (long long idx = i0; idx < j.n; idx += stride) dst[idx] = 0.f;
+  } else {
+    double* dst = reinterpret_cast<double*>(j.dst);
+    for (long long idx = i0; idx < j.n; idx += stride) dst[idx] = 0.0;
+  }
+}
+
+int train_prep_launch(const PrepTable* t, cudaStream_t st) {
+  if (!t || t->n <= 0) return VC_OK;
+  if (t->n > kMaxPrepJobs) return VC_ERR_ARG;
+  train_prep_kernel<<<dim3(24, t->n), 256, 0, st>>>(*t);
   return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
 }
 

@@ -32,6 +32,10 @@ int pack_scene_launch(const float* img, int W, int C, const int* xs, const int* 
 int zero_halo_launch(void* sps, int S, int n_patches, int P, cudaStream_t stream);
 int gather_f32_launch(const float* img, int H, int W, int C, const int* xy, const unsigned char* ops, int n, int P,
                       int center_mode, float* out, cudaStream_t stream);
+// gather_tma.cu -- the same gather through a 3-D tensor map (cp.async.bulk.tensor) + bulk stores; VC_ERR_UNSUPPORTED when the
+// raster cannot be described by a tensor map (C % 4 != 0, misaligned) -> fall back to gather_f32_launch
+int gather_tma_launch(const float* img, int H, int W, int C, const int* xy, const unsigned char* ops, int n, int P, int center_mode,
+                      float* out, cudaStream_t stream);
 int gather_labels_launch(const void* gt, int gt_elem_bytes, int H, int W, const int* xy, const unsigned char* ops, int n, int P,
                          int center_mode, long long* labels, cudaStream_t stream);
 int scene_index_launch(const int* xs, const int* ys, int nx, int ny, int first, int count, int W, int C1, int C2, int P,
@@ -85,9 +89,24 @@ int tokens_tc_launch(const void* f_sps, const void* tparams, int n_patches, int 
 
 // wgrad_tc.cu -- weight gradients (rows are the reduction axis; both operands MN-major)
 size_t wgrad_workspace_bytes(int SB, int ntaps);
+// `defer` (nullable): instead of launching the split-K reduction, append it to the table; the caller then runs
+// wgrad_reduce_batched_launch once for the whole backward pass (every deferred job needs its own workspace)
+constexpr int kMaxWgradJobs = 20;
+struct WgradReduceJob {
+  const float* part;
+  float* out;
+  float* out_bias;
+  long long sm, sn, st;
+  int nparts, ntaps, N, M, Nr, bias_col, accumulate;
+};
+struct WgradReduceTable {
+  WgradReduceJob job[kMaxWgradJobs];
+  int n;
+};
 int wgrad_sps_launch(const void* A, int SA, const void* B, int SB, int n_patches, int P, int ntaps, int shift_on_a,
                      void* workspace, float* out, int M, int Nr, long long sm, long long sn, long long st,
-                     int bias_col, float* out_bias, int accumulate, cudaStream_t stream);
+                     int bias_col, float* out_bias, int accumulate, cudaStream_t stream, WgradReduceTable* defer = nullptr);
+int wgrad_reduce_batched_launch(const WgradReduceTable* t, cudaStream_t stream);
 
 
 int wgrad_reduce_launch(const float* part, int nparts, int ntaps, int N, int M, int Nr, float* out, long long sm, long long sn,
@@ -104,6 +123,29 @@ int bn_forward_launch(const void* y, void* z, int S, int C, int n_patches, int P
 int bn_backward_launch(const void* dz, const void* y, void* dy, int S, int C, int n_patches, int P, const float* scale,
                        const float* shift, const float* mean, const float* rstd, int relu, double* sums, float* dgamma,
                        float* dbeta, float* dbias, int accumulate, cudaStream_t st);
+// The same two passes in two launches each (training step: launch-count bound at small per-GPU batches): the
+// statistics are finalised / the parameter gradients written by the apply kernel itself; `sums` (2 * S * 8 doubles,
+// this call's own) must be zero on entry and is NOT cleared (the step's prep launch clears every layer's at once).
+int bn_forward_fused_launch(const void* y, void* z, int S, int C, int n_patches, int P, const float* gamma, const float* beta,
+                            float eps, float momentum, float* running_mean, float* running_var, long long* nbt, double* sums,
+                            float* scale, float* shift, float* mean, float* rstd, int relu, cudaStream_t st);
+int bn_backward_fused_launch(const void* dz, const void* y, void* dy, int S, int C, int n_patches, int P, const float* scale,
+                             const float* shift, const float* mean, const float* rstd, int relu, double* sums, float* dgamma,
+                             float* dbeta, float* dbias, cudaStream_t st);
+// One launch for the small per-step chores: type 0 pack_conv_w (src fp32 weight -> bf16 operand), 1 copy fp32,
+// 2 zero fp32, 3 zero fp64
+constexpr int kMaxPrepJobs = 40;
+struct PrepJob {
+  const float* src;
+  void* dst;
+  long long n;
+  int type, cout, cin, taps, transpose, S_in, n_out, nsplit;
+};
+struct PrepTable {
+  PrepJob job[kMaxPrepJobs];
+  int n;
+};
+int train_prep_launch(const PrepTable* t, cudaStream_t st);
 int ce_loss_launch(const float* logits, const long long* labels, const float* weight, int n, int K, float grad_scale,
                    float* loss_out, float* dlogits, double* acc, cudaStream_t st);
 int adam_launch(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,

@@ -192,15 +192,14 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_sps_tc_kernel(WgradArgs a) {
 // column n == bias_col (if >= 0) goes to out_bias[m] instead (the "ones" slice of the B operand).
 // A block owns 32 consecutive (tap, m, n) elements; its 8 warps sum interleaved subsets of the
 // partials and are combined in a fixed order (deterministic, coalesced 128-byte reads).
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int ntaps, int N, int M,
-                                                           int Nr, float* __restrict__ out, long long sm, long long sn,
-                                                           long long st, int bias_col, float* __restrict__ out_bias,
-                                                           int accumulate) {
+__device__ __forceinline__ void wgrad_reduce_body(const float* __restrict__ part, int nparts, int ntaps, int N, int M, int Nr,
+                                                  float* __restrict__ out, long long sm, long long sn, long long st, int bias_col,
+                                                  float* __restrict__ out_bias, int accumulate, int block, int nblocks) {
   __shared__ float red[8][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long total = (long long)ntaps * M * N;
   const long long pstride = (long long)ntaps * 128 * N;
-  for (long long base = (long long)blockIdx.x * 32; base < total; base += (long long)gridDim.x * 32) {
+  for (long long base = (long long)block * 32; base < total; base += (long long)nblocks * 32) {
     const long long idx = base + lane;
     int n = 0, m = 0, tap = 0;
     float s = 0.f;
@@ -225,6 +224,27 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     }
     __syncthreads();
   }
+}
+
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int ntaps, int N, int M,
+                                                           int Nr, float* __restrict__ out, long long sm, long long sn,
+                                                           long long st, int bias_col, float* __restrict__ out_bias,
+                                                           int accumulate) {
+  wgrad_reduce_body(part, nparts, ntaps, N, M, Nr, out, sm, sn, st, bias_col, out_bias, accumulate, blockIdx.x, gridDim.x);
+}
+
+// every deferred reduction of one backward pass in ONE launch: blockIdx.y = job (the training step at small per-GPU
+// batches is bound by the number of launches, not by their work)
+__global__ void __launch_bounds__(256) wgrad_reduce_batched_kernel(WgradReduceTable t) {
+  const WgradReduceJob& j = t.job[blockIdx.y];
+  wgrad_reduce_body(j.part, j.nparts, j.ntaps, j.N, j.M, j.Nr, j.out, j.sm, j.sn, j.st, j.bias_col, j.out_bias, j.accumulate,
+                    blockIdx.x, gridDim.x);
+}
+
+int wgrad_reduce_batched_launch(const WgradReduceTable* t, cudaStream_t stream) {
+  if (!t || t->n <= 0) return VC_OK;
+  wgrad_reduce_batched_kernel<<<dim3(148, t->n), 256, 0, stream>>>(*t);
+  return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
 }
 
 int wgrad_reduce_launch(const float* part, int nparts, int ntaps, int N, int M, int Nr, float* out, long long sm, long long sn,
@@ -259,7 +279,7 @@ size_t wgrad_workspace_bytes(int SB, int ntaps) {
 // n_patches then carries the number of 128-row tiles.
 int wgrad_sps_launch(const void* A, int SA, const void* B, int SB, int n_patches, int P, int ntaps, int shift_on_a,
                      void* workspace, float* out, int M, int Nr, long long sm, long long sn, long long st,
-                     int bias_col, float* out_bias, int accumulate, cudaStream_t stream) {
+                     int bias_col, float* out_bias, int accumulate, cudaStream_t stream, WgradReduceTable* defer) {
   if (SA < 1 || SA > 16 || SB < 2 || (SB & 1) || SB > 32 || (ntaps != 1 && ntaps != 9) || n_patches <= 0 || P < 0 ||
       M > SA * 8 || Nr > SB * 8 || !workspace || (P == 0 && ntaps != 1))
     return VC_ERR_ARG;
@@ -311,6 +331,12 @@ int wgrad_sps_launch(const void* A, int SA, const void* B, int SB, int n_patches
   dim3 grid(gx, groups);
   wgrad_sps_tc_kernel<<<grid, kWgThreads, smem, stream>>>(a);
   if (cudaGetLastError() != cudaSuccess) return VC_ERR_CUDA;
+  if (defer && defer->n < kMaxWgradJobs) {      // the caller reduces every job of the pass in one launch (own workspace per job)
+    WgradReduceJob& j = defer->job[defer->n++];
+    j.part = a.part; j.out = out; j.out_bias = out_bias; j.sm = sm; j.sn = sn; j.st = st;
+    j.nparts = gx; j.ntaps = ntaps; j.N = N; j.M = M; j.Nr = Nr; j.bias_col = bias_col; j.accumulate = accumulate;
+    return VC_OK;
+  }
   const long long total = (long long)ntaps * M * N;
   int blocks = (int)((total + 31) / 32);
   if (blocks > 148 * 8) blocks = 148 * 8;
