@@ -393,6 +393,7 @@ def bench_train(args, c, rank, world, dev, dist, barrier):
     total_ms = sum(v[0] for v in prof.values())
     breakdown = {k2: round(v[0], 3) for k2, v in prof.items() if v[1]}
     breakdown["allreduce"] = round(tr.allreduce_ms(), 4)      # the one collective of the step, timed alone (0 for one rank)
+    tr.close()                                                # graphs with NCCL kernels must be gone before the group is destroyed
     return {"metric": "train_samples_per_s", "value": args.train_batch * steps / (ms / 1e3), "unit": "samples/s",
             "ms_per_step": ms / steps, "steps": steps, "global_batch": args.train_batch, "per_gpu_batch": per,
             "parallelism": f"dp{world}", "scaling": "strong", "dtype": "bf16", "optimizer": "Adam(lr=1e-3)",
@@ -431,6 +432,10 @@ def main():
     ap.add_argument("--no-infer", action="store_true", help="profiling aid: training leg only")
     ap.add_argument("--train-batch", type=int, default=4096, help="GLOBAL batch of the training leg (configs[2])")
     args = ap.parse_args()
+    # a rank that gets stuck (a collective its peers never enter, a wedged teardown) must not hold the node: dump every
+    # thread's stack to stderr and leave after VITCNN_BENCH_WATCHDOG seconds (default 15 min; the default run needs ~1.5)
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("VITCNN_BENCH_WATCHDOG", "900")), exit=True)
     c = make_cfg(args.workload, args.patch)
     H, W, C1, C2, K, P = c.H, c.W, c.C1, c.C2, c.K, c.P
     rank = int(os.environ.get("RANK", "0"))
@@ -684,6 +689,9 @@ def main():
             line["train"] = train_line
         print(json.dumps(line), flush=True)
     if world > 1:
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 

@@ -17,6 +17,7 @@ canonical order of include/vitcnn.h) so that packing, all-reduce and Adam are si
 from __future__ import annotations
 
 import ctypes
+import weakref
 
 import numpy as np
 import torch
@@ -325,7 +326,10 @@ class Trainer:
         self.world = self.dist.get_world_size(process_group) if self.dist else 1
         self.use_graph, self.graph_warmup = use_graph, graph_warmup
         self._graphs = {}       # batch size -> (graph, static xy, static loss)
-        self.state.on_evict.append(lambda n: self._graphs.pop(n, None))
+        # (weak: the state must not keep the trainer -- and with it CUDA graphs that captured NCCL kernels -- alive in a
+        # reference cycle; a communicator cannot be destroyed while such a graph exists)
+        me = weakref.ref(self)
+        self.state.on_evict.append(lambda n, me=me: me() is not None and me()._graphs.pop(n, None))
         self.launches_per_step = 0
         self._eager_steps = 0
 
@@ -345,6 +349,10 @@ class Trainer:
         self._base_lr = base_lr
         self.set_lr(base_lr * gamma ** (epoch // step_size))
         return self.lr
+
+    def close(self) -> None:
+        """Drop the captured CUDA graphs (they hold NCCL kernels: ``destroy_process_group`` waits for them to be gone)."""
+        self._graphs.clear()
 
     def allreduce_ms(self, iters: int = 20) -> float:
         """Device time of the gradient all-reduce alone (one flat fp32 bucket, NCCL), CUDA events, mean of `iters`
