@@ -123,6 +123,24 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) { 
       mbar_arrive(bar);
 #endif
     };
+    // MUFU-phase lock (VC_TC_MUFU_LOCK): the three slots' warps on one SM sub-partition share its MUFU pipe; left alone they
+    // drift into the softmax phases together (processor sharing: all three finish late, then all three leave the pipe idle).
+    // First-come-first-served per sub-partition lets one warp run its exponentials at the full pipe rate while the others
+    // are still in (or return to) their latency-bound phases.
+    uint32_t* mufu_lock = reinterpret_cast<uint32_t*>(smem + MISC + M_LOCK) + wq;
+    auto mufu_acquire = [&]() {
+#if VC_TC_MUFU_LOCK
+      if (lane == 0)
+        while (atomicCAS(mufu_lock, 0u, 1u) != 0u) __nanosleep(40);
+      __syncwarp();
+#endif
+    };
+    auto mufu_release = [&]() {
+#if VC_TC_MUFU_LOCK
+      __syncwarp();
+      if (lane == 0) atomicExch(mufu_lock, 0u);
+#endif
+    };
     auto publish = [&]() {
       fence_proxy_async();
       tc_fence_before();
@@ -235,6 +253,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) { 
           tc_fence_after();
           read_o(h - 1);
         }
+        mufu_acquire();
 #if VC_TC_LD16
         // 16-key half chunks, double buffered: the TMEM load of half chunk c + 1 is in flight while c is exponentiated
         {
@@ -299,6 +318,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) { 
           }
         }
 #endif
+        mufu_release();
         publish();
       };
       if (exact_softmax) {
@@ -336,6 +356,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) { 
       {
         uint32_t v[2][32];
         tmem_ld32(tl + C_S, v[0]);
+        mufu_acquire();
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           tc_wait_ld();
@@ -352,6 +373,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) { 
                    pack_bf16(gelu2(__uint_as_float(vv[6]) + b1_.z), gelu2(__uint_as_float(vv[7]) + b1_.w)));
           }
         }
+        mufu_release();
       }
       publish();
       wait_mma();

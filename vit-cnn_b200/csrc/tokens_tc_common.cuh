@@ -43,7 +43,8 @@ constexpr uint32_t ONES = SLOT0 + kSlots * SLOT_BYTES;  // [128][8] = (1,0,0,0,0
 constexpr uint32_t MASK = ONES + SLAB;             // [128 keys][8] = (0 | -30000 for padded keys, 0, ..): K's second K chunk
 constexpr uint32_t MISC = MASK + SLAB;            // q0 [slots][32] f32, wmax [slots][4][4] f32, barriers [slots][5], tmem slot
 constexpr uint32_t M_Q0 = 0, M_WMAX = M_Q0 + kSlots * 128, M_BARS = M_WMAX + kSlots * 64, M_TMEM = M_BARS + kSlots * 40;
-constexpr uint32_t SMEM_BYTES = MISC + ((M_TMEM + 4 + 127) & ~127u);
+constexpr uint32_t M_LOCK = M_TMEM + 8;            // [4] one word per SM sub-partition: which slot's warp holds its MUFU pipe (VC_TC_MUFU_LOCK)
+constexpr uint32_t SMEM_BYTES = MISC + ((M_LOCK + 16 + 127) & ~127u);
 // ---- TMEM columns inside a slot's 160: S / qkv / fc1 accumulators at 0, two 16-column O_h buffers at 128 (the
 // 32-column fusion / proj / fc2 accumulators reuse them) ----
 constexpr uint32_t C_SLOT = 160, C_S = 0, C_O = 128, C_SMALL = 128;
@@ -246,6 +247,7 @@ __device__ __forceinline__ void tc_setup(const TcArgs& a, uint8_t* smem, int tid
       }
       fence_mbar_init();
     }
+    if (tid < 4) reinterpret_cast<uint32_t*>(smem + MISC + M_LOCK)[tid] = 0u;
     if (tid < 32) {
       tmem_alloc(tmem_slot, 512);
       tmem_relinquish();
