@@ -130,6 +130,7 @@ StemDesc lidar_stem(const vc_model* m) {
 // depth D: 3 / 2: B = 31, the first three / two convs shared (P >= 2D + 1); 1: B = 15, conv 1 only (P >= 2).
 struct SceneWs {
   long long* boff;
+  int *rowterm, *colterm;           // block-row offset tables of the raster rows / columns (token kernel reading the planes)
   uint8_t *blocks, *var[3];
   long long RTb, plane[3], bytes;   // bytes == 0: this depth does not apply to the model / raster; else the END offset
   int nb, B, D;
@@ -147,6 +148,8 @@ SceneWs carve_scene(void* base, long long off, const StemDesc& sd, int H, int W,
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
   auto take = [&](long long bytes) { uint8_t* r = p + off; off += (bytes + 255) & ~255LL; return r; };
   s.boff = reinterpret_cast<long long*>(take(8LL * s.nb));
+  s.rowterm = reinterpret_cast<int*>(take(4LL * H));
+  s.colterm = reinterpret_cast<int*>(take(4LL * W));
   s.blocks = take(s.RTb * 16 * sd.S0);
   for (int l = 0; l < D; ++l) {
     s.plane[l] = (long long)(sd.n_out[l] / 8) * s.RTb * 16;
@@ -217,6 +220,7 @@ int neighbour_class(int L, int c, int d, int P) {
 // the neighbour's class (<= 9 planes per launch).
 int shared_stem(const StemDesc& sd, const SceneWs& sw, const float* img, int H, int W, int P, cudaStream_t st) {
   VC_LAUNCH(KC_INDEX, st, vc::block_offsets_launch(H, W, sd.C, sw.B, sw.D, sw.boff, st));
+  VC_LAUNCH(KC_INDEX, st, vc::scene_tables_launch(H, W, sw.B, sw.D, sw.rowterm, sw.colterm, st));
   VC_LAUNCH(KC_PACK, st, vc::pack_sps_launch(img, 0, 1, (long long)W * sd.C, sd.C, sw.boff, nullptr, sw.nb, sd.C, sw.B, sw.blocks,
                                              sd.S0, st));
   for (int v = 0; v < 9; ++v) {
@@ -555,14 +559,17 @@ int vc_scene_infer(const vc_model* m, const float* img1, const float* img2, int3
     const Workspace w = carve(workspace, n, m->P, m->S1, m->S2);
     const long long sl = vc::sps_rows(n, m->P) * 16;
     if ((done == 0 || n != chunk) && (mode < 3 || !lid_shared)) VC_TRY(zero_halos(w, n, m->P, st));
-    VC_LAUNCH(KC_INDEX, st, vc::scene_index_launch(xs, ys, nx, ny, first, n, W, m->C1, m->C2, m->P, m->K, w.off1, w.off2, w.oidx, nullptr,
-                                                   st));
+    // window corners of the chunk: raster offsets for the per-window gathers, (row, column) pairs for the token kernel when it
+    // reads the variant planes itself (the two uses are exclusive: the pairs live in the off1 array)
+    const bool want_xy = direct && ((mode == 3) || lid_shared);
+    VC_LAUNCH(KC_INDEX, st, vc::scene_index_launch(xs, ys, nx, ny, first, n, W, m->C1, m->C2, m->P, m->K, want_xy ? nullptr : w.off1, w.off2,
+                                                   w.oidx, want_xy ? reinterpret_cast<int*>(w.off1) : nullptr, st));
     vc::TcPlanes tp;
     memset(&tp, 0, sizeof(tp));
-    tp.xs = xs; tp.ys = ys; tp.ny = ny; tp.first = first; tp.H = H; tp.W = W;
+    tp.xy = reinterpret_cast<const int*>(w.off1);
     if (mode == 3 && direct) {
       tp.h = (const __nv_bfloat16*)sw.var[2];
-      tp.RTb = sw.RTb; tp.B = sw.B; tp.D = sw.D; tp.nbx = vc::blk_count(W, sw.B, sw.D);
+      tp.RTb = sw.RTb; tp.B = sw.B; tp.D = sw.D; tp.rowterm = sw.rowterm; tp.colterm = sw.colterm;
     } else if (mode) {
       VC_LAUNCH(KC_PACK, st, vc::border_gather_launch(sw.var[sw.D - 1], mode == 3 ? 4 : mode == 2 ? 8 : 16, sw.B, sw.D, H, W, xs, ys, ny,
                                                       first, n, m->P, mode == 3 ? w.f : mode == 2 ? w.a2 : w.a1, st));
@@ -576,7 +583,7 @@ int vc_scene_infer(const vc_model* m, const float* img1, const float* img2, int3
     }
     if (lid_shared && direct) {
       tp.l = (const __nv_bfloat16*)lw.var[2];      // same block geometry as the depth-3 HSI planes (B = 31, D = 3)
-      tp.RTb = lw.RTb; tp.B = lw.B; tp.D = lw.D; tp.nbx = vc::blk_count(W, lw.B, lw.D);
+      tp.RTb = lw.RTb; tp.B = lw.B; tp.D = lw.D; tp.rowterm = lw.rowterm; tp.colterm = lw.colterm;
     } else if (lid_shared) {
       VC_LAUNCH(KC_PACK, st, vc::border_gather_launch(lw.var[2], 4, lw.B, lw.D, H, W, xs, ys, ny, first, n, m->P, w.f + 4 * sl, st));
     } else {

@@ -271,6 +271,30 @@ int block_offsets_launch(int H, int W, int C, int B, int D, long long* off, cuda
   return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
 }
 
+// rowterm[y] = (block row of y) * blocks per row * rows per block + (y - block origin) * (B + 1); colterm[x] likewise for columns:
+// the plane row of scene pixel (y, x) is sps_halo(B) + rowterm[y] + colterm[x] (what border_gather_kernel computes inline)
+__global__ void scene_tables_kernel(int H, int W, int B, int D, int nbx, int* __restrict__ rowterm, int* __restrict__ colterm) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int PPB = sps_pp(B);
+  if (t < H) {
+    const int ky = blk_index(t, H, B, D);
+    rowterm[t] = ky * nbx * PPB + (t - blk_origin(ky, H, B, D)) * (B + 1);
+  }
+  if (t < W) {
+    const int kx = blk_index(t, W, B, D);
+    colterm[t] = kx * PPB + (t - blk_origin(kx, W, B, D));
+  }
+}
+
+int scene_tables_launch(int H, int W, int B, int D, int* rowterm, int* colterm, cudaStream_t stream) {
+  if (H < B || W < B || B <= 2 * D || !rowterm || !colterm) return VC_ERR_ARG;
+  const int nbx = blk_count(W, B, D);
+  if ((long long)blk_count(H, B, D) * nbx * sps_pp(B) >= (1LL << 31)) return VC_ERR_UNSUPPORTED;
+  const int n = H > W ? H : W;
+  scene_tables_kernel<<<(n + 255) / 256, 256, 0, stream>>>(H, W, B, D, nbx, rowterm, colterm);
+  return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
+}
+
 struct BorderGatherArgs {
   const __nv_bfloat16* v;     // [(2D+1)^2 variants][S][RTb][8]: depth-D stem variants over the scene blocks
   __nv_bfloat16* out;         // [>= S][RTo][8]: stem output of the chunk's windows (slices 0..S-1 are written)

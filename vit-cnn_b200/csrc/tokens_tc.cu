@@ -84,24 +84,22 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) { 
     const bool w0 = wq == 0;
     uint32_t ph_m = 0, ph_s = 0, ph_pv = 0;
     // stem outputs of token row r of patch b -> FBUF (8 slices x 16 B; cls row and padding rows stay zero)
+    // planes mode (shared stem, depth D): the stem output of window pixel (i, j) is the variant plane of border_class(i) x
+    // border_class(j) at the scene pixel's row in its scene block; (i, j) and with them the variant are fixed per thread
+    const int tok_i = r >= 1 && r < T ? (r - 1) / P : 0, tok_j = r >= 1 && r < T ? (r - 1) - tok_i * P : 0;
+    const bool planes = a.pl.h || a.pl.l;
+    const long long voff0 = planes ? ((long long)(border_class(tok_i, P, a.pl.D) * (2 * a.pl.D + 1) + border_class(tok_j, P, a.pl.D)) * 4 * a.pl.RTb +
+                                      sps_halo(a.pl.B)) : 0;
     auto fetch = [&](int b) {
       if (r >= 1 && r < T) {
-        const int p = r - 1, i = p / P, j = p - i * P;
-        const __nv_bfloat16* src = a.f + (HALO + (long long)b * PP + i * PW + j) * 8;
+        const __nv_bfloat16* src = a.f + (HALO + (long long)b * PP + tok_i * PW + tok_j) * 8;
         const __nv_bfloat16 *sh = src, *sl = src + 4 * a.RT * 8;
         long long ph = a.RT * 8, pls = a.RT * 8;          // slice pitch (elements) of the HSI / LiDAR source
-        if (a.pl.h || a.pl.l) {
-          // shared stem, depth D: the stem output of window pixel (i, j) is the variant plane of
-          // border_class(i) x border_class(j) at the scene pixel's row in its scene block (pack.cu)
-          const TcPlanes& q = a.pl;
-          const int widx = q.first + b, ix = widx / q.ny, iy = widx - ix * q.ny;
-          const int y = __ldg(q.xs + ix) + i, x = __ldg(q.ys + iy) + j;
-          const int ky = blk_index(y, q.H, q.B, q.D), kx = blk_index(x, q.W, q.B, q.D);
-          const long long srow = sps_halo(q.B) + (long long)(ky * q.nbx + kx) * sps_pp(q.B) +
-                                 (y - blk_origin(ky, q.H, q.B, q.D)) * (q.B + 1) + (x - blk_origin(kx, q.W, q.B, q.D));
-          const long long voff = ((long long)(border_class(i, P, q.D) * (2 * q.D + 1) + border_class(j, P, q.D)) * 4 * q.RTb + srow) * 8;
-          if (q.h) { sh = q.h + voff; ph = q.RTb * 8; }
-          if (q.l) { sl = q.l + voff; pls = q.RTb * 8; }
+        if (planes) {
+          const int2 c = __ldg(reinterpret_cast<const int2*>(a.pl.xy) + b);
+          const long long voff = (voff0 + __ldg(a.pl.rowterm + c.x + tok_i) + __ldg(a.pl.colterm + c.y + tok_j)) * 8;
+          if (a.pl.h) { sh = a.pl.h + voff; ph = a.pl.RTb * 8; }
+          if (a.pl.l) { sl = a.pl.l + voff; pls = a.pl.RTb * 8; }
         }
 #pragma unroll
         for (int s = 0; s < 4; ++s) cp_async16(fbuf + s * SLAB + row16, sh + s * ph);
@@ -614,7 +612,7 @@ int tokens_tc_launch(const void* f_sps, const void* tparams, int n_patches, int 
                      const long long* out_index, unsigned char* argmax_map, void* scratch, const TcPlanes* planes,
                      cudaStream_t stream) {
   if (n_patches <= 0 || !scratch || !tokens_tc_supported(P, K)) return VC_ERR_ARG;
-  if (planes && (planes->h || planes->l) && (P < 2 * planes->D + 1 || !planes->xs || !planes->ys)) return VC_ERR_ARG;
+  if (planes && (planes->h || planes->l) && (P < 2 * planes->D + 1 || !planes->xy || !planes->rowterm || !planes->colterm)) return VC_ERR_ARG;
   int dev = 0, max_smem = 0, num_sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);

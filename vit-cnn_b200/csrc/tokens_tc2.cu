@@ -80,21 +80,18 @@ __global__ void __launch_bounds__(tc2::threads(SLOTS), 1) tokens_tc2_kernel(TcAr
     uint32_t ph_m = 0, ph_s = 0, ph_pv = 0;
 
     // stem outputs of token row r of patch b -> FBUF: this thread brings 4 of the 8 slices (hsel 0: HSI, 1: LiDAR)
+    const int tok_i = r >= 1 && r < T ? (r - 1) / P : 0, tok_j = r >= 1 && r < T ? (r - 1) - tok_i * P : 0;
+    const __nv_bfloat16* plane = hsel ? a.pl.l : a.pl.h;
+    const long long voff0 = plane ? ((long long)(border_class(tok_i, P, a.pl.D) * (2 * a.pl.D + 1) + border_class(tok_j, P, a.pl.D)) * 4 * a.pl.RTb +
+                                     sps_halo(a.pl.B)) : 0;
     auto fetch = [&](int b) {
       if (r >= 1 && r < T) {
-        const int p = r - 1, i = p / P, j = p - i * P;
-        const __nv_bfloat16* src = a.f + ((long long)(4 * hsel) * a.RT + HALO + (long long)b * PP + i * PW + j) * 8;
+        const __nv_bfloat16* src = a.f + ((long long)(4 * hsel) * a.RT + HALO + (long long)b * PP + tok_i * PW + tok_j) * 8;
         long long pitch = a.RT * 8;
-        const __nv_bfloat16* plane = hsel ? a.pl.l : a.pl.h;
         if (plane) {
-          const TcPlanes& q = a.pl;
-          const int widx = q.first + b, ix = widx / q.ny, iy = widx - ix * q.ny;
-          const int y = __ldg(q.xs + ix) + i, x = __ldg(q.ys + iy) + j;
-          const int ky = blk_index(y, q.H, q.B, q.D), kx = blk_index(x, q.W, q.B, q.D);
-          const long long srow = sps_halo(q.B) + (long long)(ky * q.nbx + kx) * sps_pp(q.B) +
-                                 (y - blk_origin(ky, q.H, q.B, q.D)) * (q.B + 1) + (x - blk_origin(kx, q.W, q.B, q.D));
-          src = plane + ((long long)(border_class(i, P, q.D) * (2 * q.D + 1) + border_class(j, P, q.D)) * 4 * q.RTb + srow) * 8;
-          pitch = q.RTb * 8;
+          const int2 c = __ldg(reinterpret_cast<const int2*>(a.pl.xy) + b);
+          src = plane + (voff0 + __ldg(a.pl.rowterm + c.x + tok_i) + __ldg(a.pl.colterm + c.y + tok_j)) * 8;
+          pitch = a.pl.RTb * 8;
         }
 #pragma unroll
         for (int s = 0; s < 4; ++s) cp_async16(fbuf + (4 * hsel + s) * SLAB + row16, src + s * pitch);

@@ -75,14 +75,19 @@ bool tokens_tc_supported(int P, int K);
 // Stem outputs read straight from the variant planes of the shared stem (dense scenes, sharing depth D on B x B
 // scene blocks): h / l = [(2D+1)^2 variants][4 slices][RTb][8] conv-3 planes of the HSI / LiDAR stem (null: that
 // half comes from slices 0-3 / 4-7 of f_sps); patch b of the launch is window first + b of the (xs, ys) grid.
+// xy: int32 [n][2] top-left corner (row, column) of every window of the launch (scene_index_launch); rowterm [H] / colterm [W]:
+// block-row offset of raster row y / column x inside the block that holds it (scene_tables_launch), so that the plane row of
+// a scene pixel is sps_halo(B) + rowterm[y] + colterm[x] -- two table reads instead of divisions per token and patch.
 struct TcPlanes {
   const __nv_bfloat16* h;
   const __nv_bfloat16* l;
-  const int* xs;
-  const int* ys;
+  const int* xy;
+  const int* rowterm;
+  const int* colterm;
   long long RTb;
-  int ny, first, H, W, B, D, nbx;
+  int B, D;
 };
+int scene_tables_launch(int H, int W, int B, int D, int* rowterm, int* colterm, cudaStream_t stream);
 int tokens_tc_launch(const void* f_sps, const void* tparams, int n_patches, int P, int K, float* logits,
                      const long long* out_index, unsigned char* argmax_map, void* scratch, const TcPlanes* planes,
                      cudaStream_t stream);
