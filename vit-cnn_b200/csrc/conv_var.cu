@@ -12,6 +12,11 @@
 // conv's order (K step, then tap 0..8, dropped taps skipped), so the results are bit-identical to the per-window
 // conv (tests/test_gpu_scene.py::test_shared_stem_is_bit_identical_to_the_per_window_path).
 //
+// Accumulators: TMEM is used as a RING of slots, each with its own full / empty barrier pair.  Where two whole units fit the
+// 512 columns (conv 3: 7 x 32 = 224 each) a slot is a unit: classic double buffering.  Conv 2 of the HSI stem needs 5 x 64 = 320
+// columns per unit, so there a slot is ONE variant (8 slots): the epilogue drains a variant as soon as its last instruction has
+// landed while the issuer is already filling the following slots with the next variants / the next unit.
+//
 // Geometry: scene blocks of B = 31 pixels as SPS "patches" (pitch PW = 32 rows, lead halo 40 rows: vc_common.cuh),
 // so every slab a tap row needs starts at a multiple of 8 rows = 128 bytes: slab(dy) = rows [R0 + 32 dy - 8,
 // R0 + 32 dy + 136) of the input plane, the tap (dy, dx) reads it at row offset 8 + dx.
@@ -34,7 +39,7 @@ struct ConvVarArgs {
   const float* bias;          // [n]
   __nv_bfloat16* out;         // [NC*NC planes][n/8][RT][8]: conv L variants
   long long RT, in_plane, out_plane;     // rows per slice; elements per input / output plane
-  int S_in, n, NC, NP, B, n_blocks, ntiles, relu, nstages, nbuf;
+  int S_in, n, NC, NP, B, n_blocks, ntiles, relu, nstages, nslots, vps;   // vps: variants per ring slot (1, or NC = a whole unit)
   signed char ry[cv::kMaxNC][3];         // input row class of tap row dy for output row class cy (-1: outside the window)
   signed char rx[cv::kMaxNC][3];         // input column class of tap column dx for output column class cx
 };
@@ -42,9 +47,17 @@ struct ConvVarArgs {
 __global__ void __launch_bounds__(cv::kThreads) conv_var_kernel(ConvVarArgs a) {
   using namespace cv;
   extern __shared__ __align__(128) uint8_t smem[];
+  // issue table: for (row class, column class, tap) the 16-byte-unit offset of the tap's A operand inside a stage, or
+  // 0xFFFFFFFF when the tap leaves the window -- the issuing thread must spend as few instructions per MMA as possible
+  __shared__ uint32_t tap_tab[kMaxNC * kMaxNC * 9];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int PW = a.B + 1, HALO = sps_halo(a.B), PP = sps_pp(a.B);
   const int KS = a.S_in / 2, NC = a.NC, NP = a.NP, n = a.n;
+  for (int t = threadIdx.x; t < NC * NC * 9; t += blockDim.x) {
+    const int tap = t % 9, cx = (t / 9) % NC, cy = t / (9 * NC);
+    const int d = tap / 3, e = tap % 3, rxp = a.rx[cx][e];
+    tap_tab[t] = (a.ry[cy][d] < 0 || rxp < 0) ? 0xFFFFFFFFu : (uint32_t)((d * NP + rxp) * 2) * (kSlabBytes >> 4) + (uint32_t)(8 + e - 1);
+  }
   const uint32_t a_bytes = 3u * (uint32_t)NP * 2u * kSlabBytes;          // input slabs of one K step: [dy][rx][2 slices]
   const uint32_t w_bytes = 9u * 2u * (uint32_t)n * 16u;                  // weights of one K step: [tap][2 slices][n][8]
   const uint32_t stage_bytes = a_bytes + w_bytes;
@@ -56,9 +69,9 @@ __global__ void __launch_bounds__(cv::kThreads) conv_var_kernel(ConvVarArgs a) {
   uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bi_s + n) + 7) & ~uintptr_t(7));
   uint64_t* full = bars;
   uint64_t* empty = bars + a.nstages;
-  uint64_t* tfull = bars + 2 * a.nstages;     // [2]
-  uint64_t* tempty = tfull + 2;               // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* tfull = bars + 2 * a.nstages;     // [nslots <= 32]
+  uint64_t* tempty = tfull + 32;              // [nslots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 32);
 
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     sc_s[i] = a.scale[i];
@@ -69,7 +82,7 @@ __global__ void __launch_bounds__(cv::kThreads) conv_var_kernel(ConvVarArgs a) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < a.nslots; ++b) {
       mbar_init(&tfull[b], 1);
       mbar_init(&tempty[b], 128);
     }
@@ -83,7 +96,8 @@ __global__ void __launch_bounds__(cv::kThreads) conv_var_kernel(ConvVarArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t buf_cols = (uint32_t)(NC * n);          // accumulators of one unit, side by side
+  const int nslots = a.nslots, vps = a.vps;               // accumulator ring: slot = (variants issued so far) / vps % nslots
+  const int spu = NC / vps;                               // slots per unit (NC, or 1)
 
   if (warp == 0) {
     // ===== producer: per (unit, K step) the slabs of every input plane the unit's taps read + the K step's weights =====
@@ -128,46 +142,60 @@ __global__ void __launch_bounds__(cv::kThreads) conv_var_kernel(ConvVarArgs a) {
     const uint32_t a_lbo_lo = (uint32_t)(umma_desc(0, kSlabBytes, 128) & 0xFFFF0000u);
     const uint32_t b_lbo_lo = (uint32_t)(umma_desc(0, (uint32_t)n * 16u, 128) & 0xFFFF0000u);
     const uint32_t s_lo0 = (smem_u32(stage_s) & 0x3FFFFu) >> 4;
-    int st = 0, acc = 0;
-    uint32_t ph = 0, accph = 0;
+    int st = 0;
+    uint32_t ph = 0;
+    int slot0 = 0;                        // ring slot of this unit's column class 0 ...
+    uint32_t lap0 = 0;                    // ... and the parity of its lap around the ring (no divisions on the issue path)
     for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
       const int cy = u % NC;
-      mbar_wait(&tempty[acc], accph ^ 1u);
-      tc_fence_after();
-      const uint32_t d_base = tmem_base + (uint32_t)acc * buf_cols;
       for (int ks = 0; ks < KS; ++ks) {
         mbar_wait(&full[st], ph);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t a_lo0 = a_lbo_lo | (s_lo0 + (uint32_t)st * (stage_bytes >> 4));
-          const uint32_t b_lo0 = b_lbo_lo | (s_lo0 + (uint32_t)st * (stage_bytes >> 4) + (a_bytes >> 4));
+        const uint32_t a_lo0 = a_lbo_lo | (s_lo0 + (uint32_t)st * (stage_bytes >> 4));
+        const uint32_t b_lo0 = b_lbo_lo | (s_lo0 + (uint32_t)st * (stage_bytes >> 4) + (a_bytes >> 4));
+        if (ks == 0) {                    // the slots' previous tenants have been drained by the epilogue
+          int slot = slot0;
+          uint32_t lap = lap0;
+          for (int k = 0; k < spu; ++k) {
+            mbar_wait(&tempty[slot], lap ^ 1u);
+            if (++slot == nslots) { slot = 0; lap ^= 1u; }
+          }
+          tc_fence_after();
+        }
+        if (elect_one()) {                // one warp-uniform region issues the whole K step: instruction issue must not stall
+          int slot = slot0, sub = 0;
+          const uint32_t* tab = tap_tab + cy * NC * 9;
+          uint32_t d_col = tmem_base + (uint32_t)(slot * vps * n);
           for (int cx = 0; cx < NC; ++cx) {
-            uint32_t go = ks != 0 ? 1u : 0u;        // the first instruction of a unit overwrites the accumulator
+            uint32_t go = ks != 0 ? 1u : 0u;        // the first instruction of a variant overwrites its accumulator
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-              const int d = tap / 3, e = tap % 3;
-              const int rxp = a.rx[cx][e];
-              if (a.ry[cy][d] < 0 || rxp < 0) continue;           // the tap leaves the window: zero padding
-              umma_bf16(d_base + (uint32_t)(cx * n),
-                        a_hi | (uint64_t)(a_lo0 + (uint32_t)((d * NP + rxp) * 2) * (kSlabBytes >> 4) + (uint32_t)(8 + e - 1)),
-                        b_hi | (uint64_t)(b_lo0 + (uint32_t)tap * (uint32_t)(2 * n)), idesc, go);
+              const uint32_t off = tab[cx * 9 + tap];
+              if (off == 0xFFFFFFFFu) continue;                   // the tap leaves the window: zero padding
+              umma_bf16(d_col, a_hi | (uint64_t)(a_lo0 + off), b_hi | (uint64_t)(b_lo0 + (uint32_t)tap * (uint32_t)(2 * n)), idesc, go);
               go = 1u;
+            }
+            d_col += (uint32_t)n;
+            if (++sub == vps) {           // last variant of the slot: it is complete after the last K step
+              if (ks + 1 == KS) umma_commit(&tfull[slot]);
+              sub = 0;
+              if (++slot == nslots) { slot = 0; d_col = tmem_base; }
             }
           }
           umma_commit(&empty[st]);
-          if (ks + 1 == KS) umma_commit(&tfull[acc]);
         }
         __syncwarp();
         if (++st == a.nstages) { st = 0; ph ^= 1u; }
       }
-      if (++acc == a.nbuf) { acc = 0; accph ^= 1u; }
+      slot0 += spu;
+      if (slot0 >= nslots) { slot0 -= nslots; lap0 ^= 1u; }
     }
   } else {
     // ===== epilogue: TMEM -> affine (+ReLU) -> bf16 -> the 2L+1 output planes of this row class =====
     const int quarter = warp & 3;
     const int row_in_tile = quarter * 32 + lane;
-    int acc = 0;
-    uint32_t accph = 0;
+    int slot = 0, sub = 0;
+    uint32_t lap = 0;
     for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
       const int tile = u / NC, cy = u - tile * NC;
       const long long r = (long long)tile * 128 + row_in_tile;
@@ -176,14 +204,16 @@ __global__ void __launch_bounds__(cv::kThreads) conv_var_kernel(ConvVarArgs a) {
       const int q = (int)(r - b * PP);
       const int i = q / PW, j = q - i * PW;
       const bool valid = (b < a.n_blocks) && (i < a.B) && (j < a.B);
-      mbar_wait(&tfull[acc], accph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * buf_cols;
       for (int cx = 0; cx < NC; ++cx) {
+        if (sub == 0) {
+          mbar_wait(&tfull[slot], lap);
+          tc_fence_after();
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((slot * vps + sub) * n);
         __nv_bfloat16* op = a.out + (long long)(cy * NC + cx) * a.out_plane;
         for (int c0 = 0; c0 < n; c0 += 16) {
           uint32_t v[16];
-          tmem_ld16(taddr + (uint32_t)(cx * n + c0), v);
+          tmem_ld16(taddr + (uint32_t)c0, v);
           tc_wait_ld();
           uint32_t pk[8];
 #pragma unroll
@@ -198,10 +228,13 @@ __global__ void __launch_bounds__(cv::kThreads) conv_var_kernel(ConvVarArgs a) {
           *reinterpret_cast<uint4*>(op + ((long long)slice * a.RT + R) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           *reinterpret_cast<uint4*>(op + ((long long)(slice + 1) * a.RT + R) * 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
+        if (++sub == vps) {
+          tc_fence_before();
+          mbar_arrive(&tempty[slot]);
+          sub = 0;
+          if (++slot == nslots) { slot = 0; lap ^= 1u; }
+        }
       }
-      tc_fence_before();
-      mbar_arrive(&tempty[acc]);
-      if (++acc == a.nbuf) { acc = 0; accph ^= 1u; }
     }
   }
 
@@ -239,14 +272,18 @@ int conv_var_launch(const void* in, int S_in, const void* w, const float* scale,
   a.S_in = S_in; a.n = n_out; a.NC = NC; a.NP = NP; a.B = B; a.n_blocks = n_blocks;
   a.ntiles = sps_tiles(n_blocks, B);
   a.relu = relu;
-  a.nbuf = 2 * NC * n_out <= 512 ? 2 : 1;       // double-buffered accumulators when two units' worth fit TMEM
+  // accumulator ring (see the header): two whole units when they fit TMEM (one barrier pair per unit: measured faster for
+  // conv 3, 3.17 vs 3.72 ms at the Houston shape), else one slot per variant (conv 2 of the HSI stem: 3.71 vs 4.38 ms)
+  a.vps = 2 * NC * n_out <= 512 ? NC : 1;
+  a.nslots = 512 / (a.vps * n_out);
+  if (a.nslots > 32) a.nslots = 32;
   for (int c = 0; c < kMaxNC; ++c)
     for (int d = 0; d < 3; ++d) {
       a.ry[c][d] = c < NC ? ry[c * 3 + d] : -1;
       a.rx[c][d] = c < NC ? rx[c * 3 + d] : -1;
     }
   const size_t stage = (size_t)3 * NP * 2 * kSlabBytes + (size_t)9 * 2 * n_out * 16;
-  const size_t fixed = (size_t)n_out * 8 + 8 + (2 * 4 + 4) * 8 + 16 + 128;
+  const size_t fixed = (size_t)n_out * 8 + 8 + (2 * 4 + 64) * 8 + 16 + 128;
   int nst = 4;
   while (nst > 1 && nst * stage + fixed > (size_t)max_smem) --nst;
   if (nst < 2) return VC_ERR_UNSUPPORTED;
