@@ -241,13 +241,16 @@ int vc_forward_patches(const vc_model* m, const float* hsi, const int64_t hsi_st
  * [H][W][K] at the window centre (untouched pixels are left as they are: zero-fill first),
  * argmax_map (nullable) uint8 [H][W].  Row-band sharding = disjoint window ranges per GPU.
  *
- * Shared stem: the output of the first d HSI stem convs at a window pixel depends on the window only through
+ * Shared stem: the output of the first d stem convs at a window pixel depends on the window only through
  * the zero padding at the window border ((2d+1) row classes x (2d+1) column classes).  When m->w_h1_border is
  * set, the raster is large enough, the windows are dense enough for it to pay and the workspace holds
- * vc_scene_workspace_bytes(), the variants are computed once per call on overlapping scene blocks -- all three
- * convs on 31 x 31 blocks when P >= 7, conv 1 only on 15 x 15 blocks otherwise (P >= 2) -- and every window's
- * stem output is gathered from them (same bits as the per-window convs).  With only
- * vc_workspace_bytes(chunk, ...) of workspace the per-window path runs. */
+ * vc_scene_workspace_bytes(), the variants are computed once per call on overlapping scene blocks: the HSI stem to
+ * the depth vc_scene_shared_depth() reports (all three convs on 31 x 31 blocks when P >= 7, conv 1 only on 15 x 15
+ * blocks otherwise, P >= 2), the LiDAR stem to depth 3 whenever P >= 7 and H, W >= 31.  Every window's stem output is
+ * then taken from the variant planes (same bits as the per-window convs): read in place by the token kernel when it is
+ * the tcgen05 one (82 <= P*P + 1 <= 128) and the depth is 3, gathered into the chunk's buffers otherwise.  With only
+ * vc_workspace_bytes(chunk, ...) of workspace, or without w_h1_border, the per-window path runs (three tcgen05 convs per
+ * stem: the same kernels and accumulation order, so vc_forward_patches and vc_scene_infer agree bit for bit). */
 int64_t vc_scene_workspace_bytes(const vc_model* m, int32_t H, int32_t W, int32_t chunk);
 /* how many HSI stem convs vc_scene_infer would share for this call (0 = per-window path); instrumentation */
 int32_t vc_scene_shared_depth(const vc_model* m, int32_t H, int32_t W, int32_t chunk, int64_t n_windows, int64_t workspace_bytes);
