@@ -759,48 +759,6 @@ int check_train(const vc_train* t, ConvPlan pl[7]) {
   return make_plans(t, pl) ? VC_OK : VC_ERR_UNSUPPORTED;
 }
 
-int train_forward_core(const vc_train* t, const ConvPlan pl[7], const TrainWs& w, int n, float* logits, cudaStream_t st) {
-  const int P = t->P;
-  // bf16 operand forms of the current fp32 master weights, conv biases, cleared BatchNorm sums: ONE launch
-  vc::PrepTable pt;
-  pt.n = 0;
-  auto add = [&](int type, const float* src, void* dst, long long n_) -> vc::PrepJob& {
-    vc::PrepJob& j = pt.job[pt.n++];
-    memset(&j, 0, sizeof(j));
-    j.type = type; j.src = src; j.dst = dst; j.n = n_;
-    return j;
-  };
-  for (int i = 0; i < 7; ++i) {
-    const ConvPlan& c = pl[i];
-    vc::PrepJob& f = add(0, t->params + t->off[4 * i], w.wf[i], (long long)c.taps * c.S_in * c.n_out * 8);
-    f.cout = c.cout; f.cin = c.cin; f.taps = c.taps; f.transpose = 0; f.S_in = c.S_in; f.n_out = c.n_out; f.nsplit = c.nsplit;
-    if (c.has_dgrad) {
-      vc::PrepJob& d = add(0, t->params + t->off[4 * i], w.wd[i], (long long)c.taps * c.d_S_in * c.d_n_out * 8);
-      d.cout = c.cout; d.cin = c.cin; d.taps = c.taps; d.transpose = 1; d.S_in = c.d_S_in; d.n_out = c.d_n_out; d.nsplit = c.d_nsplit;
-    }
-    add(1, t->params + t->off[4 * i + 1], w.bias_pad[i], c.cout);
-  }
-  add(3, nullptr, w.sums, 14 * 256);
-  VC_LAUNCH(KC_MISC, st, vc::train_prep_launch(&pt, st));
-  VC_LAUNCH(KC_MISC, st, vc::pack_segments_launch(t->params, w.blob, (const long long*)t->blob_segments, t->n_blob_segments, st));
-  // stems: conv (+bias) -> raw y -> BatchNorm with batch statistics -> ReLU -> z
-  for (int i = 0; i < 7; ++i) {
-    const ConvPlan& c = pl[i];
-    const uint8_t* in = (i == 0) ? w.a0 : (i == 3) ? w.l0 : (i == 6) ? w.f : w.z[i - 1];
-    const int cls = i == 0 ? KC_CONV_H1 : i == 1 ? KC_CONV_H2 : i == 2 ? KC_CONV_H3 : i < 6 ? KC_CONV_L : KC_TOKENS;
-    VC_LAUNCH(cls, st, vc::conv_sps_launch(in, c.S_in, w.wf[i], w.ones, w.bias_pad[i], w.y[i], 0, c.n_out, c.nsplit, n, P, c.taps,
-                                           0, 0, 0, st));
-    VC_LAUNCH(KC_BN, st, vc::bn_forward_fused_launch(w.y[i], w.z[i], c.n_out / 8, c.cout, n, P, t->params + t->off[4 * i + 2],
-                                                     t->params + t->off[4 * i + 3], t->bn_eps, t->bn_momentum, t->bn_running_mean[i],
-                                                     t->bn_running_var[i], (long long*)t->bn_num_batches[i], w.sums + 256 * i,
-                                                     w.bn_scale[i], w.bn_shift[i], w.bn_mean[i], w.bn_rstd[i], 1, st));
-  }
-  const unsigned int thr = drop_threshold(t);
-  if (thr) bump_seed_kernel<<<1, 1, 0, st>>>(t->drop_seed);     // a fresh mask set for this step
-  VC_LAUNCH(KC_TOKENS, st, vc::transformer_fwd_launch(w.z[6], w.blob, n, P, t->K, logits, nullptr, nullptr, 1, thr, t->drop_seed, st));
-  return VC_OK;
-}
-
 // Side streams of the training step: the weight-gradient GEMMs of a layer depend only on that layer's dz and on forward
 // activations, never on each other or on the data-gradient chain, so they run on a second stream beside the
 // BatchNorm-backward -> data-gradient chain (fork / join with events; under CUDA-graph capture they become parallel
@@ -837,6 +795,55 @@ int stream_dep(SideStreams* ss, cudaStream_t from, cudaStream_t to) {
   cudaEvent_t e = ss->ev[ss->next];
   ss->next = (ss->next + 1) & 31;
   if (cudaEventRecord(e, from) != cudaSuccess || cudaStreamWaitEvent(to, e, 0) != cudaSuccess) return VC_ERR_CUDA;
+  return VC_OK;
+}
+
+int train_forward_core(const vc_train* t, const ConvPlan pl[7], const TrainWs& w, int n, float* logits, cudaStream_t st) {
+  const int P = t->P;
+  // bf16 operand forms of the current fp32 master weights, conv biases, cleared BatchNorm sums: ONE launch
+  vc::PrepTable pt;
+  pt.n = 0;
+  auto add = [&](int type, const float* src, void* dst, long long n_) -> vc::PrepJob& {
+    vc::PrepJob& j = pt.job[pt.n++];
+    memset(&j, 0, sizeof(j));
+    j.type = type; j.src = src; j.dst = dst; j.n = n_;
+    return j;
+  };
+  for (int i = 0; i < 7; ++i) {
+    const ConvPlan& c = pl[i];
+    vc::PrepJob& f = add(0, t->params + t->off[4 * i], w.wf[i], (long long)c.taps * c.S_in * c.n_out * 8);
+    f.cout = c.cout; f.cin = c.cin; f.taps = c.taps; f.transpose = 0; f.S_in = c.S_in; f.n_out = c.n_out; f.nsplit = c.nsplit;
+    if (c.has_dgrad) {
+      vc::PrepJob& d = add(0, t->params + t->off[4 * i], w.wd[i], (long long)c.taps * c.d_S_in * c.d_n_out * 8);
+      d.cout = c.cout; d.cin = c.cin; d.taps = c.taps; d.transpose = 1; d.S_in = c.d_S_in; d.n_out = c.d_n_out; d.nsplit = c.d_nsplit;
+    }
+    add(1, t->params + t->off[4 * i + 1], w.bias_pad[i], c.cout);
+  }
+  add(3, nullptr, w.sums, 14 * 256);
+  VC_LAUNCH(KC_MISC, st, vc::train_prep_launch(&pt, st));
+  VC_LAUNCH(KC_MISC, st, vc::pack_segments_launch(t->params, w.blob, (const long long*)t->blob_segments, t->n_blob_segments, st));
+  // stems: conv (+bias) -> raw y -> BatchNorm with batch statistics -> ReLU -> z.  The LiDAR chain (layers 3-5) is independent
+  // of the HSI chain (0-2) until the fusion conv (6): it runs on a side stream (a parallel branch of the captured graph)
+  SideStreams* ss = side_streams();
+  cudaStream_t main_st = st, lidar_st = ss ? ss->s[1] : st;
+  if (ss) VC_TRY(stream_dep(ss, main_st, lidar_st));
+  for (int i = 0; i < 7; ++i) {
+    const ConvPlan& c = pl[i];
+    if (i == 6 && ss) VC_TRY(stream_dep(ss, lidar_st, main_st));
+    st = (i >= 3 && i < 6) ? lidar_st : main_st;
+    const uint8_t* in = (i == 0) ? w.a0 : (i == 3) ? w.l0 : (i == 6) ? w.f : w.z[i - 1];
+    const int cls = i == 0 ? KC_CONV_H1 : i == 1 ? KC_CONV_H2 : i == 2 ? KC_CONV_H3 : i < 6 ? KC_CONV_L : KC_TOKENS;
+    VC_LAUNCH(cls, st, vc::conv_sps_launch(in, c.S_in, w.wf[i], w.ones, w.bias_pad[i], w.y[i], 0, c.n_out, c.nsplit, n, P, c.taps,
+                                           0, 0, 0, st));
+    VC_LAUNCH(KC_BN, st, vc::bn_forward_fused_launch(w.y[i], w.z[i], c.n_out / 8, c.cout, n, P, t->params + t->off[4 * i + 2],
+                                                     t->params + t->off[4 * i + 3], t->bn_eps, t->bn_momentum, t->bn_running_mean[i],
+                                                     t->bn_running_var[i], (long long*)t->bn_num_batches[i], w.sums + 256 * i,
+                                                     w.bn_scale[i], w.bn_shift[i], w.bn_mean[i], w.bn_rstd[i], 1, st));
+  }
+  st = main_st;
+  const unsigned int thr = drop_threshold(t);
+  if (thr) bump_seed_kernel<<<1, 1, 0, st>>>(t->drop_seed);     // a fresh mask set for this step
+  VC_LAUNCH(KC_TOKENS, st, vc::transformer_fwd_launch(w.z[6], w.blob, n, P, t->K, logits, nullptr, nullptr, 1, thr, t->drop_seed, st));
   return VC_OK;
 }
 
@@ -904,9 +911,12 @@ int train_backward_core(const vc_train* t, const ConvPlan pl[7], const TrainWs& 
   // ---- convolutions, last to first ----
   const int order[7] = {6, 2, 1, 0, 5, 4, 3};
   const long long sl = w.RT * 16;
+  cudaStream_t lidar_st = ss ? ss->s[1] : st;      // layers 5, 4, 3 beside layers 2, 1, 0 once the fusion layer's data gradient exists
   for (int oi = 0; oi < 7; ++oi) {
     const int i = order[oi];
     const ConvPlan& c = pl[i];
+    if (oi == 1 && ss) VC_TRY(stream_dep(ss, main_st, lidar_st));
+    st = (i >= 3 && i < 6) ? lidar_st : main_st;
     uint8_t* dz = i == 6 ? w.dzf : i == 2 ? w.df : i == 1 ? w.dzh2 : i == 0 ? w.dzh1 : i == 5 ? w.df + 4 * sl : i == 4 ? w.dzl2 : w.dzl1;
     const uint8_t* x = (i == 0) ? w.a0 : (i == 3) ? w.l0 : (i == 6) ? w.f : w.z[i - 1];
     VC_LAUNCH(KC_BN, st, vc::bn_backward_fused_launch(dz, w.y[i], dz, c.n_out / 8, c.cout, n, P, w.bn_scale[i], w.bn_shift[i],
@@ -920,8 +930,12 @@ int train_backward_core(const vc_train* t, const ConvPlan pl[7], const TrainWs& 
                                                   c.taps, 0, 0, 0, st));
     }
   }
+  st = main_st;
   VC_LAUNCH(KC_WGRAD, wst, vc::wgrad_reduce_batched_launch(&rt, wst));
-  if (ss) VC_TRY(stream_dep(ss, wst, st));         // join: every gradient is in place when the caller's stream continues
+  if (ss) {                                        // join: every gradient is in place when the caller's stream continues
+    VC_TRY(stream_dep(ss, lidar_st, st));
+    VC_TRY(stream_dep(ss, wst, st));
+  }
   return VC_OK;
 }
 
