@@ -599,7 +599,7 @@ def main():
         sb = Bb - 2 * D
         return ((band_rows_dev - Bb + sb - 1) // sb + 1) * ((W - Bb + sb - 1) // sb + 1)
 
-    Bb = 31 if depth >= 2 else 15
+    Bb = int(_lib.lib().vc_scene_block(band_rows_dev, W, max(int(depth), 1)))
     nb = n_blocks(Bb, max(depth, 1)) if depth else 0
     pairs = (49, 169, 361)                                            # issued (variant, tap) pairs of conv 1 / 2 / 3: 7^2, 13^2, 19^2
     blk_px = Bb * Bb
@@ -608,8 +608,9 @@ def main():
            else 2.0 * P * P * cout_h[l] * cin_h[l] * 9 * nwin for l in range(3)]
     lidar_shared = bool(depth) and P >= 7 and band_rows_dev >= 31 and W >= 31 and os.environ.get("VITCNN_LIDAR_SHARED", "1") != "0"
     cin_l, cout_l = (C2, 8, 16), (8, 16, 32)
-    nb_l = n_blocks(31, 3) if lidar_shared else 0
-    w_l = sum(2.0 * cout_l[l] * cin_l[l] * pairs[l] * 31 * 31 * nb_l * scenes if lidar_shared
+    Bl = int(_lib.lib().vc_scene_block(band_rows_dev, W, 3))
+    nb_l = n_blocks(Bl, 3) if lidar_shared else 0
+    w_l = sum(2.0 * cout_l[l] * cin_l[l] * pairs[l] * Bl * Bl * nb_l * scenes if lidar_shared
               else 2.0 * P * P * cout_l[l] * cin_l[l] * 9 * nwin for l in range(3))
     tc_tokens = 82 <= T_ <= 128 and os.environ.get("VITCNN_TOKENS_IMPL") != "0"
     direct = depth == 3 and tc_tokens
@@ -630,7 +631,7 @@ def main():
         # plus, when the token kernel does not read the planes itself, the per-window SPS rows written and read
         "pack": ("pack_sps_kernel (scene blocks -> bf16 SPS)" + ("" if direct else " + border_gather_kernel (stem variants -> window SPS)")
                  if depth else "pack_strip_kernel (TMA-staged patch gather -> bf16 SPS)", "hbm",
-                 (float((C1 * 4 + S1 * 16) * nb * 1024 + (C2 * 4 + 32) * nb_l * 1024) * scenes if depth else 0.0)
+                 (float((C1 * 4 + S1 * 16) * nb * (Bb + 1) ** 2 + (C2 * 4 + 32) * nb_l * (Bl + 1) ** 2) * scenes if depth else 0.0)
                  + (0.0 if direct else float(2 * (g_slices + (4 if lidar_shared else 2)) * (P + 1) * (P + 1) * 16) * nwin), 1e9, hbm, "GB/s"),
     }
 

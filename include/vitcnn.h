@@ -245,14 +245,17 @@ int vc_forward_patches(const vc_model* m, const float* hsi, const int64_t hsi_st
  * the zero padding at the window border ((2d+1) row classes x (2d+1) column classes).  When m->w_h1_border is
  * set, the raster is large enough, the windows are dense enough for it to pay and the workspace holds
  * vc_scene_workspace_bytes(), the variants are computed once per call on overlapping scene blocks: the HSI stem to
- * the depth vc_scene_shared_depth() reports (all three convs on 31 x 31 blocks when P >= 7, conv 1 only on 15 x 15
- * blocks otherwise, P >= 2), the LiDAR stem to depth 3 whenever P >= 7 and H, W >= 31.  Every window's stem output is
+ * the depth vc_scene_shared_depth() reports (all three convs on 31 / 63 / 95-pixel blocks when P >= 7, conv 1 only on
+ * 15 x 15 blocks otherwise, P >= 2), the LiDAR stem to depth 3 whenever P >= 7 and H, W >= 31.  Every window's stem output is
  * then taken from the variant planes (same bits as the per-window convs): read in place by the token kernel when it is
  * the tcgen05 one (82 <= P*P + 1 <= 128) and the depth is 3, gathered into the chunk's buffers otherwise.  With only
  * vc_workspace_bytes(chunk, ...) of workspace, or without w_h1_border, the per-window path runs (three tcgen05 convs per
  * stem: the same kernels and accumulation order, so vc_forward_patches and vc_scene_infer agree bit for bit). */
 int64_t vc_scene_workspace_bytes(const vc_model* m, int32_t H, int32_t W, int32_t chunk);
-/* how many HSI stem convs vc_scene_infer would share for this call (0 = per-window path); instrumentation */
+/* edge of the scene blocks the shared stem would use for an H x W raster at this sharing depth (15 / 31 / 63 / 95) and
+ * how many HSI stem convs vc_scene_infer would share for this call (0 = per-window path); instrumentation, and what a host
+ * pipeline needs to cut a scene into sub-bands at whole block rows */
+int32_t vc_scene_block(int32_t H, int32_t W, int32_t depth);
 int32_t vc_scene_shared_depth(const vc_model* m, int32_t H, int32_t W, int32_t chunk, int64_t n_windows, int64_t workspace_bytes);
 int vc_scene_infer(const vc_model* m, const float* img1, const float* img2, int32_t H, int32_t W, const int32_t* xs,
                    const int32_t* ys, int32_t nx, int32_t ny, int64_t first_window, int64_t n_windows, int32_t chunk,

@@ -143,6 +143,7 @@ _PROTOS = {
     "vc_forward_patches": (c_int32, [POINTER(VcModel), c_void_p, POINTER(c_int64), c_void_p, POINTER(c_int64),
                                      c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
     "vc_scene_workspace_bytes": (c_int64, [POINTER(VcModel), c_int32, c_int32, c_int32]),
+    "vc_scene_block": (c_int32, [c_int32, c_int32, c_int32]),
     "vc_scene_shared_depth": (c_int32, [POINTER(VcModel), c_int32, c_int32, c_int32, c_int64, c_int64]),
     "vc_scene_infer": (c_int32, [POINTER(VcModel), c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32,
                                  c_int32, c_int64, c_int64, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),

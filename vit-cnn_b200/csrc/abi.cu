@@ -136,10 +136,32 @@ struct SceneWs {
   int nb, B, D;
 };
 
+// Edge of the scene blocks.  Depth 1 (conv 1 only, small patches): 15.  Depth >= 2: a block's exact region is B - 2D wide, so
+// small blocks recompute a lot ((31 / 25)^2 = 1.54x at depth 3) while large ones overshoot the raster; pick, among the edges
+// with B + 1 a multiple of 32 (whole tiles per block, aligned slabs in conv_var.cu), the one with the fewest block rows in
+// total.  Houston scene at depth 3: 1 064 blocks of 31 (1.09 M rows), 238 of 63 (0.97 M), 88 of 95 (0.81 M).  95 is the
+// largest: the CTA-pair conv-1 kernel stages 128 + 2 (B + 9) rows per tile.  VITCNN_SCENE_BLOCK forces an edge.
+int scene_block(int H, int W, int depth) {
+  if (depth < 2) return 15;
+  static const int forced = [] {
+    const char* e = getenv("VITCNN_SCENE_BLOCK");
+    return e ? atoi(e) : 0;
+  }();
+  int best = 31;
+  long long best_rows = -1;
+  for (int B = 31; B <= 95; B += 32) {
+    if (H < B || W < B) break;
+    if (forced && B != forced) continue;
+    const long long rows = (long long)vc::blk_count(H, B, depth) * vc::blk_count(W, B, depth) * (B + 1) * (B + 1);
+    if (best_rows < 0 || rows < best_rows) { best = B; best_rows = rows; }
+  }
+  return best;
+}
+
 SceneWs carve_scene(void* base, long long off, const StemDesc& sd, int H, int W, int P, int depth) {
   SceneWs s;
   memset(&s, 0, sizeof(s));
-  const int B = depth >= 2 ? 31 : 15, D = depth;
+  const int B = scene_block(H, W, depth), D = depth;
   if (depth < 1 || depth > 3 || H < B || W < B || P < (depth == 1 ? 2 : 2 * depth + 1)) return s;
   s.B = B;
   s.D = D;
@@ -582,7 +604,7 @@ int vc_scene_infer(const vc_model* m, const float* img1, const float* img2, int3
       if (rc != VC_OK) return fail(rc, "scene gather (hsi)");
     }
     if (lid_shared && direct) {
-      tp.l = (const __nv_bfloat16*)lw.var[2];      // same block geometry as the depth-3 HSI planes (B = 31, D = 3)
+      tp.l = (const __nv_bfloat16*)lw.var[2];      // same block geometry as the depth-3 HSI planes (same B, D = 3)
       tp.RTb = lw.RTb; tp.B = lw.B; tp.D = lw.D; tp.rowterm = lw.rowterm; tp.colterm = lw.colterm;
     } else if (lid_shared) {
       VC_LAUNCH(KC_PACK, st, vc::border_gather_launch(lw.var[2], 4, lw.B, lw.D, H, W, xs, ys, ny, first, n, m->P, w.f + 4 * sl, st));
@@ -596,6 +618,8 @@ int vc_scene_infer(const vc_model* m, const float* img1, const float* img2, int3
   }
   return VC_OK;
 }
+
+int32_t vc_scene_block(int32_t H, int32_t W, int32_t depth) { return scene_block(H, W, depth); }
 
 int32_t vc_scene_shared_depth(const vc_model* m, int32_t H, int32_t W, int32_t chunk, int64_t n_windows, int64_t workspace_bytes) {
   if (check_model(m) != VC_OK || chunk <= 0) return -1;

@@ -17,9 +17,9 @@
 // columns per unit, so there a slot is ONE variant (8 slots): the epilogue drains a variant as soon as its last instruction has
 // landed while the issuer is already filling the following slots with the next variants / the next unit.
 //
-// Geometry: scene blocks of B = 31 pixels as SPS "patches" (pitch PW = 32 rows, lead halo 40 rows: vc_common.cuh),
-// so every slab a tap row needs starts at a multiple of 8 rows = 128 bytes: slab(dy) = rows [R0 + 32 dy - 8,
-// R0 + 32 dy + 136) of the input plane, the tap (dy, dx) reads it at row offset 8 + dx.
+// Geometry: scene blocks of B = 31 / 63 / 95 pixels as SPS "patches" (pitch PW = B + 1 rows, lead halo B + 9 rows, both
+// multiples of 8: vc_common.cuh), so every slab a tap row needs starts at a multiple of 8 rows = 128 bytes: slab(dy) =
+// rows [R0 + PW dy - 8, R0 + PW dy + 136) of the input plane, the tap (dy, dx) reads it at row offset 8 + dx.
 #include "vc_common.cuh"
 #include "vc_kernels.h"
 
@@ -252,7 +252,7 @@ int conv_var_launch(const void* in, int S_in, const void* w, const float* scale,
   using namespace cv;
   const int NC = 2 * L + 1, NP = 2 * L - 1;
   if (L < 2 || NC > kMaxNC || S_in <= 0 || (S_in & 1) || n_out % 16 || n_out < 16 || n_out > 128 || n_blocks <= 0) return VC_ERR_ARG;
-  if (B != 31 || NC * n_out > 512) return VC_ERR_UNSUPPORTED;       // slab alignment needs PW = 32, HALO = 40
+  if ((B + 1) % 8 != 0 || NC * n_out > 512) return VC_ERR_UNSUPPORTED;   // slab alignment: PW = B + 1 and HALO = B + 9 multiples of 8
   static int max_smem = 0, num_sms = 0;
   if (!max_smem) {
     int dev = 0;

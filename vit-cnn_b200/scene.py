@@ -62,7 +62,8 @@ def predict_scene_host(net, img1: torch.Tensor, img2: torch.Tensor, stride: int 
     if stride == 1 and nsub > 1 and os.environ.get("VITCNN_SUBBAND_SPLIT", "blocks") != "equal":
         depth = _shared_depth(net, nrows // nsub + P - 1, W, (nrows // nsub) * len(geo["ys"]), chunk, dev)
         if depth > 0:
-            bounds = subband_bounds(nrows, P, pipeline, 31 if depth >= 2 else 15, depth,
+            block = int(_lib.lib().vc_scene_block(nrows // nsub + P - 1, W, depth))
+            bounds = subband_bounds(nrows, P, pipeline, block, depth,
                                     lead_small=os.environ.get("VITCNN_SUBBAND_LEAD", "even") == "small")
             nsub = len(bounds) - 1
     with torch.cuda.device(dev):
