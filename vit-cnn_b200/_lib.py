@@ -13,7 +13,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_uint8, c_void
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libvitcnn.so")
-SOURCES = ["abi.cu", "conv_tc.cu", "conv_var.cu", "pack.cu", "gather_tma.cu", "transformer.cu", "tokens_tc.cu", "tokens_tc2.cu", "lidar_stem.cu", "metrics.cu", "wgrad_tc.cu", "wgrad_small.cu", "train.cu", "tokens_bwd.cu"]
+SOURCES = ["abi.cu", "conv_tc.cu", "conv_var.cu", "pack.cu", "gather_tma.cu", "transformer.cu", "tokens_tc.cu", "tokens_tc2.cu", "tokens_tm.cu", "lidar_stem.cu", "metrics.cu", "wgrad_tc.cu", "wgrad_small.cu", "train.cu", "tokens_bwd.cu"]
 HEADERS = ["tokens_tc_common.cuh", "vc_common.cuh", "vc_kernels.h", "vc_tparams.h", "vc_tokens.cuh", os.path.join("..", "..", "include", "vitcnn.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

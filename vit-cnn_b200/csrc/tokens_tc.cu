@@ -41,6 +41,7 @@ namespace vc {
 // wait only for tensor-core completions (tcgen05.commit mbarriers).
 __global__ void __launch_bounds__(tc::kThreads, 1) tokens_tc_kernel(TcArgs a) {   // 15 warps -> 128 registers (the file is allocated per 4 warps)
   using namespace tc;
+  if (a.run_flag && *a.run_flag == 0.f) return;     // fallback launch behind tokens_tm_kernel: nothing to do
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool issuer = warp >= 4 * kSlots;
@@ -604,7 +605,8 @@ __global__ void __launch_bounds__(kTailThreads) tokens_tail_kernel(TailArgs a) {
   if (a.argmax_map) a.argmax_map[orow] = (unsigned char)best;
 }
 
-size_t tokens_tc_scratch_bytes(int n_patches) { return (size_t)n_patches * tc::kTailFloats * 4; }
+// staging area of tokens_tm_main_launch, then one cls record per patch
+size_t tokens_tc_scratch_bytes(int n_patches) { return tokens_tm_stage_bytes() + (size_t)n_patches * tc::kTailFloats * 4; }
 
 bool tokens_tc_supported(int P, int K) { return P >= 1 && P * P + 1 <= 128 && K >= 1 && K <= 64; }
 
@@ -621,7 +623,9 @@ int tokens_tc_launch(const void* f_sps, const void* tparams, int n_patches, int 
   TcArgs a;
   a.f = (const __nv_bfloat16*)f_sps;
   a.blob = (const uint8_t*)tparams;
-  a.tail = (float*)scratch;
+  float* stage = (float*)scratch;
+  a.tail = (float*)((uint8_t*)scratch + tokens_tm_stage_bytes());
+  a.run_flag = nullptr;
   a.RT = sps_rows(n_patches, P);
   a.n_patches = n_patches;
   a.P = P;
@@ -646,10 +650,24 @@ int tokens_tc_launch(const void* f_sps, const void* tparams, int n_patches, int 
     const char* e = getenv("VITCNN_TC_SPLIT");
     return e ? atoi(e) : 0;
   }();
+  // VITCNN_TC_KERNEL = tm3 (default) / tm4: tokens_tm_kernel with three / four patches in flight per CTA, and
+  // tokens_tc_kernel behind it gated on the prep kernel's flag (weights whose attention logits need the row maximum);
+  // tc: tokens_tc_kernel only.
+  static const int tm_slots = [] {
+    const char* e = getenv("VITCNN_TC_KERNEL");
+    if (!e || !strcmp(e, "tm3")) return 3;
+    if (!strcmp(e, "tm4")) return 4;
+    return 0;
+  }();
   if (split > 0) {
     const int rc = tokens_tc2_main_launch(a, n_patches, num_sms, split, stream);
     if (rc != VC_OK) return rc;
   } else {
+    if (tm_slots > 0) {
+      const int rc = tokens_tm_main_launch(a, stage, n_patches, num_sms, max_smem, tm_slots, stream);
+      if (rc != VC_OK) return rc;
+      a.run_flag = stage + kTmFlagIndex;
+    }
     if (cudaFuncSetAttribute(tokens_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES) != cudaSuccess)
       return VC_ERR_CUDA;
     int blocks = (n_patches + tc::kSlots - 1) / tc::kSlots;

@@ -58,6 +58,7 @@ struct TcArgs {
   float* tail;              // [n][kTailFloats]
   long long RT;
   int n_patches, P, T, stagger_ns;
+  const float* run_flag;    // nullable: the kernel runs only if *run_flag != 0 (fallback behind tokens_tm_kernel)
   TLayout L;
 };
 
@@ -347,6 +348,12 @@ __device__ __forceinline__ void tc_issuer(const TcArgs& a, uint32_t sb, uint32_t
     }
   }
 }
+
+// tokens_tm.cu: probabilities / hidden units through TMEM, per-channel vectors in the constant bank (no-row-maximum softmax
+// only: `stage` receives the flag that gates the fallback launch of tokens_tc_kernel)
+size_t tokens_tm_stage_bytes();
+int tokens_tm_main_launch(const TcArgs& a, float* stage, int n_patches, int num_sms, int max_smem, int slots, cudaStream_t stream);
+constexpr int kTmFlagIndex = tc::V_TOTAL;   // stage[kTmFlagIndex] != 0: the softmax needs its row maximum
 
 // tokens_tc2.cu: the main kernel with two threads per token row (`slots` patches in flight per CTA)
 int tokens_tc2_main_launch(const TcArgs& a, int n_patches, int num_sms, int slots, cudaStream_t stream);

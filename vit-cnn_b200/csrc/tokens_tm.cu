@@ -1,0 +1,665 @@
+// Token stage on tcgen05 with the attention probabilities and the MLP hidden units handed to the tensor core
+// THROUGH TMEM (tcgen05.st + TMEM-sourced A operand) instead of shared memory, and the per-channel vectors
+// (folded BN, LayerNorm gamma / beta, biases) read as constant-bank operands instead of shared-memory loads.
+//
+// Same function, parameter blob, stem-input addressing, cls record and tail kernel as tokens_tc.cu (whose header
+// describes the layout tricks: one patch = one M = 128 tile, token row r = TMEM lane r = thread r of a 128-thread
+// group, head_dim 8 padded to K = 16 by pointing the second K chunk at a ones / mask slab, softmax denominators
+// from a ones column of V, last block pruned to the cls query).  What the ncu record of tokens_tc_kernel showed
+// (profiles/r02_tokens_stalls.txt, r02_tokens_variants.txt): MUFU 46 % busy, issue 39 %, and every phase of a slot
+// stretched ~1.8x as soon as three slots share an SM -- the softmax phases because they share the MUFU, all the
+// others because their shared-memory loads / stores queue behind the other slots' MUFU instructions in the same
+// MIO queue; plus one exposed tensor-core round trip per head (the next head's probabilities could not be written
+// before PV of the previous head had released the single 32 KB P buffer).  This kernel removes those:
+//
+//  * S_h is produced in key chunks of CK columns into a ring of RD TMEM buffers (3 slots: 2 x 64 keys, 4 slots:
+//    3 x 32 keys).  A row thread reads a chunk, exponentiates, packs to bf16 and stores the probabilities back
+//    over the first half of the SAME columns (tcgen05.st); PV takes its A operand from there (K = CK keys per
+//    step, accumulating into O_h) and the S chunk RD steps ahead is issued right behind it into the freed buffer,
+//    so the row threads never wait for a PV and S chunks are ready before they are needed;
+//  * fc1's accumulators are overwritten in place by the packed GELU outputs, fc2 reads them from TMEM;
+//    the 32 KB P / hidden buffer of a slot is gone (24 KB of shared memory per slot instead of 56 KB, ~60 % less
+//    shared-memory traffic per patch, 80 fewer 16-byte stores per row and patch);
+//  * the 640 per-channel constants live in __constant__ memory (filled per launch by a one-block prep kernel and a
+//    device-to-device copy on the same stream) and enter the FFMAs as c[bank][offset] operands: no loads, no
+//    registers, nothing in the MIO queue;
+//  * the static bound that decides whether the softmax may skip the row maximum is evaluated once by the prep
+//    kernel.  This kernel implements the no-maximum path only; when the bound fails it exits at once and
+//    tokens_tc_kernel (launched right behind it, gated on the same flag) does the work.
+#include <mutex>
+#include "tokens_tc_common.cuh"
+
+namespace vc {
+
+namespace tm {
+using tc::SLAB;
+using tc::V_BFC1; using tc::V_BFC2; using tc::V_BPROJ; using tc::V_BQKV; using tc::V_BQKV2; using tc::V_FBI; using tc::V_FSC;
+using tc::V_L2B; using tc::V_L2G; using tc::V_LN1B; using tc::V_LN1G; using tc::V_LN2B; using tc::V_LN2G; using tc::V_TOTAL;
+constexpr int V_EXACT = V_TOTAL, V_EXACT_CLS = V_TOTAL + 1;   // flags (0 / 1) behind the vectors
+constexpr int kVecFloats = V_TOTAL + 16;
+constexpr size_t kStageBytes = 4096;                          // staging area at the head of the scratch buffer
+
+__constant__ float c_vec[kVecFloats];
+
+template <int SLOTS>
+struct Cfg {
+  static constexpr int CK = SLOTS >= 4 ? 32 : 64;       // keys per attention step
+  static constexpr int RD = SLOTS >= 4 ? 3 : 2;         // S chunk buffers per slot
+  static constexpr uint32_t C_O = RD * CK;              // two 16-column O_h buffers / the 32-column accumulators
+  static constexpr uint32_t C_SLOT = C_O + 32;
+  static constexpr int kThreads = SLOTS * 5 * 32;       // 4 row warps + 1 MMA-issuer warp per slot
+  static constexpr uint32_t POS = tc::W_QKV2 + 6144;    // weights as in tc:: (W_FUS .. W_QKV2), then pos-embed rows
+  static constexpr uint32_t SLOT0 = POS + 128 * 32 * 4;
+  static constexpr uint32_t S_QBUF = 0, S_ABUF = 0, S_KBUF = 4 * SLAB, S_VBUF = 8 * SLAB, S_FBUF = S_KBUF;
+  static constexpr uint32_t SLOT_BYTES = 12 * SLAB;
+  static constexpr uint32_t ONES = SLOT0 + SLOTS * SLOT_BYTES;
+  static constexpr uint32_t MASK = ONES + SLAB;
+  static constexpr uint32_t MISC = MASK + SLAB;
+  static constexpr uint32_t M_Q0 = 0, M_WMAX = M_Q0 + SLOTS * 128, M_BARS = M_WMAX + SLOTS * 64, M_TMEM = M_BARS + SLOTS * 128;
+  static constexpr uint32_t SMEM_BYTES = MISC + ((M_TMEM + 16 + 127) & ~127u);
+  static_assert(SLOTS * C_SLOT <= 512, "TMEM columns");
+};
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem: lane = row, 2 bf16 per 32-bit column, K = 16 -> 8 columns] . B[smem descriptor]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier wait whose try_wait may stay suspended in hardware for up to ~10 us before it reports "not yet" (the plain
+// form came back every ~60 cycles: a fifth of the instructions tokens_tc_kernel issued were these polling loops).
+// Bounded: a protocol bug must surface as a trapped kernel, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait_s(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok, spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(10000u)
+        : "memory");
+    if (!ok && ++spins > (1u << 22)) __trap();
+  } while (!ok);
+}
+
+// LayerNorm (eps 1e-6) of the row held by this thread, gamma / beta from the constant bank -> bf16 -> K-major A operand
+template <int G, int B>
+__device__ __forceinline__ void ln_store_c(const float (&x)[32], uint32_t dst_row) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) s += x[c];
+  const float mean = s * (1.f / 32.f);
+  float v = 0.f;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) { const float d = x[c] - mean; v = fmaf(d, d, v); }
+  const float rs = rsqrtf(v * (1.f / 32.f) + 1e-6f);
+  const float nm = -mean * rs;
+#pragma unroll
+  for (int sl = 0; sl < 4; ++sl) {
+    uint32_t p[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c0 = 8 * sl + 2 * e;
+      p[e] = pack_bf16(fmaf(fmaf(x[c0], rs, nm), c_vec[G + c0], c_vec[B + c0]),
+                       fmaf(fmaf(x[c0 + 1], rs, nm), c_vec[G + c0 + 1], c_vec[B + c0 + 1]));
+    }
+    sts128(dst_row + sl * SLAB, p[0], p[1], p[2], p[3]);
+  }
+}
+
+// One block: the per-channel vectors in the order of tc::V_* (q biases pre-scaled), then the two flags of the static
+// bound on |q.k| (see tc_setup in tokens_tc_common.cuh: same arithmetic, evaluated once per launch instead of per CTA)
+__global__ void __launch_bounds__(128) tm_prep_kernel(const uint8_t* blob, TLayout L, float* out) {
+  __shared__ float scr[256];
+  const int tid = threadIdx.x;
+  const float qscale = 0.35355339059327376220f * 1.44269504088896340736f;
+  auto copy_v = [&](int dst, int src, int n, float scale_first32) {
+    for (int i = tid; i < n; i += 128) {
+      const float v = __ldg(reinterpret_cast<const float*>(blob + src) + i);
+      out[dst + i] = i < 32 ? v * scale_first32 : v;
+    }
+  };
+  copy_v(V_FSC, L.fus_scale, 32, 1.f);
+  copy_v(V_FBI, L.fus_bias, 32, 1.f);
+  copy_v(V_LN1G, L.layer[0].ln1_g, 32, 1.f);
+  copy_v(V_LN1B, L.layer[0].ln1_b, 32, 1.f);
+  copy_v(V_BQKV, L.layer[0].bqkv, 96, qscale);
+  copy_v(V_BPROJ, L.layer[0].bproj, 32, 1.f);
+  copy_v(V_LN2G, L.layer[0].ln2_g, 32, 1.f);
+  copy_v(V_LN2B, L.layer[0].ln2_b, 32, 1.f);
+  copy_v(V_BFC1, L.layer[0].bfc1, 128, 1.f);
+  copy_v(V_BFC2, L.layer[0].bfc2, 32, 1.f);
+  copy_v(V_L2G, L.layer[1].ln1_g, 32, 1.f);
+  copy_v(V_L2B, L.layer[1].ln1_b, 32, 1.f);
+  copy_v(V_BQKV2, L.layer[1].bqkv, 96, qscale);
+  {
+    const int l = tid >> 6, n = tid & 63;
+    const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(blob + L.layer[l].wqkv) + n * kLdD;
+    const float* g = reinterpret_cast<const float*>(blob + L.layer[l].ln1_g);
+    const float* be = reinterpret_cast<const float*>(blob + L.layer[l].ln1_b);
+    float f2 = 0.f, bs = __ldg(reinterpret_cast<const float*>(blob + L.layer[l].bqkv) + n);
+    for (int c = 0; c < 32; ++c) {
+      const float wv = __bfloat162float(w[c]);
+      f2 = fmaf(wv * __ldg(g + c), wv * __ldg(g + c), f2);
+      bs = fmaf(wv, __ldg(be + c), bs);
+    }
+    scr[2 * tid] = f2;
+    scr[2 * tid + 1] = bs * bs;
+  }
+  __syncthreads();
+  if (tid < 2) {
+    const float* s = scr + 128 * tid;
+    bool exact = false;
+    for (int h = 0; h < 4; ++h) {
+      float qf = 0.f, qb = 0.f, kf = 0.f, kb = 0.f;
+      for (int n = 0; n < 8; ++n) {
+        qf += s[2 * (8 * h + n)]; qb += s[2 * (8 * h + n) + 1];
+        kf += s[2 * (32 + 8 * h + n)]; kb += s[2 * (32 + 8 * h + n) + 1];
+      }
+      const float bound = qscale * (sqrtf(32.f * qf) + sqrtf(qb)) * (sqrtf(32.f * kf) + sqrtf(kb));
+      if (!(bound < 100.f)) exact = true;
+    }
+    out[V_EXACT + tid] = exact ? 1.f : 0.f;
+  }
+  for (int i = V_TOTAL + 2 + tid; i < kVecFloats; i += 128) out[i] = 0.f;
+}
+
+}  // namespace tm
+
+template <int SLOTS>
+__global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(TcArgs a) {
+  using C = tm::Cfg<SLOTS>;
+  using namespace tm;
+  constexpr int CK = C::CK, RD = C::RD;
+  if (c_vec[V_EXACT] != 0.f) return;      // the softmax needs its row maximum: tokens_tc_kernel runs instead
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool issuer = warp >= 4 * SLOTS;
+  const int slot = issuer ? warp - 4 * SLOTS : warp >> 2;
+  const int r = tid & 127, wq = warp & 3;
+  const int T = a.T, P = a.P;
+  const TLayout& L = a.L;
+  const uint32_t sb = smem_u32(smem);
+  float* q0_s = reinterpret_cast<float*>(smem + C::MISC + C::M_Q0) + slot * 32;          // [32]
+  float* wmax_s = reinterpret_cast<float*>(smem + C::MISC + C::M_WMAX) + slot * 16;      // [4 warps][4 heads]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::MISC + C::M_BARS) + slot * 16;
+  uint64_t* b_rp = bars + 0;      // row threads: operands of the next GEMM are written (128 arrivals)
+  uint64_t* b_mma = bars + 1;     // tensor core: the GEMM just issued (fusion / qkv / proj / fc1 / fc2 / kv2) is done
+  uint64_t* b_pv = bars + 2;      // tensor core: O_h is complete
+  uint64_t* b_s = bars + 3;       // [RD] tensor core: the S chunk in ring buffer k is in TMEM (and the PV that read the buffer is done)
+  // [RD] row threads: the probabilities in ring buffer k are written (128 arrivals).  One barrier per buffer: S chunks are
+  // issued ahead, so a row thread may finish step i + 1 before another has finished step i -- on a shared barrier its
+  // second arrival would complete the phase of step i; on buffer k it cannot arrive again before PV of step i has run.
+  uint64_t* b_p = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::MISC + C::M_TMEM);
+  const float qscale = 0.35355339059327376220f * 1.44269504088896340736f;  // hd^-0.5 * log2(e)
+  const bool exact_cls = c_vec[V_EXACT_CLS] != 0.f;
+
+  // ---------------- one-time image of the parameters in the layouts the tensor core reads ----------------
+  {
+    auto copy_w = [&](uint32_t dst, int src, int N, int K, int ld, bool halve = false) {
+      for (int i = tid; i < N * (K / 8); i += C::kThreads) {
+        const int n = i % N, kc = i / N;
+        uint4 g = __ldg(reinterpret_cast<const uint4*>(a.blob + src + (size_t)(n * ld + kc * 8) * 2));
+        if (halve) {   // exact in bf16: one less in the exponent field (weights are far from subnormal)
+          __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&g);
+          for (int e = 0; e < 4; ++e) hp[e] = __hmul2(hp[e], __floats2bfloat162_rn(0.5f, 0.5f));
+        }
+        *reinterpret_cast<uint4*>(smem + dst + (size_t)kc * N * 16 + n * 16) = g;
+      }
+    };
+    copy_w(tc::W_FUS, L.wfus, 32, 64, kLdFus);
+    copy_w(tc::W_QKV1, L.layer[0].wqkv, 96, 32, kLdD);
+    copy_w(tc::W_PROJ1, L.layer[0].wproj, 32, 32, kLdD);
+    copy_w(tc::W_FC1, L.layer[0].wfc1, 128, 32, kLdD);
+    copy_w(tc::W_FC2, L.layer[0].wfc2, 32, 128, kLdHid, true);   // the 0.5 of GELU lives here: H = 2 gelu(.)
+    copy_w(tc::W_QKV2, L.layer[1].wqkv, 96, 32, kLdD);
+    // pos-embed rows (row 0 = cls + pos[0], rows >= T zero), 16-byte granules swizzled by row
+    const float* pos = reinterpret_cast<const float*>(a.blob + L.pos);
+    const float* cls = reinterpret_cast<const float*>(a.blob + L.cls);
+    for (int i = tid; i < 128 * 8; i += C::kThreads) {
+      const int row = i >> 3, g = i & 7;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < T) {
+        v = __ldg(reinterpret_cast<const float4*>(pos + row * 32 + 4 * g));
+        if (row == 0) {
+          const float4 c = __ldg(reinterpret_cast<const float4*>(cls + 4 * g));
+          v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+        }
+      }
+      *reinterpret_cast<float4*>(smem + C::POS + row * 128 + ((g ^ (row & 7)) << 4)) = v;
+    }
+    // slot buffers, ONES / MASK slabs: zeros first
+    for (uint32_t i = tid; i < (SLOTS * C::SLOT_BYTES + 2 * SLAB) / 16; i += C::kThreads)
+      *reinterpret_cast<uint4*>(smem + C::SLOT0 + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    for (int i = tid; i < 128; i += C::kThreads) {
+      *reinterpret_cast<uint32_t*>(smem + C::ONES + i * 16) = 0x00003F80u;                 // bf16 1.0
+      *reinterpret_cast<uint32_t*>(smem + C::MASK + i * 16) = i >= T ? 0x0000C6EAu : 0u;   // bf16 -29952 for padded keys
+    }
+    if (tid == 0) {
+      for (int s = 0; s < SLOTS; ++s) {
+        uint64_t* bb = reinterpret_cast<uint64_t*>(smem + C::MISC + C::M_BARS) + s * 16;
+        mbar_init(bb + 0, 128);
+        for (int k = 1; k < 8; ++k) mbar_init(bb + k, 1);
+        for (int k = 8; k < 16; ++k) mbar_init(bb + k, 128);
+      }
+      fence_mbar_init();
+    }
+    if (tid < 32) {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tb = tmem_base + (uint32_t)slot * C::C_SLOT;             // columns of this slot (issuer view)
+  const uint32_t tl = tb + ((uint32_t)(wq * 32) << 16);                   // + the 32 lanes of this warp
+  const uint32_t slot_s = sb + C::SLOT0 + (uint32_t)slot * C::SLOT_BYTES;
+  const uint32_t fbuf = slot_s + C::S_FBUF, abuf = slot_s + C::S_ABUF, qbuf = slot_s + C::S_QBUF, kbuf = slot_s + C::S_KBUF,
+                 vbuf = slot_s + C::S_VBUF;
+  const int NK = (T + 31) & ~31;                    // keys rounded to the 32-column chunks the row threads read
+  const int SPH = (NK + CK - 1) / CK, NS = 4 * SPH; // attention steps per head / per patch
+  const int nslots = SLOTS * (int)gridDim.x;
+  const int b0 = SLOTS * (int)blockIdx.x + slot;
+
+  if (issuer) {
+    // ============================ MMA issuer of this slot ============================
+    uint32_t ph_rp = 0, ph_p = 0;
+    int rb = 0;               // ring buffer of the next attention step (ph_p: parity of its "probabilities written" barrier)
+    auto ready = [&]() {      // the row threads have written the operands of the next MMA group
+      mbar_wait_s(b_rp, ph_rp);
+      ph_rp ^= 1u;
+      tc_fence_after();
+    };
+    // D[128 x N] (TMEM column `col`) = A[128 x 16 ksteps] (K-major slabs at `abase`) . W^T (weights [k/8][N][8] at `wbase`)
+    auto issue_gemm = [&](uint32_t col, uint32_t abase, uint32_t wbase, int N, int ksteps) {
+      if (elect_one()) {
+        for (int k = 0; k < ksteps; ++k)
+          umma_bf16(tb + col, umma_desc(abase + 2 * k * SLAB, SLAB, 128), umma_desc(wbase + 2 * k * N * 16, (uint32_t)N * 16u, 128),
+                    idesc(N, 0), k ? 1u : 0u);
+        umma_commit(b_mma);
+      }
+      __syncwarp();
+    };
+    // S chunk of step j -> ring buffer `buf`: A chunks (Q_h, ones), B chunks (keys [c CK, +keys) of K_h, their mask rows)
+    auto issue_s = [&](int j, int buf) {
+      const int h = j / SPH, c = j - h * SPH;
+      const int keys = min(CK, NK - c * CK);
+      const uint32_t qa = qbuf + h * SLAB, ka = kbuf + h * SLAB;
+      umma_bf16(tb + buf * CK, umma_desc(qa, (sb + C::ONES) - qa, 128), umma_desc(ka + c * CK * 16, (sb + C::MASK) - ka, 128),
+                idesc(keys, 0), 0u);
+      umma_commit(b_s + buf);
+    };
+    for (int b = b0; b < a.n_patches; b += nslots) {
+      ready(); issue_gemm(C::C_O, fbuf, sb + tc::W_FUS, 32, 4);       // fusion 1x1 conv
+      ready(); issue_gemm(0, abuf, sb + tc::W_QKV1, 96, 2);           // qkv
+      ready();
+      if (elect_one()) {
+        for (int j = 0; j < RD && j < NS; ++j) issue_s(j, (rb + j) % RD);
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int i = 0; i < NS; ++i) {
+        const int h = i / SPH, c = i - h * SPH;
+        mbar_wait_s(b_p + rb, ph_p);                  // the probabilities of step i are in the first half of buffer rb
+        tc_fence_after();
+        if (elect_one()) {
+          // O_h[128 x 16] (+)= P[128 x keys] . [V_h | ones]: B is MN-major, N chunk 0 = V_h slab, chunk 1 = ONES slab
+          const int keys = min(CK, NK - c * CK);
+          const uint32_t vb = vbuf + h * SLAB;
+          for (int kk = 0; kk < keys / 16; ++kk)
+            umma_bf16_ts(tb + C::C_O + 16 * (h & 1), tb + rb * CK + 8 * kk,
+                         umma_desc(vb + (c * CK / 16 + kk) * 256, 128, (sb + C::ONES) - vb), idesc(16, 1), (c | kk) ? 1u : 0u);
+          if (c == SPH - 1) umma_commit(b_pv);
+          if (i + RD < NS) issue_s(i + RD, rb);       // the buffer is free as soon as this PV has read it (in-order pipe)
+        }
+        __syncwarp();
+        if (++rb == RD) { rb = 0; ph_p ^= 1u; }
+      }
+      ready(); issue_gemm(C::C_O, abuf, sb + tc::W_PROJ1, 32, 2);     // proj
+      ready(); issue_gemm(0, abuf, sb + tc::W_FC1, 128, 2);           // fc1
+      ready();                                                        // fc2: A = packed hidden units in TMEM columns 0..63
+      if (elect_one()) {
+        for (int k = 0; k < 8; ++k)
+          umma_bf16_ts(tb + C::C_O, tb + 8 * k, umma_desc(sb + tc::W_FC2 + 2 * k * 32 * 16, 32 * 16, 128), idesc(32, 0), k ? 1u : 0u);
+        umma_commit(b_mma);
+      }
+      __syncwarp();
+      ready(); issue_gemm(0, abuf, sb + tc::W_QKV2, 96, 2);           // last block: q (cls row), k, v
+    }
+  } else {
+    // ============================ row threads ============================
+    const uint32_t row16 = (uint32_t)r * 16u;
+    const int PW = P + 1, PP = sps_pp(P), HALO = sps_halo(P);
+    const int bar_id = 1 + slot;
+    const bool w0 = wq == 0;
+    uint32_t ph_m = 0, ph_pv = 0, rpar = 0;
+    int rbuf = 0;
+    // stem outputs of token row r of patch b -> FBUF (8 slices x 16 B; cls row and padding rows stay zero); see tokens_tc.cu
+    const int tok_i = r >= 1 && r < T ? (r - 1) / P : 0, tok_j = r >= 1 && r < T ? (r - 1) - tok_i * P : 0;
+    const bool planes = a.pl.h || a.pl.l;
+    const long long voff0 = planes ? ((long long)(border_class(tok_i, P, a.pl.D) * (2 * a.pl.D + 1) + border_class(tok_j, P, a.pl.D)) * 4 * a.pl.RTb +
+                                      sps_halo(a.pl.B)) : 0;
+    auto fetch = [&](int b) {
+      if (r >= 1 && r < T) {
+        const __nv_bfloat16* src = a.f + (HALO + (long long)b * PP + tok_i * PW + tok_j) * 8;
+        const __nv_bfloat16 *sh = src, *sl = src + 4 * a.RT * 8;
+        long long ph = a.RT * 8, pls = a.RT * 8;          // slice pitch (elements) of the HSI / LiDAR source
+        if (planes) {
+          const int2 c = __ldg(reinterpret_cast<const int2*>(a.pl.xy) + b);
+          const long long voff = (voff0 + __ldg(a.pl.rowterm + c.x + tok_i) + __ldg(a.pl.colterm + c.y + tok_j)) * 8;
+          if (a.pl.h) { sh = a.pl.h + voff; ph = a.pl.RTb * 8; }
+          if (a.pl.l) { sl = a.pl.l + voff; pls = a.pl.RTb * 8; }
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s) cp_async16(fbuf + s * SLAB + row16, sh + s * ph);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) cp_async16(fbuf + (4 + s) * SLAB + row16, sl + s * pls);
+      } else {          // the buffer doubles as K / V: the cls row and the padding rows are zeroed every time
+#pragma unroll
+        for (int s = 0; s < 8; ++s) sts128(fbuf + s * SLAB + row16, 0u, 0u, 0u, 0u);
+      }
+    };
+    auto publish = [&]() {        // shared-memory operands written by this thread -> visible to the tensor core
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(b_rp);
+    };
+    auto publish_tmem = [&](uint64_t* bar) {   // TMEM operands stored by this thread (and its TMEM reads) are complete
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(bar);
+    };
+    auto wait_mma = [&]() {
+      mbar_wait_s(b_mma, ph_m);
+      ph_m ^= 1u;
+      tc_fence_after();
+    };
+    if (b0 < a.n_patches) fetch(b0);
+
+    for (int b = b0; b < a.n_patches; b += nslots) {
+      float x[32];   // residual stream of token row r
+      // ================= fusion 1x1 conv (64 -> 32) + folded BN + ReLU, + cls / pos =================
+      cp_async_wait_all();
+      publish();
+      wait_mma();
+      {
+        uint32_t v[32];
+        tmem_ld32(tl + C::C_O, v);
+        tc_wait_ld();
+        const float rowmask = (r >= 1 && r < T) ? 1.f : 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 p = lds_f4(sb + C::POS + r * 128 + ((g ^ (r & 7)) << 4));
+          x[4 * g + 0] = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * g + 0]), c_vec[V_FSC + 4 * g + 0], c_vec[V_FBI + 4 * g + 0]), 0.f), rowmask, p.x);
+          x[4 * g + 1] = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * g + 1]), c_vec[V_FSC + 4 * g + 1], c_vec[V_FBI + 4 * g + 1]), 0.f), rowmask, p.y);
+          x[4 * g + 2] = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * g + 2]), c_vec[V_FSC + 4 * g + 2], c_vec[V_FBI + 4 * g + 2]), 0.f), rowmask, p.z);
+          x[4 * g + 3] = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * g + 3]), c_vec[V_FSC + 4 * g + 3], c_vec[V_FBI + 4 * g + 3]), 0.f), rowmask, p.w);
+        }
+      }
+
+      // ================= block 1: LN1 -> qkv =================
+      ln_store_c<V_LN1G, V_LN1B>(x, abuf + row16);
+      publish();
+      wait_mma();
+#pragma unroll
+      for (int part = 0; part < 3; ++part) {
+        uint32_t v[32];
+        tmem_ld32(tl + 32 * part, v);
+        tc_wait_ld();
+        const uint32_t dst = (part == 0 ? qbuf : part == 1 ? kbuf : vbuf) + row16;
+        const float sc = part == 0 ? qscale : 1.f;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          uint32_t p[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            p[e] = pack_bf16(fmaf(__uint_as_float(v[8 * h + 2 * e]), sc, c_vec[V_BQKV + 32 * part + 8 * h + 2 * e]),
+                             fmaf(__uint_as_float(v[8 * h + 2 * e + 1]), sc, c_vec[V_BQKV + 32 * part + 8 * h + 2 * e + 1]));
+          sts128(dst + h * SLAB, p[0], p[1], p[2], p[3]);
+        }
+      }
+      publish();
+
+      // ================= attention: 4 heads x SPH key chunks =================
+      // p = 2^s (the static bound holds: no row maximum; padded keys arrive at -29952 -> 0), packed to bf16 over the
+      // first half of the chunk's own TMEM columns.  O_h (two 16-column buffers) is read one step after its last PV
+      // was issued, normalised by column 8 (the denominator of the bf16 probabilities) and written to slab h of the
+      // Q buffer (= A operand of proj; every S of head h is complete by then).
+      auto read_o = [&](int h) {
+        uint32_t o[16];
+        mbar_wait_s(b_pv, ph_pv);
+        ph_pv ^= 1u;
+        tc_fence_after();
+        tmem_ld16(tl + C::C_O + 16 * (h & 1), o);
+        tc_wait_ld();
+        const float il = 1.f / __uint_as_float(o[8]);
+        sts128(abuf + h * SLAB + row16, pack_bf16(__uint_as_float(o[0]) * il, __uint_as_float(o[1]) * il),
+               pack_bf16(__uint_as_float(o[2]) * il, __uint_as_float(o[3]) * il),
+               pack_bf16(__uint_as_float(o[4]) * il, __uint_as_float(o[5]) * il),
+               pack_bf16(__uint_as_float(o[6]) * il, __uint_as_float(o[7]) * il));
+      };
+#pragma unroll 1
+      for (int h = 0; h < 4; ++h) {
+#pragma unroll 1
+        for (int c = 0; c < SPH; ++c) {
+          mbar_wait_s(b_s + rbuf, rpar);
+          tc_fence_after();
+          const uint32_t scol = tl + (uint32_t)(rbuf * CK);
+          const int keys = min(CK, NK - c * CK);
+#pragma unroll
+          for (int sub = 0; sub < CK / 32; ++sub) {
+            if (32 * sub < keys) {
+              uint32_t sc[32], pk[16];
+              tmem_ld32(scol + 32 * sub, sc);
+              tc_wait_ld();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) pk[e] = pack_bf16(ex2(__uint_as_float(sc[2 * e])), ex2(__uint_as_float(sc[2 * e + 1])));
+              tmem_st16(scol + 16 * sub, pk);
+            }
+          }
+          // O_{h-1}: with one step per head it must be taken BEFORE this arrival (else PV of head h could complete b_pv a
+          // second time before this thread has seen the first), otherwise one step later, when its PV is surely done
+          if (c == 0 && h > 0 && SPH == 1) read_o(h - 1);
+          publish_tmem(b_p + rbuf);
+          if (++rbuf == RD) { rbuf = 0; rpar ^= 1u; }
+          if (c == 0 && h > 0 && SPH > 1) read_o(h - 1);
+        }
+      }
+      {   // O_3: wait first, then start the next patch's input over the dead K / V buffers
+        uint32_t o[16];
+        mbar_wait_s(b_pv, ph_pv);
+        ph_pv ^= 1u;
+        tc_fence_after();
+        if (b + nslots < a.n_patches) fetch(b + nslots);
+        tmem_ld16(tl + C::C_O + 16, o);
+        tc_wait_ld();
+        const float il = 1.f / __uint_as_float(o[8]);
+        sts128(abuf + 3 * SLAB + row16, pack_bf16(__uint_as_float(o[0]) * il, __uint_as_float(o[1]) * il),
+               pack_bf16(__uint_as_float(o[2]) * il, __uint_as_float(o[3]) * il),
+               pack_bf16(__uint_as_float(o[4]) * il, __uint_as_float(o[5]) * il),
+               pack_bf16(__uint_as_float(o[6]) * il, __uint_as_float(o[7]) * il));
+      }
+      publish();
+      wait_mma();
+      {
+        uint32_t v[32];
+        tmem_ld32(tl + C::C_O, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) x[c] += __uint_as_float(v[c]) + c_vec[V_BPROJ + c];
+      }
+
+      // ================= MLP: LN2 -> fc1 (+bias, GELU, in place) -> fc2 (+bias, +residual) =================
+      ln_store_c<V_LN2G, V_LN2B>(x, abuf + row16);
+      publish();
+      wait_mma();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32], pk[16];
+        tmem_ld32(tl + 32 * c, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          pk[e] = pack_bf16(gelu2(__uint_as_float(v[2 * e]) + c_vec[V_BFC1 + 32 * c + 2 * e]),
+                            gelu2(__uint_as_float(v[2 * e + 1]) + c_vec[V_BFC1 + 32 * c + 2 * e + 1]));
+        tmem_st16(tl + 16 * c, pk);       // columns [16 c, 16 c + 16) were read with chunk c / 2
+      }
+      publish_tmem(b_rp);
+      wait_mma();
+      {
+        uint32_t v[32];
+        tmem_ld32(tl + C::C_O, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) x[c] += __uint_as_float(v[c]) + c_vec[V_BFC2 + c];
+      }
+
+      // ================= last block: K / V of every token, attention of the cls query only =================
+      ln_store_c<V_L2G, V_L2B>(x, abuf + row16);
+      publish();
+      wait_mma();
+      float* trec = a.tail + (long long)b * tc::kTailFloats;
+      {
+        uint32_t kk[32], vv[32];
+        tmem_ld32(tl + 32, kk);
+        tmem_ld32(tl + 64, vv);
+        if (w0) {     // the cls token is row 0: its (scaled) query and its residual stream
+          uint32_t qq[32];
+          tmem_ld32(tl, qq);
+          tc_wait_ld();
+          if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              q0_s[c] = fmaf(__uint_as_float(qq[c]), qscale, c_vec[V_BQKV2 + c]);
+              trec[144 + c] = x[c];
+            }
+          }
+        }
+        tc_wait_ld();
+        bar_sync(bar_id, 128);
+        float sc[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float4 q0 = lds_f4(smem_u32(q0_s) + 32 * h), q1 = lds_f4(smem_u32(q0_s) + 32 * h + 16);
+          float d = q0.x * (__uint_as_float(kk[8 * h + 0]) + c_vec[V_BQKV2 + 32 + 8 * h + 0]);
+          d = fmaf(q0.y, __uint_as_float(kk[8 * h + 1]) + c_vec[V_BQKV2 + 32 + 8 * h + 1], d);
+          d = fmaf(q0.z, __uint_as_float(kk[8 * h + 2]) + c_vec[V_BQKV2 + 32 + 8 * h + 2], d);
+          d = fmaf(q0.w, __uint_as_float(kk[8 * h + 3]) + c_vec[V_BQKV2 + 32 + 8 * h + 3], d);
+          d = fmaf(q1.x, __uint_as_float(kk[8 * h + 4]) + c_vec[V_BQKV2 + 32 + 8 * h + 4], d);
+          d = fmaf(q1.y, __uint_as_float(kk[8 * h + 5]) + c_vec[V_BQKV2 + 32 + 8 * h + 5], d);
+          d = fmaf(q1.z, __uint_as_float(kk[8 * h + 6]) + c_vec[V_BQKV2 + 32 + 8 * h + 6], d);
+          d = fmaf(q1.w, __uint_as_float(kk[8 * h + 7]) + c_vec[V_BQKV2 + 32 + 8 * h + 7], d);
+          sc[h] = r < T ? d : -INFINITY;
+          if (exact_cls) {           // the maximum over all keys is only needed when 2^s could overflow
+            float mw = sc[h];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+            if (lane == 0) wmax_s[wq * 4 + h] = mw;
+          }
+        }
+        if (exact_cls) bar_sync(bar_id, 128);
+        float val[32], pl[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float m = exact_cls ? fmaxf(fmaxf(wmax_s[h], wmax_s[4 + h]), fmaxf(wmax_s[8 + h], wmax_s[12 + h])) : 0.f;
+          const float p = ex2(sc[h] - m);
+          pl[h] = p;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) val[8 * h + e] = p * (__uint_as_float(vv[8 * h + e]) + c_vec[V_BQKV2 + 64 + 8 * h + e]);
+        }
+        // butterfly reduction over the 32 rows of this warp: lane i ends with sum over rows of val[i]
+#pragma unroll
+        for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < n / 2; ++i) {
+            const float send = up ? val[i] : val[i + n / 2];
+            const float keep = up ? val[i + n / 2] : val[i];
+            val[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        {   // denominators: head = 2 * bit4 + bit3 of the lane after two halving steps, then a full reduce over bits 2..0
+          const bool up4 = (lane & 16) != 0, up3 = (lane & 8) != 0;
+          float a0 = (up4 ? pl[2] : pl[0]) + __shfl_xor_sync(0xffffffffu, up4 ? pl[0] : pl[2], 16);
+          float a1 = (up4 ? pl[3] : pl[1]) + __shfl_xor_sync(0xffffffffu, up4 ? pl[1] : pl[3], 16);
+          float l = (up3 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, up3 ? a0 : a1, 8);
+          l += __shfl_xor_sync(0xffffffffu, l, 4);
+          l += __shfl_xor_sync(0xffffffffu, l, 2);
+          l += __shfl_xor_sync(0xffffffffu, l, 1);
+          trec[wq * 36 + lane] = val[0];
+          if ((lane & 7) == 0) trec[wq * 36 + 32 + (lane >> 3)] = l;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid < 32) tmem_dealloc(tmem_base, 512);
+}
+
+template <int SLOTS>
+static int tm_launch_slots(const TcArgs& a, int n_patches, int num_sms, int max_smem, cudaStream_t stream) {
+  using C = tm::Cfg<SLOTS>;
+  if ((int)C::SMEM_BYTES > max_smem) return VC_ERR_UNSUPPORTED;
+  if (cudaFuncSetAttribute(tokens_tm_kernel<SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES) != cudaSuccess)
+    return VC_ERR_CUDA;
+  int blocks = (n_patches + SLOTS - 1) / SLOTS;
+  if (blocks > num_sms) blocks = num_sms;
+  tokens_tm_kernel<SLOTS><<<blocks, C::kThreads, C::SMEM_BYTES, stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? VC_OK : VC_ERR_CUDA;
+}
+
+size_t tokens_tm_stage_bytes() { return tm::kStageBytes; }
+
+// Prep kernel -> constant bank -> main kernel on `stream`.  `stage` = tm::kStageBytes of device memory owned by the
+// caller's scratch buffer; stage[V_EXACT] stays readable for the gated fallback launch (tokens_tc.cu).
+int tokens_tm_main_launch(const TcArgs& a, float* stage, int n_patches, int num_sms, int max_smem, int slots, cudaStream_t stream) {
+  // The constant bank is one per device: a launch on another stream must not overwrite it under a kernel still running.
+  static std::mutex mu;
+  static cudaEvent_t ev[64] = {};
+  static cudaStream_t last[64] = {};
+  static bool have[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return VC_ERR_UNSUPPORTED;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(stream, &cap);
+  const bool track = cap == cudaStreamCaptureStatusNone;
+  std::lock_guard<std::mutex> lock(mu);
+  if (track && have[dev] && last[dev] != stream && cudaStreamWaitEvent(stream, ev[dev], 0) != cudaSuccess) return VC_ERR_CUDA;
+  tm::tm_prep_kernel<<<1, 128, 0, stream>>>(a.blob, a.L, stage);
+  if (cudaGetLastError() != cudaSuccess) return VC_ERR_CUDA;
+  if (cudaMemcpyToSymbolAsync(tm::c_vec, stage, tm::kVecFloats * sizeof(float), 0, cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+    return VC_ERR_CUDA;
+  const int rc = slots >= 4 ? tm_launch_slots<4>(a, n_patches, num_sms, max_smem, stream) : tm_launch_slots<3>(a, n_patches, num_sms, max_smem, stream);
+  if (rc != VC_OK) return rc;
+  if (track) {
+    if (!ev[dev] && cudaEventCreateWithFlags(&ev[dev], cudaEventDisableTiming) != cudaSuccess) return VC_ERR_CUDA;
+    if (cudaEventRecord(ev[dev], stream) != cudaSuccess) return VC_ERR_CUDA;
+    last[dev] = stream;
+    have[dev] = true;
+  }
+  return VC_OK;
+}
+
+}  // namespace vc
