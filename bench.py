@@ -625,7 +625,9 @@ def main():
                     "tensor", w_h[2], 1e12, tf_sust, "TFLOP/s"),
         "conv_lidar": ("LiDAR stem shared at depth 3: conv_sps_tc_kernel x 9 (conv 1) + conv_var_kernel (conv 2, conv 3) (tcgen05)"
                        if lidar_shared else "conv_sps_tc_kernel x 3 (LiDAR stem per window, tcgen05)", "tensor", w_l, 1e12, tf_sust, "TFLOP/s"),
-        "tokens": (("tokens_tc_kernel + tokens_tail_kernel (token stage, tcgen05" + (", stem inputs read from the variant planes)" if direct else ")"))
+        "tokens": (((("tokens_tc_kernel" if os.environ.get("VITCNN_TC_KERNEL") == "tc" else "tokens_tm_kernel (probabilities / hidden units through TMEM, %s patches in flight per SM)"
+                      % ("3" if os.environ.get("VITCNN_TC_KERNEL") == "tm3" else "4"))
+                     + " + tokens_tail_kernel (token stage, tcgen05") + (", stem inputs read from the variant planes)" if direct else ")"))
                    if tc_tokens else "transformer_fwd_kernel (token stage, mma.sync)", "tensor", float(token_flops) * nwin, 1e12, tf_sust, "TFLOP/s"),
         # HBM bytes that must move in the gather / packing launches: block packing (fp32 raster read, bf16 SPS written),
         # plus, when the token kernel does not read the planes itself, the per-window SPS rows written and read

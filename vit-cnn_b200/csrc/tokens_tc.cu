@@ -650,13 +650,13 @@ int tokens_tc_launch(const void* f_sps, const void* tparams, int n_patches, int 
     const char* e = getenv("VITCNN_TC_SPLIT");
     return e ? atoi(e) : 0;
   }();
-  // VITCNN_TC_KERNEL = tm3 (default) / tm4: tokens_tm_kernel with three / four patches in flight per CTA, and
+  // VITCNN_TC_KERNEL = tm4 (default) / tm3: tokens_tm_kernel with four / three patches in flight per CTA, and
   // tokens_tc_kernel behind it gated on the prep kernel's flag (weights whose attention logits need the row maximum);
   // tc: tokens_tc_kernel only.
   static const int tm_slots = [] {
     const char* e = getenv("VITCNN_TC_KERNEL");
-    if (!e || !strcmp(e, "tm3")) return 3;
-    if (!strcmp(e, "tm4")) return 4;
+    if (!e || !strcmp(e, "tm4")) return 4;
+    if (!strcmp(e, "tm3")) return 3;
     return 0;
   }();
   if (split > 0) {

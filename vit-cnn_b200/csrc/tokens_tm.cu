@@ -77,22 +77,52 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// mbarrier wait whose try_wait may stay suspended in hardware for up to ~10 us before it reports "not yet" (the plain
-// form came back every ~60 cycles: a fifth of the instructions tokens_tc_kernel issued were these polling loops).
-// Bounded: a protocol bug must surface as a trapped kernel, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait_s(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t ok, spins = 0;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity), "r"(10000u)
-        : "memory");
-    if (!ok && ++spins > (1u << 22)) __trap();
-  } while (!ok);
+// mbarrier operations on 32-bit shared-memory addresses (computed once per thread: the generic-pointer forms re-derive
+// the shared window base at every use).  The wait tries once without any bookkeeping (in the attention loop the S chunk
+// is normally there already) and only then enters the bounded polling loop: a protocol bug must surface as a trapped
+// kernel, never as a hung GPU.  VC_TM_WAIT_HINT: try_wait with a suspend-time hint (compiles to NANOSLEEP.SYNCS between
+// two phase checks) instead of the plain form in the polling loop.
+#ifndef VC_TM_WAIT_HINT
+#define VC_TM_WAIT_HINT 1
+#endif
+__device__ __forceinline__ bool mbar_try_a(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try_hint_a(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity), "r"(10000u)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
+  if (mbar_try_a(addr, parity)) return;
+  uint32_t spins = 0;
+  while (!(VC_TM_WAIT_HINT ? mbar_try_hint_a(addr, parity) : mbar_try_a(addr, parity)))
+    if (++spins > (1u << 22)) __trap();
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t addr) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ float rcp_fast(float v) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
 }
 
 // LayerNorm (eps 1e-6) of the row held by this thread, gamma / beta from the constant bank -> bf16 -> K-major A operand
@@ -195,15 +225,15 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
   const uint32_t sb = smem_u32(smem);
   float* q0_s = reinterpret_cast<float*>(smem + C::MISC + C::M_Q0) + slot * 32;          // [32]
   float* wmax_s = reinterpret_cast<float*>(smem + C::MISC + C::M_WMAX) + slot * 16;      // [4 warps][4 heads]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::MISC + C::M_BARS) + slot * 16;
-  uint64_t* b_rp = bars + 0;      // row threads: operands of the next GEMM are written (128 arrivals)
-  uint64_t* b_mma = bars + 1;     // tensor core: the GEMM just issued (fusion / qkv / proj / fc1 / fc2 / kv2) is done
-  uint64_t* b_pv = bars + 2;      // tensor core: O_h is complete
-  uint64_t* b_s = bars + 3;       // [RD] tensor core: the S chunk in ring buffer k is in TMEM (and the PV that read the buffer is done)
+  const uint32_t bars = sb + C::MISC + C::M_BARS + (uint32_t)slot * 128u;   // 16 mbarriers per slot (shared addresses)
+  const uint32_t b_rp = bars + 0;      // row threads: operands of the next GEMM are written (128 arrivals)
+  const uint32_t b_mma = bars + 8;     // tensor core: the GEMM just issued (fusion / qkv / proj / fc1 / fc2 / kv2) is done
+  const uint32_t b_pv = bars + 16;     // tensor core: O_h is complete
+  const uint32_t b_s = bars + 24;      // [RD] tensor core: the S chunk in ring buffer k is in TMEM (and the PV that read the buffer is done)
   // [RD] row threads: the probabilities in ring buffer k are written (128 arrivals).  One barrier per buffer: S chunks are
   // issued ahead, so a row thread may finish step i + 1 before another has finished step i -- on a shared barrier its
   // second arrival would complete the phase of step i; on buffer k it cannot arrive again before PV of step i has run.
-  uint64_t* b_p = bars + 8;
+  const uint32_t b_p = bars + 64;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::MISC + C::M_TMEM);
   const float qscale = 0.35355339059327376220f * 1.44269504088896340736f;  // hd^-0.5 * log2(e)
   const bool exact_cls = c_vec[V_EXACT_CLS] != 0.f;
@@ -252,7 +282,7 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
     }
     if (tid == 0) {
       for (int s = 0; s < SLOTS; ++s) {
-        uint64_t* bb = reinterpret_cast<uint64_t*>(smem + C::MISC + C::M_BARS) + s * 16;
+        uint64_t* bb = reinterpret_cast<uint64_t*>(smem + C::MISC + C::M_BARS) + s * 16;   // order: see b_rp .. b_p
         mbar_init(bb + 0, 128);
         for (int k = 1; k < 8; ++k) mbar_init(bb + k, 1);
         for (int k = 8; k < 16; ++k) mbar_init(bb + k, 128);
@@ -280,69 +310,90 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
   const int b0 = SLOTS * (int)blockIdx.x + slot;
 
   if (issuer) {
-    // ============================ MMA issuer of this slot ============================
-    uint32_t ph_rp = 0, ph_p = 0;
-    int rb = 0;               // ring buffer of the next attention step (ph_p: parity of its "probabilities written" barrier)
-    auto ready = [&]() {      // the row threads have written the operands of the next MMA group
-      mbar_wait_s(b_rp, ph_rp);
-      ph_rp ^= 1u;
-      tc_fence_after();
-    };
-    // D[128 x N] (TMEM column `col`) = A[128 x 16 ksteps] (K-major slabs at `abase`) . W^T (weights [k/8][N][8] at `wbase`)
-    auto issue_gemm = [&](uint32_t col, uint32_t abase, uint32_t wbase, int N, int ksteps) {
-      if (elect_one()) {
-        for (int k = 0; k < ksteps; ++k)
-          umma_bf16(tb + col, umma_desc(abase + 2 * k * SLAB, SLAB, 128), umma_desc(wbase + 2 * k * N * 16, (uint32_t)N * 16u, 128),
-                    idesc(N, 0), k ? 1u : 0u);
-        umma_commit(b_mma);
-      }
-      __syncwarp();
-    };
-    // S chunk of step j -> ring buffer `buf`: A chunks (Q_h, ones), B chunks (keys [c CK, +keys) of K_h, their mask rows)
-    auto issue_s = [&](int j, int buf) {
-      const int h = j / SPH, c = j - h * SPH;
-      const int keys = min(CK, NK - c * CK);
-      const uint32_t qa = qbuf + h * SLAB, ka = kbuf + h * SLAB;
-      umma_bf16(tb + buf * CK, umma_desc(qa, (sb + C::ONES) - qa, 128), umma_desc(ka + c * CK * 16, (sb + C::MASK) - ka, 128),
-                idesc(keys, 0), 0u);
-      umma_commit(b_s + buf);
-    };
-    for (int b = b0; b < a.n_patches; b += nslots) {
-      ready(); issue_gemm(C::C_O, fbuf, sb + tc::W_FUS, 32, 4);       // fusion 1x1 conv
-      ready(); issue_gemm(0, abuf, sb + tc::W_QKV1, 96, 2);           // qkv
-      ready();
-      if (elect_one()) {
-        for (int j = 0; j < RD && j < NS; ++j) issue_s(j, (rb + j) % RD);
-      }
-      __syncwarp();
-#pragma unroll 1
-      for (int i = 0; i < NS; ++i) {
-        const int h = i / SPH, c = i - h * SPH;
-        mbar_wait_s(b_p + rb, ph_p);                  // the probabilities of step i are in the first half of buffer rb
+    // ============================ MMA issuer of this slot: one thread ============================
+    // Descriptors are kept as 64-bit values and stepped by constant increments: the start-address field counts 16-byte
+    // units from bit 0, the leading-byte-offset field from bit 16 (no carries: every address is below 256 KB).
+    if (lane == 0) {
+      uint32_t ph_rp = 0, ph_p = 0;
+      int rb = 0;               // ring buffer of the next attention step (ph_p: parity of its "probabilities written" barrier)
+      auto ready = [&]() {      // the row threads have written the operands of the next GEMM
+        mbar_wait_a(b_rp, ph_rp);
+        ph_rp ^= 1u;
         tc_fence_after();
-        if (elect_one()) {
-          // O_h[128 x 16] (+)= P[128 x keys] . [V_h | ones]: B is MN-major, N chunk 0 = V_h slab, chunk 1 = ONES slab
-          const int keys = min(CK, NK - c * CK);
-          const uint32_t vb = vbuf + h * SLAB;
-          for (int kk = 0; kk < keys / 16; ++kk)
-            umma_bf16_ts(tb + C::C_O + 16 * (h & 1), tb + rb * CK + 8 * kk,
-                         umma_desc(vb + (c * CK / 16 + kk) * 256, 128, (sb + C::ONES) - vb), idesc(16, 1), (c | kk) ? 1u : 0u);
-          if (c == SPH - 1) umma_commit(b_pv);
-          if (i + RD < NS) issue_s(i + RD, rb);       // the buffer is free as soon as this PV has read it (in-order pipe)
+      };
+      // D[128 x N] (TMEM column `col`) = A[128 x 16 ksteps] (K-major slabs at `abase`) . W^T (weights [k/8][N][8] at `wbase`)
+      auto issue_gemm = [&](uint32_t col, uint32_t abase, uint32_t wbase, int N, int ksteps) {
+        uint64_t da = umma_desc(abase, SLAB, 128), dw = umma_desc(wbase, (uint32_t)N * 16u, 128);
+        const uint32_t id = idesc(N, 0);
+        for (int k = 0; k < ksteps; ++k) {
+          umma_bf16(tb + col, da, dw, id, k ? 1u : 0u);
+          da += (2 * SLAB) >> 4;
+          dw += (uint64_t)(2 * N);      // 2 N 16-byte rows per K step
         }
-        __syncwarp();
-        if (++rb == RD) { rb = 0; ph_p ^= 1u; }
+        umma_commit_a(b_mma);
+      };
+      const uint32_t ones = sb + C::ONES, mask = sb + C::MASK;
+      // head 0, chunk 0: Q / K descriptors (A chunks (Q_h, ones), B chunks (keys of K_h, their mask rows)) and the V descriptor
+      const uint64_t dq0 = umma_desc(qbuf, ones - qbuf, 128), dk0 = umma_desc(kbuf, mask - kbuf, 128);
+      const uint64_t dv0 = umma_desc(vbuf, 128, ones - vbuf);
+      const uint64_t d_head = (uint64_t)(SLAB >> 4) - ((uint64_t)(SLAB >> 4) << 16);   // next head: start + SLAB, LBO - SLAB
+      const uint64_t dv_head = (uint64_t)(SLAB >> 4) - ((uint64_t)(SLAB >> 4) << 32);  // V: the ones slab sits in the SBO field
+      const uint32_t id_pv = idesc(16, 1);
+      for (int b = b0; b < a.n_patches; b += nslots) {
+        ready(); issue_gemm(C::C_O, fbuf, sb + tc::W_FUS, 32, 4);       // fusion 1x1 conv
+        ready(); issue_gemm(0, abuf, sb + tc::W_QKV1, 96, 2);           // qkv
+        ready();
+        // S chunk of step (hs, cs) -> ring buffer: issued RD steps ahead of the PV that frees the buffer
+        int hs = 0, cs = 0;
+        uint64_t dq = dq0, dk = dk0;
+        auto issue_s = [&](int buf) {
+          const int keys = CK == 32 ? 32 : min(CK, NK - cs * CK);
+          umma_bf16(tb + buf * CK, dq, dk + (uint64_t)(cs * CK), idesc(keys, 0), 0u);
+          umma_commit_a(b_s + 8 * buf);
+          if (++cs == SPH) { cs = 0; ++hs; dq += d_head; dk += d_head; }
+        };
+        {
+          int buf = rb;
+          for (int j = 0; j < RD && j < NS; ++j) {
+            issue_s(buf);
+            if (++buf == RD) buf = 0;
+          }
+        }
+        uint64_t dv = dv0;
+#pragma unroll 1
+        for (int h = 0; h < 4; ++h) {
+#pragma unroll 1
+          for (int c = 0; c < SPH; ++c) {
+            mbar_wait_a(b_p + 8 * rb, ph_p);              // the probabilities of step (h, c) are in the first half of buffer rb
+            tc_fence_after();
+            // O_h[128 x 16] (+)= P[128 x keys] . [V_h | ones]: B is MN-major, N chunk 0 = V_h slab, chunk 1 = ONES slab
+            const int ksteps = (CK == 32 ? 32 : min(CK, NK - c * CK)) / 16;
+            const uint32_t d_o = tb + C::C_O + 16 * (h & 1), a_p = tb + rb * CK;
+            uint64_t dvk = dv + (uint64_t)(c * CK);       // 16 keys = 256 B = 16 units per K step
+            for (int kk = 0; kk < ksteps; ++kk) {
+              umma_bf16_ts(d_o, a_p + 8 * kk, dvk, id_pv, (c | kk) ? 1u : 0u);
+              dvk += 16;
+            }
+            if (c == SPH - 1) umma_commit_a(b_pv);
+            if (hs < 4) issue_s(rb);                      // the buffer is free as soon as this PV has read it (in-order pipe)
+            if (++rb == RD) { rb = 0; ph_p ^= 1u; }
+          }
+          dv += dv_head;
+        }
+        ready(); issue_gemm(C::C_O, abuf, sb + tc::W_PROJ1, 32, 2);     // proj
+        ready(); issue_gemm(0, abuf, sb + tc::W_FC1, 128, 2);           // fc1
+        ready();                                                        // fc2: A = packed hidden units in TMEM columns 0..63
+        {
+          uint64_t dw = umma_desc(sb + tc::W_FC2, 32 * 16, 128);
+          const uint32_t id = idesc(32, 0);
+          for (int k = 0; k < 8; ++k) {
+            umma_bf16_ts(tb + C::C_O, tb + 8 * k, dw, id, k ? 1u : 0u);
+            dw += 64;
+          }
+          umma_commit_a(b_mma);
+        }
+        ready(); issue_gemm(0, abuf, sb + tc::W_QKV2, 96, 2);           // last block: q (cls row), k, v
       }
-      ready(); issue_gemm(C::C_O, abuf, sb + tc::W_PROJ1, 32, 2);     // proj
-      ready(); issue_gemm(0, abuf, sb + tc::W_FC1, 128, 2);           // fc1
-      ready();                                                        // fc2: A = packed hidden units in TMEM columns 0..63
-      if (elect_one()) {
-        for (int k = 0; k < 8; ++k)
-          umma_bf16_ts(tb + C::C_O, tb + 8 * k, umma_desc(sb + tc::W_FC2 + 2 * k * 32 * 16, 32 * 16, 128), idesc(32, 0), k ? 1u : 0u);
-        umma_commit(b_mma);
-      }
-      __syncwarp();
-      ready(); issue_gemm(0, abuf, sb + tc::W_QKV2, 96, 2);           // last block: q (cls row), k, v
     }
   } else {
     // ============================ row threads ============================
@@ -380,15 +431,15 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
     auto publish = [&]() {        // shared-memory operands written by this thread -> visible to the tensor core
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(b_rp);
+      mbar_arrive_a(b_rp);
     };
-    auto publish_tmem = [&](uint64_t* bar) {   // TMEM operands stored by this thread (and its TMEM reads) are complete
+    auto publish_tmem = [&](uint32_t bar) {   // TMEM operands stored by this thread (and its TMEM reads) are complete
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(bar);
+      mbar_arrive_a(bar);
     };
     auto wait_mma = [&]() {
-      mbar_wait_s(b_mma, ph_m);
+      mbar_wait_a(b_mma, ph_m);
       ph_m ^= 1u;
       tc_fence_after();
     };
@@ -445,12 +496,12 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
       // Q buffer (= A operand of proj; every S of head h is complete by then).
       auto read_o = [&](int h) {
         uint32_t o[16];
-        mbar_wait_s(b_pv, ph_pv);
+        mbar_wait_a(b_pv, ph_pv);
         ph_pv ^= 1u;
         tc_fence_after();
         tmem_ld16(tl + C::C_O + 16 * (h & 1), o);
         tc_wait_ld();
-        const float il = 1.f / __uint_as_float(o[8]);
+        const float il = rcp_fast(__uint_as_float(o[8]));
         sts128(abuf + h * SLAB + row16, pack_bf16(__uint_as_float(o[0]) * il, __uint_as_float(o[1]) * il),
                pack_bf16(__uint_as_float(o[2]) * il, __uint_as_float(o[3]) * il),
                pack_bf16(__uint_as_float(o[4]) * il, __uint_as_float(o[5]) * il),
@@ -460,13 +511,13 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
       for (int h = 0; h < 4; ++h) {
 #pragma unroll 1
         for (int c = 0; c < SPH; ++c) {
-          mbar_wait_s(b_s + rbuf, rpar);
+          mbar_wait_a(b_s + 8 * rbuf, rpar);
           tc_fence_after();
           const uint32_t scol = tl + (uint32_t)(rbuf * CK);
-          const int keys = min(CK, NK - c * CK);
+          const int keys = CK == 32 ? 32 : min(CK, NK - c * CK);
 #pragma unroll
           for (int sub = 0; sub < CK / 32; ++sub) {
-            if (32 * sub < keys) {
+            if (CK == 32 || 32 * sub < keys) {
               uint32_t sc[32], pk[16];
               tmem_ld32(scol + 32 * sub, sc);
               tc_wait_ld();
@@ -478,20 +529,20 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
           // O_{h-1}: with one step per head it must be taken BEFORE this arrival (else PV of head h could complete b_pv a
           // second time before this thread has seen the first), otherwise one step later, when its PV is surely done
           if (c == 0 && h > 0 && SPH == 1) read_o(h - 1);
-          publish_tmem(b_p + rbuf);
+          publish_tmem(b_p + 8 * rbuf);
           if (++rbuf == RD) { rbuf = 0; rpar ^= 1u; }
           if (c == 0 && h > 0 && SPH > 1) read_o(h - 1);
         }
       }
       {   // O_3: wait first, then start the next patch's input over the dead K / V buffers
         uint32_t o[16];
-        mbar_wait_s(b_pv, ph_pv);
+        mbar_wait_a(b_pv, ph_pv);
         ph_pv ^= 1u;
         tc_fence_after();
         if (b + nslots < a.n_patches) fetch(b + nslots);
         tmem_ld16(tl + C::C_O + 16, o);
         tc_wait_ld();
-        const float il = 1.f / __uint_as_float(o[8]);
+        const float il = rcp_fast(__uint_as_float(o[8]));
         sts128(abuf + 3 * SLAB + row16, pack_bf16(__uint_as_float(o[0]) * il, __uint_as_float(o[1]) * il),
                pack_bf16(__uint_as_float(o[2]) * il, __uint_as_float(o[3]) * il),
                pack_bf16(__uint_as_float(o[4]) * il, __uint_as_float(o[5]) * il),
@@ -547,9 +598,11 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
           tc_wait_ld();
           if (lane == 0) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              q0_s[c] = fmaf(__uint_as_float(qq[c]), qscale, c_vec[V_BQKV2 + c]);
-              trec[144 + c] = x[c];
+            for (int c = 0; c < 32; c += 4) {
+              *reinterpret_cast<float4*>(q0_s + c) =
+                  make_float4(fmaf(__uint_as_float(qq[c]), qscale, c_vec[V_BQKV2 + c]), fmaf(__uint_as_float(qq[c + 1]), qscale, c_vec[V_BQKV2 + c + 1]),
+                              fmaf(__uint_as_float(qq[c + 2]), qscale, c_vec[V_BQKV2 + c + 2]), fmaf(__uint_as_float(qq[c + 3]), qscale, c_vec[V_BQKV2 + c + 3]));
+              *reinterpret_cast<float4*>(trec + 144 + c) = make_float4(x[c], x[c + 1], x[c + 2], x[c + 3]);
             }
           }
         }
