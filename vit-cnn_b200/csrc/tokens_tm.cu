@@ -55,7 +55,9 @@ struct Cfg {
   static constexpr uint32_t ONES = SLOT0 + SLOTS * SLOT_BYTES;
   static constexpr uint32_t MASK = ONES + SLAB;
   static constexpr uint32_t MISC = MASK + SLAB;
-  static constexpr uint32_t M_Q0 = 0, M_WMAX = M_Q0 + SLOTS * 128, M_BARS = M_WMAX + SLOTS * 64, M_TMEM = M_BARS + SLOTS * 128;
+  // q0: [slot][row warp][32] fp32 cls query (one copy per warp); y0: [slot][2][32] bf16 LayerNorm output of the cls row
+  static constexpr uint32_t M_Q0 = 0, M_Y0 = M_Q0 + SLOTS * 512, M_WMAX = M_Y0 + SLOTS * 128, M_BARS = M_WMAX + SLOTS * 64,
+                            M_TMEM = M_BARS + SLOTS * 128;
   static constexpr uint32_t SMEM_BYTES = MISC + ((M_TMEM + 16 + 127) & ~127u);
   static_assert(SLOTS * C_SLOT <= 512, "TMEM columns");
 };
@@ -127,7 +129,7 @@ __device__ __forceinline__ float rcp_fast(float v) {
 
 // LayerNorm (eps 1e-6) of the row held by this thread, gamma / beta from the constant bank -> bf16 -> K-major A operand
 template <int G, int B>
-__device__ __forceinline__ void ln_store_c(const float (&x)[32], uint32_t dst_row) {
+__device__ __forceinline__ void ln_store_c(const float (&x)[32], uint32_t dst_row, uint32_t dst2 = 0u) {
   float s = 0.f;
 #pragma unroll
   for (int c = 0; c < 32; ++c) s += x[c];
@@ -147,6 +149,7 @@ __device__ __forceinline__ void ln_store_c(const float (&x)[32], uint32_t dst_ro
                        fmaf(fmaf(x[c0 + 1], rs, nm), c_vec[G + c0 + 1], c_vec[B + c0 + 1]));
     }
     sts128(dst_row + sl * SLAB, p[0], p[1], p[2], p[3]);
+    if (dst2) sts128(dst2 + sl * 16, p[0], p[1], p[2], p[3]);
   }
 }
 
@@ -223,7 +226,8 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
   const int T = a.T, P = a.P;
   const TLayout& L = a.L;
   const uint32_t sb = smem_u32(smem);
-  float* q0_s = reinterpret_cast<float*>(smem + C::MISC + C::M_Q0) + slot * 32;          // [32]
+  float* q0_s = reinterpret_cast<float*>(smem + C::MISC + C::M_Q0) + (issuer ? 0 : warp * 32);   // [32] per row warp
+  const uint32_t y0_s = sb + C::MISC + C::M_Y0 + (uint32_t)slot * 128u;                  // [2][4 x 16 B]
   float* wmax_s = reinterpret_cast<float*>(smem + C::MISC + C::M_WMAX) + slot * 16;      // [4 warps][4 heads]
   const uint32_t bars = sb + C::MISC + C::M_BARS + (uint32_t)slot * 128u;   // 16 mbarriers per slot (shared addresses)
   const uint32_t b_rp = bars + 0;      // row threads: operands of the next GEMM are written (128 arrivals)
@@ -340,7 +344,7 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
       const uint64_t dv_head = (uint64_t)(SLAB >> 4) - ((uint64_t)(SLAB >> 4) << 32);  // V: the ones slab sits in the SBO field
       const uint32_t id_pv = idesc(16, 1);
       for (int b = b0; b < a.n_patches; b += nslots) {
-        ready(); issue_gemm(C::C_O, fbuf, sb + tc::W_FUS, 32, 4);       // fusion 1x1 conv
+        if (b == b0) { ready(); issue_gemm(C::C_O, fbuf, sb + tc::W_FUS, 32, 4); }   // fusion 1x1 conv of the first patch
         ready(); issue_gemm(0, abuf, sb + tc::W_QKV1, 96, 2);           // qkv
         ready();
         // S chunk of step (hs, cs) -> ring buffer: issued RD steps ahead of the PV that frees the buffer
@@ -392,7 +396,27 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
           }
           umma_commit_a(b_mma);
         }
-        ready(); issue_gemm(0, abuf, sb + tc::W_QKV2, 96, 2);           // last block: q (cls row), k, v
+        ready();
+        {   // last block: k, v of every token (the cls query is computed by the row threads), columns 0..63 -- and, in the
+            // same hand-off, the fusion 1x1 conv of the slot's NEXT patch (its input has landed over the dead K / V buffers)
+          uint64_t da = umma_desc(abuf, SLAB, 128), dw = umma_desc(sb + tc::W_QKV2 + 32 * 16, 96 * 16, 128);
+          const uint32_t id = idesc(64, 0);
+          for (int k = 0; k < 2; ++k) {
+            umma_bf16(tb, da, dw, id, k ? 1u : 0u);
+            da += (2 * SLAB) >> 4;
+            dw += 2 * 96;
+          }
+          if (b + nslots < a.n_patches) {
+            uint64_t df = umma_desc(fbuf, SLAB, 128), dwf = umma_desc(sb + tc::W_FUS, 32 * 16, 128);
+            const uint32_t idf = idesc(32, 0);
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16(tb + C::C_O, df, dwf, idf, k ? 1u : 0u);
+              df += (2 * SLAB) >> 4;
+              dwf += 64;
+            }
+          }
+          umma_commit_a(b_mma);
+        }
       }
     }
   } else {
@@ -400,7 +424,6 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
     const uint32_t row16 = (uint32_t)r * 16u;
     const int PW = P + 1, PP = sps_pp(P), HALO = sps_halo(P);
     const int bar_id = 1 + slot;
-    const bool w0 = wq == 0;
     uint32_t ph_m = 0, ph_pv = 0, rpar = 0;
     int rbuf = 0;
     // stem outputs of token row r of patch b -> FBUF (8 slices x 16 B; cls row and padding rows stay zero); see tokens_tc.cu
@@ -448,9 +471,12 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
     for (int b = b0; b < a.n_patches; b += nslots) {
       float x[32];   // residual stream of token row r
       // ================= fusion 1x1 conv (64 -> 32) + folded BN + ReLU, + cls / pos =================
-      cp_async_wait_all();
-      publish();
-      wait_mma();
+      // (first patch of the slot: its own hand-off; later ones were issued with kv2 of the previous patch)
+      if (b == b0) {
+        cp_async_wait_all();
+        publish();
+        wait_mma();
+      }
       {
         uint32_t v[32];
         tmem_ld32(tl + C::C_O, v);
@@ -584,30 +610,41 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
       }
 
       // ================= last block: K / V of every token, attention of the cls query only =================
-      ln_store_c<V_L2G, V_L2B>(x, abuf + row16);
+      // The cls query q0 = qscale (W_q y_0 + b_q) is computed by the CUDA cores of every row warp (lane c: channel c) from
+      // the bf16 LayerNorm output of row 0 while the K / V GEMM is in flight: no TMEM read of a single lane, no barrier
+      // between the GEMM and the scores (the one barrier here sits where every thread waits for the hand-off anyway).
+      const uint32_t y0buf = y0_s + 64u * ((uint32_t)(b - b0) / (uint32_t)nslots & 1u);
+      ln_store_c<V_L2G, V_L2B>(x, abuf + row16, r == 0 ? y0buf : 0u);
+      cp_async_wait_all();            // the next patch's fusion input (issued after the last PV) has landed
       publish();
-      wait_mma();
       float* trec = a.tail + (long long)b * tc::kTailFloats;
+      if (r == 0) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(trec + 144 + c) = make_float4(x[c], x[c + 1], x[c + 2], x[c + 3]);
+      }
+      bar_sync(bar_id, 128);          // y_0 is in shared memory (its buffer is reused two patches later: another barrier in between)
+      {
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+          uint4 yv, wv;
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(yv.x), "=r"(yv.y), "=r"(yv.z), "=r"(yv.w) : "r"(y0buf + kc * 16));
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(wv.x), "=r"(wv.y), "=r"(wv.z), "=r"(wv.w)
+                       : "r"(sb + tc::W_QKV2 + kc * 96 * 16 + lane * 16));
+          acc0 = fmaf(bf_lo(yv.x), bf_lo(wv.x), acc0); acc1 = fmaf(bf_hi(yv.x), bf_hi(wv.x), acc1);
+          acc0 = fmaf(bf_lo(yv.y), bf_lo(wv.y), acc0); acc1 = fmaf(bf_hi(yv.y), bf_hi(wv.y), acc1);
+          acc0 = fmaf(bf_lo(yv.z), bf_lo(wv.z), acc0); acc1 = fmaf(bf_hi(yv.z), bf_hi(wv.z), acc1);
+          acc0 = fmaf(bf_lo(yv.w), bf_lo(wv.w), acc0); acc1 = fmaf(bf_hi(yv.w), bf_hi(wv.w), acc1);
+        }
+        q0_s[lane] = fmaf(acc0 + acc1, qscale, c_vec[V_BQKV2 + lane]);
+        __syncwarp();
+      }
+      wait_mma();
       {
         uint32_t kk[32], vv[32];
-        tmem_ld32(tl + 32, kk);
-        tmem_ld32(tl + 64, vv);
-        if (w0) {     // the cls token is row 0: its (scaled) query and its residual stream
-          uint32_t qq[32];
-          tmem_ld32(tl, qq);
-          tc_wait_ld();
-          if (lane == 0) {
-#pragma unroll
-            for (int c = 0; c < 32; c += 4) {
-              *reinterpret_cast<float4*>(q0_s + c) =
-                  make_float4(fmaf(__uint_as_float(qq[c]), qscale, c_vec[V_BQKV2 + c]), fmaf(__uint_as_float(qq[c + 1]), qscale, c_vec[V_BQKV2 + c + 1]),
-                              fmaf(__uint_as_float(qq[c + 2]), qscale, c_vec[V_BQKV2 + c + 2]), fmaf(__uint_as_float(qq[c + 3]), qscale, c_vec[V_BQKV2 + c + 3]));
-              *reinterpret_cast<float4*>(trec + 144 + c) = make_float4(x[c], x[c + 1], x[c + 2], x[c + 3]);
-            }
-          }
-        }
+        tmem_ld32(tl, kk);
+        tmem_ld32(tl + 32, vv);
         tc_wait_ld();
-        bar_sync(bar_id, 128);
         float sc[4];
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
