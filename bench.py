@@ -531,16 +531,31 @@ def main():
         vitcnn_b200.predict_scene_host(net, img1_h, img2_h, rank=rank, world=world, chunk=args.chunk, logits_out=lg_h,
                                        argmax_out=am_h, sync=sync)
 
+    host_s = [0.0, 0]         # host time spent queueing (time.perf_counter around the calls: no synchronisation inside)
+
     def e2e_step():          # every scene: H2D of the band from pinned memory, kernels, D2H of its maps; the next scene's
+        t0 = time.perf_counter()
         for _ in range(scenes):   # upload overlaps this one's tail (the final synchronize of the timed region drains all)
             e2e_scene(False)
+        host_s[0] += time.perf_counter() - t0
+        host_s[1] += 1
     if args.no_e2e or args.windows:
         ms_e2e = float("nan")
     else:
         for _ in range(max(args.warmup, 3)):     # the caching allocator must have seen the streaming depth before the timed region
             e2e_step()
+        host_s[0], host_s[1] = 0.0, 0
         ms_e2e = timed(e2e_step, args.steps)
+    host_queue_ms = host_s[0] / max(host_s[1], 1) * 1e3
     band_rows = band.stop - band.start
+    # what the host link alone allows: the same pinned -> HBM uploads with no kernels in between (the e2e leg cannot be
+    # faster than this; on the round-2 boxes a Houston scene's 386 MB take ~34 ms, i.e. the leg is link-bound once the
+    # device needs less than that)
+    def h2d_only():
+        for _ in range(scenes):
+            img1_h[band].to(dev, non_blocking=True)
+            img2_h[band].to(dev, non_blocking=True)
+    ms_h2d = float("nan") if (args.no_e2e or args.windows) else timed(h2d_only, args.steps)
     h2d = scenes * band_rows * W * (C1 + C2) * 4
     d2h = scenes * (out_rows.stop - out_rows.start) * W * (K * 4 + 1)
     e2e_val = pixels_per_step * args.steps / (ms_e2e / 1e3)
@@ -677,6 +692,7 @@ def main():
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_val, "unit": "pixels/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
+                        "host_queue_ms_per_step": host_queue_ms, "h2d_only_ms_per_step": ms_h2d / args.steps, "h2d_only_gb_per_s": h2d / (ms_h2d / args.steps) / 1e6,
                         "api": "vitcnn_b200.predict_scene_host(sync=False): scene after scene, double-buffered pinned results"},
                 "strong": strong,
                 "roofline": roofline,
