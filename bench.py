@@ -627,7 +627,7 @@ def main():
     nb_l = n_blocks(Bl, 3) if lidar_shared else 0
     w_l = sum(2.0 * cout_l[l] * cin_l[l] * pairs[l] * Bl * Bl * nb_l * scenes if lidar_shared
               else 2.0 * P * P * cout_l[l] * cin_l[l] * 9 * nwin for l in range(3))
-    tc_tokens = 82 <= T_ <= 128 and os.environ.get("VITCNN_TOKENS_IMPL") != "0"
+    tc_tokens = 26 <= T_ <= 128 and os.environ.get("VITCNN_TOKENS_IMPL") != "0"
     direct = depth == 3 and tc_tokens
     g_slices = {0: S1, 1: 16, 2: 8, 3: 4}[depth]
     shared_name = "conv_var_kernel: all %d border-class variants per launch, one work unit per (tile, row class) (%s, tcgen05)"

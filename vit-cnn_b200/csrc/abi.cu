@@ -318,18 +318,18 @@ int zero_halos(const Workspace& w, int n, int P, cudaStream_t st) {
   return VC_OK;
 }
 
-// Which token-stage kernel: the tcgen05 kernel (tokens_tc.cu) treats one patch as one M = 128 tile, so it wins where
-// the token set fills most of the tile (measured per 32 768 patches, tcgen05 vs mma.sync: P = 11 1.41 vs 1.75 ms,
-// P = 10 1.41 vs 1.51, P = 9 1.29 vs 1.42, P = 8 1.28 vs 1.17, P = 7 1.27 vs 0.95): default = tcgen05 for
-// 82 <= P*P + 1 <= 128 (P = 9, 10, 11), mma.sync otherwise.  VITCNN_TOKENS_IMPL=0 / 1 forces mma.sync / tcgen05
-// (where it applies).
+// Which token-stage kernel: the tcgen05 kernels (tokens_tm.cu, tokens_tc.cu) treat one patch as one M = 128 tile.  Measured
+// per 131 072 patches, tokens_tm_kernel<4> vs the mma.sync kernel (transformer.cu): P = 11 4.63 vs 7.0 ms, P = 8 4.08 vs 4.59,
+// P = 7 3.55 vs 3.84, P = 5 3.02 vs 3.22 (round 1, tokens_tc_kernel: the mma.sync kernel still won below P = 9): default =
+// tcgen05 for 26 <= P*P + 1 <= 128 (P = 5 .. 11), mma.sync otherwise (larger token sets do not fit the tile; smaller ones
+// are not measured).  VITCNN_TOKENS_IMPL=0 / 1 forces mma.sync / tcgen05 (where it applies).
 bool use_tokens_tc(int P, int K) {
   static const int forced = [] {
     const char* e = getenv("VITCNN_TOKENS_IMPL");
     return e ? atoi(e) : -1;
   }();
   if (!vc::tokens_tc_supported(P, K) || forced == 0) return false;
-  return forced == 1 || P * P + 1 >= 82;
+  return forced == 1 || P * P + 1 >= 26;
 }
 
 // stems + token stage on packed inputs already in w.a0 / w.l0.
