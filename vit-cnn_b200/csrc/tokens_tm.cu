@@ -309,15 +309,18 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
   const uint32_t fbuf = slot_s + C::S_FBUF, abuf = slot_s + C::S_ABUF, qbuf = slot_s + C::S_QBUF, kbuf = slot_s + C::S_KBUF,
                  vbuf = slot_s + C::S_VBUF;
   const int NK = (T + 31) & ~31;                    // keys rounded to the 32-column chunks the row threads read
-  const int SPH = (NK + CK - 1) / CK, NS = 4 * SPH; // attention steps per head / per patch
+  const int SPH = (NK + CK - 1) / CK;             // attention steps per head
   const int nslots = SLOTS * (int)gridDim.x;
   const int b0 = SLOTS * (int)blockIdx.x + slot;
 
   if (issuer) {
-    // ============================ MMA issuer of this slot: one thread ============================
+    // ============================ MMA issuer warp of this slot ============================
+    // Warp-uniform control flow (every lane waits and steps the descriptors; they live in uniform registers), the
+    // tcgen05 instructions themselves sit in `if (elect_one())` blocks: inside a divergent `lane == 0` region the
+    // compiler wraps every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~14 instructions each).
     // Descriptors are kept as 64-bit values and stepped by constant increments: the start-address field counts 16-byte
     // units from bit 0, the leading-byte-offset field from bit 16 (no carries: every address is below 256 KB).
-    if (lane == 0) {
+    {
       uint32_t ph_rp = 0, ph_p = 0;
       int rb = 0;               // ring buffer of the next attention step (ph_p: parity of its "probabilities written" barrier)
       auto ready = [&]() {      // the row threads have written the operands of the next GEMM
@@ -327,14 +330,17 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
       };
       // D[128 x N] (TMEM column `col`) = A[128 x 16 ksteps] (K-major slabs at `abase`) . W^T (weights [k/8][N][8] at `wbase`)
       auto issue_gemm = [&](uint32_t col, uint32_t abase, uint32_t wbase, int N, int ksteps) {
-        uint64_t da = umma_desc(abase, SLAB, 128), dw = umma_desc(wbase, (uint32_t)N * 16u, 128);
-        const uint32_t id = idesc(N, 0);
-        for (int k = 0; k < ksteps; ++k) {
-          umma_bf16(tb + col, da, dw, id, k ? 1u : 0u);
-          da += (2 * SLAB) >> 4;
-          dw += (uint64_t)(2 * N);      // 2 N 16-byte rows per K step
+        if (elect_one()) {
+          uint64_t da = umma_desc(abase, SLAB, 128), dw = umma_desc(wbase, (uint32_t)N * 16u, 128);
+          const uint32_t id = idesc(N, 0);
+          for (int k = 0; k < ksteps; ++k) {
+            umma_bf16(tb + col, da, dw, id, k ? 1u : 0u);
+            da += (2 * SLAB) >> 4;
+            dw += (uint64_t)(2 * N);      // 2 N 16-byte rows per K step
+          }
+          umma_commit_a(b_mma);
         }
-        umma_commit_a(b_mma);
+        __syncwarp();
       };
       const uint32_t ones = sb + C::ONES, mask = sb + C::MASK;
       // head 0, chunk 0: Q / K descriptors (A chunks (Q_h, ones), B chunks (keys of K_h, their mask rows)) and the V descriptor
@@ -350,16 +356,20 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
         // S chunk of step (hs, cs) -> ring buffer: issued RD steps ahead of the PV that frees the buffer
         int hs = 0, cs = 0;
         uint64_t dq = dq0, dk = dk0;
-        auto issue_s = [&](int buf) {
+        auto issue_s = [&](int buf) {        // called by the elected lane; the step counters advance on every lane (s_next)
           const int keys = CK == 32 ? 32 : min(CK, NK - cs * CK);
           umma_bf16(tb + buf * CK, dq, dk + (uint64_t)(cs * CK), idesc(keys, 0), 0u);
           umma_commit_a(b_s + 8 * buf);
+        };
+        auto s_next = [&]() {
           if (++cs == SPH) { cs = 0; ++hs; dq += d_head; dk += d_head; }
         };
         {
           int buf = rb;
-          for (int j = 0; j < RD && j < NS; ++j) {
-            issue_s(buf);
+          for (int j = 0; j < RD && hs < 4; ++j) {
+            if (elect_one()) issue_s(buf);
+            __syncwarp();
+            s_next();
             if (++buf == RD) buf = 0;
           }
         }
@@ -368,18 +378,23 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
         for (int h = 0; h < 4; ++h) {
 #pragma unroll 1
           for (int c = 0; c < SPH; ++c) {
-            mbar_wait_a(b_p + 8 * rb, ph_p);              // the probabilities of step (h, c) are in the first half of buffer rb
-            tc_fence_after();
             // O_h[128 x 16] (+)= P[128 x keys] . [V_h | ones]: B is MN-major, N chunk 0 = V_h slab, chunk 1 = ONES slab
             const int ksteps = (CK == 32 ? 32 : min(CK, NK - c * CK)) / 16;
             const uint32_t d_o = tb + C::C_O + 16 * (h & 1), a_p = tb + rb * CK;
-            uint64_t dvk = dv + (uint64_t)(c * CK);       // 16 keys = 256 B = 16 units per K step
-            for (int kk = 0; kk < ksteps; ++kk) {
-              umma_bf16_ts(d_o, a_p + 8 * kk, dvk, id_pv, (c | kk) ? 1u : 0u);
-              dvk += 16;
+            const uint64_t dvk0 = dv + (uint64_t)(c * CK);    // 16 keys = 256 B = 16 units per K step
+            mbar_wait_a(b_p + 8 * rb, ph_p);                  // the probabilities of step (h, c) are in the first half of buffer rb
+            tc_fence_after();
+            if (elect_one()) {
+              uint64_t dvk = dvk0;
+              for (int kk = 0; kk < ksteps; ++kk) {
+                umma_bf16_ts(d_o, a_p + 8 * kk, dvk, id_pv, (c | kk) ? 1u : 0u);
+                dvk += 16;
+              }
+              if (c == SPH - 1) umma_commit_a(b_pv);
+              if (hs < 4) issue_s(rb);                        // the buffer is free as soon as this PV has read it (in-order pipe)
             }
-            if (c == SPH - 1) umma_commit_a(b_pv);
-            if (hs < 4) issue_s(rb);                      // the buffer is free as soon as this PV has read it (in-order pipe)
+            __syncwarp();
+            if (hs < 4) s_next();
             if (++rb == RD) { rb = 0; ph_p ^= 1u; }
           }
           dv += dv_head;
@@ -387,7 +402,7 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
         ready(); issue_gemm(C::C_O, abuf, sb + tc::W_PROJ1, 32, 2);     // proj
         ready(); issue_gemm(0, abuf, sb + tc::W_FC1, 128, 2);           // fc1
         ready();                                                        // fc2: A = packed hidden units in TMEM columns 0..63
-        {
+        if (elect_one()) {
           uint64_t dw = umma_desc(sb + tc::W_FC2, 32 * 16, 128);
           const uint32_t id = idesc(32, 0);
           for (int k = 0; k < 8; ++k) {
@@ -396,9 +411,11 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
           }
           umma_commit_a(b_mma);
         }
+        __syncwarp();
         ready();
-        {   // last block: k, v of every token (the cls query is computed by the row threads), columns 0..63 -- and, in the
-            // same hand-off, the fusion 1x1 conv of the slot's NEXT patch (its input has landed over the dead K / V buffers)
+        if (elect_one()) {
+          // last block: k, v of every token (the cls query is computed by the row threads), columns 0..63 -- and, in the
+          // same hand-off, the fusion 1x1 conv of the slot's NEXT patch (its input has landed over the dead K / V buffers)
           uint64_t da = umma_desc(abuf, SLAB, 128), dw = umma_desc(sb + tc::W_QKV2 + 32 * 16, 96 * 16, 128);
           const uint32_t id = idesc(64, 0);
           for (int k = 0; k < 2; ++k) {
@@ -417,6 +434,7 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
           }
           umma_commit_a(b_mma);
         }
+        __syncwarp();
       }
     }
   } else {
