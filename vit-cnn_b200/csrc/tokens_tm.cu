@@ -41,6 +41,9 @@ constexpr size_t kStageBytes = 4096;                          // staging area at
 
 __constant__ float c_vec[kVecFloats];
 
+#ifndef VC_TM_PARKX
+#define VC_TM_PARKX 0      // 1: tm4 parks the residual stream in shared memory during the attention (measured: +1 %, off)
+#endif
 template <int SLOTS>
 struct Cfg {
   static constexpr int CK = SLOTS >= 4 ? 32 : 64;       // keys per attention step
@@ -51,7 +54,11 @@ struct Cfg {
   static constexpr uint32_t POS = tc::W_QKV2 + 6144;    // weights as in tc:: (W_FUS .. W_QKV2), then pos-embed rows
   static constexpr uint32_t SLOT0 = POS + 128 * 32 * 4;
   static constexpr uint32_t S_QBUF = 0, S_ABUF = 0, S_KBUF = 4 * SLAB, S_VBUF = 8 * SLAB, S_FBUF = S_KBUF;
-  static constexpr uint32_t SLOT_BYTES = 12 * SLAB;
+  // four slots run at 96 registers per thread: the residual stream (32 fp32 per row) is parked in shared memory from
+  // LayerNorm 1 to the proj epilogue, so the attention loop keeps its addresses in registers instead of recomputing them
+  static constexpr bool kParkX = VC_TM_PARKX && SLOTS >= 4;
+  static constexpr uint32_t S_XBUF = 12 * SLAB;          // [8][128 rows][4 fp32]
+  static constexpr uint32_t SLOT_BYTES = (kParkX ? 20 : 12) * SLAB;
   static constexpr uint32_t ONES = SLOT0 + SLOTS * SLOT_BYTES;
   static constexpr uint32_t MASK = ONES + SLAB;
   static constexpr uint32_t MISC = MASK + SLAB;
@@ -121,6 +128,9 @@ __device__ __forceinline__ void mbar_arrive_a(uint32_t addr) {
 __device__ __forceinline__ void umma_commit_a(uint32_t addr) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
 }
+// Make a value opaque to the compiler: it then lives in a register instead of being re-derived from tid / the shared
+// window base inside the loops (S2R / S2UR + shifts at every use under register pressure).
+__device__ __forceinline__ void pin(uint32_t& v) { asm volatile("" : "+r"(v)); }
 __device__ __forceinline__ float rcp_fast(float v) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
@@ -225,11 +235,13 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
   const int r = tid & 127, wq = warp & 3;
   const int T = a.T, P = a.P;
   const TLayout& L = a.L;
-  const uint32_t sb = smem_u32(smem);
+  uint32_t sb = smem_u32(smem);
+  pin(sb);
   float* q0_s = reinterpret_cast<float*>(smem + C::MISC + C::M_Q0) + (issuer ? 0 : warp * 32);   // [32] per row warp
   const uint32_t y0_s = sb + C::MISC + C::M_Y0 + (uint32_t)slot * 128u;                  // [2][4 x 16 B]
   float* wmax_s = reinterpret_cast<float*>(smem + C::MISC + C::M_WMAX) + slot * 16;      // [4 warps][4 heads]
-  const uint32_t bars = sb + C::MISC + C::M_BARS + (uint32_t)slot * 128u;   // 16 mbarriers per slot (shared addresses)
+  uint32_t bars = sb + C::MISC + C::M_BARS + (uint32_t)slot * 128u;   // 16 mbarriers per slot (shared addresses)
+  pin(bars);
   const uint32_t b_rp = bars + 0;      // row threads: operands of the next GEMM are written (128 arrivals)
   const uint32_t b_mma = bars + 8;     // tensor core: the GEMM just issued (fusion / qkv / proj / fc1 / fc2 / kv2) is done
   const uint32_t b_pv = bars + 16;     // tensor core: O_h is complete
@@ -304,8 +316,10 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
   }
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tb = tmem_base + (uint32_t)slot * C::C_SLOT;             // columns of this slot (issuer view)
-  const uint32_t tl = tb + ((uint32_t)(wq * 32) << 16);                   // + the 32 lanes of this warp
-  const uint32_t slot_s = sb + C::SLOT0 + (uint32_t)slot * C::SLOT_BYTES;
+  uint32_t tl = tb + ((uint32_t)(wq * 32) << 16);                   // + the 32 lanes of this warp
+  uint32_t slot_s = sb + C::SLOT0 + (uint32_t)slot * C::SLOT_BYTES;
+  pin(tl);
+  pin(slot_s);
   const uint32_t fbuf = slot_s + C::S_FBUF, abuf = slot_s + C::S_ABUF, qbuf = slot_s + C::S_QBUF, kbuf = slot_s + C::S_KBUF,
                  vbuf = slot_s + C::S_VBUF;
   const int NK = (T + 31) & ~31;                    // keys rounded to the 32-column chunks the row threads read
@@ -439,7 +453,8 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
     }
   } else {
     // ============================ row threads ============================
-    const uint32_t row16 = (uint32_t)r * 16u;
+    uint32_t row16 = (uint32_t)r * 16u;
+    pin(row16);
     const int PW = P + 1, PP = sps_pp(P), HALO = sps_halo(P);
     const int bar_id = 1 + slot;
     uint32_t ph_m = 0, ph_pv = 0, rpar = 0;
@@ -513,6 +528,12 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
       // ================= block 1: LN1 -> qkv =================
       ln_store_c<V_LN1G, V_LN1B>(x, abuf + row16);
       publish();
+      if (C::kParkX) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          sts128(slot_s + C::S_XBUF + g * SLAB + row16, __float_as_uint(x[4 * g]), __float_as_uint(x[4 * g + 1]), __float_as_uint(x[4 * g + 2]),
+                 __float_as_uint(x[4 * g + 3]));
+      }
       wait_mma();
 #pragma unroll
       for (int part = 0; part < 3; ++part) {
@@ -598,6 +619,13 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
         uint32_t v[32];
         tmem_ld32(tl + C::C_O, v);
         tc_wait_ld();
+        if (C::kParkX) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 xv = lds_f4(slot_s + C::S_XBUF + g * SLAB + row16);
+            x[4 * g] = xv.x; x[4 * g + 1] = xv.y; x[4 * g + 2] = xv.z; x[4 * g + 3] = xv.w;
+          }
+        }
 #pragma unroll
         for (int c = 0; c < 32; ++c) x[c] += __uint_as_float(v[c]) + c_vec[V_BPROJ + c];
       }
