@@ -13,18 +13,19 @@ stall = [(i, h[6:]) for i, h in enumerate(hdr) if h.startswith('stall_') and 'No
 tot = sum(int(r[isamp] or 0) for r in data)
 inst_tot = sum(int(r[ia] or 0) for r in data)
 print(f"total samples {tot}, warp instructions {inst_tot} = {inst_tot / npatch:.0f} per patch")
-# landmarks: UTCHMMA lines delimit the issuer; row-thread code starts at the first LDGSTS
-marks = []
-first_mma = next(i for i, r in enumerate(data) if 'UTCHMMA' in r[isrc])
-last_mma = max(i for i, r in enumerate(data) if 'UTCHMMA' in r[isrc] or 'UTCBAR' in r[isrc])
-ldgsts = next(i for i, r in enumerate(data) if 'LDGSTS' in r[isrc] and i > last_mma)
-ldtm = [i for i, r in enumerate(data) if re.search(r'LDTM', r[isrc]) and i > last_mma]
-sttm = [i for i, r in enumerate(data) if 'STTM' in r[isrc] and i > last_mma]
-mufu_ex2 = [i for i, r in enumerate(data) if 'MUFU.EX2' in r[isrc] and i > last_mma]
-tanh = [i for i, r in enumerate(data) if 'MUFU.TANH' in r[isrc] and i > last_mma]
-regions = [("setup", 0, first_mma - 40), ("issuer", first_mma - 40, ldgsts - 60), ("fetch+fusion+LN1+qkv", ldgsts - 60, mufu_ex2[0] - 40),
-           ("attention", mufu_ex2[0] - 40, tanh[0] - 400), ("proj+LN2", tanh[0] - 400, tanh[0] - 20), ("fc1 GELU", tanh[0] - 20, tanh[-1] + 40),
-           ("fc2+LN3+cls", tanh[-1] + 40, len(data))]
+# landmarks in order of appearance: the issuer warp's code starts at the first UTCHMMA, the row threads' at the first LDGSTS
+# (stem-input fetch) behind it; code the compiler moved out of line (polling slow paths, a second copy of the issuer's MMAs) sits
+# behind the last MUFU.TANH + cls code and is reported as "tail of the listing"
+idx = lambda pat, lo=0: [i for i, r in enumerate(data) if re.search(pat, r[isrc]) and i >= lo]
+first_mma = idx(r'UTCHMMA')[0]
+ldgsts = idx(r'LDGSTS', first_mma)[0]
+ex2 = idx(r'MUFU\.EX2', ldgsts)
+tanh = idx(r'MUFU\.TANH', ldgsts)
+late_mma = [i for i in idx(r'UTCHMMA') if i > tanh[-1]]
+end_rows = late_mma[0] - 40 if late_mma else len(data)
+regions = [("setup", 0, first_mma - 40), ("issuer", first_mma - 40, ldgsts - 60), ("fetch+fusion+LN1+qkv", ldgsts - 60, ex2[0] - 40),
+           ("attention", ex2[0] - 40, tanh[0] - 400), ("proj+LN2", tanh[0] - 400, tanh[0] - 20), ("fc1 GELU", tanh[0] - 20, tanh[-1] + 40),
+           ("fc2+LN3+cls", tanh[-1] + 40, end_rows), ("tail of the listing", end_rows, len(data))]
 for name, a, b in regions:
     s = collections.Counter(); n = 0; inst = 0
     for r in data[a:b]:
