@@ -545,8 +545,13 @@ def main():
         for _ in range(max(args.warmup, 3)):     # the caching allocator must have seen the streaming depth before the timed region
             e2e_step()
         host_s[0], host_s[1] = 0.0, 0
+        st0 = torch.cuda.memory_stats(dev)
         ms_e2e = timed(e2e_step, args.steps)
+        st1 = torch.cuda.memory_stats(dev)
+        e2e_allocs = {k: (st1.get(k, 0) - st0.get(k, 0)) / args.steps for k in ("num_device_alloc", "num_device_free", "num_alloc_retries")}
     host_queue_ms = host_s[0] / max(host_s[1], 1) * 1e3
+    if args.no_e2e or args.windows:
+        e2e_allocs = {}
     band_rows = band.stop - band.start
     # what the host link alone allows: the same pinned -> HBM uploads with no kernels in between (the e2e leg cannot be
     # faster than this; on the round-2 boxes a Houston scene's 386 MB take ~34 ms, i.e. the leg is link-bound once the
@@ -692,7 +697,7 @@ def main():
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_val, "unit": "pixels/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
-                        "host_queue_ms_per_step": host_queue_ms, "h2d_only_ms_per_step": ms_h2d / args.steps, "h2d_only_gb_per_s": h2d / (ms_h2d / args.steps) / 1e6,
+                        "host_queue_ms_per_step": host_queue_ms, "cuda_mallocs_per_step": e2e_allocs, "h2d_only_ms_per_step": ms_h2d / args.steps, "h2d_only_gb_per_s": h2d / (ms_h2d / args.steps) / 1e6,
                         "api": "vitcnn_b200.predict_scene_host(sync=False): scene after scene, double-buffered pinned results"},
                 "strong": strong,
                 "roofline": roofline,

@@ -74,27 +74,45 @@ def predict_scene_host(net, img1: torch.Tensor, img2: torch.Tensor, stride: int 
             up.wait_stream(main)
         elif len(inflight) >= 2:              # bounded look-ahead: staging memory of at most two calls
             up.wait_event(inflight.pop(0))
-        staged, done = [], []
+        if sync:
+            for ev in inflight:               # streaming calls still in flight own the staging slots
+                up.wait_event(ev)
+        # Device staging of this call (rasters of every sub-band, their result maps) comes from a persistent arena with two
+        # slots, one per call in flight: a steady stream of calls performs no cudaMalloc (fresh `.to(dev)` / torch.zeros
+        # tensors were only reusable after their recorded streams had drained, so the caching allocator kept growing:
+        # ~3 cudaMalloc per scene, 2 - 15 ms of host time per call depending on the box)
+        subs = []
         for k in range(nsub):
             a, b = bounds[k], bounds[k + 1]
             if a == b:
-                staged.append(None)
+                subs.append(None)
                 continue
             xa, xb = x0 + int(xs_rel[a]), x0 + int(xs_rel[b - 1]) + P           # raster rows of the sub-band
+            subs.append((xa, xb, xs_rel[a:b] + x0 - xa))
+        C1, C2 = img1.shape[2], img2.shape[2]
+        views = _stage_views(dev, [(xb - xa, W, C1, C2, K) for (xa, xb, _) in (s for s in subs if s is not None)])
+        staged, vi = [], 0
+        for k in range(nsub):
+            if subs[k] is None:
+                staged.append(None)
+                continue
+            xa, xb, xs_k = subs[k]
+            b1, b2, lg, am = views[vi]
+            vi += 1
             with torch.cuda.stream(up):
-                b1 = img1[xa:xb].to(dev, non_blocking=True)
-                b2 = img2[xa:xb].to(dev, non_blocking=True)
+                b1.copy_(img1[xa:xb], non_blocking=True)
+                b2.copy_(img2[xa:xb], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(up)
-            staged.append((b1, b2, ev, xa, xs_rel[a:b] + x0 - xa))
+            staged.append((b1, b2, lg, am, ev, xa, xs_k))
         for k in range(nsub):
             if staged[k] is None:
                 continue
-            b1, b2, ev, xa, xs_k = staged[k]
+            b1, b2, lg, am, ev, xa, xs_k = staged[k]
             main.wait_event(ev)
-            b1.record_stream(main)
-            b2.record_stream(main)
-            lg, am = net.predict_scene(b1, b2, stride=stride, chunk=chunk, xs=xs_k)
+            lg.zero_()
+            am.zero_()
+            net.predict_scene(b1, b2, stride=stride, chunk=chunk, xs=xs_k, logits_map=lg, argmax_map=am)
             o0, o1 = xa + int(xs_k[0]) + P2, xa + int(xs_k[-1]) + P2 + 1       # map rows with window centres
             l0 = int(xs_k[0]) + P2
             cev = torch.cuda.Event()
@@ -103,9 +121,6 @@ def predict_scene_host(net, img1: torch.Tensor, img2: torch.Tensor, stride: int 
             with torch.cuda.stream(down):
                 logits_out[o0:o1].copy_(lg[l0:l0 + (o1 - o0)], non_blocking=True)
                 argmax_out[o0:o1].copy_(am[l0:l0 + (o1 - o0)], non_blocking=True)
-            lg.record_stream(down)
-            am.record_stream(down)
-            done.append((lg, am))
         if sync:
             main.wait_stream(down)
             main.synchronize()
@@ -142,6 +157,34 @@ def _shared_depth(net, rows: int, W: int, count: int, chunk: int, dev) -> int:
 
 
 _STREAMS = {}
+_ARENA = {}      # device -> [arena uint8 tensor, next slot]
+
+
+def _stage_views(dev, shapes):
+    """Views (raster 1, raster 2, logits map, argmax map) per sub-band into the next slot of the device's staging arena.
+    The arena holds two slots (at most two calls are in flight per device); it grows -- after a device synchronise, so
+    nothing in flight loses its memory -- when a call needs more than a slot holds."""
+    def rnd(n):
+        return (n + 255) & ~255
+    need = sum(rnd(r * w * c1 * 4) + rnd(r * w * c2 * 4) + rnd(r * w * k * 4) + rnd(r * w) for (r, w, c1, c2, k) in shapes)
+    ent = _ARENA.get(dev)
+    if ent is None or ent[0].numel() < 2 * need:
+        torch.cuda.synchronize(dev)
+        ent = _ARENA[dev] = [torch.empty(2 * need, dtype=torch.uint8, device=dev), 0]
+    arena, slot = ent
+    half = arena.numel() // 2
+    ent[1] = slot ^ 1
+    off = slot * half
+    out = []
+    for (r, w, c1, c2, k) in shapes:
+        def take(nbytes, dtype, shape):
+            nonlocal off
+            v = arena[off:off + nbytes].view(dtype).view(shape)
+            off += rnd(nbytes)
+            return v
+        out.append((take(r * w * c1 * 4, torch.float32, (r, w, c1)), take(r * w * c2 * 4, torch.float32, (r, w, c2)),
+                    take(r * w * k * 4, torch.float32, (r, w, k)), take(r * w, torch.uint8, (r, w))))
+    return out
 
 
 def _copy_streams(dev):
