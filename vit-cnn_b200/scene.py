@@ -45,7 +45,10 @@ def predict_scene_host(net, img1: torch.Tensor, img2: torch.Tensor, stride: int 
         # call).  Streaming: the next call's first upload already overlaps this call's tail, so fewer, larger sub-bands win (each
         # one re-runs the shared stem's ~25 launches).  Measured, Houston scene on one B200, ms per scene at 1 / 2 / 3 / 4 / 6
         # sub-bands: streaming 41.2 / 40.9 / 42.1 / 42.5 / 42.9, single 48.3 / 45.1 / 45.0 / 44.7 / 44.4 (device only: 40.2)
-        pipeline = int(os.environ.get("VITCNN_PIPELINE", "6" if sync else "2"))
+        # A short band (one of many ranks' share of a scene: 43 window rows at 8 GPUs) goes as ONE sub-band when streaming:
+        # every sub-band re-runs the shared stem's launches on whole scene blocks, and with 8 ranks on 16 host cores the
+        # queueing itself (41 ms per 8-band step, device 38 ms) was what bounded the end-to-end rate.
+        pipeline = int(os.environ.get("VITCNN_PIPELINE", "6" if sync else ("2" if len(geo["xs"]) > 96 else "1")))
     # Software pipeline over `pipeline` sub-bands of the band: the pinned-host -> HBM upload of sub-band
     # k+1 and the HBM -> host download of sub-band k-1 run on copy streams while sub-band k computes,
     # so the PCIe traffic (386 MB up, 42 MB down for a Houston scene) hides behind the kernels.
