@@ -129,8 +129,12 @@ int vc_tokens_forward(const void* f_sps, const void* tparams, int32_t n_patches,
                       const int64_t* out_index, uint8_t* argmax_map, void* stream);
 /* The same token stage on the tcgen05 tensor cores (eval mode; the token set of a patch must fit one
  * M = 128 tile: P*P + 1 <= 128, else VC_ERR_UNSUPPORTED).  scratch: caller-owned device buffer of
- * vc_tokens_tc_scratch_bytes(n_patches) bytes.  vc_forward_patches / vc_scene_infer pick this kernel
- * themselves when it applies (scratch = a dead part of their workspace). */
+ * vc_tokens_tc_scratch_bytes(n_patches) bytes (a 4 KB staging area for the per-launch constants, then one
+ * 704-byte cls record per patch).  vc_forward_patches / vc_scene_infer pick this kernel themselves when it
+ * applies (P = 5 .. 11; scratch = a dead part of their workspace).  Kernels: tokens_tm_kernel (probabilities and
+ * MLP hidden units handed to the tensor core through TMEM, per-channel vectors in the constant bank; launches on
+ * different streams of one device are ordered by an event because that bank is per device) with
+ * tokens_tc_kernel behind it for weights whose attention logits need the softmax row maximum. */
 int64_t vc_tokens_tc_scratch_bytes(int32_t n_patches);
 int vc_tokens_forward_tc(const void* f_sps, const void* tparams, int32_t n_patches, int32_t P, int32_t K, float* logits,
                          const int64_t* out_index, uint8_t* argmax_map, void* scratch, int64_t scratch_bytes, void* stream);
