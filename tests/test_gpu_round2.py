@@ -95,8 +95,9 @@ def _scene_in_child(tmp_path, name, env, P=11):
 
 def test_kernel_variants_selected_by_environment(tmp_path):
     """Same scene through (a) the defaults, (b) the round-1 per-variant launches of the shared stem, (c) no LiDAR sharing,
-    (d) sharing depth 2 with per-window conv 3 and the variant gather: all bit-identical maps.  (e) the two-threads-per-row
-    token kernel and (f) the mma.sync token kernel sum in different orders: equal within the kernel tolerance."""
+    (d) sharing depth 2 with per-window conv 3 and the variant gather: all bit-identical maps.  (e) the other token kernels
+    (three patches in flight, the shared-memory predecessor, two threads per row, mma.sync) sum in different orders: equal
+    within the kernel tolerance."""
     base_l, base_a = _scene_in_child(tmp_path, "base", {})
     assert (base_l != 0).any()
     for name, env in (("planes", {"VITCNN_STEM_IMPL": "planes"}), ("nolidar", {"VITCNN_LIDAR_SHARED": "0"}),
@@ -104,7 +105,10 @@ def test_kernel_variants_selected_by_environment(tmp_path):
         lg, am = _scene_in_child(tmp_path, name, env)
         assert torch.equal(lg, base_l) and torch.equal(am, base_a), name
     scale = base_l.abs().max().item()
-    for name, env in (("split3", {"VITCNN_TC_SPLIT": "3"}), ("split1", {"VITCNN_TC_SPLIT": "1"}), ("mma", {"VITCNN_TOKENS_IMPL": "0"})):
+    # the token-kernel family: tokens_tm_kernel with three patches in flight, tokens_tc_kernel alone (the exact-softmax
+    # fallback run unconditionally), its two-threads-per-row variant, the mma.sync kernel
+    for name, env in (("tm3", {"VITCNN_TC_KERNEL": "tm3"}), ("tc", {"VITCNN_TC_KERNEL": "tc"}), ("split3", {"VITCNN_TC_SPLIT": "3"}),
+                      ("split1", {"VITCNN_TC_SPLIT": "1"}), ("mma", {"VITCNN_TOKENS_IMPL": "0"})):
         lg, am = _scene_in_child(tmp_path, name, env)
         assert (lg - base_l).abs().max().item() <= 5e-3 * scale, name
         assert (lg == 0).eq(base_l == 0).all(), name
