@@ -41,6 +41,24 @@ constexpr size_t kStageBytes = 4096;                          // staging area at
 
 __constant__ float c_vec[kVecFloats];
 
+// VC_TM_FOLD: LayerNorm gamma / beta, the folded-BN scale of the fusion conv, the query scale and every bias are folded into
+// the GEMMs.  Weights image: W'[n][k] = W[n][k] * gamma[k] * rowscale[n] (bf16); biases b'[n] = rowscale[n] (b[n] + W[n] . beta)
+// ride as one more K step of every GEMM: A = the ones slab (rows (1,0,..,0) for both K chunks, leading-byte offset 0), B = two
+// extra chunks behind the weights holding (hi(b'), 0, ..) and (lo(b'), 0, ..) -- a bf16 pair keeps 16 mantissa bits.  The
+// epilogues lose their per-channel FFMA / FADD (416 instructions per token row and patch).
+#ifndef VC_TM_FOLD
+#define VC_TM_FOLD 1
+#endif
+constexpr bool kFold = VC_TM_FOLD != 0;
+constexpr int kXC = kFold ? 2 : 0;         // extra 8-element K chunks per weight matrix (bias hi / lo)
+// shared-memory image of the weights, [k / 8][N][8] bf16 each
+constexpr uint32_t W_FUS = 0;
+constexpr uint32_t W_QKV1 = W_FUS + (8 + kXC) * 32 * 16;
+constexpr uint32_t W_PROJ1 = W_QKV1 + (4 + kXC) * 96 * 16;
+constexpr uint32_t W_FC1 = W_PROJ1 + (4 + kXC) * 32 * 16;
+constexpr uint32_t W_FC2 = W_FC1 + (4 + kXC) * 128 * 16;
+constexpr uint32_t W_QKV2 = W_FC2 + (16 + kXC) * 32 * 16;
+constexpr uint32_t W_END = W_QKV2 + (4 + kXC) * 96 * 16;
 #ifndef VC_TM_PARKX
 #define VC_TM_PARKX 0      // 1: tm4 parks the residual stream in shared memory during the attention (measured: +1 %, off)
 #endif
@@ -51,7 +69,7 @@ struct Cfg {
   static constexpr uint32_t C_O = RD * CK;              // two 16-column O_h buffers / the 32-column accumulators
   static constexpr uint32_t C_SLOT = C_O + 32;
   static constexpr int kThreads = SLOTS * 5 * 32;       // 4 row warps + 1 MMA-issuer warp per slot
-  static constexpr uint32_t POS = tc::W_QKV2 + 6144;    // weights as in tc:: (W_FUS .. W_QKV2), then pos-embed rows
+  static constexpr uint32_t POS = W_END;                // weights (W_FUS .. W_QKV2), then pos-embed rows
   static constexpr uint32_t SLOT0 = POS + 128 * 32 * 4;
   static constexpr uint32_t S_QBUF = 0, S_ABUF = 0, S_KBUF = 4 * SLAB, S_VBUF = 8 * SLAB, S_FBUF = S_KBUF;
   // four slots run at 96 registers per thread: the residual stream (32 fp32 per row) is parked in shared memory from
@@ -155,8 +173,9 @@ __device__ __forceinline__ void ln_store_c(const float (&x)[32], uint32_t dst_ro
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int c0 = 8 * sl + 2 * e;
-      p[e] = pack_bf16(fmaf(fmaf(x[c0], rs, nm), c_vec[G + c0], c_vec[B + c0]),
-                       fmaf(fmaf(x[c0 + 1], rs, nm), c_vec[G + c0 + 1], c_vec[B + c0 + 1]));
+      p[e] = kFold ? pack_bf16(fmaf(x[c0], rs, nm), fmaf(x[c0 + 1], rs, nm))      // gamma / beta live in the next GEMM
+                   : pack_bf16(fmaf(fmaf(x[c0], rs, nm), c_vec[G + c0], c_vec[B + c0]),
+                               fmaf(fmaf(x[c0 + 1], rs, nm), c_vec[G + c0 + 1], c_vec[B + c0 + 1]));
     }
     sts128(dst_row + sl * SLAB, p[0], p[1], p[2], p[3]);
     if (dst2) sts128(dst2 + sl * 16, p[0], p[1], p[2], p[3]);
@@ -179,15 +198,31 @@ __global__ void __launch_bounds__(128) tm_prep_kernel(const uint8_t* blob, TLayo
   copy_v(V_FBI, L.fus_bias, 32, 1.f);
   copy_v(V_LN1G, L.layer[0].ln1_g, 32, 1.f);
   copy_v(V_LN1B, L.layer[0].ln1_b, 32, 1.f);
-  copy_v(V_BQKV, L.layer[0].bqkv, 96, qscale);
   copy_v(V_BPROJ, L.layer[0].bproj, 32, 1.f);
   copy_v(V_LN2G, L.layer[0].ln2_g, 32, 1.f);
   copy_v(V_LN2B, L.layer[0].ln2_b, 32, 1.f);
-  copy_v(V_BFC1, L.layer[0].bfc1, 128, 1.f);
   copy_v(V_BFC2, L.layer[0].bfc2, 32, 1.f);
   copy_v(V_L2G, L.layer[1].ln1_g, 32, 1.f);
   copy_v(V_L2B, L.layer[1].ln1_b, 32, 1.f);
-  copy_v(V_BQKV2, L.layer[1].bqkv, 96, qscale);
+  if (!kFold) {
+    copy_v(V_BQKV, L.layer[0].bqkv, 96, qscale);
+    copy_v(V_BFC1, L.layer[0].bfc1, 128, 1.f);
+    copy_v(V_BQKV2, L.layer[1].bqkv, 96, qscale);
+  } else {
+    // b'[n] = rowscale[n] (b[n] + W[n] . beta): the LayerNorm in front of the GEMM writes (x - mean) rstd only
+    auto fold = [&](int dst, int wsrc, int bsrc, int betasrc, int N, bool qrows) {
+      for (int n = tid; n < N; n += 128) {
+        const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(blob + wsrc) + n * kLdD;
+        const float* be = reinterpret_cast<const float*>(blob + betasrc);
+        float acc = __ldg(reinterpret_cast<const float*>(blob + bsrc) + n);
+        for (int c = 0; c < 32; ++c) acc = fmaf(__bfloat162float(w[c]), __ldg(be + c), acc);
+        out[dst + n] = (qrows && n < 32) ? acc * qscale : acc;
+      }
+    };
+    fold(V_BQKV, L.layer[0].wqkv, L.layer[0].bqkv, L.layer[0].ln1_b, 96, true);
+    fold(V_BFC1, L.layer[0].wfc1, L.layer[0].bfc1, L.layer[0].ln2_b, 128, false);
+    fold(V_BQKV2, L.layer[1].wqkv, L.layer[1].bqkv, L.layer[1].ln1_b, 96, true);
+  }
   {
     const int l = tid >> 6, n = tid & 63;
     const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(blob + L.layer[l].wqkv) + n * kLdD;
@@ -256,23 +291,42 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
 
   // ---------------- one-time image of the parameters in the layouts the tensor core reads ----------------
   {
-    auto copy_w = [&](uint32_t dst, int src, int N, int K, int ld, bool halve = false) {
+    // W'[n][k] = W[n][k] * colscale[k] * rowscale[n] (* qscale for the first 32 rows when `qrows`) -> [k / 8][N][8] bf16;
+    // fold mode: two more chunks with (hi, lo) of the folded bias c_vec[bias + n] in their first element
+    auto copy_w = [&](uint32_t dst, int src, int N, int K, int ld, int colscale, int rowscale, bool qrows, float all, int bias) {
       for (int i = tid; i < N * (K / 8); i += C::kThreads) {
         const int n = i % N, kc = i / N;
         uint4 g = __ldg(reinterpret_cast<const uint4*>(a.blob + src + (size_t)(n * ld + kc * 8) * 2));
-        if (halve) {   // exact in bf16: one less in the exponent field (weights are far from subnormal)
-          __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&g);
-          for (int e = 0; e < 4; ++e) hp[e] = __hmul2(hp[e], __floats2bfloat162_rn(0.5f, 0.5f));
+        float rs = all;
+        if (kFold && rowscale >= 0) rs *= __ldg(reinterpret_cast<const float*>(a.blob + rowscale) + n);
+        if (kFold && qrows && n < 32) rs *= qscale;
+        if (rs != 1.f || (kFold && colscale >= 0)) {
+          __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(&g);
+          for (int e = 0; e < 8; ++e) {
+            const float cs = (kFold && colscale >= 0) ? __ldg(reinterpret_cast<const float*>(a.blob + colscale) + kc * 8 + e) : 1.f;
+            hp[e] = __float2bfloat16_rn(__bfloat162float(hp[e]) * cs * rs);
+          }
         }
         *reinterpret_cast<uint4*>(smem + dst + (size_t)kc * N * 16 + n * 16) = g;
       }
+      if (kFold) {
+        for (int n = tid; n < N; n += C::kThreads) {
+          const float b = c_vec[bias + n];
+          const __nv_bfloat16 hi = __float2bfloat16_rn(b), lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+          uint4 z = make_uint4(0u, 0u, 0u, 0u);
+          z.x = (uint32_t)__bfloat16_as_ushort(hi);
+          *reinterpret_cast<uint4*>(smem + dst + (size_t)(K / 8) * N * 16 + n * 16) = z;
+          z.x = (uint32_t)__bfloat16_as_ushort(lo);
+          *reinterpret_cast<uint4*>(smem + dst + (size_t)(K / 8 + 1) * N * 16 + n * 16) = z;
+        }
+      }
     };
-    copy_w(tc::W_FUS, L.wfus, 32, 64, kLdFus);
-    copy_w(tc::W_QKV1, L.layer[0].wqkv, 96, 32, kLdD);
-    copy_w(tc::W_PROJ1, L.layer[0].wproj, 32, 32, kLdD);
-    copy_w(tc::W_FC1, L.layer[0].wfc1, 128, 32, kLdD);
-    copy_w(tc::W_FC2, L.layer[0].wfc2, 32, 128, kLdHid, true);   // the 0.5 of GELU lives here: H = 2 gelu(.)
-    copy_w(tc::W_QKV2, L.layer[1].wqkv, 96, 32, kLdD);
+    copy_w(W_FUS, L.wfus, 32, 64, kLdFus, -1, L.fus_scale, false, 1.f, V_FBI);
+    copy_w(W_QKV1, L.layer[0].wqkv, 96, 32, kLdD, L.layer[0].ln1_g, -1, true, 1.f, V_BQKV);
+    copy_w(W_PROJ1, L.layer[0].wproj, 32, 32, kLdD, -1, -1, false, 1.f, V_BPROJ);
+    copy_w(W_FC1, L.layer[0].wfc1, 128, 32, kLdD, L.layer[0].ln2_g, -1, false, 1.f, V_BFC1);
+    copy_w(W_FC2, L.layer[0].wfc2, 32, 128, kLdHid, -1, -1, false, 0.5f, V_BFC2);   // the 0.5 of GELU lives here: H = 2 gelu(.)
+    copy_w(W_QKV2, L.layer[1].wqkv, 96, 32, kLdD, L.layer[1].ln1_g, -1, true, 1.f, V_BQKV2);
     // pos-embed rows (row 0 = cls + pos[0], rows >= T zero), 16-byte granules swizzled by row
     const float* pos = reinterpret_cast<const float*>(a.blob + L.pos);
     const float* cls = reinterpret_cast<const float*>(a.blob + L.cls);
@@ -342,6 +396,7 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
         ph_rp ^= 1u;
         tc_fence_after();
       };
+      const uint64_t d_ones = umma_desc(sb + C::ONES, 0, 128);      // A of the bias K step: both K chunks = the ones slab
       // D[128 x N] (TMEM column `col`) = A[128 x 16 ksteps] (K-major slabs at `abase`) . W^T (weights [k/8][N][8] at `wbase`)
       auto issue_gemm = [&](uint32_t col, uint32_t abase, uint32_t wbase, int N, int ksteps) {
         if (elect_one()) {
@@ -352,6 +407,7 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
             da += (2 * SLAB) >> 4;
             dw += (uint64_t)(2 * N);      // 2 N 16-byte rows per K step
           }
+          if (kFold) umma_bf16(tb + col, d_ones, dw, id, 1u);     // + bias: ones . (hi, lo) chunks behind the weights
           umma_commit_a(b_mma);
         }
         __syncwarp();
@@ -364,8 +420,8 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
       const uint64_t dv_head = (uint64_t)(SLAB >> 4) - ((uint64_t)(SLAB >> 4) << 32);  // V: the ones slab sits in the SBO field
       const uint32_t id_pv = idesc(16, 1);
       for (int b = b0; b < a.n_patches; b += nslots) {
-        if (b == b0) { ready(); issue_gemm(C::C_O, fbuf, sb + tc::W_FUS, 32, 4); }   // fusion 1x1 conv of the first patch
-        ready(); issue_gemm(0, abuf, sb + tc::W_QKV1, 96, 2);           // qkv
+        if (b == b0) { ready(); issue_gemm(C::C_O, fbuf, sb + W_FUS, 32, 4); }   // fusion 1x1 conv of the first patch
+        ready(); issue_gemm(0, abuf, sb + W_QKV1, 96, 2);           // qkv
         ready();
         // S chunk of step (hs, cs) -> ring buffer: issued RD steps ahead of the PV that frees the buffer
         int hs = 0, cs = 0;
@@ -413,16 +469,17 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
           }
           dv += dv_head;
         }
-        ready(); issue_gemm(C::C_O, abuf, sb + tc::W_PROJ1, 32, 2);     // proj
-        ready(); issue_gemm(0, abuf, sb + tc::W_FC1, 128, 2);           // fc1
+        ready(); issue_gemm(C::C_O, abuf, sb + W_PROJ1, 32, 2);     // proj
+        ready(); issue_gemm(0, abuf, sb + W_FC1, 128, 2);           // fc1
         ready();                                                        // fc2: A = packed hidden units in TMEM columns 0..63
         if (elect_one()) {
-          uint64_t dw = umma_desc(sb + tc::W_FC2, 32 * 16, 128);
+          uint64_t dw = umma_desc(sb + W_FC2, 32 * 16, 128);
           const uint32_t id = idesc(32, 0);
           for (int k = 0; k < 8; ++k) {
             umma_bf16_ts(tb + C::C_O, tb + 8 * k, dw, id, k ? 1u : 0u);
             dw += 64;
           }
+          if (kFold) umma_bf16(tb + C::C_O, d_ones, dw, id, 1u);
           umma_commit_a(b_mma);
         }
         __syncwarp();
@@ -430,21 +487,23 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
         if (elect_one()) {
           // last block: k, v of every token (the cls query is computed by the row threads), columns 0..63 -- and, in the
           // same hand-off, the fusion 1x1 conv of the slot's NEXT patch (its input has landed over the dead K / V buffers)
-          uint64_t da = umma_desc(abuf, SLAB, 128), dw = umma_desc(sb + tc::W_QKV2 + 32 * 16, 96 * 16, 128);
+          uint64_t da = umma_desc(abuf, SLAB, 128), dw = umma_desc(sb + W_QKV2 + 32 * 16, 96 * 16, 128);
           const uint32_t id = idesc(64, 0);
           for (int k = 0; k < 2; ++k) {
             umma_bf16(tb, da, dw, id, k ? 1u : 0u);
             da += (2 * SLAB) >> 4;
             dw += 2 * 96;
           }
+          if (kFold) umma_bf16(tb, d_ones, dw, id, 1u);
           if (b + nslots < a.n_patches) {
-            uint64_t df = umma_desc(fbuf, SLAB, 128), dwf = umma_desc(sb + tc::W_FUS, 32 * 16, 128);
+            uint64_t df = umma_desc(fbuf, SLAB, 128), dwf = umma_desc(sb + W_FUS, 32 * 16, 128);
             const uint32_t idf = idesc(32, 0);
             for (int k = 0; k < 4; ++k) {
               umma_bf16(tb + C::C_O, df, dwf, idf, k ? 1u : 0u);
               df += (2 * SLAB) >> 4;
               dwf += 64;
             }
+            if (kFold) umma_bf16(tb + C::C_O, d_ones, dwf, idf, 1u);
           }
           umma_commit_a(b_mma);
         }
@@ -518,10 +577,13 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const float4 p = lds_f4(sb + C::POS + r * 128 + ((g ^ (r & 7)) << 4));
-          x[4 * g + 0] = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * g + 0]), c_vec[V_FSC + 4 * g + 0], c_vec[V_FBI + 4 * g + 0]), 0.f), rowmask, p.x);
-          x[4 * g + 1] = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * g + 1]), c_vec[V_FSC + 4 * g + 1], c_vec[V_FBI + 4 * g + 1]), 0.f), rowmask, p.y);
-          x[4 * g + 2] = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * g + 2]), c_vec[V_FSC + 4 * g + 2], c_vec[V_FBI + 4 * g + 2]), 0.f), rowmask, p.z);
-          x[4 * g + 3] = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * g + 3]), c_vec[V_FSC + 4 * g + 3], c_vec[V_FBI + 4 * g + 3]), 0.f), rowmask, p.w);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float pe = e == 0 ? p.x : e == 1 ? p.y : e == 2 ? p.z : p.w;
+            const float cv = __uint_as_float(v[4 * g + e]);
+            x[4 * g + e] = kFold ? fmaf(fmaxf(cv, 0.f), rowmask, pe)
+                                 : fmaf(fmaxf(fmaf(cv, c_vec[V_FSC + 4 * g + e], c_vec[V_FBI + 4 * g + e]), 0.f), rowmask, pe);
+          }
         }
       }
 
@@ -547,8 +609,9 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
           uint32_t p[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e)
-            p[e] = pack_bf16(fmaf(__uint_as_float(v[8 * h + 2 * e]), sc, c_vec[V_BQKV + 32 * part + 8 * h + 2 * e]),
-                             fmaf(__uint_as_float(v[8 * h + 2 * e + 1]), sc, c_vec[V_BQKV + 32 * part + 8 * h + 2 * e + 1]));
+            p[e] = kFold ? pack_bf16(__uint_as_float(v[8 * h + 2 * e]), __uint_as_float(v[8 * h + 2 * e + 1]))
+                         : pack_bf16(fmaf(__uint_as_float(v[8 * h + 2 * e]), sc, c_vec[V_BQKV + 32 * part + 8 * h + 2 * e]),
+                                     fmaf(__uint_as_float(v[8 * h + 2 * e + 1]), sc, c_vec[V_BQKV + 32 * part + 8 * h + 2 * e + 1]));
           sts128(dst + h * SLAB, p[0], p[1], p[2], p[3]);
         }
       }
@@ -627,7 +690,7 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
           }
         }
 #pragma unroll
-        for (int c = 0; c < 32; ++c) x[c] += __uint_as_float(v[c]) + c_vec[V_BPROJ + c];
+        for (int c = 0; c < 32; ++c) x[c] += kFold ? __uint_as_float(v[c]) : __uint_as_float(v[c]) + c_vec[V_BPROJ + c];
       }
 
       // ================= MLP: LN2 -> fc1 (+bias, GELU, in place) -> fc2 (+bias, +residual) =================
@@ -641,8 +704,9 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
         tc_wait_ld();
 #pragma unroll
         for (int e = 0; e < 16; ++e)
-          pk[e] = pack_bf16(gelu2(__uint_as_float(v[2 * e]) + c_vec[V_BFC1 + 32 * c + 2 * e]),
-                            gelu2(__uint_as_float(v[2 * e + 1]) + c_vec[V_BFC1 + 32 * c + 2 * e + 1]));
+          pk[e] = kFold ? pack_bf16(gelu2(__uint_as_float(v[2 * e])), gelu2(__uint_as_float(v[2 * e + 1])))
+                        : pack_bf16(gelu2(__uint_as_float(v[2 * e]) + c_vec[V_BFC1 + 32 * c + 2 * e]),
+                                    gelu2(__uint_as_float(v[2 * e + 1]) + c_vec[V_BFC1 + 32 * c + 2 * e + 1]));
         tmem_st16(tl + 16 * c, pk);       // columns [16 c, 16 c + 16) were read with chunk c / 2
       }
       publish_tmem(b_rp);
@@ -652,7 +716,7 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
         tmem_ld32(tl + C::C_O, v);
         tc_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) x[c] += __uint_as_float(v[c]) + c_vec[V_BFC2 + c];
+        for (int c = 0; c < 32; ++c) x[c] += kFold ? __uint_as_float(v[c]) : __uint_as_float(v[c]) + c_vec[V_BFC2 + c];
       }
 
       // ================= last block: K / V of every token, attention of the cls query only =================
@@ -676,13 +740,13 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
           uint4 yv, wv;
           asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(yv.x), "=r"(yv.y), "=r"(yv.z), "=r"(yv.w) : "r"(y0buf + kc * 16));
           asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(wv.x), "=r"(wv.y), "=r"(wv.z), "=r"(wv.w)
-                       : "r"(sb + tc::W_QKV2 + kc * 96 * 16 + lane * 16));
+                       : "r"(sb + W_QKV2 + kc * 96 * 16 + lane * 16));
           acc0 = fmaf(bf_lo(yv.x), bf_lo(wv.x), acc0); acc1 = fmaf(bf_hi(yv.x), bf_hi(wv.x), acc1);
           acc0 = fmaf(bf_lo(yv.y), bf_lo(wv.y), acc0); acc1 = fmaf(bf_hi(yv.y), bf_hi(wv.y), acc1);
           acc0 = fmaf(bf_lo(yv.z), bf_lo(wv.z), acc0); acc1 = fmaf(bf_hi(yv.z), bf_hi(wv.z), acc1);
           acc0 = fmaf(bf_lo(yv.w), bf_lo(wv.w), acc0); acc1 = fmaf(bf_hi(yv.w), bf_hi(wv.w), acc1);
         }
-        q0_s[lane] = fmaf(acc0 + acc1, qscale, c_vec[V_BQKV2 + lane]);
+        q0_s[lane] = kFold ? acc0 + acc1 + c_vec[V_BQKV2 + lane] : fmaf(acc0 + acc1, qscale, c_vec[V_BQKV2 + lane]);
         __syncwarp();
       }
       wait_mma();
@@ -695,14 +759,17 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
           const float4 q0 = lds_f4(smem_u32(q0_s) + 32 * h), q1 = lds_f4(smem_u32(q0_s) + 32 * h + 16);
-          float d = q0.x * (__uint_as_float(kk[8 * h + 0]) + c_vec[V_BQKV2 + 32 + 8 * h + 0]);
-          d = fmaf(q0.y, __uint_as_float(kk[8 * h + 1]) + c_vec[V_BQKV2 + 32 + 8 * h + 1], d);
-          d = fmaf(q0.z, __uint_as_float(kk[8 * h + 2]) + c_vec[V_BQKV2 + 32 + 8 * h + 2], d);
-          d = fmaf(q0.w, __uint_as_float(kk[8 * h + 3]) + c_vec[V_BQKV2 + 32 + 8 * h + 3], d);
-          d = fmaf(q1.x, __uint_as_float(kk[8 * h + 4]) + c_vec[V_BQKV2 + 32 + 8 * h + 4], d);
-          d = fmaf(q1.y, __uint_as_float(kk[8 * h + 5]) + c_vec[V_BQKV2 + 32 + 8 * h + 5], d);
-          d = fmaf(q1.z, __uint_as_float(kk[8 * h + 6]) + c_vec[V_BQKV2 + 32 + 8 * h + 6], d);
-          d = fmaf(q1.w, __uint_as_float(kk[8 * h + 7]) + c_vec[V_BQKV2 + 32 + 8 * h + 7], d);
+          float kb[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) kb[e] = kFold ? __uint_as_float(kk[8 * h + e]) : __uint_as_float(kk[8 * h + e]) + c_vec[V_BQKV2 + 32 + 8 * h + e];
+          float d = q0.x * kb[0];
+          d = fmaf(q0.y, kb[1], d);
+          d = fmaf(q0.z, kb[2], d);
+          d = fmaf(q0.w, kb[3], d);
+          d = fmaf(q1.x, kb[4], d);
+          d = fmaf(q1.y, kb[5], d);
+          d = fmaf(q1.z, kb[6], d);
+          d = fmaf(q1.w, kb[7], d);
           sc[h] = r < T ? d : -INFINITY;
           if (exact_cls) {           // the maximum over all keys is only needed when 2^s could overflow
             float mw = sc[h];
@@ -719,7 +786,8 @@ __global__ void __launch_bounds__(tm::Cfg<SLOTS>::kThreads, 1) tokens_tm_kernel(
           const float p = ex2(sc[h] - m);
           pl[h] = p;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) val[8 * h + e] = p * (__uint_as_float(vv[8 * h + e]) + c_vec[V_BQKV2 + 64 + 8 * h + e]);
+          for (int e = 0; e < 8; ++e)
+            val[8 * h + e] = kFold ? p * __uint_as_float(vv[8 * h + e]) : p * (__uint_as_float(vv[8 * h + e]) + c_vec[V_BQKV2 + 64 + 8 * h + e]);
         }
         // butterfly reduction over the 32 rows of this warp: lane i ends with sum over rows of val[i]
 #pragma unroll
