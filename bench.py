@@ -569,6 +569,9 @@ def main():
     strong = None
     if not args.windows:
         ms_strong = timed(one_scene, args.steps)
+        if not args.no_e2e:
+            for _ in range(max(args.warmup, 3)):     # the single-scene plan has its own sub-bands and staging size: warm it up too
+                e2e_scene(True)
         ms_strong_e2e = float("nan") if args.no_e2e else timed(lambda: e2e_scene(True), args.steps)
         logits_map.zero_()
         argmax_map.zero_()
