@@ -93,3 +93,45 @@ def test_subband_bounds_cover_the_band_in_whole_block_rows(P, block, depth):
     assert subband_bounds(339, 11, 8, 31, 2) == [0, 21, 69, 117, 165, 213, 261, 309, 339]      # Houston: 15 block rows
     assert subband_bounds(339, 11, 6, 31, 2) == [0, 48, 96, 144, 192, 267, 339]                # 14 block rows
     assert subband_bounds(339, 11, 6, 31, 2, lead_small=True) == [0, 21, 69, 117, 192, 267, 339]
+
+
+def test_plan_subbands_picks_whole_block_rows_and_covers_every_window_row():
+    """utils.plan_subbands (scene.py): the spans cover every window row, only ever overlap by starting earlier, never
+    exceed the allowed count, and for the Houston scene the single-scene plan is four sub-bands of exactly one 95-row
+    block row each (the uncut scene needs four) while the streaming plan does not cut at all.  The block edge is
+    modelled as csrc/abi.cu scene_block does it (fewest block-row pixels among 31 / 63 / 95)."""
+    from vitcnn_b200.utils import plan_subbands
+    W, D = 1905, 3
+
+    def blk_count(ext, B):
+        st = B - 2 * D
+        return (ext - B + st - 1) // st + 1
+
+    def block_of(h, depth):
+        best, rows = 31, -1
+        for B in (31, 63, 95):
+            if h < B or W < B:
+                break
+            r = blk_count(h, B) * blk_count(W, B) * (B + 1) * (B + 1)
+            if rows < 0 or r < rows:
+                best, rows = B, r
+        return best
+
+    P = 11
+    cost, spans = plan_subbands(339, P, 6, True, lambda rows: D, block_of)
+    assert spans == [(0, 85), (85, 170), (170, 255), (254, 339)]
+    assert all(block_of(b - a + P - 1, D) == 95 and blk_count(b - a + P - 1, 95) == 1 for a, b in spans)
+    assert plan_subbands(339, P, 2, False, lambda rows: D, block_of)[1] == [(0, 339)]
+    assert plan_subbands(339, P, 6, True, lambda rows: 0, block_of) is None          # no shared stem: the caller keeps equal parts
+    for nrows in list(range(21, 200, 7)) + [339, 340, 700]:
+        for nmax in (1, 2, 4, 6):
+            for sync in (True, False):
+                plan = plan_subbands(nrows, P, min(nmax, max(1, nrows // 21)), sync, lambda rows: D, block_of)
+                assert plan is not None
+                spans = plan[1]
+                assert 1 <= len(spans) <= nmax and spans[0][0] == 0 and spans[-1][1] == nrows
+                covered = 0
+                for a, b in spans:
+                    assert 0 <= a < b <= nrows and a <= covered          # contiguous or overlapping, never a gap
+                    covered = max(covered, b)
+                assert covered == nrows

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 from .model import SCENE_CHUNK
-from .utils import band_geometry, subband_bounds
+from .utils import band_geometry, plan_subbands, subband_bounds
 
 
 @torch.no_grad()
@@ -64,41 +64,15 @@ def predict_scene_host(net, img1: torch.Tensor, img2: torch.Tensor, stride: int 
     bounds = [(nrows * k) // nsub for k in range(nsub + 1)]
     spans = list(zip(bounds[:-1], bounds[1:]))         # window rows [a, b) of every sub-band
     if stride == 1 and nsub > 1 and os.environ.get("VITCNN_SUBBAND_SPLIT", "blocks") != "equal":
-        # The library picks the scene-block edge (31 / 63 / 95) per call from the raster it is handed, so the number of
-        # sub-bands decides how much stem work the cuts add: a Houston scene in 4 sub-bands of 85 window rows is exactly
-        # 4 block rows of 95 (what the uncut scene needs), in 6 it is 12 block rows of 63 (twice the stem).  Plan: for every
-        # count up to `pipeline`, cut at whole block rows and estimate stem rows + the first upload (the one nothing hides)
-        # + a fixed cost per sub-band; take the cheapest.
+        # how many sub-bands, and where to cut: utils.plan_subbands (block rows of the stem vs the exposed first upload)
         L = _lib.lib()
         lead_small = os.environ.get("VITCNN_SUBBAND_LEAD", "even") == "small"
         key = (nrows, W, P, len(geo["ys"]), nsub, bool(sync), int(chunk), lead_small, str(dev), net.n_bands, net.n_bands2, net.num_classes)
         best = _PLAN.get(key)
-        for n in range(1, nsub + 1) if best is None else ():
-            rows_n = -(-nrows // n)
-            depth = _shared_depth(net, rows_n + P - 1, W, rows_n * len(geo["ys"]), chunk, dev)
-            if depth <= 0:
-                continue
-            block = int(L.vc_scene_block(rows_n + P - 1, W, depth))
-            cb = subband_bounds(nrows, P, n, block, depth, lead_small=lead_small)
-            cand, stem_rows = [], 0
-            for a, b in zip(cb[:-1], cb[1:]):
-                if b > a:
-                    # a sub-band a few rows short of one block row would make the library fall back to a smaller block
-                    # edge (two block rows of 63 instead of one of 95): start it earlier, the overlapping window rows are
-                    # simply computed (and downloaded) twice, bit-identically
-                    short = block - (b - a + P - 1)
-                    if 0 < short <= 8 and a - short >= 0:
-                        a -= short
-                    h = b - a + P - 1
-                    bk = int(L.vc_scene_block(h, W, depth))
-                    stem_rows += ((h - bk + bk - 2 * depth - 1) // (bk - 2 * depth) + 1) * (bk + 1)
-                    cand.append((a, b))
-            first = cand[0][1] - cand[0][0] + P - 1
-            # relative costs per raster row of the band's width: a stem row ~1.2 upload rows (Houston: 9.2 ms per 384 stem
-            # rows, 7 ms per 349 uploaded rows); a sub-band's launches ~8 rows
-            cost = 1.2 * stem_rows + (first if sync else 0) + 8 * len(cand)
-            if best is None or cost < best[0]:
-                best = (cost, cand)
+        if best is None:
+            best = plan_subbands(nrows, P, nsub, sync,
+                                 lambda rows: _shared_depth(net, rows + P - 1, W, rows * len(geo["ys"]), chunk, dev),
+                                 lambda h, depth: int(L.vc_scene_block(h, W, depth)), lead_small)
         if best is not None:
             _PLAN[key] = best
             spans = best[1]

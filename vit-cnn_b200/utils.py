@@ -111,6 +111,45 @@ def subband_bounds(nrows: int, P: int, pipeline: int, block: int = 0, depth: int
     return bounds
 
 
+def plan_subbands(nrows: int, P: int, nmax: int, sync: bool, depth_of, block_of, lead_small: bool = False):
+    """Sub-bands (window-row spans ``[a, b)``, possibly overlapping) of a dense band for predict_scene_host, or None
+    when no candidate has a shared stem.  The library picks the scene-block edge (31 / 63 / 95) per call from the
+    raster it is handed (``block_of(raster_rows, depth)``; ``depth_of(window_rows)`` = the sharing depth it will use), so
+    the number of sub-bands decides how much stem work the cuts add: a Houston scene in 4 sub-bands of 85 window rows is
+    exactly 4 block rows of 95 (what the uncut scene needs), in 6 it is 12 block rows of 63 (twice the stem).  For every
+    count up to ``nmax`` the band is cut at whole block rows (subband_bounds); a sub-band a few rows short of one block
+    row starts earlier instead of falling back to a smaller block edge (the overlapping window rows are simply computed
+    and downloaded twice, bit-identically); cost = stem rows + the first upload when nothing hides it (``sync``) + a
+    fixed cost per sub-band, in units of one uploaded raster row (Houston: 9.2 ms per 384 stem rows, 7 ms per 349
+    uploaded rows, ~0.15 ms of launches per sub-band).  Returns (cost, spans)."""
+    best = None
+    for n in range(1, max(1, int(nmax)) + 1):
+        rows_n = -(-nrows // n)
+        depth = depth_of(rows_n)
+        if depth <= 0:
+            continue
+        block = block_of(rows_n + P - 1, depth)
+        cb = subband_bounds(nrows, P, n, block, depth, lead_small=lead_small)
+        cand, stem_rows = [], 0
+        for a, b in zip(cb[:-1], cb[1:]):
+            if b > a:
+                short = block - (b - a + P - 1)
+                if 0 < short <= 8 and a - short >= 0:
+                    a -= short
+                h = b - a + P - 1
+                bk = block_of(h, depth)
+                step = bk - 2 * depth
+                stem_rows += ((h - bk + step - 1) // step + 1) * (bk + 1)
+                cand.append((a, b))
+        if not cand:
+            continue
+        first = cand[0][1] - cand[0][0] + P - 1
+        cost = 1.2 * stem_rows + (first if sync else 0) + 8 * len(cand)
+        if best is None or cost < best[0]:
+            best = (cost, cand)
+    return best
+
+
 def camel_to_snake(name: str) -> str:
     """utils.py:883-885: ``ViTCNN`` -> ``vi_tcnn``-style folder name of the checkpoint path (the two regular
     expressions are the identifier-splitting idiom the reference uses; the result must match for
