@@ -20,9 +20,16 @@
 //  * fc1's accumulators are overwritten in place by the packed GELU outputs, fc2 reads them from TMEM;
 //    the 32 KB P / hidden buffer of a slot is gone (24 KB of shared memory per slot instead of 56 KB, ~60 % less
 //    shared-memory traffic per patch, 80 fewer 16-byte stores per row and patch);
-//  * the 640 per-channel constants live in __constant__ memory (filled per launch by a one-block prep kernel and a
-//    device-to-device copy on the same stream) and enter the FFMAs as c[bank][offset] operands: no loads, no
-//    registers, nothing in the MIO queue;
+//  * LayerNorm gamma / beta, the fusion conv's folded-BN scale, the query scale and every bias are folded into the
+//    GEMMs (VC_TM_FOLD: scaled bf16 weight images; the bias is one more K step against the ones slab), so the epilogues
+//    are pack / ReLU / GELU / residual only; the per-channel constants that remain (cls query bias, flags; all of them
+//    with VC_TM_FOLD=0) live in __constant__ memory, filled per launch by a one-block prep kernel and a
+//    device-to-device copy on the same stream, and enter the FFMAs as uniform / constant operands: no shared-memory
+//    loads, nothing in the MIO queue;
+//  * the next patch's fusion GEMM is issued with the K / V GEMM of the last block, the cls query is computed by the row
+//    warps while that GEMM is in flight (no single-lane TMEM read, no barrier behind the GEMM);
+//  * the MMA-issuer warps run warp-uniform control flow with the tcgen05 instructions in elect blocks (UTCHMMA takes
+//    uniform-register operands: inside a divergent region every one of them costs an ELECT / R2UR.BROADCAST loop);
 //  * the static bound that decides whether the softmax may skip the row maximum is evaluated once by the prep
 //    kernel.  This kernel implements the no-maximum path only; when the bound fails it exits at once and
 //    tokens_tc_kernel (launched right behind it, gated on the same flag) does the work.
