@@ -10,7 +10,8 @@ included, no collective), i.e. one scene's worth of windows per GPU per step (we
 Prints ONE JSON line (rank 0):
   value        pixels/s with the rasters resident in HBM (CUDA events, max over ranks);
   e2e          the same through the public host-buffer API (predict_scene_host: pinned H2D of every band,
-               D2H of its logits / argmax map, every step);
+               D2H of its logits / argmax map, every step); also the host time spent queueing a step, the cudaMalloc
+               count of the timed region and the upload-only time of the same bytes (what the link alone allows);
   strong       ONE scene split over the N ranks: ms per scene (max over ranks, barrier to barrier), device and
                end to end, and an order-independent integer checksum of the assembled maps against the map one
                GPU computes alone (row bands must reproduce it bit for bit);
